@@ -1,0 +1,91 @@
+// Library-level entry points of the C ABI: error text, version, device query, GEMM dispatch.
+#include "common.cuh"
+
+#include <mutex>
+#include <string.h>
+
+namespace bnn {
+
+namespace {
+thread_local char g_err[512] = "";
+}
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return BNN_ERR_CUDA;
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+int gemm_tc_dispatch(const bnn_gemm_desc& g, cudaStream_t stream);
+int gemm_simt_dispatch(const bnn_gemm_desc& g, cudaStream_t stream);
+
+}  // namespace bnn
+
+using namespace bnn;
+
+extern "C" const char* bnn_last_error(void) { return g_err; }
+
+extern "C" int bnn_version(void) { return BNN_B200_VERSION; }
+
+extern "C" int bnn_device_query(int* sm_count_host, int* cc_major_host, int* cc_minor_host) {
+    int dev = 0;
+    BNN_CUDA(cudaGetDevice(&dev));
+    int sms = 0, maj = 0, mnr = 0;
+    BNN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    BNN_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+    BNN_CUDA(cudaDeviceGetAttribute(&mnr, cudaDevAttrComputeCapabilityMinor, dev));
+    if (sm_count_host) *sm_count_host = sms;
+    if (cc_major_host) *cc_major_host = maj;
+    if (cc_minor_host) *cc_minor_host = mnr;
+    return BNN_OK;
+}
+
+extern "C" int bnn_gemm(const bnn_gemm_desc* g, int impl, bnn_stream_t stream) {
+    BNN_CHECK_ARG(g != nullptr, "bnn_gemm: null descriptor");
+    BNN_CHECK_ARG(g->M > 0 && g->N > 0 && g->K > 0 && g->batch >= 1,
+                  "bnn_gemm: empty shape M=%d N=%d K=%d batch=%d", g->M, g->N, g->K, g->batch);
+    BNN_CHECK_ARG(g->in_dtype == BNN_DT_I8 || g->in_dtype == BNN_DT_F16, "bnn_gemm: bad in_dtype %d",
+                  g->in_dtype);
+    BNN_CHECK_ARG(g->epilogue >= BNN_EPI_STORE_F32 && g->epilogue <= BNN_EPI_SGD_F32,
+                  "bnn_gemm: bad epilogue %d", g->epilogue);
+    BNN_CHECK_ARG(g->in_dtype == BNN_DT_I8 ||
+                      (g->epilogue != BNN_EPI_STORE_S32 && g->epilogue != BNN_EPI_STORE_S16),
+                  "bnn_gemm: integer stores need int8 operands");
+    BNN_CHECK_ARG(g->epilogue != BNN_EPI_STORE_S16 || g->K * (int64_t)g->n_pass < 32768,
+                  "bnn_gemm: K too large for an int16 result");
+    BNN_CHECK_ARG(g->n_pass >= 1 && g->n_pass <= BNN_GEMM_MAX_PASS, "bnn_gemm: n_pass %d out of range",
+                  g->n_pass);
+    BNN_CHECK_ARG(g->A[0] && g->B[0] && g->D, "bnn_gemm: null operand");
+    for (int p = 0; p < g->n_pass; ++p) {
+        BNN_CHECK_ARG(g->pa[p] >= 0 && g->pa[p] <= 1 && g->pb[p] >= 0 && g->pb[p] <= 1,
+                      "bnn_gemm: pass %d refers to a piece outside {0,1}", p);
+        BNN_CHECK_ARG(g->A[g->pa[p]] && g->B[g->pb[p]], "bnn_gemm: pass %d uses a null piece", p);
+    }
+    BNN_CHECK_ARG(g->ldd >= g->N, "bnn_gemm: ldd < N");
+    BNN_CHECK_ARG(g->batch == 1 || g->stride_d >= (int64_t)g->M * g->ldd,
+                  "bnn_gemm: batched output needs stride_d >= M*ldd");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (impl == BNN_GEMM_TCGEN05) return gemm_tc_dispatch(*g, s);
+    if (impl == BNN_GEMM_SIMT) return gemm_simt_dispatch(*g, s);
+    set_error("bnn_gemm: unknown impl %d", impl);
+    return BNN_ERR_ARG;
+}

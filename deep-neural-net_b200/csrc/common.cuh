@@ -1,0 +1,80 @@
+// Shared host/device helpers for libbnn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/bnn_b200.h"
+
+namespace bnn {
+
+// ---- error reporting across the C ABI (no exceptions cross the boundary) -------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define BNN_CHECK_ARG(cond, ...)                                  \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            ::bnn::set_error(__VA_ARGS__);                        \
+            return BNN_ERR_ARG;                                   \
+        }                                                         \
+    } while (0)
+
+#define BNN_CUDA(call)                                            \
+    do {                                                          \
+        cudaError_t _e = (call);                                  \
+        if (_e != cudaSuccess) return ::bnn::cuda_fail(_e, #call);\
+    } while (0)
+
+#define BNN_LAUNCH_CHECK(name)                                    \
+    do {                                                          \
+        cudaError_t _e = cudaGetLastError();                      \
+        if (_e != cudaSuccess) return ::bnn::cuda_fail(_e, name); \
+    } while (0)
+
+__host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+// ---- device helpers -------------------------------------------------------------------------
+// Reference sign convention: +1 iff x >= 0 (so -0.0 -> +1, NaN -> "not >= 0" -> bit 0).
+// mlpcode/layers.py:278-279, activation.py:110-111.
+__device__ __forceinline__ uint32_t sign_bit_ge0(float x) { return x >= 0.0f ? 1u : 0u; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Power-of-two scale that maps |x| <= bound into the fp16 range with head-room:
+// s = 2^(14 - ceil(log2(bound))), so |x*s| <= 2^14 < 65504.  bound <= 0 -> s = 1.
+__device__ __forceinline__ float split_scale_from_bound(float bound) {
+    if (!(bound > 0.0f) || !isfinite(bound)) return 1.0f;
+    int e;
+    float m = frexpf(bound, &e);  // bound = m * 2^e, m in [0.5,1)
+    int ce = (m == 0.5f) ? e - 1 : e;  // ceil(log2(bound))
+    int sh = 14 - ce;
+    sh = sh > 120 ? 120 : (sh < -120 ? -120 : sh);
+    return ldexpf(1.0f, sh);
+}
+
+// hi/lo fp16 split of a pre-scaled fp32 value: x*s = hi + lo + O(2^-22 |x*s|).
+__device__ __forceinline__ void split_f16(float xs, __half& hi, __half& lo) {
+    hi = __float2half_rn(xs);
+    lo = __float2half_rn(xs - __half2float(hi));
+}
+
+}  // namespace bnn

@@ -1,0 +1,244 @@
+// sign() binarization, bit packing and operand-layout kernels (all HBM-bound).
+//   A1  BinaryLayer.binarize   mlpcode/layers.py:275-281   (+1 iff x >= 0)
+//   A6  unitstep               mlpcode/activation.py:106-113
+// plus the fp32 -> 2 x fp16 split that feeds the real-valued tensor-core GEMMs.
+#include "common.cuh"
+
+namespace bnn {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Row packing: one warp produces one 32-bit word per ballot; coalesced 128-byte reads.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ bool is_plus(T v);
+template <>
+__device__ __forceinline__ bool is_plus<float>(float v) { return v >= 0.0f; }
+template <>
+__device__ __forceinline__ bool is_plus<int8_t>(int8_t v) { return v > 0; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x, int R, int C,
+                                                        long long ldx, uint32_t* __restrict__ bits,
+                                                        long long ldw) {
+    const int words = (C + 31) >> 5;
+    const long long total = (long long)R * words;
+    const int lane = threadIdx.x & 31;
+    long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long wstride = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (; w < total; w += wstride) {  // warp-uniform
+        const int r = (int)(w / words), cw = (int)(w % words);
+        const int c = cw * 32 + lane;
+        const bool p = (c < C) && is_plus<T>(x[(long long)r * ldx + c]);
+        const uint32_t word = __ballot_sync(0xffffffffu, p);
+        if (lane == 0) bits[(long long)r * ldw + cw] = word;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Transposing weight binarization: W[K,N] fp32 -> K-major +-1 copies [N, K].
+// Tile = 128 (k) x 32 (n): reads are 128-byte row segments, writes are 128 consecutive k per n.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+binarize_t_kernel(const float* __restrict__ W, int K, int N, int8_t* __restrict__ wt_i8,
+                  long long ld_i8, __half* __restrict__ wt_f16, long long ld_f16,
+                  uint32_t* __restrict__ wt_bits, long long ld_bits) {
+    __shared__ uint32_t s[128][33];
+    const int k0 = blockIdx.y * 128, n0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int k = warp + 8 * i;
+        const int gk = k0 + k, gn = n0 + lane;
+        float v = -1.0f;
+        if (gk < K && gn < N) v = __ldg(W + (long long)gk * N + gn);
+        s[k][lane] = sign_bit_ge0(v);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = warp * 4 + i;
+        const int gn = n0 + n;
+        if (gn >= N) continue;  // warp-uniform
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int gk = k0 + kk * 32 + lane;
+            const bool valid = gk < K;
+            const uint32_t bit = valid ? s[kk * 32 + lane][n] : 0u;
+            const uint32_t word = __ballot_sync(0xffffffffu, bit != 0u);
+            if (wt_bits && lane == 0 && (k0 + kk * 32) < K)
+                wt_bits[(long long)gn * ld_bits + ((k0 + kk * 32) >> 5)] = word;
+            if (valid) {
+                if (wt_i8) wt_i8[(long long)gn * ld_i8 + gk] = bit ? (int8_t)1 : (int8_t)-1;
+                if (wt_f16)
+                    wt_f16[(long long)gn * ld_f16 + gk] =
+                        __ushort_as_half(bit ? (unsigned short)0x3C00 : (unsigned short)0xBC00);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_bits_kernel(const uint32_t* __restrict__ bits, int R, int C, long long ldw,
+                   int8_t* __restrict__ out_i8, long long ld_i8, __half* __restrict__ out_f16,
+                   long long ld_f16) {
+    const long long total = (long long)R * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / C), c = (int)(i % C);
+        const uint32_t b = (bits[(long long)r * ldw + (c >> 5)] >> (c & 31)) & 1u;
+        if (out_i8) out_i8[(long long)r * ld_i8 + c] = b ? (int8_t)1 : (int8_t)-1;
+        if (out_f16)
+            out_f16[(long long)r * ld_f16 + c] =
+                __ushort_as_half(b ? (unsigned short)0x3C00 : (unsigned short)0xBC00);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// max |x| via integer atomicMax on the float bit pattern (non-negative floats order like uints).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, long long n,
+                                                     uint32_t* __restrict__ out) {
+    float m = 0.0f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n4 = (aligned16(x) ? n / 4 : 0);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (long long j = i; j < n4; j += stride) {
+        const float4 v = __ldg(x4 + j);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (long long j = n4 * 4 + i; j < n; j += stride) m = fmaxf(m, fabsf(__ldg(x + j)));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 -> fp16 hi/lo split, row-major and transposed (64 x 64 tiles through shared memory).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ x, int R, int C, long long ldx,
+                 const float* __restrict__ bound, __half* __restrict__ hi, __half* __restrict__ lo,
+                 long long ld_rm, __half* __restrict__ hi_t, __half* __restrict__ lo_t,
+                 long long ld_t, float* __restrict__ scale_out) {
+    __shared__ __half sh[64][66];
+    __shared__ __half sl[64][66];
+    const float s = split_scale_from_bound(__ldg(bound));
+    if (scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *scale_out = s;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    const int tc = threadIdx.x & 63, tr = threadIdx.x >> 6;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int r = tr + 4 * i;
+        const int gr = r0 + r, gc = c0 + tc;
+        __half h = __ushort_as_half(0), l = __ushort_as_half(0);
+        if (gr < R && gc < C) {
+            split_f16(__ldg(x + (long long)gr * ldx + gc) * s, h, l);
+            if (hi) {
+                hi[(long long)gr * ld_rm + gc] = h;
+                lo[(long long)gr * ld_rm + gc] = l;
+            }
+        }
+        sh[r][tc] = h;
+        sl[r][tc] = l;
+    }
+    if (!hi_t) return;
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int c = tr + 4 * i;
+        const int gr = r0 + tc, gc = c0 + c;
+        if (gr < R && gc < C) {
+            hi_t[(long long)gc * ld_t + gr] = sh[tc][c];
+            lo_t[(long long)gc * ld_t + gr] = sl[tc][c];
+        }
+    }
+}
+
+}  // namespace
+}  // namespace bnn
+
+using namespace bnn;
+
+extern "C" int bnn_pack_sign_rows(const float* x, int R, int C, int64_t ldx, uint32_t* bits,
+                                  int64_t ldw, bnn_stream_t stream) {
+    BNN_CHECK_ARG(R >= 0 && C >= 0, "bnn_pack_sign_rows: negative shape");
+    if (R == 0 || C == 0) return BNN_OK;
+    BNN_CHECK_ARG(x && bits, "bnn_pack_sign_rows: null pointer");
+    BNN_CHECK_ARG(ldx >= C && ldw >= (C + 31) / 32, "bnn_pack_sign_rows: pitch too small");
+    const long long warps = (long long)R * ((C + 31) / 32);
+    const int grid = (int)((warps * 32 + 255) / 256 < 148 * 16 ? (warps * 32 + 255) / 256 : 148 * 16);
+    pack_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, C, ldx, bits, ldw);
+    BNN_LAUNCH_CHECK("pack_rows_kernel<float>");
+    return BNN_OK;
+}
+
+extern "C" int bnn_pack_i8_rows(const int8_t* x, int R, int C, int64_t ldx, uint32_t* bits,
+                                int64_t ldw, bnn_stream_t stream) {
+    BNN_CHECK_ARG(R >= 0 && C >= 0, "bnn_pack_i8_rows: negative shape");
+    if (R == 0 || C == 0) return BNN_OK;
+    BNN_CHECK_ARG(x && bits, "bnn_pack_i8_rows: null pointer");
+    BNN_CHECK_ARG(ldx >= C && ldw >= (C + 31) / 32, "bnn_pack_i8_rows: pitch too small");
+    const long long warps = (long long)R * ((C + 31) / 32);
+    const int grid = (int)((warps * 32 + 255) / 256 < 148 * 16 ? (warps * 32 + 255) / 256 : 148 * 16);
+    pack_rows_kernel<int8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, C, ldx, bits, ldw);
+    BNN_LAUNCH_CHECK("pack_rows_kernel<int8_t>");
+    return BNN_OK;
+}
+
+extern "C" int bnn_binarize_weights_t(const float* W, int K, int N, int8_t* wt_i8, int64_t ld_i8,
+                                      void* wt_f16, int64_t ld_f16, uint32_t* wt_bits,
+                                      int64_t ld_bits, bnn_stream_t stream) {
+    BNN_CHECK_ARG(W && K > 0 && N > 0, "bnn_binarize_weights_t: bad input");
+    BNN_CHECK_ARG(!wt_i8 || ld_i8 >= K, "bnn_binarize_weights_t: ld_i8 < K");
+    BNN_CHECK_ARG(!wt_f16 || ld_f16 >= K, "bnn_binarize_weights_t: ld_f16 < K");
+    BNN_CHECK_ARG(!wt_bits || ld_bits >= (K + 31) / 32, "bnn_binarize_weights_t: ld_bits too small");
+    dim3 grid(cdiv(N, 32), cdiv(K, 128));
+    BNN_CHECK_ARG(grid.y <= 65535, "bnn_binarize_weights_t: K too large");
+    binarize_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        W, K, N, wt_i8, ld_i8, static_cast<__half*>(wt_f16), ld_f16, wt_bits, ld_bits);
+    BNN_LAUNCH_CHECK("binarize_t_kernel");
+    return BNN_OK;
+}
+
+extern "C" int bnn_unpack_bits(const uint32_t* bits, int R, int C, int64_t ldw, int8_t* out_i8,
+                               int64_t ld_i8, void* out_f16, int64_t ld_f16, bnn_stream_t stream) {
+    BNN_CHECK_ARG(bits && R > 0 && C > 0, "bnn_unpack_bits: bad input");
+    const long long total = (long long)R * C;
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    unpack_bits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        bits, R, C, ldw, out_i8, ld_i8, static_cast<__half*>(out_f16), ld_f16);
+    BNN_LAUNCH_CHECK("unpack_bits_kernel");
+    return BNN_OK;
+}
+
+extern "C" int bnn_absmax_f32(const float* x, int64_t n, uint32_t* absmax_bits, int zero_first,
+                              bnn_stream_t stream) {
+    BNN_CHECK_ARG(absmax_bits && n >= 0, "bnn_absmax_f32: bad input");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (zero_first) BNN_CUDA(cudaMemsetAsync(absmax_bits, 0, sizeof(uint32_t), s));
+    if (n == 0) return BNN_OK;
+    BNN_CHECK_ARG(x, "bnn_absmax_f32: null x");
+    const long long blocks = (n / 4 + 255) / 256;
+    const int grid = (int)(blocks < 148 * 8 ? (blocks > 0 ? blocks : 1) : 148 * 8);
+    absmax_kernel<<<grid, 256, 0, s>>>(x, n, absmax_bits);
+    BNN_LAUNCH_CHECK("absmax_kernel");
+    return BNN_OK;
+}
+
+extern "C" int bnn_split_f16(const float* x, int R, int C, int64_t ldx, const float* bound, void* hi,
+                             void* lo, int64_t ld_rm, void* hi_t, void* lo_t, int64_t ld_t,
+                             float* scale_out, bnn_stream_t stream) {
+    BNN_CHECK_ARG(x && bound && R > 0 && C > 0, "bnn_split_f16: bad input");
+    BNN_CHECK_ARG((hi == nullptr) == (lo == nullptr) && (hi_t == nullptr) == (lo_t == nullptr),
+                  "bnn_split_f16: hi/lo must be given in pairs");
+    BNN_CHECK_ARG(!hi || ld_rm >= C, "bnn_split_f16: ld_rm < C");
+    BNN_CHECK_ARG(!hi_t || ld_t >= R, "bnn_split_f16: ld_t < R");
+    dim3 grid(cdiv(C, 64), cdiv(R, 64));
+    BNN_CHECK_ARG(grid.y <= 65535, "bnn_split_f16: R too large");
+    split_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        x, R, C, ldx, bound, static_cast<__half*>(hi), static_cast<__half*>(lo), ld_rm,
+        static_cast<__half*>(hi_t), static_cast<__half*>(lo_t), ld_t, scale_out);
+    BNN_LAUNCH_CHECK("split_f16_kernel");
+    return BNN_OK;
+}

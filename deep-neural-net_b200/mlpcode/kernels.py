@@ -1,0 +1,229 @@
+"""Typed Python front-ends of the libbnn_b200 entry points (one function per C symbol).
+
+Arguments are CUDA torch tensors used purely as device buffers; shapes/pitches are derived from
+them and passed to the C ABI together with raw pointers and torch's current stream.  Nothing here
+computes on the host and nothing falls back to another backend.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import _native as nat
+from .device import ptr, stream_ptr
+
+launch_count = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+# launches (kernels + memsets are not counted) issued per C call
+_LAUNCHES = {"bnn_minmax_u8": 2}
+
+
+def _call(name, *args):
+    global launch_count
+    nat.call(name, *args, stream_ptr())
+    launch_count += _LAUNCHES.get(name, 1)
+
+
+def gemm_impl() -> int:
+    """Product path is tcgen05; BNN_GEMM_IMPL=simt selects the CUDA-core cross-check kernel."""
+    v = os.environ.get("BNN_GEMM_IMPL", "tcgen05").lower()
+    if v in ("tcgen05", "tc"):
+        return nat.GEMM_TCGEN05
+    if v == "simt":
+        return nat.GEMM_SIMT
+    raise ValueError(f"BNN_GEMM_IMPL={v!r}: expected 'tcgen05' or 'simt'")
+
+
+def _ld(t: torch.Tensor) -> int:
+    assert t.stride(-1) == 1, "innermost dimension must be contiguous"
+    return t.stride(-2) if t.ndim >= 2 else t.shape[0]
+
+
+# ------------------------------------------------------------------------------- packing
+def pack_sign_rows(x: torch.Tensor, bits: torch.Tensor) -> None:
+    R, Cc = x.shape
+    _call("bnn_pack_sign_rows", ptr(x), R, Cc, _ld(x), ptr(bits), _ld(bits))
+
+
+def pack_i8_rows(x: torch.Tensor, C_: int, bits: torch.Tensor) -> None:
+    _call("bnn_pack_i8_rows", ptr(x), x.shape[0], C_, _ld(x), ptr(bits), _ld(bits))
+
+
+def binarize_weights_t(W: torch.Tensor, wt_i8=None, wt_f16=None, wt_bits=None) -> None:
+    K, N = W.shape
+    assert W.is_contiguous()
+    _call("bnn_binarize_weights_t", ptr(W), K, N,
+          ptr(wt_i8), _ld(wt_i8) if wt_i8 is not None else 0,
+          ptr(wt_f16), _ld(wt_f16) if wt_f16 is not None else 0,
+          ptr(wt_bits), _ld(wt_bits) if wt_bits is not None else 0)
+
+
+def unpack_bits(bits: torch.Tensor, C_: int, out_i8=None, out_f16=None) -> None:
+    _call("bnn_unpack_bits", ptr(bits), bits.shape[0], C_, _ld(bits),
+          ptr(out_i8), _ld(out_i8) if out_i8 is not None else 0,
+          ptr(out_f16), _ld(out_f16) if out_f16 is not None else 0)
+
+
+def absmax_f32(x: torch.Tensor, out_bits: torch.Tensor, zero_first=True) -> None:
+    assert x.is_contiguous()
+    _call("bnn_absmax_f32", ptr(x), x.numel(), ptr(out_bits), int(zero_first))
+
+
+def split_f16(x: torch.Tensor, bound: torch.Tensor, hi=None, lo=None, hi_t=None, lo_t=None,
+              scale_out=None) -> None:
+    R, Cc = x.shape
+    _call("bnn_split_f16", ptr(x), R, Cc, _ld(x), ptr(bound), ptr(hi), ptr(lo),
+          _ld(hi) if hi is not None else 0, ptr(hi_t), ptr(lo_t),
+          _ld(hi_t) if hi_t is not None else 0, ptr(scale_out))
+
+
+# ------------------------------------------------------------------------------- GEMMs
+def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),), sa=None,
+         sb=None, host_scale=1.0, batch=1, stride_a=0, stride_b=0, stride_d=0, impl=None) -> None:
+    """D = epi(sum_p A[pa] @ B[pb]^T); A/B are sequences of 1..2 operand-piece tensors."""
+    d = nat.GemmDesc()
+    d.M, d.N, d.K, d.batch = M, N, K, batch
+    d.in_dtype, d.epilogue, d.n_pass = in_dtype, epilogue, len(passes)
+    for i, (a, b) in enumerate(passes):
+        d.pa[i], d.pb[i] = a, b
+    for i in range(2):
+        d.A[i] = ptr(A[i]) if i < len(A) else None
+        d.B[i] = ptr(B[i]) if i < len(B) else None
+    d.lda, d.ldb, d.stride_a, d.stride_b = lda, ldb, stride_a, stride_b
+    d.D, d.ldd, d.stride_d = ptr(D), ldd, stride_d
+    d.sa, d.sb = ptr(sa), ptr(sb)
+    d.host_scale = host_scale
+    _call("bnn_gemm", C.byref(d), gemm_impl() if impl is None else impl)
+
+
+def gemm_popc(a_bits, b_bits, M, N, K, D, out_s16=True) -> None:
+    _call("bnn_gemm_popc", ptr(a_bits), _ld(a_bits), ptr(b_bits), _ld(b_bits), M, N, K, ptr(D),
+          _ld(D), nat.EPI_STORE_S16 if out_s16 else nat.EPI_STORE_S32)
+
+
+# ------------------------------------------------------------------------------- batch norm
+def z_dtype_of(Z: torch.Tensor) -> int:
+    return {torch.float32: nat.Z_F32, torch.int16: nat.Z_S16, torch.int32: nat.Z_S32}[Z.dtype]
+
+
+def colstats(Z, B, N, sums, accumulate=False) -> None:
+    _call("bnn_colstats", ptr(Z), z_dtype_of(Z), B, N, _ld(Z), ptr(sums), int(accumulate))
+
+
+def bn_stats_finalize(sums, N, count, mu, var) -> None:
+    _call("bnn_bn_stats_finalize", ptr(sums), N, float(count), ptr(mu), ptr(var))
+
+
+def bn_apply(Z, B, N, mu, var, gamma, beta, eps, out_f32=None, act_i8=None, act_t16=None,
+             act_bits=None) -> None:
+    _call("bnn_bn_apply", ptr(Z), z_dtype_of(Z), B, N, _ld(Z), ptr(mu), ptr(var), ptr(gamma),
+          ptr(beta), eps,
+          ptr(out_f32), _ld(out_f32) if out_f32 is not None else 0,
+          ptr(act_i8), _ld(act_i8) if act_i8 is not None else 0,
+          ptr(act_t16), _ld(act_t16) if act_t16 is not None else 0,
+          ptr(act_bits), _ld(act_bits) if act_bits is not None else 0)
+
+
+def softmax_xent(logits, B, Cc, onehot=None, probs=None, loss_rows=None, grad=None, count=None,
+                 loss_sum=None) -> None:
+    _call("bnn_softmax_xent", ptr(logits), B, Cc, _ld(logits), ptr(onehot), ptr(probs),
+          ptr(loss_rows), ptr(grad), float(count if count is not None else B), ptr(loss_sum))
+
+
+def bn_bwd_reduce(delta, Z, B, N, mu, red, red_max, accumulate=False) -> None:
+    _call("bnn_bn_bwd_reduce", ptr(delta), _ld(delta), ptr(Z), z_dtype_of(Z), _ld(Z), B, N,
+          ptr(mu), ptr(red), ptr(red_max), int(accumulate))
+
+
+def bn_bwd_finalize(red, red_max, N, count, mu, var, eps, gamma, beta, mu_run, sigma_run, lr,
+                    momentum, sums, coef, bound_bits, dgamma_out=None, dbeta_out=None) -> None:
+    _call("bnn_bn_bwd_finalize", ptr(red), ptr(red_max), N, float(count), ptr(mu), ptr(var), eps,
+          ptr(gamma), ptr(beta), ptr(mu_run), ptr(sigma_run), lr, momentum, ptr(sums), ptr(coef),
+          ptr(bound_bits), ptr(dgamma_out), ptr(dbeta_out))
+
+
+def bn_bwd_apply(delta, Z, B, N, mu, coef, bound, out_f32=None, d_hi=None, d_lo=None, dt_hi=None,
+                 dt_lo=None, scale_out=None) -> None:
+    _call("bnn_bn_bwd_apply", ptr(delta), _ld(delta), ptr(Z), z_dtype_of(Z), _ld(Z), B, N, ptr(mu),
+          ptr(coef), ptr(bound),
+          ptr(out_f32), _ld(out_f32) if out_f32 is not None else 0,
+          ptr(d_hi), ptr(d_lo), _ld(d_hi) if d_hi is not None else 0,
+          ptr(dt_hi), ptr(dt_lo), _ld(dt_hi) if dt_hi is not None else 0, ptr(scale_out))
+
+
+def sgd_update(p, g, lr) -> None:
+    assert p.is_contiguous() and g.is_contiguous() and p.numel() == g.numel()
+    _call("bnn_sgd_update", ptr(p), ptr(g), p.numel(), lr)
+
+
+def count_correct(scores, B, Cc, labels_i32, correct_i32) -> None:
+    _call("bnn_count_correct", ptr(scores), B, Cc, _ld(scores), ptr(labels_i32), ptr(correct_i32))
+
+
+# ------------------------------------------------------------------------------- fault injection
+def bernoulli_threshold(p: float) -> int:
+    """floor(p * 2^32) as the kernels' 64-bit compare threshold (p >= 1 flips everything)."""
+    if p <= 0:
+        return 0
+    return min(1 << 32, int(p * 4294967296.0))
+
+
+def flip_weights_bernoulli(*, N, K, p, seed, stream_id, trial0, n_trials, wt_i8=None, wt_bits=None,
+                           out_i8=None, out_f16=None, out_bits=None, mask_bits=None) -> None:
+    """Outputs are [n_trials, N, ld] tensors (or None)."""
+    def st(t):
+        return t.stride(0) if t is not None else 0
+
+    ld_bits = 0
+    for t in (wt_bits, out_bits, mask_bits):
+        if t is not None:
+            ld_bits = t.stride(-2)
+    ld_i8 = 0
+    for t in (wt_i8, out_i8):
+        if t is not None:
+            ld_i8 = t.stride(-2)
+    _call("bnn_flip_weights_bernoulli", ptr(wt_i8), ld_i8, ptr(wt_bits), ld_bits, N, K,
+          bernoulli_threshold(p), seed & (2**64 - 1), stream_id, trial0, n_trials,
+          ptr(out_i8), st(out_i8), ptr(out_f16), out_f16.stride(-2) if out_f16 is not None else 0,
+          st(out_f16), ptr(out_bits), st(out_bits), ptr(mask_bits), st(mask_bits))
+
+
+def flip_weights_exactk(*, N, K, total, offset, seed, trial0, k_per_trial, k_max, io_i8=None,
+                        io_f16=None, io_bits=None) -> None:
+    n_trials = k_per_trial.numel()
+
+    def st(t):
+        return t.stride(0) if (t is not None and t.ndim == 3) else 0
+
+    def ld(t):
+        return t.stride(-2) if t is not None else 0
+
+    _call("bnn_flip_weights_exactk", N, K, total, offset, seed & (2**64 - 1), trial0, n_trials,
+          ptr(k_per_trial), k_max, ptr(io_i8), ld(io_i8), st(io_i8), ptr(io_f16), ld(io_f16),
+          st(io_f16), ptr(io_bits), ld(io_bits), st(io_bits))
+
+
+def flip_weights_mask(mask_kn_u8, K, N, io_i8=None, io_f16=None, io_bits=None) -> None:
+    def ld(t):
+        return t.stride(-2) if t is not None else 0
+
+    _call("bnn_flip_weights_mask", ptr(mask_kn_u8), K, N, ptr(io_i8), ld(io_i8), ptr(io_f16),
+          ld(io_f16), ptr(io_bits), ld(io_bits))
+
+
+def flip_images(inp_u8, k, mode, seed, trial0, n_trials, out_u8) -> None:
+    R, F = inp_u8.shape
+    assert inp_u8.is_contiguous() and out_u8.is_contiguous()
+    _call("bnn_flip_images", ptr(inp_u8), R, F, k, mode, seed & (2**64 - 1), trial0, n_trials,
+          ptr(out_u8))
+
+
+def minmax_u8(inp_u8, minmax_u32, minmax_f32=None) -> None:
+    _call("bnn_minmax_u8", ptr(inp_u8), inp_u8.numel(), ptr(minmax_u32), ptr(minmax_f32))
+
+
+def normalize_u8(inp_u8, mn, mx, new_min, new_max, out_f32) -> None:
+    _call("bnn_normalize_u8", ptr(inp_u8), inp_u8.numel(), ptr(mn), ptr(mx), new_min, new_max,
+          ptr(out_f32))

@@ -1,0 +1,500 @@
+"""B200-native drop-in for the reference's layer classes (mlpcode/layers.py).
+
+Same class names, constructor arguments, methods and attributes as the reference
+(`Layer`, `BatchNormLayer`, `LinearLayer`, `BinaryLayer`; `build`, `forward`, `backwards`,
+`load_parameters`, `loadBatchNormParams`, `batchNormParams`, `addCallback`, `clearCallbacks`,
+`weights`, `bias`, `cache`, `batchNormLayer`), but every array lives in HBM and every arithmetic
+step is a libbnn_b200 kernel:
+
+  forward  (layers.py:283-292, 209-238, 74-99)
+    binarize W -> K-major +-1 operands        bnn_binarize_weights_t
+    z = X . sign(W)                           bnn_gemm   (+-1 x +-1: tcgen05 kind::i8, exact int32;
+                                                          real x +-1: fp16 hi/lo split, kind::f16)
+    batch statistics / running statistics     bnn_colstats + bnn_bn_stats_finalize
+    BN + sign (or softmax / identity)         bnn_bn_apply (+ bnn_softmax_xent)
+  backward (layers.py:247-271, 101-127)
+    BN backward, gamma/beta SGD, running stats   bnn_bn_bwd_reduce / _finalize / _apply
+    dX = delta' . W^T  (latent, pre-update W)    bnn_gemm (3 fp16 split products, fp32 accumulate)
+    W -= lr * X^T . delta'                       bnn_gemm with the fused SGD epilogue
+
+Hidden activations travel between layers as `SignActivation` (int8 +-1 operand + transposed fp16
+copy for the next layer's dW) instead of fp32 arrays; `.t` materialises the fp32 view on demand.
+Only the configuration the BNN scripts use is implemented on the device: batch-norm on, no bias
+(network.py:37-41 disables bias whenever batch-norm is on).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import kernels as K_
+from .activation import ActivationFuncs as af
+from .callbacks import Callback
+from .device import DeviceArray, asarray, empty, pad_to, require_cuda, to_tensor, zeros
+
+
+def binary_gemm_variant() -> str:
+    """'i8' (tcgen05 kind::i8, default — chosen from the ncu comparison in profiles/) or 'popc'."""
+    v = os.environ.get("BNN_BINARY_GEMM", "i8").lower()
+    if v not in ("i8", "popc"):
+        raise ValueError(f"BNN_BINARY_GEMM={v!r}: expected 'i8' or 'popc'")
+    return v
+
+
+class SignActivation(DeviceArray):
+    """Output of a sign-activated layer: values in {+1,-1} kept in GEMM-operand form."""
+
+    def __init__(self, i8, n, t16=None, bits=None):
+        self.i8, self.n, self.t16, self.bits = i8, n, t16, bits
+        self._dense = None
+
+    @property
+    def t(self):  # fp32 [B, n] view for generic consumers (not used on the hot path)
+        if self._dense is None:
+            self._dense = self.i8[:, : self.n].to(torch.float32)
+        return self._dense
+
+    @t.setter
+    def t(self, v):
+        self._dense = v
+
+    @property
+    def shape(self):
+        return (self.i8.shape[0], self.n)
+
+    @property
+    def ndim(self):
+        return 2
+
+    @property
+    def size(self):
+        return self.i8.shape[0] * self.n
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float32)
+
+    def __len__(self):
+        return self.i8.shape[0]
+
+
+class SoftmaxOutput(DeviceArray):
+    """Softmax probabilities that remember their logits, so loss + gradient fuse into one kernel."""
+
+    def __init__(self, probs, logits):
+        super().__init__(probs)
+        self.logits = logits
+        self.fused = None  # (loss_rows, grad, loss_sum) once mlpcode.loss has run
+
+
+class _Workspace:
+    """Named device buffers, allocated once per (name, shape, dtype) and reused across steps."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, name, shape, dtype, zero=False):
+        key = (name, tuple(shape), dtype)
+        b = self._bufs.get(key)
+        if b is None:
+            b = zeros(shape, dtype) if zero else empty(shape, dtype)
+            self._bufs[key] = b
+        return b
+
+    def clear(self):
+        self._bufs.clear()
+
+
+class _NoComm:
+    world = 1
+
+    def allreduce_sum(self, t):
+        return None
+
+
+class Layer:
+    def __init__(self, layerUnits: int, gpu=False):
+        self.layerUnits = layerUnits
+        self.gpu = gpu
+        self.cache = {}
+        self.isBuilt = False
+
+    def build(self):
+        self.isBuilt = True
+
+
+class BatchNormLayer(Layer):
+    EPSILON = 1e-4
+    MA_BETA = 0.9  # moving-average coefficient of the running statistics
+
+    def __init__(self, layerUnits: int, gpu=False):
+        super().__init__(layerUnits, gpu=gpu)
+        self.beta = None
+        self.gamma = None
+        self.mu = None
+        self.sigma = None  # running VARIANCE (layers.py:121-123), despite the name
+        self._ws = _Workspace()
+        self.comm = _NoComm()
+
+    @property
+    def parameter_shape(self):
+        return (self.layerUnits,)
+
+    @property
+    def batchNormParams(self):
+        assert self.isBuilt
+        return (self.gamma, self.beta, self.mu, self.sigma)
+
+    def loadBatchNormParams(self, gamma, beta, mu, sigma):
+        shp = self.parameter_shape
+        for a in (gamma, beta, mu, sigma):
+            assert tuple(a.shape) == shp
+        # like the reference, the layer adopts the arrays it is given (device copies are made only
+        # for host inputs)
+        self.gamma = asarray(gamma, np.float32)
+        self.beta = asarray(beta, np.float32)
+        self.mu = asarray(mu, np.float32)
+        self.sigma = asarray(sigma, np.float32)
+
+    def build(self):
+        n = self.layerUnits
+        if self.beta is None:
+            self.beta = DeviceArray(zeros((n,)))
+        if self.gamma is None:
+            self.gamma = DeviceArray(torch.ones((n,), dtype=torch.float32, device=require_cuda()))
+        if self.mu is None:
+            self.mu = DeviceArray(zeros((n,)))
+        if self.sigma is None:
+            self.sigma = DeviceArray(torch.ones((n,), dtype=torch.float32, device=require_cuda()))
+        super().build()
+
+    # -- device primitives shared with BinaryLayer ----------------------------------------
+    def batch_stats(self, Z, B):
+        """Column mean / population variance of Z over the GLOBAL batch (layers.py:81-82)."""
+        n = self.layerUnits
+        sums = self._ws.get("sums", (2, n), torch.float64)
+        mu = self._ws.get("mu_b", (n,), torch.float32)
+        var = self._ws.get("var_b", (n,), torch.float32)
+        K_.colstats(Z, B, n, sums)
+        self.comm.allreduce_sum(sums)  # sync-BN: exact (integer-valued fp64 sums) for +-1 layers
+        K_.bn_stats_finalize(sums, n, B * self.comm.world, mu, var)
+        return sums, mu, var
+
+    def backward_kernels(self, delta, Z, B, sums, mu, var, lr, want_f32, d_rm, d_t, scale):
+        n = self.layerUnits
+        red = self._ws.get("red", (2, n), torch.float64)
+        red_max = self._ws.get("red_max", (2, n), torch.int32)
+        coef = self._ws.get("coef", (3, n), torch.float32)
+        bound = self._ws.get("bound", (1,), torch.float32)  # written as uint32 bits of a float
+        K_.bn_bwd_reduce(delta, Z, B, n, mu, red, red_max)
+        self.comm.allreduce_sum(red)
+        K_.bn_bwd_finalize(red, red_max, n, B * self.comm.world, mu, var, self.EPSILON,
+                           self.gamma.t, self.beta.t, self.mu.t, self.sigma.t, lr, self.MA_BETA,
+                           sums, coef, bound)
+        out = empty((B, n)) if want_f32 else None
+        K_.bn_bwd_apply(delta, Z, B, n, mu, coef, bound, out_f32=out,
+                        d_hi=d_rm[0] if d_rm else None, d_lo=d_rm[1] if d_rm else None,
+                        dt_hi=d_t[0] if d_t else None, dt_lo=d_t[1] if d_t else None,
+                        scale_out=scale)
+        return out
+
+    # -- reference API on fp32 arrays -------------------------------------------------------
+    def forward(self, Z, isTrain=True):
+        assert self.isBuilt
+        self.cache.clear()
+        Zt = to_tensor(Z, torch.float32)
+        B, n = Zt.shape
+        out = empty((B, n))
+        if isTrain:
+            sums, mu, var = self.batch_stats(Zt, B)
+            K_.bn_apply(Zt, B, n, mu, var, self.gamma.t, self.beta.t, self.EPSILON, out_f32=out)
+            self.cache.update(input=Zt, mu=mu, var=var, sums=sums, output=out)
+        else:
+            K_.bn_apply(Zt, B, n, self.mu.t, self.sigma.t, self.gamma.t, self.beta.t, self.EPSILON,
+                        out_f32=out)
+        return DeviceArray(out)
+
+    def backwards(self, delta, lr: float):
+        Zt = self.cache["input"]
+        B = Zt.shape[0]
+        d = to_tensor(delta, torch.float32)
+        out = self.backward_kernels(d, Zt, B, self.cache["sums"], self.cache["mu"],
+                                    self.cache["var"], float(lr), True, None, None, None)
+        self.cache.clear()
+        return DeviceArray(out)
+
+
+class LinearLayer(Layer):
+    def __init__(self, layerUnits: int, inputUnits: int, useBias=False, gpu=False, batchNorm=False):
+        super().__init__(layerUnits, gpu=gpu)
+        self.inputUnits = inputUnits
+        self.useBias = useBias
+        self.weights = None
+        self.bias = None
+        self.activation = None
+        self.batchNorm = batchNorm
+        self.callbacks = []
+        self.comm = _NoComm()
+        self.skip_input_grad = False  # set on the first layer: its dX is discarded (network.py:389-390)
+        self._ws = _Workspace()
+        if batchNorm:
+            self.batchNormLayer = BatchNormLayer(layerUnits, gpu=gpu)
+
+    @property
+    def weights_shape(self):
+        return self.inputUnits, self.layerUnits
+
+    @property
+    def bias_shape(self):
+        return (self.layerUnits,)
+
+    @property
+    def batchNormParams(self):
+        assert self.batchNorm
+        return self.batchNormLayer.batchNormParams
+
+    def load_parameters(self, weights, bias=None):
+        assert tuple(weights.shape) == self.weights_shape
+        self.weights = asarray(weights, np.float32)
+        if self.useBias:
+            raise NotImplementedError("bias is outside the B200 hot path (batch-norm nets drop it, "
+                                      "network.py:37-41)")
+
+    def loadBatchNormParams(self, gamma, beta, mu, sigma):
+        assert self.batchNorm
+        self.batchNormLayer.loadBatchNormParams(gamma, beta, mu, sigma)
+
+    def addCallback(self, callback: Callback):
+        self.callbacks.append(callback)
+
+    def clearCallbacks(self):
+        self.callbacks.clear()
+
+    def set_comm(self, comm):
+        self.comm = comm
+        if self.batchNorm:
+            self.batchNormLayer.comm = comm
+
+    def build(self, activation: af = None):
+        if not self.gpu:
+            raise NotImplementedError("this build is the device path only (useGpu=True); run the "
+                                      "reference NumPy classes for CPU execution")
+        if self.useBias or not self.batchNorm:
+            raise NotImplementedError("B200 hot path implements batch-norm layers without bias (the "
+                                      "configuration of every BNN script in the reference)")
+        dev = require_cuda()
+        if self.weights is None:
+            # same distribution as layers.py:191-194 (randn * sqrt(1/K)); the stream differs
+            w = torch.randn(self.weights_shape, dtype=torch.float32, device=dev)
+            self.weights = DeviceArray(w * float(np.sqrt(1.0 / self.inputUnits)))
+        self.activation = activation
+        if activation is not None and activation not in (af.sign, af.softmax, af.identity):
+            raise NotImplementedError(f"activation {activation} is outside the BNN hot path")
+        if self.batchNorm:
+            self.batchNormLayer.build()
+        super().build()
+
+    def forward(self, X, isTrain=True):
+        raise NotImplementedError("real-valued LinearLayer is out of scope; use BinaryLayer")
+
+    def backwards(self, dA, lr: float, activDeriv=True):
+        raise NotImplementedError("real-valued LinearLayer is out of scope; use BinaryLayer")
+
+
+class BinaryLayer(LinearLayer):
+    # ------------------------------------------------------------------ reference-style helper
+    @staticmethod
+    def binarize(x):
+        """+1 where x >= 0 else -1, as a new fp32 device array (layers.py:275-281)."""
+        xt = to_tensor(x, torch.float32)
+        two_d = xt if xt.ndim == 2 else xt.reshape(1, -1)
+        R, Cn = two_d.shape
+        bits = zeros((R, pad_to(Cn, 32) // 32), torch.int32)
+        K_.pack_sign_rows(two_d, bits)
+        i8 = empty((R, pad_to(Cn, 16)), torch.int8)
+        K_.unpack_bits(bits, Cn, out_i8=i8)
+        return DeviceArray(i8[:, :Cn].to(torch.float32).reshape(xt.shape))
+
+    # ------------------------------------------------------------------ operand preparation
+    def _weight_operands(self, real_input: bool):
+        Kd, N = self.weights_shape
+        ws = self._ws
+        ops = {}
+        ops["bits"] = ws.get("wt_bits", (N, pad_to(Kd, 32) // 32), torch.int32, zero=True)
+        if real_input:
+            ops["f16"] = ws.get("wt_f16", (N, pad_to(Kd, 8)), torch.float16, zero=True)
+        else:
+            ops["i8"] = ws.get("wt_i8", (N, pad_to(Kd, 16)), torch.int8, zero=True)
+        K_.binarize_weights_t(self.weights.t, wt_i8=ops.get("i8"), wt_f16=ops.get("f16"),
+                              wt_bits=ops["bits"])
+        return ops
+
+    def _real_input_operands(self, Xt, train: bool):
+        B, Kd = Xt.shape
+        ws = self._ws
+        amax = ws.get("x_amax", (1,), torch.float32)
+        scale = ws.get("x_scale", (1,), torch.float32)
+        hi = ws.get(f"x_hi{B}", (B, pad_to(Kd, 8)), torch.float16, zero=True)
+        lo = ws.get(f"x_lo{B}", (B, pad_to(Kd, 8)), torch.float16, zero=True)
+        hi_t = lo_t = None
+        if train:
+            hi_t = ws.get(f"xt_hi{B}", (Kd, pad_to(B, 8)), torch.float16, zero=True)
+            lo_t = ws.get(f"xt_lo{B}", (Kd, pad_to(B, 8)), torch.float16, zero=True)
+        K_.absmax_f32(Xt, amax)
+        K_.split_f16(Xt, amax, hi=hi, lo=lo, hi_t=hi_t, lo_t=lo_t, scale_out=scale)
+        return dict(hi=hi, lo=lo, hi_t=hi_t, lo_t=lo_t, scale=scale)
+
+    def _apply_foreign_callback(self, cb, wops):
+        """Any callable with the reference signature `cb(weight, gpu=)` (layers.py:218): it is
+        handed the binarized weight as an fp32 [K, N] device array and its result is re-packed."""
+        Kd, N = self.weights_shape
+        dense = empty((N, pad_to(Kd, 16)), torch.int8)
+        K_.unpack_bits(wops["bits"], Kd, out_i8=dense)
+        w_kn = DeviceArray(dense[:, :Kd].t().contiguous().to(torch.float32))
+        new_w = to_tensor(cb(w_kn, gpu=self.gpu), torch.float32)
+        assert tuple(new_w.shape) == (Kd, N)
+        K_.binarize_weights_t(new_w, wt_i8=wops.get("i8"), wt_f16=wops.get("f16"),
+                              wt_bits=wops["bits"])
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, X, isTrain=True):
+        assert self.isBuilt
+        Kd, N = self.weights_shape
+        ws = self._ws
+        bn = self.batchNormLayer
+        self.cache.clear()
+
+        real_input = not isinstance(X, SignActivation)
+        if real_input:
+            Xt = to_tensor(X, torch.float32)
+            assert Xt.ndim == 2 and Xt.shape[1] == Kd, f"expected [B, {Kd}] input, got {tuple(Xt.shape)}"
+            B = Xt.shape[0]
+        else:
+            assert X.n == Kd
+            B = X.i8.shape[0]
+
+        wops = self._weight_operands(real_input)
+        # fault-injection hooks act on the already-binarized weight, eval mode only (layers.py:215-218)
+        if not isTrain:
+            for cb in self.callbacks:
+                if hasattr(cb, "apply_to_layer"):
+                    cb.apply_to_layer(self, wops)
+                else:
+                    self._apply_foreign_callback(cb, wops)
+
+        # ---- z = X . sign(W)
+        if real_input:
+            xin = self._real_input_operands(Xt, isTrain)
+            Z = ws.get(f"z_f32_{B}", (B, pad_to(N, 4)), torch.float32)
+            K_.gemm(M=B, N=N, K=Kd, A=(xin["hi"], xin["lo"]), B=(wops["f16"],),
+                    lda=xin["hi"].stride(0), ldb=wops["f16"].stride(0), D=Z, ldd=Z.stride(0),
+                    in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32, passes=((0, 0), (1, 0)),
+                    sa=xin["scale"])
+        else:
+            xin = X
+            s16 = Kd < 32768
+            Z = ws.get(f"z_int_{B}", (B, pad_to(N, 8)), torch.int16 if s16 else torch.int32)
+            if binary_gemm_variant() == "popc":
+                if X.bits is None:
+                    X.bits = ws.get(f"x_bits{B}", (B, pad_to(Kd, 32) // 32), torch.int32, zero=True)
+                    K_.pack_i8_rows(X.i8, Kd, X.bits)
+                K_.gemm_popc(X.bits, wops["bits"], B, N, Kd, Z, out_s16=s16)
+            else:
+                K_.gemm(M=B, N=N, K=Kd, A=(X.i8,), B=(wops["i8"],), lda=X.i8.stride(0),
+                        ldb=wops["i8"].stride(0), D=Z, ldd=Z.stride(0), in_dtype=nat.DT_I8,
+                        epilogue=nat.EPI_STORE_S16 if s16 else nat.EPI_STORE_S32)
+
+        # ---- batch-norm statistics
+        if isTrain:
+            sums, mu, var = bn.batch_stats(Z, B)
+        else:
+            sums, mu, var = None, bn.mu.t, bn.sigma.t
+
+        # ---- BN + activation
+        if self.activation == af.sign:
+            act_i8 = ws.get(f"a_i8_{B}", (B, pad_to(N, 16)), torch.int8, zero=True)
+            act_t16 = ws.get(f"a_t16_{B}", (N, pad_to(B, 8)), torch.float16, zero=True) if isTrain else None
+            act_bits = None
+            if binary_gemm_variant() == "popc":
+                act_bits = ws.get(f"a_bits{B}", (B, pad_to(N, 32) // 32), torch.int32, zero=True)
+            K_.bn_apply(Z, B, N, mu, var, bn.gamma.t, bn.beta.t, bn.EPSILON, act_i8=act_i8,
+                        act_t16=act_t16, act_bits=act_bits)
+            out = SignActivation(act_i8, N, t16=act_t16, bits=act_bits)
+        else:
+            logits = empty((B, N))
+            K_.bn_apply(Z, B, N, mu, var, bn.gamma.t, bn.beta.t, bn.EPSILON, out_f32=logits)
+            if self.activation == af.softmax:
+                probs = empty((B, N))
+                K_.softmax_xent(logits, B, N, probs=probs)
+                out = SoftmaxOutput(probs, logits)
+            else:  # identity / None
+                out = DeviceArray(logits)
+
+        if isTrain:
+            self.cache.update(input=xin, z=Z, a=out, sums=sums, mu=mu, var=var, B=B,
+                              real_input=real_input)
+        return out
+
+    # ------------------------------------------------------------------ backward
+    def backwards(self, dA, lr: float, activDeriv=True):
+        assert "input" in self.cache
+        assert "z" in self.cache
+        Kd, N = self.weights_shape
+        ws = self._ws
+        c = self.cache
+        B, Z, xin = c["B"], c["z"], c["input"]
+        lr = float(lr)
+        # STE: hard_tanh_derivative evaluated on the post-sign activations is the identity
+        # (activation.py:122-131 via layers.py:252-254), and softmax+CE arrives pre-differentiated.
+        delta = to_tensor(dA, torch.float32)
+        assert tuple(delta.shape) == (B, N)
+
+        Np, Bp = pad_to(N, 8), pad_to(B, 8)
+        d_hi = ws.get(f"d_hi{B}", (B, Np), torch.float16, zero=True)
+        d_lo = ws.get(f"d_lo{B}", (B, Np), torch.float16, zero=True)
+        dt_hi = ws.get(f"dt_hi{B}", (N, Bp), torch.float16, zero=True)
+        dt_lo = ws.get(f"dt_lo{B}", (N, Bp), torch.float16, zero=True)
+        d_scale = ws.get("d_scale", (1,), torch.float32)
+        need_dx = not self.skip_input_grad
+        self.batchNormLayer.backward_kernels(delta, Z, B, c["sums"], c["mu"], c["var"], lr, False,
+                                             (d_hi, d_lo) if need_dx else None, (dt_hi, dt_lo),
+                                             d_scale)
+
+        # ---- dX = delta' . W^T with the latent, pre-update weights (layers.py:266)
+        dX = None
+        if need_dx:
+            w_amax = ws.get("w_amax", (1,), torch.float32)
+            w_scale = ws.get("w_scale", (1,), torch.float32)
+            w_hi = ws.get("w_hi", (Kd, Np), torch.float16, zero=True)
+            w_lo = ws.get("w_lo", (Kd, Np), torch.float16, zero=True)
+            K_.absmax_f32(self.weights.t, w_amax)
+            K_.split_f16(self.weights.t, w_amax, hi=w_hi, lo=w_lo, scale_out=w_scale)
+            dX = empty((B, pad_to(Kd, 4)))
+            K_.gemm(M=B, N=Kd, K=N, A=(d_hi, d_lo), B=(w_hi, w_lo), lda=Np, ldb=Np, D=dX,
+                    ldd=dX.stride(0), in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32,
+                    passes=((0, 0), (0, 1), (1, 0)), sa=d_scale, sb=w_scale)
+            dX = dX[:, :Kd]
+
+        # ---- dW = X^T . delta'  (layers.py:260) and W -= lr * dW (:268)
+        if c["real_input"]:
+            A, passes, sa = (xin["hi_t"], xin["lo_t"]), ((0, 0), (0, 1), (1, 0)), xin["scale"]
+        else:
+            A, passes, sa = (xin.t16,), ((0, 0), (0, 1)), None
+        Wt = self.weights.t
+        if self.comm.world == 1:
+            K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=Wt, ldd=N,
+                    in_dtype=nat.DT_F16, epilogue=nat.EPI_SGD_F32, passes=passes, sa=sa, sb=d_scale,
+                    host_scale=lr)
+        else:
+            dW = ws.get("dW", (Kd, N), torch.float32)
+            K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=dW, ldd=N,
+                    in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32, passes=passes, sa=sa,
+                    sb=d_scale)
+            self.comm.allreduce_sum(dW)  # batch-sharded dW -> global dW (NCCL over NVLink)
+            K_.sgd_update(Wt, dW, lr)
+
+        self.cache.clear()
+        return DeviceArray(dX) if dX is not None else None

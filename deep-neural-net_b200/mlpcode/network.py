@@ -1,0 +1,297 @@
+"""`Network` for the B200 path — same public surface as mlpcode/network.py:22-484.
+
+Construction, `compile`, `train`, `predict`, `predict_classes`, `evaluate`, `get_accuracy`,
+`addCallbacks` / `clearCallbacks`, `load_weights`, `loadBatchNormParameters`, `weights`, `biases`,
+`batchNormParams` behave as in the reference; the per-batch work is delegated to the device layers
+in mlpcode.layers.  Differences, all forced by the environment and documented in DESIGN.md:
+
+  * only binarized, batch-normalised, bias-free networks run (the BNN configuration);
+  * checkpoints are `.npz` files with the reference's HDF5 key layout (h5py is not in the image);
+  * `train_step(X, y)` exposes the body of the private `__updateBatch` (network.py:372-392) as the
+    public per-batch call that bench.py and the data-parallel driver use;
+  * with torch.distributed initialised, `set_data_parallel()` shards nothing itself — the caller
+    feeds each rank its batch shard — but makes batch-norm statistics, the loss gradient and dW
+    global, so N ranks reproduce the single-GPU (and reference) step.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import List, Union
+
+import numpy as np
+import torch
+
+from . import kernels as K_
+from . import loss as loss_mod
+from .activation import ACTIVATION_FUNCTIONS
+from .activation import ActivationFuncs as af
+from .callbacks import Callback
+from .device import DeviceArray, asarray, asnumpy, to_tensor, zeros
+from .layers import BatchNormLayer, BinaryLayer, LinearLayer, _NoComm
+from .loss import LOSS_DERIVATES, LOSS_FUNCS
+from .loss import LossFuncs as lf
+from .optim import LRScheduler
+
+ModelLayer = Union[LinearLayer, BinaryLayer, BatchNormLayer]
+MODELDIR = Path(__file__).resolve().parent / "models"
+
+
+class Network(object):
+    def __init__(self, units: List[int], useGpu=False, binarized=False, useBias=False,
+                 useBatchNorm=False):
+        if useBatchNorm and useBias:
+            print("Won't use bias with BatchNorm, as it will automatically get cancelled in the "
+                  "normalization step")
+            useBias = False
+        self.isBinarized = binarized
+        self.useBias = useBias
+        self.useGpu = useGpu
+        self.useBatchNorm = useBatchNorm
+        self.unitList = list(units)
+        layer_cls = BinaryLayer if binarized else LinearLayer
+        self._layers: List[ModelLayer] = [
+            layer_cls(n_out, n_in, gpu=useGpu, useBias=useBias, batchNorm=useBatchNorm)
+            for n_out, n_in in zip(units[1:], units[:-1])
+        ]
+        for i, layer in enumerate(self._layers):
+            layer.layer_index = i
+        if self._layers:
+            self._layers[0].skip_input_grad = True
+        self._lossF: lf = None
+        self._outAf: af = None
+        self._lr: LRScheduler = None
+        self._compiled = False
+        self._comm = _NoComm()
+
+    # ------------------------------------------------------------------ parameters
+    @property
+    def isCompiled(self) -> bool:
+        return self._compiled
+
+    @property
+    def weights(self):
+        return [layer.weights for layer in self._layers]
+
+    @property
+    def biases(self):
+        if self.useBias:
+            return [layer.bias for layer in self._layers]
+        return [None for _ in self.unitList[:-1]]
+
+    @property
+    def batchNormParams(self):
+        assert self.useBatchNorm
+        cols = ([], [], [], [])
+        for layer in self._layers:
+            for dst, v in zip(cols, layer.batchNormParams):
+                dst.append(v)
+        return cols
+
+    def _copyBnParams(self):
+        return tuple([p.copy() for p in group] for group in self.batchNormParams)
+
+    @property
+    def linearLayers(self):
+        return [layer for layer in self._layers if isinstance(layer, LinearLayer)]
+
+    def load_weights(self, weights, biases=None):
+        if not self.useBias:
+            biases = [None] * len(weights)
+        assert len(weights) == len(self._layers) == len(biases)
+        for layer, w, b in zip(self.linearLayers, weights, biases):
+            layer.load_parameters(w, b)
+
+    def loadBatchNormParameters(self, gammas, betas, mus, sigmas):
+        n = len(self._layers)
+        assert len(gammas) == len(betas) == len(mus) == len(sigmas) == n
+        for layer, g, b, m, s in zip(self._layers, gammas, betas, mus, sigmas):
+            layer.loadBatchNormParams(g, b, m, s)
+
+    # ------------------------------------------------------------------ callbacks
+    def addCallbacks(self, callbacks: Union[Callback, List[Callback]], num_layers: int = None):
+        if num_layers is None:
+            num_layers = len(self._layers)
+        assert num_layers > 0
+        if isinstance(callbacks, list):
+            assert len(callbacks) == num_layers
+        else:
+            callbacks = [callbacks] * num_layers
+        for layer, cb in zip(self._layers[:num_layers], callbacks):
+            layer.addCallback(cb)
+
+    def clearCallbacks(self):
+        for layer in self._layers:
+            layer.clearCallbacks()
+
+    # ------------------------------------------------------------------ data parallel
+    def set_data_parallel(self, comm) -> None:
+        """comm: object with `.world` and `.allreduce_sum(tensor)` (see mlpcode.parallel)."""
+        self._comm = comm
+        for layer in self._layers:
+            layer.set_comm(comm)
+
+    # ------------------------------------------------------------------ checkpoints (.npz bridge)
+    @staticmethod
+    def fromModel(filePth, useGpu=False, binarized=False):
+        """Load a checkpoint with the key layout of the reference's HDF5 files
+        (network.py:157-228: units, useBias, useBatchNorm, weights/weights_i, gammas/gammas_i, ...),
+        stored as `.npz` because h5py is unavailable."""
+        filePth = Path(filePth)
+        assert filePth.exists()
+        with np.load(filePth) as fp:
+            units = [int(u) for u in fp["units"]]
+            useBias = bool(fp["useBias"])
+            useBN = bool(fp["useBatchNorm"])
+            if useBN and useBias:
+                useBias = False
+            nn = Network(units, useGpu=useGpu, useBias=useBias, binarized=binarized,
+                         useBatchNorm=useBN)
+            n = len(units) - 1
+            nn.load_weights([fp[f"weights/weights_{i}"].astype(np.float32) for i in range(n)])
+            if useBN:
+                nn.loadBatchNormParameters(
+                    *[[fp[f"{g}/{g}_{i}"].astype(np.float32) for i in range(n)]
+                      for g in ("gammas", "betas", "mus", "sigmas")])
+        return nn
+
+    def save_weights(self, modelName: str, binarized=False, directory=None):
+        directory = Path(directory) if directory is not None else MODELDIR
+        directory.mkdir(parents=True, exist_ok=True)
+        path = directory / f"{modelName}{'_binarized' if binarized else ''}.npz"
+        blob = {"units": np.array(self.unitList, dtype=np.uint32), "useBias": np.array(self.useBias),
+                "useBatchNorm": np.array(self.useBatchNorm)}
+        for i, w in enumerate(self.weights):
+            blob[f"weights/weights_{i}"] = asnumpy(w)
+        if self.useBatchNorm:
+            for name, group in zip(("gammas", "betas", "mus", "sigmas"), self.batchNormParams):
+                for i, v in enumerate(group):
+                    blob[f"{name}/{name}_{i}"] = asnumpy(v)
+        np.savez(path, **blob)
+        print(f"Saving model to {path}")
+        return path
+
+    # ------------------------------------------------------------------ compile
+    def compile(self, lr: Union[LRScheduler, float] = 1e-3, hiddenAf: af = af.sigmoid,
+                outAf: af = af.softmax, lossF: lf = lf.cross_entropy) -> None:
+        assert hiddenAf in ACTIVATION_FUNCTIONS
+        assert outAf in ACTIVATION_FUNCTIONS
+        assert lossF in LOSS_FUNCS
+        if self.isBinarized and hiddenAf != af.sign:
+            print(f"Changing hidden activation function to {af.sign} for BNN")
+            hiddenAf = af.sign
+        for layer in self._layers[:-1]:
+            layer.build(hiddenAf)
+        self._layers[-1].build(outAf)
+        self._lossF, self._outAf = lossF, outAf
+        if isinstance(lr, float):
+            self._lr = LRScheduler(alpha=lr)
+        elif isinstance(lr, LRScheduler):
+            self._lr = lr
+        else:
+            raise ValueError("Invalid value for learning rate (only float or LRScheduler allowed)")
+        self._compiled = True
+
+    # ------------------------------------------------------------------ training
+    def train(self, trainX, trainY, epochs: int, batch_size=1, shuffle=True, valX=None, valY=None,
+              save_best_params=True):
+        if not self._compiled:
+            print("\nEXCEPTION: Must compile the model before running train")
+            return
+        trainX = asarray(trainX, np.float32)
+        trainY = asarray(trainY)
+        n = len(trainX)
+        best_acc, best_epoch, best = -1.0, -1, None
+        costs, train_accs, val_accs = [], [], []
+        has_val = valX is not None
+        if has_val:
+            valX = asarray(valX, np.float32)
+            valY = asarray(valY)
+            if valY.shape[0] != valY.size:  # one-hot -> labels (network.py:298-299)
+                valY = valY.argmax(axis=1)
+        print(f"\n\nStarting training (binarized: {self.isBinarized})")
+        print("=" * 20)
+        print()
+        for epoch in range(epochs):
+            if shuffle:
+                perm = torch.randperm(n, device=trainX.t.device)
+                trainX, trainY = trainX[perm], trainY[perm]
+            batch_costs = [self.train_step(bx, by)
+                           for bx, by in self.get_batches(trainX, trainY, batch_size, n)]
+            self._lr.step()
+            cost = sum(batch_costs) / len(batch_costs)
+            acc = self.get_accuracy(trainX, trainY.argmax(axis=1))
+            train_accs.append(acc)
+            costs.append(cost)
+            line = f"Epoch {epoch + 1} / {epochs}\tAccuracy : {acc:0.3f}%"
+            if has_val:
+                acc = self.get_accuracy(valX, valY)
+                val_accs.append(acc)
+                line += f"\tVal Acc: {acc:0.3f}%"
+            print(line + f"\tLoss: {cost:.02f}")
+            if save_best_params and acc > best_acc:
+                best_acc, best_epoch = acc, epoch
+                best = ([w.copy() for w in self.weights],
+                        self._copyBnParams() if self.useBatchNorm else None)
+        if save_best_params and best is not None:
+            kind = "Validation" if has_val else "Training"
+            print("\nBest {0} Accuracy:\t{1:.03f}% (epoch: {2})".format(kind, float(best_acc),
+                                                                       best_epoch))
+            print("Switching to best params\n")
+            self.load_weights(best[0])
+            if self.useBatchNorm:
+                self.loadBatchNormParameters(*best[1])
+        history = {"loss": costs, "accuracy": train_accs}
+        if has_val:
+            history["val_accuracy"] = val_accs
+        return history
+
+    def train_step_async(self, X, y, lr: float = None):
+        """One SGD step on one batch (the body of `__updateBatch`, network.py:372-392) without the
+        host read of the loss; returns the device array of per-sample losses."""
+        lr = self._lr.value if lr is None else lr
+        output = self.predict(X, isTraining=True)
+        loss_mod.GLOBAL_BATCH_SCALE = self._comm.world
+        cost = LOSS_FUNCS[self._lossF](output, y)
+        fused = self._lossF == lf.cross_entropy and self._outAf in (af.softmax, af.sigmoid)
+        delta = LOSS_DERIVATES[self._lossF](output, y, with_softmax=fused)
+        delta = self._layers[-1].backwards(delta, lr, activDeriv=not fused)
+        for layer in reversed(self._layers[:-1]):
+            delta = layer.backwards(delta, lr)
+        return cost
+
+    def train_step(self, X, y, lr: float = None) -> float:
+        return float(self.train_step_async(X, y, lr).mean())
+
+    _Network__updateBatch = lambda self, batch, lr: self.train_step(batch[0], batch[1], lr)  # noqa: E731
+
+    # ------------------------------------------------------------------ inference
+    def predict(self, X, isTraining=False):
+        a = X
+        for layer in self._layers:
+            a = layer.forward(a, isTrain=isTraining)
+        return a
+
+    def predict_classes(self, X):
+        return self.predict(X, isTraining=False).argmax(axis=1)
+
+    def evaluate(self, X, y, batch_size=-1):
+        """Number of correctly classified rows; y holds class labels (not one-hot)."""
+        labels = to_tensor(y).reshape(-1).to(torch.int32)
+        correct = zeros((1,), torch.int32)
+        n = X.shape[0]
+        step = n if batch_size == -1 else batch_size
+        for k in range(0, n, step):
+            bx = X[k:k + step]
+            scores = self.predict(bx, isTraining=False)
+            st = scores.t
+            K_.count_correct(st, st.shape[0], st.shape[1], labels[k:k + step].contiguous(), correct)
+        return int(correct.item())
+
+    def get_accuracy(self, X, y, batch_size=-1):
+        return self.evaluate(X, y, batch_size=batch_size) * 100.0 / X.shape[0]
+
+    @staticmethod
+    def get_batches(X, y, batch_size: int, n: int):
+        if batch_size == -1:
+            return [(X, y)]
+        return ((X[k:k + batch_size], y[k:k + batch_size]) for k in range(0, n, batch_size))

@@ -1,0 +1,299 @@
+/*
+ * libbnn_b200 — C ABI of the B200-native (sm_100a) binarized-dense-layer hot path.
+ *
+ * This is the drop-in boundary for ONE path of volf52/deep-neural-net: the binarized dense layer
+ * (mlpcode/layers.py) and the bit-flip error-injection callbacks (mlpcode/callbacks.py).  The
+ * reference has no FFI of its own — its seam is the Python class surface of mlpcode.layers selected
+ * by `Layer.xp` (layers.py:10-15) — so every entry point below names the reference code it
+ * replaces (file:line relative to the reference root).  The host side that calls these through
+ * ctypes lives in deep-neural-net_b200/mlpcode/ and mirrors the reference classes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the library never allocates or
+ *     frees caller-visible memory (small internal scratch excepted) and never takes ownership;
+ *   - matrices are row-major; `ld*` are row pitches in ELEMENTS; operands read by TMA need a
+ *     16-byte aligned base and a pitch that is a multiple of 16 bytes;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant per stream;
+ *   - return value: 0 on success, negative BNN_ERR_* otherwise; bnn_last_error() gives the text.
+ *     No exceptions cross the ABI.  There is no CPU fallback: without a usable sm_100 device every
+ *     compute entry point fails with BNN_ERR_CUDA.
+ *   - sign convention (layers.py:278-279, activation.py:110-111, callbacks.py:68-72):
+ *     +1 <-> bit 1 <-> (x >= 0), -1 <-> bit 0; sign(-0.0) = +1; NaN packs as bit 0.
+ */
+#ifndef BNN_B200_H
+#define BNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNN_B200_VERSION 100
+
+typedef void* bnn_stream_t; /* cudaStream_t */
+
+enum {
+    BNN_OK = 0,
+    BNN_ERR_ARG = -1,         /* bad shape / pitch / alignment / enum */
+    BNN_ERR_CUDA = -2,        /* CUDA runtime or driver error (text in bnn_last_error) */
+    BNN_ERR_UNSUPPORTED = -3  /* valid request this build does not implement */
+};
+
+/* ---------------------------------------------------------------------------------------------
+ * Library / device
+ * ------------------------------------------------------------------------------------------- */
+const char* bnn_last_error(void);
+int bnn_version(void);
+/* Fills SM count and compute capability of the current device. */
+int bnn_device_query(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * A1  sign() binarization and bit packing       (BinaryLayer.binarize, layers.py:275-281;
+ *                                                 unitstep, activation.py:106-113)
+ * ------------------------------------------------------------------------------------------- */
+
+/* bits[r, w] bit j = (x[r, 32w + j] >= 0); pad bits of the last word are 0.
+ * x: [R, C] fp32 pitch ldx; bits: [R, ldw] uint32, ldw >= ceil(C/32). */
+int bnn_pack_sign_rows(const float* x, int R, int C, int64_t ldx, uint32_t* bits, int64_t ldw,
+                       bnn_stream_t stream);
+
+/* Same packing for an int8 +-1 matrix (bit = value > 0). */
+int bnn_pack_i8_rows(const int8_t* x, int R, int C, int64_t ldx, uint32_t* bits, int64_t ldw,
+                     bnn_stream_t stream);
+
+/* Transposing binarization of a latent weight matrix W[K, N] (fp32, pitch N) into the K-major
+ * operand layouts the forward GEMMs read.  Any output may be NULL.
+ *   wt_i8  [N, ld_i8 ]  int8  +-1                 (tcgen05 kind::i8 operand)
+ *   wt_f16 [N, ld_f16]  fp16  +-1                 (tcgen05 kind::f16 operand, real-input layer 0)
+ *   wt_bits[N, ld_bits] uint32, bit j of word w = (W[32w+j, n] >= 0), pad bits 0 (XOR+popc operand,
+ *                       and the "packed weights" the fault kernels mutate) */
+int bnn_binarize_weights_t(const float* W, int K, int N, int8_t* wt_i8, int64_t ld_i8,
+                           void* wt_f16, int64_t ld_f16, uint32_t* wt_bits, int64_t ld_bits,
+                           bnn_stream_t stream);
+
+/* Expand packed sign bits [R, ldw] back to int8 +-1 [R, C] (pitch ldo) and/or fp16 +-1. */
+int bnn_unpack_bits(const uint32_t* bits, int R, int C, int64_t ldw, int8_t* out_i8, int64_t ld_i8,
+                    void* out_f16, int64_t ld_f16, bnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fp32 -> 2 x fp16 split operands for the real-valued GEMMs (layer-0 forward, dW, dX).
+ * x*s = hi + lo (+ O(2^-22)), s = 2^(14 - ceil(log2(bound))) a power of two, so three fp16
+ * tensor-core products hi*hi + hi*lo + lo*hi with fp32 accumulation reproduce an fp32 SGEMM
+ * (X.dot(W), layers.py:220,260,266) to better than SGEMM's own rounding error.
+ * ------------------------------------------------------------------------------------------- */
+
+/* absmax_bits <- max(absmax_bits, bits(max|x|)) (uint32 view of a non-negative float; the caller
+ * zeroes it, or passes zero_first=1). */
+int bnn_absmax_f32(const float* x, int64_t n, uint32_t* absmax_bits, int zero_first,
+                   bnn_stream_t stream);
+
+/* Split x[R, C] (pitch ldx).  bound: device float >= max|x| (e.g. the absmax above).
+ * Row-major pieces hi/lo [R, ld_rm] and/or transposed pieces hi_t/lo_t [C, ld_t] (fp16), any pair may
+ * be NULL.  scale_out (device float, may be NULL) receives s.  Pad columns between the logical
+ * width and the pitch are never written and never read by the GEMMs. */
+int bnn_split_f16(const float* x, int R, int C, int64_t ldx, const float* bound, void* hi, void* lo,
+                  int64_t ld_rm, void* hi_t, void* lo_t, int64_t ld_t, float* scale_out,
+                  bnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A2/A9  GEMMs                                    (X.dot(weight) layers.py:220;
+ *                                                  input.T.dot(delta) :260; delta.dot(W.T) :266;
+ *                                                  weights -= lr*dw :268)
+ * D[b][M, N] = epilogue( sum_p  A[pa[p]][b][M, K] * B[pb[p]][b][N, K]^T )
+ * Both operands K-major (row-major with the contraction index contiguous).
+ * ------------------------------------------------------------------------------------------- */
+enum { BNN_DT_I8 = 0, BNN_DT_F16 = 1 };
+enum {
+    BNN_EPI_STORE_F32 = 0, /* D fp32  = acc * host_scale / (sa*sb)                       */
+    BNN_EPI_STORE_S32 = 1, /* D int32 = acc                      (I8 only)               */
+    BNN_EPI_STORE_S16 = 2, /* D int16 = acc                      (I8 only, |acc| < 2^15) */
+    BNN_EPI_SGD_F32 = 3    /* D fp32 -= acc * host_scale / (sa*sb)   (fused SGD update)  */
+};
+enum {
+    BNN_GEMM_TCGEN05 = 0, /* TMA + tcgen05.mma + TMEM accumulators (product path)          */
+    BNN_GEMM_SIMT = 1     /* plain fp32/int32 CUDA-core kernel: cross-check + tiny shapes */
+};
+#define BNN_GEMM_MAX_PASS 4
+
+typedef struct bnn_gemm_desc {
+    int32_t M, N, K;
+    int32_t batch;    /* >= 1 */
+    int32_t in_dtype; /* BNN_DT_* */
+    int32_t epilogue; /* BNN_EPI_* */
+    int32_t n_pass;   /* 1..BNN_GEMM_MAX_PASS */
+    int32_t pa[BNN_GEMM_MAX_PASS];
+    int32_t pb[BNN_GEMM_MAX_PASS];
+    const void* A[2]; /* operand pieces, each [batch][M, lda] */
+    const void* B[2]; /* operand pieces, each [batch][N, ldb] */
+    int64_t lda, ldb; /* row pitch, elements */
+    int64_t stride_a, stride_b; /* batch stride in elements; 0 = operand shared by all batches */
+    void* D;
+    int64_t ldd, stride_d;
+    const float* sa; /* device scalars (may be NULL = 1): the split scales of A and B */
+    const float* sb;
+    float host_scale; /* 1 for plain stores, lr for BNN_EPI_SGD_F32 */
+    int32_t reserved;
+} bnn_gemm_desc;
+
+int bnn_gemm(const bnn_gemm_desc* desc_host, int impl, bnn_stream_t stream);
+
+/* Variant A of the binary GEMM: XOR + popc on CUDA cores over packed sign bits.
+ * D[m, n] = K - 2*popc(a_bits[m,:] ^ b_bits[n,:]); pad bits must be equal in A and B (the pack
+ * kernels write zeros).  out_dtype: 1 = int32 (BNN_EPI_STORE_S32), 2 = int16. */
+int bnn_gemm_popc(const uint32_t* a_bits, int64_t lda_w, const uint32_t* b_bits, int64_t ldb_w,
+                  int M, int N, int K, void* D, int64_t ldd, int out_dtype, bnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A4/A5/A6  batch-norm forward + sign / softmax      (BatchNormLayer.forward layers.py:74-99;
+ *                                                      unitstep activation.py:106-113)
+ * ------------------------------------------------------------------------------------------- */
+enum { BNN_Z_F32 = 0, BNN_Z_S16 = 1, BNN_Z_S32 = 2 };
+
+/* Per-column sum and sum of squares over the B rows of Z[B, N] (pitch ldz), accumulated in fp64
+ * (exact and order independent for the integer-valued Z of +-1 x +-1 layers).  sums: [2, N]
+ * doubles (sum, sumsq); accumulate=0 overwrites, 1 adds (used when a batch arrives in chunks). */
+int bnn_colstats(const void* Z, int z_dtype, int B, int N, int64_t ldz, double* sums,
+                 int accumulate, bnn_stream_t stream);
+
+/* mu = sum/count, var = sumsq/count - mu^2 (population variance, Z.var(axis=0) layers.py:82).
+ * count is the GLOBAL batch size when sums were all-reduced across ranks. */
+int bnn_bn_stats_finalize(const double* sums, int N, double count, float* mu, float* var,
+                          bnn_stream_t stream);
+
+/* out = gamma * ((Z - mu) / sqrt(var + eps)) + beta          (train, layers.py:84-86)  or
+ * out = (((Z - mu) / sqrt(sigma + eps)) * gamma) + beta      (eval,  layers.py:94-97; pass the
+ * running mean / running variance `sigma` as mu / var).  Both are the same fp32 operation sequence
+ * (sub, sqrt, div, mul, add — multiplication commutes bit-exactly); it is evaluated with explicit
+ * round-to-nearest operations, no FMA contraction, so that for identical Z and parameters the sign
+ * decisions equal NumPy's.  Outputs (any may be NULL):
+ *   out_f32 [B, ld_f32]   BN output (pre-activation, cache["z"])
+ *   act_i8  [B, ld_i8]    sign(out) as int8 +-1            (next layer's forward operand)
+ *   act_t16 [N, ld_t16]   sign(out) transposed, fp16 +-1   (next layer's dW operand)
+ *   act_bits[B, ld_bits]  sign(out) packed, 32 columns per word */
+int bnn_bn_apply(const void* Z, int z_dtype, int B, int N, int64_t ldz, const float* mu,
+                 const float* var, const float* gamma, const float* beta, float eps,
+                 float* out_f32, int64_t ld_f32, int8_t* act_i8, int64_t ld_i8, void* act_t16,
+                 int64_t ld_t16, uint32_t* act_bits, int64_t ld_bits, bnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A6/A10  output activation, loss and its gradient   (softmax activation.py:44-53;
+ *         cross_entropy_loss loss.py:10-36; cross_entropy_derivative(with_softmax) loss.py:58-66)
+ * ------------------------------------------------------------------------------------------- */
+/* logits [B, C] (pitch ldl) -> probs [B, C] (softmax, then clipped to [1e-15, 1-1e-15] exactly as
+ * loss.py:32 does in place), loss_rows[b] = -sum_c y*log(p), grad [B, C] = (p - y) / count,
+ * loss_sum (device double) = sum_b loss_rows[b].  onehot: int8 [B, C] (may be NULL when only probs
+ * are wanted); probs / loss_rows / grad / loss_sum may be NULL.  C <= 32. */
+int bnn_softmax_xent(const float* logits, int B, int C, int64_t ldl, const int8_t* onehot,
+                     float* probs, float* loss_rows, float* grad, double count, double* loss_sum,
+                     bnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A7/A8  backward through sign (identity STE) and batch-norm, in-place SGD on gamma/beta,
+ *        running statistics                            (layers.py:101-127, :252-258;
+ *                                                       hard_tanh_derivative activation.py:122-131)
+ * ------------------------------------------------------------------------------------------- */
+/* red[0,n] = sum_b delta[b,n]; red[1,n] = sum_b delta[b,n]*(Z[b,n]-mu[n])      (doubles [2, N]);
+ * red_max[0,n] = bits(max_b |delta[b,n]|); red_max[1,n] = bits(max_b |Z[b,n]-mu[n]|)  (uint32 [2, N],
+ * float bit patterns).  accumulate=0 zeroes both first. */
+int bnn_bn_bwd_reduce(const float* delta, int64_t ldd, const void* Z, int z_dtype, int64_t ldz,
+                      int B, int N, const float* mu, double* red, uint32_t* red_max, int accumulate,
+                      bnn_stream_t stream);
+
+/* From the (all-reduced) reductions build the per-column coefficients of
+ *   delta' = c0*delta + c1*(Z-mu) + c2         (== layers.py:107-113)
+ * then apply `gamma -= lr*dGamma; beta -= lr*dBeta` (:114-118) and the running-statistic update
+ * mu_run = 0.9*mu_run + 0.1*mu, sigma_run = 0.9*sigma_run + 0.1*var (:120-123).
+ * coef: [3, N] floats.  bound_bits: device uint32 receiving bits(max_n bound |delta'|) via atomicMax
+ * (zeroed by the call).  count = global batch size.  sums (may be NULL): the forward column sums,
+ * used for the rounding residue mean(Z) - mu of layers.py:109-110.  dgamma_out / dbeta_out (may be
+ * NULL) receive the parameter gradients. */
+int bnn_bn_bwd_finalize(const double* red, const uint32_t* red_max, int N, double count,
+                        const float* mu, const float* var, float eps, float* gamma, float* beta,
+                        float* mu_run, float* sigma_run, float lr, double momentum,
+                        const double* sums, float* coef, uint32_t* bound_bits, float* dgamma_out,
+                        float* dbeta_out, bnn_stream_t stream);
+
+/* delta' (see above) written as fp32 (out_f32, may be NULL) and/or as scaled fp16 hi/lo pieces in
+ * both operand layouts: d_hi/d_lo [B, ld_rm] (dX operand) and dt_hi/dt_lo [N, ld_t] (dW operand).
+ * bound: device float (the value behind bound_bits); scale_out receives the split scale. */
+int bnn_bn_bwd_apply(const float* delta, int64_t ldd, const void* Z, int z_dtype, int64_t ldz,
+                     int B, int N, const float* mu, const float* coef,
+                     const float* bound, float* out_f32, int64_t ld_f32, void* d_hi, void* d_lo,
+                     int64_t ld_rm, void* dt_hi, void* dt_lo, int64_t ld_t, float* scale_out,
+                     bnn_stream_t stream);
+
+/* p[i] -= lr * g[i]     (weights -= lr*dw, layers.py:268, for the data-parallel path where dW is
+ * all-reduced before the update). */
+int bnn_sgd_update(float* p, const float* g, int64_t n, float lr, bnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A11  weight fault injection                          (ErrorCallback._flipBNNMask
+ *                                                       callbacks.py:79-83, dispatch :94-98)
+ * Flips act on the K-major binarized copy WbT[N, K]; element (n, k) has linear index e = n*K + k.
+ * In-kernel RNG: Philox4x32-10, key = (seed_lo, seed_hi), counter = (e/4 lo, e/4 hi, stream_id,
+ * trial); word e%4 of the output decides element e: flip iff word < threshold.
+ * ------------------------------------------------------------------------------------------- */
+/* Bernoulli(p) flips for trials [trial0, trial0+n_trials) in ONE launch.  threshold =
+ * floor(p * 2^32) as uint64 (p = 1 -> 2^32 flips everything).  Inputs: clean wt_i8 [N, ld_i8] and/or
+ * wt_bits [N, ld_bits].  Outputs per trial t (any may be NULL), trial stride given in elements:
+ *   out_i8 [t][N, ld_i8], out_f16 [t][N, ld_f16], out_bits [t][N, ld_bits],
+ *   mask_bits [t][N, ld_bits] (the flip mask itself, packed like wt_bits). */
+int bnn_flip_weights_bernoulli(const int8_t* wt_i8, int64_t ld_i8, const uint32_t* wt_bits,
+                               int64_t ld_bits, int N, int K, uint64_t threshold, uint64_t seed,
+                               uint32_t stream_id, uint32_t trial0, int n_trials, int8_t* out_i8,
+                               int64_t out_i8_stride, void* out_f16, int64_t ld_f16,
+                               int64_t out_f16_stride, uint32_t* out_bits, int64_t out_bits_stride,
+                               uint32_t* mask_bits, int64_t mask_stride, bnn_stream_t stream);
+
+/* Exact-k flips without replacement over a weight space of `total` elements (all layers of the
+ * network concatenated, this layer owning [offset, offset + N*K)).  Position i of trial t is
+ * P_t(i), i < k_t, where P_t is a keyed cycle-walking Feistel bijection on [0, total) (key from
+ * Philox(seed, trial)); positions are distinct by construction.  k_per_trial: device int32
+ * [n_trials].  The outputs must already hold a copy of the clean weights (in/out). */
+int bnn_flip_weights_exactk(int N, int K, uint64_t total, uint64_t offset, uint64_t seed,
+                            uint32_t trial0, int n_trials, const int32_t* k_per_trial, int k_max,
+                            int8_t* io_i8, int64_t ld_i8, int64_t io_i8_stride, void* io_f16,
+                            int64_t ld_f16, int64_t io_f16_stride, uint32_t* io_bits,
+                            int64_t ld_bits, int64_t io_bits_stride, bnn_stream_t stream);
+
+/* External-mask mode: apply a caller-supplied boolean mask[K, N] (uint8, the reference's own
+ * `uniform(size=W.shape) < p`, callbacks.py:81) to the K-major copies. */
+int bnn_flip_weights_mask(const uint8_t* mask_kn, int K, int N, int8_t* io_i8, int64_t ld_i8,
+                          void* io_f16, int64_t ld_f16, uint32_t* io_bits, int64_t ld_bits,
+                          bnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A12  image fault injection                           (ImageErrorCallback.intError
+ *                                                       callbacks.py:130-147, __call__ :149-172)
+ * Per image row of F bytes: flip exactly min(k, candidates) distinct bits, MSB-first bit order
+ * (np.unpackbits); mode 2 = any bit, 0 = among 0-bits, 1 = among 1-bits.  The positions are the
+ * first k outputs of a keyed Feistel bijection over the candidate ranks, key from
+ * Philox(seed, trial, row).  in: [R, F] uint8 (shared by all trials); out: [n_trials][R, F].
+ * F <= 4096. */
+int bnn_flip_images(const uint8_t* in, int R, int F, int k, int mode, uint64_t seed, uint32_t trial0,
+                    int n_trials, uint8_t* out, bnn_stream_t stream);
+
+/* uint8 -> fp32 affine map used by utils.normalize (utils.py:178-187) with caller-supplied
+ * min/max (device floats): y = ((x - mn) * (new_max - new_min)) / (mx - mn) + new_min, in the
+ * reference's operation order. */
+int bnn_normalize_u8(const uint8_t* in, int64_t n, const float* mn, const float* mx, float new_min,
+                     float new_max, float* out, bnn_stream_t stream);
+
+/* Global min/max of a uint8 buffer: minmax (device uint32[2]) <- {min, max}; minmax_f32 (device
+ * float[2], may be NULL) receives the same as floats for bnn_normalize_u8. */
+int bnn_minmax_u8(const uint8_t* in, int64_t n, uint32_t* minmax, float* minmax_f32,
+                  bnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A13  evaluation helper                                (predict_classes network.py:401-404,
+ *                                                        evaluate :406-421)
+ * correct += #{ b : argmax_c scores[b, c] == labels[b] } (first maximum wins, as ndarray.argmax).
+ * ------------------------------------------------------------------------------------------- */
+int bnn_count_correct(const float* scores, int B, int C, int64_t lds, const int32_t* labels,
+                      int32_t* correct, bnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNN_B200_H */

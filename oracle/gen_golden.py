@@ -1,0 +1,266 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (volf52/deep-neural-net).
+
+Run in the build container only (`python oracle/gen_golden.py`): it needs /root/reference, which does
+not exist on the GPU box.  The reference is imported from a throw-away copy (importing
+mlpcode.network creates a models/ directory, mlpcode/utils.py:19-21) with oracle/refshim first on
+sys.path (cupy -> numpy stand-in, empty h5py).  For every fixture the NumPy oracle
+(oracle/bnn_oracle.py) is run on the same inputs and must agree EXACTLY with the reference before
+the reference's outputs are written — that is the pin of the oracle.
+"""
+from __future__ import annotations
+
+import shutil
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REPO = HERE.parent
+GOLDEN = REPO / "tests" / "golden"
+REFERENCE = Path("/root/reference")
+
+
+def import_reference():
+    tmp = Path(tempfile.mkdtemp(prefix="bnn_ref_"))
+    shutil.copytree(REFERENCE, tmp / "ref")
+    sys.path.insert(0, str(tmp / "ref"))
+    sys.path.insert(0, str(HERE / "refshim"))
+    import mlpcode.layers as L  # noqa: E402
+    import mlpcode.activation as A  # noqa: E402
+    import mlpcode.loss as Lo  # noqa: E402
+    import mlpcode.callbacks as Cb  # noqa: E402
+    import mlpcode.network as Nw  # noqa: E402
+    import mlpcode.utils as U  # noqa: E402
+    return L, A, Lo, Cb, Nw, U
+
+
+def exact(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape != b.shape or not np.array_equal(a, b, equal_nan=True):
+        raise SystemExit(f"oracle != reference for {what}: max|diff| = "
+                         f"{np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))}")
+
+
+def make_net(Nw, A, Lo, units, params, out_af):
+    nn = Nw.Network(units, useGpu=False, binarized=True, useBatchNorm=True)
+    nn.compile(lr=0.01, hiddenAf=A.ActivationFuncs.sign, outAf=out_af,
+               lossF=Lo.LossFuncs.cross_entropy)
+    nn.load_weights([w.copy() for w in params["W"]])
+    nn.loadBatchNormParameters([b["gamma"].copy() for b in params["bn"]],
+                               [b["beta"].copy() for b in params["bn"]],
+                               [b["mu"].copy() for b in params["bn"]],
+                               [b["sigma"].copy() for b in params["bn"]])
+    return nn
+
+
+def net_state(nn):
+    g, b, m, s = nn.batchNormParams
+    return dict(W=[w.copy() for w in nn.weights],
+                bn=[dict(gamma=g[i].copy(), beta=b[i].copy(), mu=m[i].copy(), sigma=s[i].copy())
+                    for i in range(len(g))])
+
+
+def flat_state(prefix, st):
+    out = {}
+    for i, w in enumerate(st["W"]):
+        out[f"{prefix}W{i}"] = w
+        for k, v in st["bn"][i].items():
+            out[f"{prefix}{k}{i}"] = v
+    return out
+
+
+def main():
+    sys.path.insert(0, str(HERE))
+    L, A, Lo, Cb, Nw, U = import_reference()
+    import bnn_oracle as O
+
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    af = A.ActivationFuncs
+
+    # ------------------------------------------------------------------ elementwise ops (A1, A6, A7)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((9, 37), dtype=np.float32)
+    x[0, :4] = [0.0, -0.0, 1e-30, -1e-30]
+    ref_bin = L.BinaryLayer.binarize(x)
+    exact(O.binarize(x), ref_bin, "binarize")
+    ref_step = A.unitstep(x)
+    exact(O.unitstep(x), ref_step, "unitstep")
+    dA = rng.standard_normal((9, 37), dtype=np.float32)
+    ste = A.hard_tanh_derivative(dA, ref_step)
+    exact(dA, ste, "STE identity on +-1 activations")
+    logits = rng.standard_normal((13, 10), dtype=np.float32) * 3
+    ref_sm = A.softmax(logits)
+    exact(O.softmax(logits), ref_sm, "softmax")
+    y = np.eye(10, dtype=np.int8)[rng.integers(0, 10, 13)]
+    sm1, sm2 = ref_sm.copy(), ref_sm.copy()
+    sm1[0, 0] = 0.0  # exercise the lower clip
+    sm2[0, 0] = 0.0
+    ref_loss = Lo.cross_entropy_loss(sm1, y)
+    exact(O.cross_entropy_loss(sm2, y), ref_loss, "cross_entropy_loss")
+    exact(sm1, sm2, "in-place clip")
+    ref_grad = Lo.cross_entropy_derivative(sm1.copy(), y, with_softmax=True)
+    exact(O.cross_entropy_derivative_softmax(sm2.copy(), y), ref_grad, "cross_entropy_derivative")
+    np.savez(GOLDEN / "elementwise.npz", x=x, binarized=ref_bin, unitstep=ref_step, dA=dA, ste=ste,
+             logits=logits, softmax=ref_sm, onehot=y, clipped=sm1, loss=ref_loss, grad=ref_grad)
+
+    # ------------------------------------------------------------------ batch norm (A4, A5, A8)
+    rng = np.random.default_rng(12)
+    B, N = 48, 21
+    Zi = rng.integers(-30, 31, (B, N)).astype(np.float32) * 2  # integer valued like a +-1 GEMM
+    gamma = (rng.random(N, dtype=np.float32) + 0.5)
+    gamma[3] = -gamma[3]
+    beta = rng.standard_normal(N, dtype=np.float32) * 0.1
+    mu_run = rng.standard_normal(N, dtype=np.float32)
+    sig_run = rng.random(N, dtype=np.float32) + 0.5
+    bn = L.BatchNormLayer(N)
+    bn.loadBatchNormParams(gamma.copy(), beta.copy(), mu_run.copy(), sig_run.copy())
+    bn.build()
+    out_tr = bn.forward(Zi.copy(), isTrain=True)
+    o_out, o_cache = O.bn_forward_train(Zi.copy(), gamma.copy(), beta.copy())
+    exact(o_out, out_tr, "bn train forward")
+    delta = rng.standard_normal((B, N), dtype=np.float32) * 1e-3
+    batch_mu, batch_var = bn.cache["mu"].copy(), bn.cache["var"].copy()
+    new_delta = bn.backwards(delta.copy(), lr=0.05)
+    op = dict(gamma=gamma.copy(), beta=beta.copy(), mu=mu_run.copy(), sigma=sig_run.copy())
+    o_nd, o_dg, o_db = O.bn_backward(delta.copy(), o_cache, op, 0.05)
+    exact(o_nd, new_delta, "bn backward delta")
+    for k, v in zip(("gamma", "beta", "mu", "sigma"), bn.batchNormParams):
+        exact(op[k], v, f"bn backward {k}")
+    bn2 = L.BatchNormLayer(N)
+    bn2.loadBatchNormParams(gamma.copy(), beta.copy(), mu_run.copy(), sig_run.copy())
+    bn2.build()
+    out_ev = bn2.forward(Zi.copy(), isTrain=False)
+    exact(O.bn_forward_eval(Zi.copy(), gamma, beta, mu_run, sig_run), out_ev, "bn eval forward")
+    np.savez(GOLDEN / "batchnorm.npz", Z=Zi, gamma=gamma, beta=beta, mu_run=mu_run, sigma_run=sig_run,
+             out_train=out_tr, batch_mu=batch_mu, batch_var=batch_var, delta=delta, lr=np.float32(0.05),
+             new_delta=new_delta, dgamma=o_dg, dbeta=o_db,
+             gamma_after=bn.gamma, beta_after=bn.beta, mu_after=bn.mu, sigma_after=bn.sigma,
+             out_eval=out_ev)
+
+    # ------------------------------------------------------------------ training steps (A2, A9, A10, A13)
+    for name, units, B, steps, seed in (("train_tiny", [20, 16, 12, 10], 16, 3, 21),
+                                        ("train_small", [784, 64, 32, 10], 32, 2, 22),
+                                        ("train_ragged", [50, 33, 10], 19, 2, 23)):
+        rng = np.random.default_rng(seed)
+        params = O.new_params(units, rng)
+        for b in params["bn"]:  # non-trivial BN state
+            b["gamma"] += rng.standard_normal(b["gamma"].shape, dtype=np.float32) * 0.1
+            b["beta"] += rng.standard_normal(b["beta"].shape, dtype=np.float32) * 0.1
+        X = rng.random((steps, B, units[0]), dtype=np.float32) * 2 - 1
+        Y = np.eye(10, dtype=np.int8)[rng.integers(0, 10, (steps, B))]
+        nn = make_net(Nw, A, Lo, units, params, af.softmax)
+        op = O.copy_params(params)
+        blob = dict(units=np.array(units), X=X, Y=Y, lr=np.float32(0.01))
+        blob.update(flat_state("init_", params))
+        costs = []
+        for s in range(steps):
+            # stage tensors of the first step for teacher-forced parity
+            if s == 0:
+                acts, a = [], X[0]
+                for layer in nn._layers:
+                    a = layer.forward(a, isTrain=True)
+                    acts.append((layer.cache["z"].copy(), np.asarray(a).copy()))
+                for i, (z, a_) in enumerate(acts):
+                    blob[f"s0_bn_out{i}"], blob[f"s0_act{i}"] = z, a_
+                rec = {}
+                o_tmp = O.copy_params(op)
+                O.train_step(o_tmp, X[0].copy(), Y[0], 0.01, record=rec)
+                for i in range(len(units) - 1):
+                    blob[f"s0_dW{i}"] = rec["dW"][i]
+                    blob[f"s0_dX{i}"] = rec["dX"][i]
+                    blob[f"s0_delta_bn{i}"] = rec["delta_bn"][i]
+                    blob[f"s0_z{i}"] = rec["caches"][i]["z_pre"]
+                blob["s0_dLdA"] = rec["dLdA"]
+            c_ref = nn._Network__updateBatch((X[s].copy(), Y[s]), 0.01)
+            c_or = O.train_step(op, X[s].copy(), Y[s], 0.01)
+            exact(c_or, c_ref, f"{name} cost step {s}")
+            st = net_state(nn)
+            for i in range(len(units) - 1):
+                exact(op["W"][i], st["W"][i], f"{name} W{i} step {s}")
+                for k in ("gamma", "beta", "mu", "sigma"):
+                    exact(op["bn"][i][k], st["bn"][i][k], f"{name} {k}{i} step {s}")
+            costs.append(c_ref)
+            blob.update(flat_state(f"after{s}_", st))
+        blob["costs"] = np.array(costs, np.float64)
+        # eval-mode predictions with the trained state (running statistics)
+        Xe = rng.random((B + 5, units[0]), dtype=np.float32) * 2 - 1
+        pe = nn.predict(Xe.copy(), isTraining=False)
+        exact(O.predict(op, Xe.copy()), pe, f"{name} eval predict")
+        blob["X_eval"], blob["probs_eval"] = Xe, pe
+        labels = rng.integers(0, 10, B + 5).astype(np.uint8)
+        blob["labels_eval"] = labels
+        blob["acc_eval"] = np.float64(nn.get_accuracy(Xe.copy(), labels))
+        assert O.accuracy(op, Xe.copy(), labels) == float(blob["acc_eval"])
+        np.savez_compressed(GOLDEN / f"{name}.npz", **blob)
+
+    # ------------------------------------------------------------------ weight faults (A3, A11)
+    rng = np.random.default_rng(31)
+    units = [40, 24, 10]
+    params = O.new_params(units, rng)
+    Xf = rng.random((30, 40), dtype=np.float32) * 2 - 1
+    labels = rng.integers(0, 10, 30).astype(np.uint8)
+    nn = make_net(Nw, A, Lo, units, params, af.softmax)
+    Wb = L.BinaryLayer.binarize(params["W"][0])
+    cb = Cb.ErrorCallback(0.2, mode=2, bnn=True)
+    np.random.seed(77)
+    flipped = cb(Wb)
+    np.random.seed(77)
+    mask0 = np.random.uniform(size=Wb.shape) < 0.2
+    exact(O.flip_bnn_mask(Wb, mask0), flipped, "ErrorCallback._flipBNNMask")
+    # full eval with a callback on every layer: one fresh mask per layer per forward, drawn in order
+    nn.addCallbacks(Cb.ErrorCallback(0.1, mode=2, bnn=True))
+    np.random.seed(78)
+    probs_fault = nn.predict(Xf.copy(), isTraining=False)
+    np.random.seed(78)
+    masks = [np.random.uniform(size=w.shape) < 0.1 for w in params["W"]]
+    hooks = [(lambda m: (lambda Wq: O.flip_bnn_mask(Wq, m)))(m) for m in masks]
+    exact(O.predict(params, Xf.copy(), weight_hooks=hooks), probs_fault, "faulty predict")
+    np.random.seed(78)
+    acc_fault = nn.get_accuracy(Xf.copy(), labels)
+    nn.clearCallbacks()
+    blob = dict(units=np.array(units), X=Xf, labels=labels, cb_Wb=Wb, cb_mask=mask0, cb_flipped=flipped,
+                probs_fault=probs_fault, acc_fault=np.float64(acc_fault),
+                probs_clean=nn.predict(Xf.copy(), isTraining=False))
+    for i, m in enumerate(masks):
+        blob[f"mask{i}"] = m
+    blob.update(flat_state("", params))
+    np.savez_compressed(GOLDEN / "weight_faults.npz", **blob)
+
+    # ------------------------------------------------------------------ image faults (A12) + normalize
+    rng = np.random.default_rng(41)
+    imgs = rng.integers(0, 256, (6, 49), dtype=np.uint8)
+    imgs[0] = 0
+    imgs[1] = 255
+    blob = dict(images=imgs)
+    for mode in (0, 1, 2):
+        icb = Cb.ImageErrorCallback(0.14, mode=mode)
+        np.random.seed(90 + mode)
+        out = icb(imgs)
+        # replay the reference's draws through the oracle's explicit-index flip
+        np.random.seed(90 + mode)
+        mine = np.empty_like(imgs)
+        for r in range(imgs.shape[0]):
+            unpacked = np.unpackbits(imgs[r])
+            nbits = round(0.14 * unpacked.size)
+            if mode == 2:
+                idx = np.random.choice(unpacked.size, nbits, replace=False)
+            else:
+                chosen, = np.where(unpacked == mode)
+                idx = np.random.choice(chosen, min(chosen.size, nbits), replace=False)
+            mine[r] = O.flip_image_row(imgs[r], idx)
+        exact(mine, out, f"ImageErrorCallback mode {mode}")
+        blob[f"out_mode{mode}"] = out
+    blob["k"] = np.int64(round(0.14 * 49 * 8))
+    norm = U.normalize(imgs, newMin=-1, newMax=1)
+    exact(O.normalize(imgs, -1, 1), norm.astype(np.float32), "normalize")
+    blob["normalized"] = norm.astype(np.float32)
+    np.savez_compressed(GOLDEN / "image_faults.npz", **blob)
+
+    sizes = {p.name: p.stat().st_size for p in sorted(GOLDEN.glob("*.npz"))}
+    print("golden fixtures written:", sizes)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,158 @@
+"""CPU: the oracle against the fixtures generated from the reference, and the C restatement against
+NumPy / published known-answer vectors.  These pin the checker the GPU tests rely on."""
+import numpy as np
+import pytest
+
+from conftest import params_from_golden
+
+
+def test_elementwise_against_reference(golden, oracle):
+    g = golden("elementwise")
+    assert np.array_equal(oracle.binarize(g["x"]), g["binarized"])
+    assert np.array_equal(oracle.unitstep(g["x"]), g["unitstep"])
+    # sign(0) = sign(-0) = +1
+    assert g["binarized"][0, 0] == 1 and g["binarized"][0, 1] == 1 and g["binarized"][0, 3] == -1
+    # STE is numerically the identity on post-sign activations
+    assert np.array_equal(g["ste"], g["dA"])
+    assert np.array_equal(oracle.softmax(g["logits"]), g["softmax"])
+    sm = g["softmax"].copy()
+    sm[0, 0] = 0.0
+    assert np.array_equal(oracle.cross_entropy_loss(sm, g["onehot"]), g["loss"])
+    assert np.array_equal(sm, g["clipped"])
+    assert np.array_equal(oracle.cross_entropy_derivative_softmax(sm.copy(), g["onehot"]), g["grad"])
+
+
+def test_batchnorm_against_reference(golden, oracle):
+    g = golden("batchnorm")
+    out, cache = oracle.bn_forward_train(g["Z"].copy(), g["gamma"].copy(), g["beta"].copy())
+    assert np.array_equal(out, g["out_train"])
+    assert np.array_equal(cache["mu"], g["batch_mu"]) and np.array_equal(cache["var"], g["batch_var"])
+    p = dict(gamma=g["gamma"].copy(), beta=g["beta"].copy(), mu=g["mu_run"].copy(),
+             sigma=g["sigma_run"].copy())
+    nd, dg, db = oracle.bn_backward(g["delta"].copy(), cache, p, float(g["lr"]))
+    assert np.array_equal(nd, g["new_delta"])
+    for k in ("gamma", "beta", "mu", "sigma"):
+        assert np.array_equal(p[k], g[f"{k}_after"]), k
+    ev = oracle.bn_forward_eval(g["Z"].copy(), g["gamma"], g["beta"], g["mu_run"], g["sigma_run"])
+    assert np.array_equal(ev, g["out_eval"])
+
+
+@pytest.mark.parametrize("name", ["train_tiny", "train_small", "train_ragged"])
+def test_train_steps_against_reference(golden, oracle, name):
+    g = golden(name)
+    units = [int(u) for u in g["units"]]
+    n = len(units) - 1
+    p = params_from_golden(g, "init_", n)
+    for s in range(g["X"].shape[0]):
+        cost = oracle.train_step(p, g["X"][s].copy(), g["Y"][s], float(g["lr"]))
+        assert cost == g["costs"][s]
+        for i in range(n):
+            assert np.array_equal(p["W"][i], g[f"after{s}_W{i}"])
+            for k in ("gamma", "beta", "mu", "sigma"):
+                assert np.array_equal(p["bn"][i][k], g[f"after{s}_{k}{i}"]), (s, i, k)
+    assert np.array_equal(oracle.predict(p, g["X_eval"].copy()), g["probs_eval"])
+    assert oracle.accuracy(p, g["X_eval"].copy(), g["labels_eval"]) == float(g["acc_eval"])
+
+
+def test_weight_faults_against_reference(golden, oracle):
+    g = golden("weight_faults")
+    assert np.array_equal(oracle.flip_bnn_mask(g["cb_Wb"], g["cb_mask"]), g["cb_flipped"])
+    units = [int(u) for u in g["units"]]
+    p = params_from_golden(g, "", len(units) - 1)
+    hooks = [(lambda m: (lambda W: oracle.flip_bnn_mask(W, m)))(g[f"mask{i}"])
+             for i in range(len(units) - 1)]
+    assert np.array_equal(oracle.predict(p, g["X"].copy(), weight_hooks=hooks), g["probs_fault"])
+    assert np.array_equal(oracle.predict(p, g["X"].copy()), g["probs_clean"])
+
+
+def test_image_faults_against_reference(golden, oracle):
+    g = golden("image_faults")
+    imgs, k = g["images"], int(g["k"])
+    for mode in (0, 1, 2):
+        out = g[f"out_mode{mode}"]
+        diff = np.unpackbits(imgs ^ out, axis=1)
+        before = np.unpackbits(imgs, axis=1)
+        for r in range(imgs.shape[0]):
+            cand = before.shape[1] if mode == 2 else int((before[r] == mode).sum())
+            assert diff[r].sum() == min(k, cand)          # exactly k distinct flips
+            if mode != 2:                                  # only candidate bits were touched
+                assert np.all(before[r][diff[r] == 1] == mode)
+    assert np.array_equal(oracle.normalize(imgs, -1, 1), g["normalized"])
+
+
+# ------------------------------------------------------------------------- C restatement
+def test_c_pack_matches_numpy(oracle):
+    rng = np.random.default_rng(0)
+    for R, C in ((1, 1), (3, 31), (5, 32), (4, 33), (7, 100)):
+        x = rng.standard_normal((R, C)).astype(np.float32)
+        x[0, 0] = -0.0
+        assert np.array_equal(oracle.c_pack_sign_rows(x), oracle.pack_sign_rows(x))
+        assert np.array_equal(oracle.unpack_sign_rows(oracle.pack_sign_rows(x), C), oracle.binarize(x))
+    W = rng.standard_normal((45, 7)).astype(np.float32)
+    assert np.array_equal(oracle.c_pack_weights_t(W), oracle.pack_sign_rows(np.ascontiguousarray(W.T)))
+
+
+def test_c_xnor_gemm_is_the_pm1_product(oracle):
+    rng = np.random.default_rng(1)
+    for M, N, K in ((3, 5, 1), (4, 4, 31), (9, 6, 64), (5, 11, 200)):
+        a = np.sign(rng.standard_normal((M, K))).astype(np.float32)
+        b = np.sign(rng.standard_normal((N, K))).astype(np.float32)
+        a[a == 0] = 1
+        b[b == 0] = 1
+        ref = (a @ b.T).astype(np.int32)                 # X.dot(W) on +-1 operands, layers.py:220
+        assert np.array_equal(oracle.c_gemm_pm1(a.astype(np.int8), b.astype(np.int8)), ref)
+        got = oracle.c_gemm_xnor(oracle.pack_sign_rows(a), oracle.pack_sign_rows(b), K)
+        assert np.array_equal(got, ref)
+
+
+def test_philox_known_answers(oracle):
+    """Random123 v1.09 kat_vectors, philox4x32-10."""
+    assert oracle.c_philox((0, 0, 0, 0), (0, 0)) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+    f = 0xFFFFFFFF
+    assert oracle.c_philox((f, f, f, f), (f, f)) == (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
+    assert oracle.c_philox((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344),
+                           (0xA4093822, 0x299F31D0)) == (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)
+
+
+def test_bernoulli_mask_statistics_and_determinism(oracle):
+    K, N = 96, 50
+    m1 = oracle.c_bernoulli_mask(K, N, 0.2, seed=5, stream=1, trial=0)
+    m2 = oracle.c_bernoulli_mask(K, N, 0.2, seed=5, stream=1, trial=0)
+    m3 = oracle.c_bernoulli_mask(K, N, 0.2, seed=5, stream=1, trial=1)
+    assert np.array_equal(m1, m2) and not np.array_equal(m1, m3)
+    assert abs(m1.mean() - 0.2) < 4 * np.sqrt(0.2 * 0.8 / (K * N))
+    assert not oracle.c_bernoulli_mask(K, N, 0.0, 5, 1, 0).any()
+    assert oracle.c_bernoulli_mask(K, N, 1.0, 5, 1, 0).all()
+
+
+def test_exactk_positions_are_distinct_and_cover(oracle):
+    for total in (1, 2, 7, 64, 1000, 36_806_656):
+        k = min(total, 1000)
+        pos = oracle.c_exactk_positions(total, seed=9, trial=3, k=k)
+        assert pos.max() < total and len(np.unique(pos)) == k
+    # a bijection: asking for every index yields a permutation
+    pos = oracle.c_exactk_positions(777, seed=1, trial=0, k=777)
+    assert np.array_equal(np.sort(pos), np.arange(777, dtype=np.uint64))
+    assert not np.array_equal(pos, oracle.c_exactk_positions(777, seed=1, trial=1, k=777))
+
+
+def test_c_image_flips_follow_reference_semantics(golden, oracle):
+    g = golden("image_faults")
+    imgs, k = g["images"], int(g["k"])
+    before = np.unpackbits(imgs, axis=1)
+    for mode in (0, 1, 2):
+        out = oracle.c_flip_image_rows(imgs, k, mode, seed=3, trial=0)
+        diff = np.unpackbits(imgs ^ out, axis=1)
+        for r in range(imgs.shape[0]):
+            cand = before.shape[1] if mode == 2 else int((before[r] == mode).sum())
+            assert diff[r].sum() == min(k, cand)
+            if mode != 2:
+                assert np.all(before[r][diff[r] == 1] == mode)
+        assert not np.array_equal(out, oracle.c_flip_image_rows(imgs, k, mode, seed=3, trial=1))
+    # uniformity of the chosen positions over many trials (mode 2)
+    row = np.zeros((1, 16), np.uint8)
+    hits = np.zeros(128)
+    for t in range(400):
+        hits += np.unpackbits(oracle.c_flip_image_rows(row, 16, 2, seed=11, trial=t), axis=1)[0]
+    assert hits.sum() == 400 * 16
+    assert hits.min() > 20 and hits.max() < 85        # mean 50, sd ~6.6
