@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — BNN MLP training throughput on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Own arm: K timed steps of the 784-4096-4096-4096-10 binarized MLP (BASELINE configs[1]), batch 8192
+per GPU (weak scaling; N = 8 is configs[2]'s global batch 65536), through mlpcode.network.Network
+on libbnn_b200 kernels.  `value` is timed with the inputs resident in HBM; `e2e` repeats the
+measurement through the public per-batch call with pinned HOST buffers (H2D of X and y, D2H of the
+loss inside the timed region).  `roofline` describes the dominant kernel, timed live with CUDA events
+on the launching stream; `binary_gemm` is the +-1 x +-1 forward GEMM the metric's second half names;
+`cpu_baseline` is the oracle port of the reference NumPy path timed on this box's host cores.
+
+Reference arm (--impl reference): the reference's CPU path for the same workload — the NumPy oracle
+port (the reference itself is Python + CuPy/h5py imports and cannot travel to the GPU box; the port is
+pinned bit-exactly against it by oracle/gen_golden.py) with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO / "deep-neural-net_b200"))
+
+UNITS = [784, 4096, 4096, 4096, 10]
+BATCH = 8192
+LR = 0.01
+METRIC, UNIT = "BNN MLP train samples/s", "samples/s"
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "784-4096-4096-4096-10 binarized MLP training step, batch 8192 per GPU "
+                    "(BASELINE configs[1]; at N=8 the global batch is configs[2]'s 65536)",
+        "units": UNITS, "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus,
+        "parallelism": f"dp{n_gpus}", "lr": LR,
+        "l2": "per-step working set ~1.3 GB of activations/operands >> 126 MB L2 (no flush needed)",
+    }
+
+
+def synthetic_batch(seed, batch):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    X = rng.random((batch, UNITS[0]), dtype=np.float32) * 2 - 1
+    Y = np.eye(10, dtype=np.int8)[rng.integers(0, 10, batch)]
+    return X, Y
+
+
+def synthetic_params():
+    import numpy as np
+    rng = np.random.default_rng(0)
+    return [(rng.standard_normal((k, n), dtype=np.float32) * np.float32(np.sqrt(1.0 / k)))
+            for k, n in zip(UNITS[:-1], UNITS[1:])]
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max((p.get("num_threads", 1) for p in threadpool_info()), default=1)
+        return int(n)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference NumPy path)
+# ------------------------------------------------------------------------------------------------
+def cpu_train_samples_per_s(steps, warmup, budget_s):
+    """Times oracle.train_step on a bounded sample of the workload; returns (samples/s, sample text)."""
+    sys.path.insert(0, str(REPO / "oracle"))
+    import numpy as np
+    import bnn_oracle as O
+    W = synthetic_params()
+    params = dict(W=[w.copy() for w in W],
+                  bn=[dict(gamma=np.ones(n, np.float32), beta=np.zeros(n, np.float32),
+                           mu=np.zeros(n, np.float32), sigma=np.ones(n, np.float32)) for n in UNITS[1:]])
+    # probe with a small batch to size the sample so the whole run stays inside the budget
+    Xp, Yp = synthetic_batch(1, 512)
+    t0 = time.perf_counter()
+    O.train_step(params, Xp, Yp, LR)
+    probe = time.perf_counter() - t0
+    per_sample = probe / 512
+    batch = BATCH
+    while batch > 512 and per_sample * batch * (steps + warmup) > budget_s:
+        batch //= 2
+    X, Y = synthetic_batch(2, batch)
+    for _ in range(warmup):
+        O.train_step(params, X, Y, LR)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.train_step(params, X, Y, LR)
+        times.append(time.perf_counter() - t0)
+    dt = sum(times)
+    sample = (f"{steps} train steps at batch {batch} (of {BATCH}) after {warmup} warm-up, NumPy "
+              f"{np.__version__} oracle port of network.py:372-392")
+    return batch * steps / dt, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    val, sample = cpu_train_samples_per_s(args.steps, args.warmup, budget_s=170.0)
+    cores = host_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * BATCH / val,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.samples if t0 <= t <= t1] or [r for (_, r) in self.samples]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            parts = [p.strip() for p in r.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def measure_int8_peak(torch):
+    """cuBLASLt int8 GEMM 8192^3 (library call, outside every timed region): the int8 tensor-pipe
+    denominator SURVEY §8(d) asks the builder to measure."""
+    try:
+        n = 8192
+        a = torch.randint(-1, 2, (n, n), device="cuda", dtype=torch.int8)
+        b = torch.randint(-1, 2, (n, n), device="cuda", dtype=torch.int8)
+        for _ in range(3):
+            torch._int_mm(a, b)
+        best = 1e9
+        for _ in range(10):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            torch._int_mm(a, b)
+            e.record()
+            e.synchronize()
+            best = min(best, s.elapsed_time(e))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    from mlpcode import kernels as K
+    from mlpcode import parallel
+    from mlpcode.activation import ActivationFuncs as af
+    from mlpcode.loss import LossFuncs as lf
+    from mlpcode.network import Network
+
+    comm = parallel.init_from_env("nccl")
+    world = comm.world if comm else 1
+    rank = comm.rank if comm else 0
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    nn = Network(UNITS, useGpu=True, binarized=True, useBatchNorm=True)
+    nn.compile(lr=LR, hiddenAf=af.sign, outAf=af.softmax, lossF=lf.cross_entropy)
+    nn.load_weights(synthetic_params())
+    if comm:
+        nn.set_data_parallel(comm)
+    Xh, Yh = synthetic_batch(100 + rank, BATCH)
+    Xp, Yp = torch.from_numpy(Xh).pin_memory(), torch.from_numpy(Yh).pin_memory()
+    Xd, Yd = Xp.cuda(), Yp.cuda()
+
+    def fence():
+        torch.cuda.synchronize()
+        if comm:
+            comm.barrier()
+            torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        fence()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            step_fn()
+        e.record()
+        fence()
+        ms = torch.tensor([s.elapsed_time(e)], device="cuda", dtype=torch.float64)
+        if comm:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up, then the device-resident measurement with per-GEMM events ----------------
+    for _ in range(max(args.warmup, 3)):
+        nn.train_step_async(Xd, Yd, LR)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    K.gemm_events = []
+    launches0 = K.launch_count
+    t0 = time.perf_counter()
+    ms_total = timed(lambda: nn.train_step_async(Xd, Yd, LR), args.steps)
+    t1 = time.perf_counter()
+    launches = K.launch_count - launches0
+    events, K.gemm_events = K.gemm_events, None
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    value = world * BATCH * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end: pinned host buffers -> H2D -> step -> D2H loss, every step ------------------
+    for _ in range(2):
+        nn.train_step(Xp, Yp, LR)
+    ms_e2e = timed(lambda: nn.train_step(Xp, Yp, LR), args.steps)
+    e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        return 0
+
+    # ---- per-kernel accounting from the events recorded inside the timed region ------------------
+    groups = {}
+    for (s, e, tag, flops, passes) in events:
+        g = groups.setdefault(tag, {"ms": 0.0, "n": 0, "flops": 0.0, "exec": 0.0})
+        dt = s.elapsed_time(e)
+        g["ms"] += dt
+        g["n"] += 1
+        g["flops"] += flops
+        g["exec"] += flops * passes
+    hbm_peak, tensor_peak, peak_kind = measured_peaks()
+    split = groups.get("f16", {"ms": 0.0, "n": 0, "flops": 0.0, "exec": 0.0})
+    i8 = groups.get("i8", {"ms": 0.0, "n": 0, "flops": 0.0, "exec": 0.0})
+    roofline = None
+    if split["n"]:
+        ach = split["flops"] / (split["ms"] * 1e-3) / 1e12
+        roofline = {
+            "kernel": "gemm_tc_kernel<f16 split> (dW + dX + layer-0 forward)", "bound": "tensor",
+            "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
+            "traffic": None, "peak_source": f"bf16_tflops_sustained of {peak_kind}",
+            "executed_tflops": split["exec"] / (split["ms"] * 1e-3) / 1e12,
+            "executed_frac": split["exec"] / (split["ms"] * 1e-3) / 1e12 / tensor_peak,
+            "avg_launch_ms": split["ms"] / split["n"], "launches": split["n"],
+            "share_of_step": split["ms"] / ms_total,
+            "note": "achieved counts the ALGORITHMIC 2MNK of the fp32 product; the kernel executes "
+                    "2-3 fp16 passes per product (executed_*), so frac <= 1/2..1/3 by construction",
+        }
+    int8_peak = measure_int8_peak(torch)
+    binary = None
+    if i8["n"]:
+        tops = i8["flops"] / (i8["ms"] * 1e-3) / 1e12
+        binary = {"kernel": "gemm_tc_kernel<i8> (+-1 x +-1 forward, layers 1..3)", "achieved": tops,
+                  "unit": "TOP/s", "peak": int8_peak, "peak_source": "cuBLASLt int8 8192^3 on this box",
+                  "frac": (tops / int8_peak) if int8_peak else None,
+                  "avg_launch_ms": i8["ms"] / i8["n"], "launches": i8["n"],
+                  "share_of_step": i8["ms"] / ms_total}
+
+    cpu_val, cpu_sample = cpu_train_samples_per_s(steps=2, warmup=1, budget_s=40.0)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "i8 fwd / f16x2-split f32-acc bwd", "data": "synthetic",
+        "config": workload_config(world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(Xh.nbytes + Yh.nbytes), "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "binary_gemm": binary,
+        "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": host_threads(), "kind": "port",
+                         "sample": cpu_sample},
+        "collectives_per_step": (comm.collectives / (args.steps * 2 + max(args.warmup, 3) + 2))
+        if comm else 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    rc = run_reference(args) if args.impl == "reference" else run_gpu(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+    return rc
+
+
+if __name__ == "__main__":
+    sys.exit(main())

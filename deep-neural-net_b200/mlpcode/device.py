@@ -120,7 +120,10 @@ class DeviceArray:
         return DeviceArray(self.t[idx])
 
     def argmax(self, axis=None):
-        return DeviceArray(self.t.argmax(dim=axis) if axis is not None else self.t.argmax())
+        t = self.t
+        if t.dtype in (torch.int8, torch.uint8, torch.bool):  # one-hot labels arrive as int8
+            t = t.to(torch.int32)
+        return DeviceArray(t.argmax(dim=axis) if axis is not None else t.argmax())
 
     def sum(self, axis=None):
         return DeviceArray(self.t.sum(dim=axis) if axis is not None else self.t.sum())

@@ -15,6 +15,7 @@ from . import _native as nat
 from .device import ptr, stream_ptr
 
 launch_count = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+gemm_events = None  # bench.py sets this to a list to collect (start, end, kind, 2MNK, passes) per GEMM
 
 # launches (kernels + memsets are not counted) issued per C call
 _LAUNCHES = {"bnn_minmax_u8": 2}
@@ -95,7 +96,15 @@ def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),
     d.D, d.ldd, d.stride_d = ptr(D), ldd, stride_d
     d.sa, d.sb = ptr(sa), ptr(sb)
     d.host_scale = host_scale
+    if gemm_events is None:
+        _call("bnn_gemm", C.byref(d), gemm_impl() if impl is None else impl)
+        return
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
     _call("bnn_gemm", C.byref(d), gemm_impl() if impl is None else impl)
+    end.record()
+    gemm_events.append((start, end, "i8" if in_dtype == nat.DT_I8 else "f16",
+                        2.0 * M * N * K * batch, len(passes)))
 
 
 def gemm_popc(a_bits, b_bits, M, N, K, D, out_s16=True) -> None:

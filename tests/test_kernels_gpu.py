@@ -1,0 +1,500 @@
+"""GPU parity of every libbnn_b200 kernel against the oracle, called through the C ABI.
+
+Bar: bit-exact for integer / byte / index work (packing, +-1 GEMMs, masks, flips, batch-norm sign
+decisions on identical inputs); for floating point the tolerance is written in each test (north
+star: 1e-5 relative)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    from mlpcode import _native, kernels
+    _native.load()
+    return torch
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def pm1(rng, shape):
+    return np.where(rng.random(shape) < 0.5, -1, 1).astype(np.int8)
+
+
+def padded(a, mult, dtype=None):
+    """Copy a 2-D array into a zero buffer whose pitch is a multiple of `mult` elements."""
+    import torch
+    r, c = a.shape
+    cp = (c + mult - 1) // mult * mult
+    t = torch.zeros((r, cp), dtype=dev(a[:1, :1]).dtype if dtype is None else dtype, device="cuda")
+    t[:, :c] = dev(a)
+    return t
+
+
+# ------------------------------------------------------------------------------------- A1 packing
+@pytest.mark.parametrize("R,C", [(1, 1), (3, 31), (5, 32), (4, 33), (64, 784), (17, 4097)])
+def test_pack_sign_rows(T, oracle, R, C):
+    from mlpcode import kernels as K
+    rng = np.random.default_rng(R * 1000 + C)
+    x = rng.standard_normal((R, C)).astype(np.float32)
+    x[0, 0] = -0.0
+    x[-1, -1] = 0.0
+    words = (C + 31) // 32
+    bits = T.full((R, words + 1), -1, dtype=T.int32, device="cuda")
+    K.pack_sign_rows(dev(x), bits)
+    got = bits.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got[:, :words], oracle.pack_sign_rows(x))
+    assert np.all(got[:, words] == 0xFFFFFFFF)  # pad word beyond ceil(C/32) untouched
+
+
+@pytest.mark.parametrize("K_,N", [(32, 32), (784, 256), (100, 10), (4096, 70), (33, 129)])
+def test_binarize_weights_t(T, oracle, K_, N):
+    from mlpcode import kernels as K
+    rng = np.random.default_rng(K_ + N)
+    W = rng.standard_normal((K_, N)).astype(np.float32)
+    W[0, 0], W[1 % K_, 0] = 0.0, -0.0
+    words = (K_ + 31) // 32
+    i8 = T.zeros((N, (K_ + 15) // 16 * 16), dtype=T.int8, device="cuda")
+    f16 = T.zeros((N, (K_ + 7) // 8 * 8), dtype=T.float16, device="cuda")
+    bits = T.zeros((N, words), dtype=T.int32, device="cuda")
+    K.binarize_weights_t(dev(W), wt_i8=i8, wt_f16=f16, wt_bits=bits)
+    ref = oracle.binarize(W).T  # [N, K]
+    assert np.array_equal(i8.cpu().numpy()[:, :K_], ref.astype(np.int8))
+    assert np.array_equal(f16.cpu().numpy()[:, :K_].astype(np.float32), ref)
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), oracle.c_pack_weights_t(W))
+    # round trip through unpack
+    back = T.zeros_like(i8)
+    K.unpack_bits(bits, K_, out_i8=back)
+    assert T.equal(back[:, :K_], i8[:, :K_])
+
+
+@pytest.mark.parametrize("R,C", [(7, 10), (64, 64), (100, 784), (130, 33)])
+def test_split_f16_reconstructs_fp32(T, R, C):
+    from mlpcode import kernels as K
+    rng = np.random.default_rng(R + C)
+    x = (rng.standard_normal((R, C)) * np.exp(rng.standard_normal((R, C)) * 3) * 1e-3).astype(np.float32)
+    xd = dev(x)
+    amax = T.zeros(1, dtype=T.float32, device="cuda")
+    scale = T.zeros(1, dtype=T.float32, device="cuda")
+    Cp, Rp = (C + 7) // 8 * 8, (R + 7) // 8 * 8
+    hi, lo = (T.zeros((R, Cp), dtype=T.float16, device="cuda") for _ in range(2))
+    hit, lot = (T.zeros((C, Rp), dtype=T.float16, device="cuda") for _ in range(2))
+    K.absmax_f32(xd, amax)
+    assert amax.item() == np.abs(x).max()
+    K.split_f16(xd, amax, hi=hi, lo=lo, hi_t=hit, lo_t=lot, scale_out=scale)
+    s = scale.item()
+    assert s > 0 and np.log2(s) == int(np.log2(s))          # power of two
+    assert np.abs(x).max() * s <= 2.0 ** 14                  # head-room below fp16 max
+    rec = (hi.double() + lo.double()).cpu().numpy()[:, :C] / s
+    # two fp16 pieces carry >= 21 mantissa bits of the scaled value
+    tol = 2.0 ** -21 * np.abs(x) + 2.0 ** -24 / s
+    assert np.all(np.abs(rec - x.astype(np.float64)) <= tol)
+    assert T.equal(hit[:, :R], hi[:, :C].t()) and T.equal(lot[:, :R], lo[:, :C].t())
+
+
+# ------------------------------------------------------------------------------------- A2 GEMMs
+I8_SHAPES = [(128, 256, 128), (130, 40, 200), (256, 10, 512), (300, 300, 784), (64, 16, 32),
+             (1, 1, 16), (257, 513, 4096), (512, 4096, 256)]
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+@pytest.mark.parametrize("M,N,K_", I8_SHAPES)
+def test_gemm_i8_exact(T, oracle, impl, M, N, K_):
+    from mlpcode import _native as nat, kernels as K
+    rng = np.random.default_rng(M * 7 + N * 3 + K_)
+    a, b = pm1(rng, (M, K_)), pm1(rng, (N, K_))
+    ref = a.astype(np.int32) @ b.astype(np.int32).T
+    if M * N * K_ < 2e7:
+        assert np.array_equal(oracle.c_gemm_pm1(a, b), ref)
+    A, Bm = padded(a, 16), padded(b, 16)
+    which = nat.GEMM_TCGEN05 if impl == "tcgen05" else nat.GEMM_SIMT
+    for epi, dt, mult in ((nat.EPI_STORE_S32, T.int32, 4), (nat.EPI_STORE_S16, T.int16, 8)):
+        ldd = (N + mult - 1) // mult * mult
+        D = T.full((M, ldd), 12345, dtype=dt, device="cuda")
+        K.gemm(M=M, N=N, K=K_, A=(A,), B=(Bm,), lda=A.stride(0), ldb=Bm.stride(0), D=D, ldd=ldd,
+               in_dtype=nat.DT_I8, epilogue=epi, impl=which)
+        got = D.cpu().numpy()
+        assert np.array_equal(got[:, :N].astype(np.int32), ref)
+        assert np.all(got[:, N:] == 12345)               # nothing written past column N
+
+
+def test_gemm_i8_unaligned_output_and_batch(T):
+    from mlpcode import _native as nat, kernels as K
+    rng = np.random.default_rng(5)
+    nb, M, N, K_ = 3, 200, 70, 160
+    a, b = pm1(rng, (nb, M, K_)), pm1(rng, (nb, N, K_))
+    ref = np.einsum("bmk,bnk->bmn", a.astype(np.int32), b.astype(np.int32))
+    A, Bm = dev(a), dev(b)
+    D = T.zeros((nb, M, N + 1), dtype=T.int32, device="cuda")   # pitch 71: scalar store path
+    K.gemm(M=M, N=N, K=K_, A=(A,), B=(Bm,), lda=K_, ldb=K_, D=D, ldd=N + 1, in_dtype=nat.DT_I8,
+           epilogue=nat.EPI_STORE_S32, batch=nb, stride_a=M * K_, stride_b=N * K_,
+           stride_d=M * (N + 1), impl=nat.GEMM_TCGEN05)
+    assert np.array_equal(D.cpu().numpy()[:, :, :N], ref)
+    # operand A shared by every batch (stride 0): the layout of a fault sweep's first layer
+    D2 = T.zeros((nb, M, N + 1), dtype=T.int32, device="cuda")
+    K.gemm(M=M, N=N, K=K_, A=(A[0],), B=(Bm,), lda=K_, ldb=K_, D=D2, ldd=N + 1, in_dtype=nat.DT_I8,
+           epilogue=nat.EPI_STORE_S32, batch=nb, stride_a=0, stride_b=N * K_,
+           stride_d=M * (N + 1), impl=nat.GEMM_TCGEN05)
+    ref2 = np.einsum("mk,bnk->bmn", a[0].astype(np.int32), b.astype(np.int32))
+    assert np.array_equal(D2.cpu().numpy()[:, :, :N], ref2)
+
+
+@pytest.mark.parametrize("M,N,K_", [(5, 7, 1), (128, 128, 512), (130, 200, 784), (64, 10, 4096),
+                                    (300, 129, 33)])
+def test_gemm_popc_exact(T, oracle, M, N, K_):
+    from mlpcode import kernels as K
+    rng = np.random.default_rng(M + N + K_)
+    a, b = pm1(rng, (M, K_)), pm1(rng, (N, K_))
+    ref = a.astype(np.int32) @ b.astype(np.int32).T
+    ab = oracle.pack_sign_rows(a.astype(np.float32))
+    bb = oracle.pack_sign_rows(b.astype(np.float32))
+    if M * N * K_ < 2e7:
+        assert np.array_equal(oracle.c_gemm_xnor(ab, bb, K_), ref)
+    A, Bm = dev(ab.view(np.int32)), dev(bb.view(np.int32))
+    D = T.zeros((M, N), dtype=T.int32, device="cuda")
+    K.gemm_popc(A, Bm, M, N, K_, D, out_s16=False)
+    assert np.array_equal(D.cpu().numpy(), ref)
+    D16 = T.zeros((M, N), dtype=T.int16, device="cuda")
+    K.gemm_popc(A, Bm, M, N, K_, D16, out_s16=True)
+    assert np.array_equal(D16.cpu().numpy().astype(np.int32), ref)
+    # the pack kernel feeds the same words
+    bits = T.zeros((M, (K_ + 31) // 32), dtype=T.int32, device="cuda")
+    K.pack_i8_rows(dev(a), K_, bits)
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), ab)
+
+
+def test_binary_gemm_variants_agree_at_full_size(T):
+    """Config-2 layer shape (8192 x 4096 x 4096): tcgen05 kind::i8 and XOR+popc must agree bit for
+    bit, and satisfy the parity invariant z == K (mod 2), |z| <= K."""
+    from mlpcode import _native as nat, kernels as K
+    M, N, K_ = 8192, 4096, 4096
+    g = T.Generator(device="cuda").manual_seed(1)
+    A = (T.randint(0, 2, (M, K_), generator=g, device="cuda", dtype=T.int8) * 2 - 1)
+    Bm = (T.randint(0, 2, (N, K_), generator=g, device="cuda", dtype=T.int8) * 2 - 1)
+    Z1 = T.zeros((M, N), dtype=T.int16, device="cuda")
+    K.gemm(M=M, N=N, K=K_, A=(A,), B=(Bm,), lda=K_, ldb=K_, D=Z1, ldd=N, in_dtype=nat.DT_I8,
+           epilogue=nat.EPI_STORE_S16, impl=nat.GEMM_TCGEN05)
+    ab = T.zeros((M, K_ // 32), dtype=T.int32, device="cuda")
+    bb = T.zeros((N, K_ // 32), dtype=T.int32, device="cuda")
+    K.pack_i8_rows(A, K_, ab)
+    K.pack_i8_rows(Bm, K_, bb)
+    Z2 = T.zeros((M, N), dtype=T.int16, device="cuda")
+    K.gemm_popc(ab, bb, M, N, K_, Z2, out_s16=True)
+    assert T.equal(Z1, Z2)
+    assert int((Z1.int() & 1).sum()) == 0 and int(Z1.abs().max()) <= K_
+    # linearity spot check against a direct fp64 product of a few rows/columns
+    rows = T.tensor([0, 1, 4095, 8191], device="cuda")
+    ref = A[rows].double() @ Bm[:64].double().t()
+    assert T.equal(Z1[rows][:, :64].double(), ref)
+
+
+F16_SHAPES = [(128, 256, 64), (200, 130, 784), (256, 10, 300), (784, 64, 32), (300, 4096, 10),
+              (16, 16, 16), (1000, 520, 2048)]
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+@pytest.mark.parametrize("M,N,K_", F16_SHAPES)
+def test_gemm_f16_split_matches_fp64(T, impl, M, N, K_):
+    """Real x real product through 3 fp16 split passes: error must be at fp32-SGEMM level
+    (<= 1e-6 norm-wise, 10x below the 1e-5 parity tolerance)."""
+    from mlpcode import _native as nat, kernels as K
+    rng = np.random.default_rng(M + 2 * N + 3 * K_)
+    a = (rng.standard_normal((M, K_)) * 1e-3 * np.exp(rng.standard_normal((M, K_)))).astype(np.float32)
+    b = (rng.standard_normal((N, K_)) / 32).astype(np.float32)
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    Kp = (K_ + 7) // 8 * 8
+    ops = {}
+    for name, x in (("a", a), ("b", b)):
+        xd = dev(x)
+        amax = T.zeros(1, dtype=T.float32, device="cuda")
+        sc = T.zeros(1, dtype=T.float32, device="cuda")
+        hi, lo = (T.zeros((x.shape[0], Kp), dtype=T.float16, device="cuda") for _ in range(2))
+        K.absmax_f32(xd, amax)
+        K.split_f16(xd, amax, hi=hi, lo=lo, scale_out=sc)
+        ops[name] = (hi, lo, sc)
+    which = nat.GEMM_TCGEN05 if impl == "tcgen05" else nat.GEMM_SIMT
+    ldd = (N + 3) // 4 * 4
+    D = T.zeros((M, ldd), dtype=T.float32, device="cuda")
+    K.gemm(M=M, N=N, K=K_, A=ops["a"][:2], B=ops["b"][:2], lda=Kp, ldb=Kp, D=D, ldd=ldd,
+           in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32, passes=((0, 0), (0, 1), (1, 0)),
+           sa=ops["a"][2], sb=ops["b"][2], impl=which)
+    got = D.cpu().numpy()[:, :N]
+    assert rel_err(got, ref) < 1e-6
+    # fused SGD epilogue: W -= lr * (A B^T)
+    W0 = rng.standard_normal((M, N)).astype(np.float32)
+    Wd = dev(W0).clone()
+    K.gemm(M=M, N=N, K=K_, A=ops["a"][:2], B=ops["b"][:2], lda=Kp, ldb=Kp, D=Wd, ldd=N,
+           in_dtype=nat.DT_F16, epilogue=nat.EPI_SGD_F32, passes=((0, 0), (0, 1), (1, 0)),
+           sa=ops["a"][2], sb=ops["b"][2], host_scale=0.01, impl=which)
+    want = W0.astype(np.float64) - 0.01 * ref
+    assert rel_err(Wd.cpu().numpy(), want) < 1e-6
+    assert rel_err(Wd.cpu().numpy() - W0, -0.01 * ref) < 1e-5
+
+
+def test_gemm_rejects_bad_arguments(T):
+    from mlpcode import _native as nat, kernels as K
+    A = T.zeros((128, 100), dtype=T.int8, device="cuda")        # pitch 100 bytes: not 16-aligned
+    D = T.zeros((128, 128), dtype=T.int32, device="cuda")
+    with pytest.raises(nat.BnnError) as e:
+        K.gemm(M=128, N=128, K=100, A=(A,), B=(A,), lda=100, ldb=100, D=D, ldd=128,
+               in_dtype=nat.DT_I8, epilogue=nat.EPI_STORE_S32, impl=nat.GEMM_TCGEN05)
+    assert e.value.code == nat.BNN_ERR_ARG and "16 bytes" in str(e.value)
+    with pytest.raises(nat.BnnError):
+        K.gemm(M=0, N=128, K=128, A=(A,), B=(A,), lda=128, ldb=128, D=D, ldd=128,
+               in_dtype=nat.DT_I8, epilogue=nat.EPI_STORE_S32)
+
+
+# ------------------------------------------------------------------------------------- A4-A6 BN forward
+@pytest.mark.parametrize("B,N,zdt", [(48, 21, "s16"), (300, 130, "s16"), (64, 64, "f32"),
+                                     (257, 10, "f32"), (1, 33, "s32")])
+def test_colstats_and_bn_apply(T, oracle, B, N, zdt):
+    from mlpcode import kernels as K
+    rng = np.random.default_rng(B + N)
+    if zdt == "f32":
+        Z = (rng.standard_normal((B, N)) * 20).astype(np.float32)
+        Zd = dev(Z)
+    else:
+        Z = (rng.integers(-200, 201, (B, N)) * 2).astype(np.float32)
+        Zd = dev(Z.astype(np.int16 if zdt == "s16" else np.int32))
+    sums = T.zeros((2, N), dtype=T.float64, device="cuda")
+    mu, var = (T.zeros(N, dtype=T.float32, device="cuda") for _ in range(2))
+    K.colstats(Zd, B, N, sums)
+    z64 = Z.astype(np.float64)
+    s = sums.cpu().numpy()
+    if zdt == "f32":
+        assert rel_err(s[0], z64.sum(0)) < 1e-12 and rel_err(s[1], (z64 ** 2).sum(0)) < 1e-12
+    else:
+        assert np.array_equal(s[0], z64.sum(0)) and np.array_equal(s[1], (z64 ** 2).sum(0))
+    K.bn_stats_finalize(sums, N, B, mu, var)
+    assert np.allclose(mu.cpu().numpy(), z64.mean(0), rtol=1e-6, atol=1e-6)
+    assert np.allclose(var.cpu().numpy(), z64.var(0), rtol=1e-6, atol=1e-6)
+    # parity with NumPy's own fp32 statistics (what the reference computes) within 1e-5
+    assert rel_err(mu.cpu().numpy(), Z.mean(axis=0)) < 1e-5 or np.abs(Z.mean(axis=0)).max() < 1e-3
+    assert rel_err(var.cpu().numpy(), Z.var(axis=0)) < 1e-5
+
+    gamma = (rng.random(N) + 0.5).astype(np.float32)
+    gamma[0] = -gamma[0]
+    beta = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    mu_h, var_h = mu.cpu().numpy(), var.cpu().numpy()
+    # identical inputs + identical fp32 op order => identical bits (layers.py:84-86 / 94-97)
+    ref = oracle.bn_forward_eval(Z.copy(), gamma, beta, mu_h, var_h)
+    out = T.zeros((B, N), dtype=T.float32, device="cuda")
+    i8 = T.zeros((B, (N + 15) // 16 * 16), dtype=T.int8, device="cuda")
+    t16 = T.zeros((N, (B + 7) // 8 * 8), dtype=T.float16, device="cuda")
+    bits = T.zeros((B, (N + 31) // 32), dtype=T.int32, device="cuda")
+    K.bn_apply(Zd, B, N, mu, var, dev(gamma), dev(beta), 1e-4, out_f32=out, act_i8=i8, act_t16=t16,
+               act_bits=bits)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    sgn = oracle.unitstep(ref)
+    assert np.array_equal(i8.cpu().numpy()[:, :N], sgn.astype(np.int8))
+    assert np.array_equal(t16.cpu().numpy()[:, :B].astype(np.float32), sgn.T)
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), oracle.pack_sign_rows(ref))
+
+
+def test_softmax_xent(T, golden, oracle):
+    from mlpcode import kernels as K
+    g = golden("elementwise")
+    logits, y = g["logits"], g["onehot"]
+    B, C = logits.shape
+    probs, grad = (T.zeros((B, C), dtype=T.float32, device="cuda") for _ in range(2))
+    rows = T.zeros(B, dtype=T.float32, device="cuda")
+    tot = T.zeros(1, dtype=T.float64, device="cuda")
+    K.softmax_xent(dev(logits), B, C, onehot=dev(y), probs=probs, loss_rows=rows, grad=grad,
+                   count=B, loss_sum=tot)
+    sm = oracle.softmax(logits.copy())
+    loss = oracle.cross_entropy_loss(sm, y)
+    gr = oracle.cross_entropy_derivative_softmax(sm.copy(), y)
+    assert np.allclose(probs.cpu().numpy(), sm, rtol=1e-5, atol=1e-9)       # tolerance: 1e-5 rel
+    assert np.allclose(rows.cpu().numpy(), loss, rtol=1e-5, atol=1e-7)
+    assert np.allclose(grad.cpu().numpy(), gr, rtol=1e-5, atol=1e-9)
+    assert abs(tot.item() - float(loss.astype(np.float64).sum())) < 1e-5 * abs(loss.sum())
+    # the lower clip of loss.py:32: a logit so small its probability underflows to 0
+    lg = np.zeros((2, 10), np.float32)
+    lg[0, 3] = -200.0
+    p2 = T.zeros((2, 10), dtype=T.float32, device="cuda")
+    K.softmax_xent(dev(lg), 2, 10, probs=p2)
+    assert p2[0, 3].item() == np.float32(1e-15)
+
+
+# ------------------------------------------------------------------------------------- A8 BN backward
+def test_bn_backward_against_reference_fixture(T, golden):
+    from mlpcode import kernels as K
+    g = golden("batchnorm")
+    Z, delta = g["Z"], g["delta"]
+    B, N = Z.shape
+    Zd, dd = dev(Z.astype(np.int16)), dev(delta)
+    sums = T.zeros((2, N), dtype=T.float64, device="cuda")
+    mu, var = (T.zeros(N, dtype=T.float32, device="cuda") for _ in range(2))
+    K.colstats(Zd, B, N, sums)
+    K.bn_stats_finalize(sums, N, B, mu, var)
+    assert rel_err(mu.cpu().numpy(), g["batch_mu"]) < 1e-6
+    assert rel_err(var.cpu().numpy(), g["batch_var"]) < 1e-6
+    gamma, beta = dev(g["gamma"]).clone(), dev(g["beta"]).clone()
+    mu_run, sig_run = dev(g["mu_run"]).clone(), dev(g["sigma_run"]).clone()
+    red = T.zeros((2, N), dtype=T.float64, device="cuda")
+    red_max = T.zeros((2, N), dtype=T.int32, device="cuda")
+    coef = T.zeros((3, N), dtype=T.float32, device="cuda")
+    bound = T.zeros(1, dtype=T.float32, device="cuda")
+    dgam, dbet = (T.zeros(N, dtype=T.float32, device="cuda") for _ in range(2))
+    K.bn_bwd_reduce(dd, Zd, B, N, mu, red, red_max)
+    K.bn_bwd_finalize(red, red_max, N, B, mu, var, 1e-4, gamma, beta, mu_run, sig_run,
+                      float(g["lr"]), 0.9, sums, coef, bound, dgam, dbet)
+    Np, Bp = (N + 7) // 8 * 8, (B + 7) // 8 * 8
+    out = T.zeros((B, N), dtype=T.float32, device="cuda")
+    dhi, dlo = (T.zeros((B, Np), dtype=T.float16, device="cuda") for _ in range(2))
+    thi, tlo = (T.zeros((N, Bp), dtype=T.float16, device="cuda") for _ in range(2))
+    sc = T.zeros(1, dtype=T.float32, device="cuda")
+    K.bn_bwd_apply(dd, Zd, B, N, mu, coef, bound, out_f32=out, d_hi=dhi, d_lo=dlo, dt_hi=thi,
+                   dt_lo=tlo, scale_out=sc)
+    nd = out.cpu().numpy()
+    assert rel_err(nd, g["new_delta"]) < 1e-5                              # tolerance: 1e-5 rel
+    assert rel_err(dgam.cpu().numpy(), g["dgamma"]) < 1e-5
+    assert rel_err(dbet.cpu().numpy(), g["dbeta"]) < 1e-5
+    for name, t in (("gamma", gamma), ("beta", beta), ("mu", mu_run), ("sigma", sig_run)):
+        assert rel_err(t.cpu().numpy(), g[f"{name}_after"]) < 1e-6, name
+    # the split pieces carry delta' at fp32 precision and never overflow fp16
+    s = sc.item()
+    assert np.abs(nd).max() * s <= 2.0 ** 15 and bound.item() >= np.abs(nd).max()
+    rec = (dhi.double() + dlo.double()).cpu().numpy()[:, :N] / s
+    assert rel_err(rec, nd) < 1e-6
+    assert T.equal(thi[:, :B], dhi[:, :N].t()) and T.equal(tlo[:, :B], dlo[:, :N].t())
+
+
+def test_sgd_and_count_correct(T):
+    from mlpcode import kernels as K
+    rng = np.random.default_rng(3)
+    p, g = rng.standard_normal(10007).astype(np.float32), rng.standard_normal(10007).astype(np.float32)
+    pd = dev(p).clone()
+    K.sgd_update(pd, dev(g), np.float32(0.01))
+    assert np.array_equal(pd.cpu().numpy(), p - np.float32(0.01) * g)     # weights -= lr*dw, exact
+    scores = rng.standard_normal((1000, 10)).astype(np.float32)
+    scores[5, 2] = scores[5, 7] = 99.0                                     # tie: first maximum wins
+    labels = rng.integers(0, 10, 1000).astype(np.int32)
+    cnt = T.zeros(1, dtype=T.int32, device="cuda")
+    K.count_correct(dev(scores), 1000, 10, dev(labels), cnt)
+    assert cnt.item() == int((scores.argmax(1) == labels).sum())
+
+
+# ------------------------------------------------------------------------------------- A11 weight faults
+@pytest.mark.parametrize("K_,N", [(64, 8), (784, 33), (100, 10), (4096, 16)])
+def test_bernoulli_flips_match_oracle_mask(T, oracle, K_, N):
+    from mlpcode import kernels as K
+    rng = np.random.default_rng(K_ * N)
+    W = rng.standard_normal((K_, N)).astype(np.float32)
+    Wb = oracle.binarize(W)
+    words = (K_ + 31) // 32
+    Kp = (K_ + 15) // 16 * 16
+    i8 = T.zeros((N, Kp), dtype=T.int8, device="cuda")
+    bits = T.zeros((N, words), dtype=T.int32, device="cuda")
+    K.binarize_weights_t(dev(W), wt_i8=i8, wt_bits=bits)
+    nt, p, seed, stream = 3, 0.1, 0xC0FFEE1234, 7
+    o_i8 = T.zeros((nt, N, Kp), dtype=T.int8, device="cuda")
+    o_f16 = T.zeros((nt, N, Kp), dtype=T.float16, device="cuda")
+    o_bits = T.zeros((nt, N, words), dtype=T.int32, device="cuda")
+    m_bits = T.zeros((nt, N, words), dtype=T.int32, device="cuda")
+    K.flip_weights_bernoulli(N=N, K=K_, p=p, seed=seed, stream_id=stream, trial0=5, n_trials=nt,
+                             wt_bits=bits, out_i8=o_i8, out_f16=o_f16, out_bits=o_bits,
+                             mask_bits=m_bits)
+    for t in range(nt):
+        mask = oracle.c_bernoulli_mask(K_, N, p, seed, stream, 5 + t)       # [K, N] bool
+        want = oracle.flip_bnn_mask(Wb, mask)                               # callbacks.py:79-83
+        assert np.array_equal(o_i8[t].cpu().numpy()[:, :K_], want.T.astype(np.int8))
+        assert np.array_equal(o_f16[t].cpu().numpy()[:, :K_].astype(np.float32), want.T)
+        assert np.array_equal(o_bits[t].cpu().numpy().view(np.uint32), oracle.c_pack_weights_t(want))
+        assert np.array_equal(m_bits[t].cpu().numpy().view(np.uint32),
+                              oracle.pack_sign_rows(np.where(mask.T, 1.0, -1.0).astype(np.float32)))
+    # same result when the clean weights are supplied as int8 instead of bits
+    o2 = T.zeros((1, N, Kp), dtype=T.int8, device="cuda")
+    K.flip_weights_bernoulli(N=N, K=K_, p=p, seed=seed, stream_id=stream, trial0=5, n_trials=1,
+                             wt_i8=i8, out_i8=o2)
+    assert T.equal(o2[0], o_i8[0])
+    # p = 0 leaves the weights alone, p = 1 negates all of them
+    for pp, sign in ((0.0, 1), (1.0, -1)):
+        K.flip_weights_bernoulli(N=N, K=K_, p=pp, seed=1, stream_id=0, trial0=0, n_trials=1,
+                                 wt_bits=bits, out_i8=o2)
+        assert np.array_equal(o2[0].cpu().numpy()[:, :K_], sign * Wb.T.astype(np.int8))
+
+
+def test_exactk_flips_match_oracle_positions(T, oracle):
+    from mlpcode import kernels as K
+    dims = [(40, 24), (24, 10)]                       # (K, N) per layer
+    total = sum(k * n for k, n in dims)
+    ks = np.array([0, 1, 17, 300], np.int32)
+    seed, trial0 = 99, 4
+    offset = 0
+    flipped_total = np.zeros(len(ks), int)
+    for K_, N in dims:
+        Kp, words = (K_ + 15) // 16 * 16, (K_ + 31) // 32
+        rng = np.random.default_rng(K_)
+        base = pm1(rng, (N, K_))
+        io = T.zeros((len(ks), N, Kp), dtype=T.int8, device="cuda")
+        io[:, :, :K_] = dev(base)
+        iob = T.zeros((len(ks), N, words), dtype=T.int32, device="cuda")
+        iob[:] = dev(oracle.pack_sign_rows(base.astype(np.float32)).view(np.int32))
+        K.flip_weights_exactk(N=N, K=K_, total=total, offset=offset, seed=seed, trial0=trial0,
+                              k_per_trial=dev(ks), k_max=int(ks.max()), io_i8=io, io_bits=iob)
+        for t, k in enumerate(ks):
+            pos = oracle.c_exactk_positions(total, seed, trial0 + t, int(k)).astype(np.int64)
+            mine = pos[(pos >= offset) & (pos < offset + K_ * N)] - offset
+            want = base.copy().reshape(-1)
+            want[mine] = -want[mine]
+            want = want.reshape(N, K_)
+            assert np.array_equal(io[t].cpu().numpy()[:, :K_], want)
+            assert np.array_equal(iob[t].cpu().numpy().view(np.uint32),
+                                  oracle.pack_sign_rows(want.astype(np.float32)))
+            flipped_total[t] += len(mine)
+        offset += K_ * N
+    assert np.array_equal(flipped_total, ks)          # exactly k_t flips over the whole network
+
+
+def test_external_mask_flips(T, golden, oracle):
+    from mlpcode import kernels as K
+    g = golden("weight_faults")
+    Wb, mask = g["cb_Wb"], g["cb_mask"]                # the reference's own seeded draw
+    K_, N = Wb.shape
+    Kp, words = (K_ + 15) // 16 * 16, (K_ + 31) // 32
+    i8 = T.zeros((N, Kp), dtype=T.int8, device="cuda")
+    bits = T.zeros((N, words), dtype=T.int32, device="cuda")
+    K.binarize_weights_t(dev(Wb), wt_i8=i8, wt_bits=bits)
+    K.flip_weights_mask(dev(mask.astype(np.uint8)), K_, N, io_i8=i8, io_bits=bits)
+    assert np.array_equal(i8.cpu().numpy()[:, :K_], g["cb_flipped"].T.astype(np.int8))
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), oracle.c_pack_weights_t(g["cb_flipped"]))
+
+
+# ------------------------------------------------------------------------------------- A12 image faults
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_image_flips_match_oracle(T, golden, oracle, mode):
+    from mlpcode import kernels as K
+    g = golden("image_faults")
+    imgs, k = g["images"], int(g["k"])
+    rng = np.random.default_rng(mode)
+    big = rng.integers(0, 256, (40, 784), dtype=np.uint8)                  # MNIST-shaped rows
+    for images, kk in ((imgs, k), (big, round(0.14 * 784 * 8)), (big[:3, :5], 1000)):
+        R, F = images.shape
+        nt = 3
+        out = T.zeros((nt, R, F), dtype=T.uint8, device="cuda")
+        K.flip_images(dev(images), kk, mode, 0xABCDEF, 2, nt, out)
+        for t in range(nt):
+            want = oracle.c_flip_image_rows(images, kk, mode, 0xABCDEF, 2 + t)
+            assert np.array_equal(out[t].cpu().numpy(), want)
+
+
+def test_normalize_u8(T, golden, oracle):
+    from mlpcode import kernels as K
+    g = golden("image_faults")
+    imgs = g["images"]
+    d = dev(imgs)
+    mm = T.zeros(2, dtype=T.int32, device="cuda")
+    mmf = T.zeros(2, dtype=T.float32, device="cuda")
+    K.minmax_u8(d, mm, mmf)
+    assert mm.tolist() == [int(imgs.min()), int(imgs.max())]
+    out = T.zeros(imgs.shape, dtype=T.float32, device="cuda")
+    K.normalize_u8(d, mmf[0:1], mmf[1:2], -1.0, 1.0, out)
+    assert np.array_equal(out.cpu().numpy(), g["normalized"])              # utils.py:178-187, exact

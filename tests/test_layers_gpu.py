@@ -1,0 +1,262 @@
+"""GPU parity of the drop-in classes (mlpcode.layers / network / callbacks) against the fixtures
+generated from the reference and against the oracle on fresh seeded inputs.
+
+Tolerance (north star): bit-exact for +-1 GEMM outputs, packed weights and flip masks; 1e-5
+relative (norm-wise) for BN outputs, loss and optimiser state."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import params_from_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def build_net(units, params, out="softmax", lr=0.01):
+    from mlpcode.activation import ActivationFuncs as af
+    from mlpcode.loss import LossFuncs as lf
+    from mlpcode.network import Network
+    nn = Network(units, useGpu=True, binarized=True, useBatchNorm=True)
+    nn.compile(lr=lr, hiddenAf=af.sign, outAf=af.softmax if out == "softmax" else af.identity,
+               lossF=lf.cross_entropy)
+    nn.load_weights([w.copy() for w in params["W"]])
+    nn.loadBatchNormParameters(*[[b[k].copy() for b in params["bn"]]
+                                 for k in ("gamma", "beta", "mu", "sigma")])
+    return nn
+
+
+def state_of(nn):
+    g, b, m, s = nn.batchNormParams
+    return dict(W=[w.get() for w in nn.weights],
+                bn=[dict(gamma=g[i].get(), beta=b[i].get(), mu=m[i].get(), sigma=s[i].get())
+                    for i in range(len(g))])
+
+
+@pytest.fixture(params=["tcgen05", "simt"])
+def gemm_impl(request, monkeypatch):
+    monkeypatch.setenv("BNN_GEMM_IMPL", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("name", ["train_tiny", "train_small", "train_ragged"])
+def test_training_steps_match_reference(golden, gemm_impl, name):
+    g = golden(name)
+    units = [int(u) for u in g["units"]]
+    n = len(units) - 1
+    nn = build_net(units, params_from_golden(g, "init_", n), lr=float(g["lr"]))
+    for s in range(g["X"].shape[0]):
+        cost = nn.train_step(g["X"][s], g["Y"][s], float(g["lr"]))
+        assert abs(cost - g["costs"][s]) <= TOL * abs(g["costs"][s]), (s, cost, g["costs"][s])
+        st = state_of(nn)
+        for i in range(n):
+            assert rel_err(st["W"][i], g[f"after{s}_W{i}"]) < TOL, (s, i)
+            # the weight UPDATE itself (lr*dW), not just the weights it is a small part of
+            prev = g[f"after{s - 1}_W{i}"] if s else g[f"init_W{i}"]
+            upd_ref = g[f"after{s}_W{i}"].astype(np.float64) - prev
+            upd = st["W"][i].astype(np.float64) - prev
+            assert rel_err(upd, upd_ref) < 2e-2, (s, i)   # fp32 cancellation in W - W_prev limits this
+            for k in ("gamma", "beta", "mu", "sigma"):
+                assert rel_err(st["bn"][i][k], g[f"after{s}_{k}{i}"]) < TOL, (s, i, k)
+    probs = nn.predict(g["X_eval"]).get()
+    assert rel_err(probs, g["probs_eval"]) < TOL
+    assert nn.get_accuracy(g["X_eval"], g["labels_eval"]) == float(g["acc_eval"])
+
+
+@pytest.mark.parametrize("name", ["train_tiny", "train_small", "train_ragged"])
+def test_stage_parity_teacher_forced(golden, name):
+    """Each stage of the first step on the reference's own stage inputs: z bit-exact for +-1
+    layers, BN output within 1e-5, sign mismatches only where |BN output| is ~0, dW / dX within 1e-5."""
+    import torch
+    from mlpcode import kernels as K
+    from mlpcode.layers import SignActivation
+    g = golden(name)
+    units = [int(u) for u in g["units"]]
+    n = len(units) - 1
+    nn = build_net(units, params_from_golden(g, "init_", n), lr=float(g["lr"]))
+    B = g["X"].shape[1]
+    acts = []
+    for i, layer in enumerate(nn._layers):
+        if i == 0:
+            x_in = g["X"][0]
+        else:                                            # teacher forcing: the reference's activations
+            a = g[f"s0_act{i - 1}"]
+            i8 = torch.zeros((B, (a.shape[1] + 15) // 16 * 16), dtype=torch.int8, device="cuda")
+            i8[:, :a.shape[1]] = torch.from_numpy(a.astype(np.int8)).cuda()
+            t16 = torch.zeros((a.shape[1], (B + 7) // 8 * 8), dtype=torch.float16, device="cuda")
+            t16[:, :B] = torch.from_numpy(a.T.astype(np.float16).copy()).cuda()
+            x_in = SignActivation(i8, a.shape[1], t16=t16)
+        out = layer.forward(x_in, isTrain=True)
+        z = layer.cache["z"][:, :units[i + 1]].cpu().numpy()
+        if i == 0:
+            assert rel_err(z, g["s0_z0"]) < 1e-6          # real x +-1 through the fp16 split GEMM
+        else:
+            assert np.array_equal(z.astype(np.float32), g[f"s0_z{i}"])   # bit-exact integers
+        bn_ref = g[f"s0_bn_out{i}"]
+        if i < n - 1:
+            got = out.t.cpu().numpy()
+            bad = got != g[f"s0_act{i}"]
+            assert np.all(np.abs(bn_ref[bad]) < 1e-4 * np.abs(bn_ref).max()), f"layer {i}"
+            assert bad.mean() < 1e-3
+        else:
+            assert rel_err(out.logits.cpu().numpy(), bn_ref) < TOL
+            assert rel_err(out.get(), g["s0_act" + str(i)]) < TOL
+        acts.append(out)
+    # backward, teacher forced with the reference's incoming deltas
+    lr = float(g["lr"])
+    for i in reversed(range(n)):
+        layer = nn._layers[i]
+        d_in = g["s0_dLdA"] if i == n - 1 else g[f"s0_dX{i + 1}"]
+        w_before = layer.weights.get().astype(np.float64)
+        dX = layer.backwards(torch.from_numpy(d_in).cuda(), lr, activDeriv=False)
+        dW = (w_before - layer.weights.get().astype(np.float64)) / lr
+        assert rel_err(dW, g[f"s0_dW{i}"]) < 5e-3, i     # recovered through fp32 W: cancellation
+        if i > 0:
+            assert rel_err(dX.get(), g[f"s0_dX{i}"]) < TOL, i
+        else:
+            assert dX is None                            # layer-0 dX is dead work in the reference
+
+
+def test_popc_and_i8_variants_are_bit_identical(golden, monkeypatch):
+    g = golden("train_small")
+    units = [int(u) for u in g["units"]]
+    outs = {}
+    for variant in ("i8", "popc"):
+        monkeypatch.setenv("BNN_BINARY_GEMM", variant)
+        nn = build_net(units, params_from_golden(g, "after1_", len(units) - 1))
+        a = g["X_eval"]
+        zs = []
+        for layer in nn._layers:
+            a = layer.forward(a, isTrain=True)
+            zs.append(layer.cache["z"].clone())
+        outs[variant] = zs
+    import torch
+    for z1, z2 in zip(outs["i8"][1:], outs["popc"][1:]):
+        assert torch.equal(z1, z2)
+
+
+def test_weight_fault_callbacks(golden, oracle):
+    from mlpcode.callbacks import ErrorCallback
+    g = golden("weight_faults")
+    units = [int(u) for u in g["units"]]
+    n = len(units) - 1
+    params = params_from_golden(g, "", n)
+    nn = build_net(units, params)
+    assert rel_err(nn.predict(g["X"]).get(), g["probs_clean"]) < TOL
+    # (i) external-mask mode: the reference's own seeded draws, one mask per layer
+    cbs = [ErrorCallback(0.1, mode=2, bnn=True, mask_source=(lambda m: (lambda shape: m))(g[f"mask{i}"]))
+           for i in range(n)]
+    nn.addCallbacks(cbs)
+    assert rel_err(nn.predict(g["X"]).get(), g["probs_fault"]) < TOL
+    assert nn.get_accuracy(g["X"], g["labels"]) == float(g["acc_fault"])
+    nn.clearCallbacks()
+    assert rel_err(nn.predict(g["X"]).get(), g["probs_clean"]) < TOL   # latent weights untouched
+    # (ii) in-kernel RNG mode: equals the oracle network run with the oracle's restatement of the mask
+    cb = ErrorCallback(0.2, mode=2, bnn=True, seed=4242)
+    nn.addCallbacks(cb)
+    got = nn.predict(g["X"]).get()
+    masks = [oracle.c_bernoulli_mask(units[i], units[i + 1], 0.2, 4242, i, i) for i in range(n)]
+    # one shared callback object: its call counter advances layer by layer (trial = call index)
+    hooks = [(lambda m: (lambda W: oracle.flip_bnn_mask(W, m)))(m) for m in masks]
+    want = oracle.predict(params, g["X"].copy(), weight_hooks=hooks)
+    assert rel_err(got, want) < TOL
+    # a second forward draws fresh masks (callbacks.py:81 draws per call)
+    assert not np.array_equal(nn.predict(g["X"]).get(), got)
+    # reference call signature on a dense +-1 array
+    cb2 = ErrorCallback(0.2, mode=2, bnn=True, seed=7)
+    flipped = cb2(g["cb_Wb"], gpu=True).get()
+    m = oracle.c_bernoulli_mask(*g["cb_Wb"].shape, 0.2, 7, 0, 0)
+    assert np.array_equal(flipped, oracle.flip_bnn_mask(g["cb_Wb"], m))
+
+
+def test_image_error_callback_and_normalize(golden, oracle):
+    import torch
+    from mlpcode import kernels as K
+    from mlpcode.callbacks import ImageErrorCallback
+    g = golden("image_faults")
+    imgs = g["images"]
+    for mode in (0, 1, 2):
+        icb = ImageErrorCallback(0.14, mode=mode, seed=31)
+        assert icb.flips_per_row(imgs.shape[1]) == int(g["k"])
+        out = icb(imgs, gpu=True).get()
+        assert np.array_equal(out, oracle.c_flip_image_rows(imgs, int(g["k"]), mode, 31, 0))
+        out2 = icb(imgs, gpu=True).get()                      # next call = next trial
+        assert np.array_equal(out2, oracle.c_flip_image_rows(imgs, int(g["k"]), mode, 31, 1))
+    assert ImageErrorCallback(0, mode=2)(imgs) is imgs         # p == 0 returns the input (callbacks.py:150)
+    with pytest.raises(ValueError):
+        ImageErrorCallback(0.1)(imgs.astype(np.float32))
+
+
+def test_batchnorm_layer_api(golden):
+    from mlpcode.layers import BatchNormLayer
+    g = golden("batchnorm")
+    N = g["Z"].shape[1]
+    bn = BatchNormLayer(N, gpu=True)
+    bn.loadBatchNormParams(g["gamma"].copy(), g["beta"].copy(), g["mu_run"].copy(), g["sigma_run"].copy())
+    bn.build()
+    assert rel_err(bn.forward(g["Z"], isTrain=False).get(), g["out_eval"]) < TOL
+    assert rel_err(bn.forward(g["Z"], isTrain=True).get(), g["out_train"]) < TOL
+    nd = bn.backwards(g["delta"], float(g["lr"]))
+    assert rel_err(nd.get(), g["new_delta"]) < TOL
+    for k, v in zip(("gamma", "beta", "mu", "sigma"), bn.batchNormParams):
+        assert rel_err(v.get(), g[f"{k}_after"]) < TOL, k
+    assert bn.cache == {}
+
+
+def test_network_api_surface(golden, tmp_path, capsys):
+    from mlpcode.activation import ActivationFuncs as af
+    from mlpcode.network import Network
+    g = golden("train_tiny")
+    units = [int(u) for u in g["units"]]
+    n = len(units) - 1
+    nn = build_net(units, params_from_golden(g, "init_", n))
+    path = nn.save_weights("tiny", directory=tmp_path)
+    nn2 = Network.fromModel(path, useGpu=True, binarized=True)
+    nn2.compile(hiddenAf=af.sign, outAf=af.softmax)
+    assert np.array_equal(nn2.predict(g["X_eval"]).get(), nn.predict(g["X_eval"]).get())
+    assert nn2.unitList == units and nn2.useBatchNorm and not nn2.useBias
+    X = g["X"].reshape(-1, units[0])
+    Y = g["Y"].reshape(-1, 10)
+    hist = nn.train(X, Y, epochs=2, batch_size=16, valX=g["X_eval"],
+                    valY=np.eye(10, dtype=np.int8)[g["labels_eval"]])
+    assert len(hist["loss"]) == 2 and len(hist["val_accuracy"]) == 2 and np.isfinite(hist["loss"]).all()
+    assert "Best Validation Accuracy" in capsys.readouterr().out
+    classes = nn.predict_classes(g["X_eval"])
+    assert classes.shape == (g["X_eval"].shape[0],)
+    # identity output (the sweep scripts compile with outAf=identity, imageBitflipTrainModelSel.py:21)
+    nn3 = build_net(units, params_from_golden(g, "after2_", n), out="identity")
+    logits = nn3.predict(g["X_eval"]).get()
+    assert np.array_equal(logits.argmax(1), g["probs_eval"].argmax(1))
+    with pytest.raises(NotImplementedError):
+        Network(units, useGpu=True, binarized=False, useBatchNorm=True).compile()
+
+
+def test_config2_step_properties():
+    """Full-size (784-4096-4096-4096-10, B=8192) step: finite loss, deterministic, the tcgen05 and
+    SIMT paths agree, and a linearity property of dW: lr -> 2*lr doubles the update."""
+    import torch
+    units, B = [784, 4096, 4096, 4096, 10], 8192
+    rng = np.random.default_rng(0)
+    import bnn_oracle as O
+    params = O.new_params(units, rng)
+    X = torch.from_numpy(rng.random((B, 784), dtype=np.float32) * 2 - 1).cuda()
+    Y = torch.from_numpy(np.eye(10, dtype=np.int8)[rng.integers(0, 10, B)]).cuda()
+    results = {}
+    for tag, lr, env in (("a", 0.01, "tcgen05"), ("b", 0.01, "tcgen05"), ("c", 0.02, "tcgen05")):
+        os.environ["BNN_GEMM_IMPL"] = env
+        nn = build_net(units, params, lr=lr)
+        cost = nn.train_step(X, Y, lr)
+        results[tag] = (cost, [w.t.clone() for w in nn.weights], nn.batchNormParams[0][0].t.clone())
+    os.environ.pop("BNN_GEMM_IMPL", None)
+    assert np.isfinite(results["a"][0]) and abs(results["a"][0] - np.log(10)) < 1.5
+    assert abs(results["a"][0] - results["b"][0]) < 1e-6
+    for wa, wb in zip(results["a"][1], results["b"][1]):
+        assert bool(torch.isfinite(wa).all())
+        assert float((wa.double() - wb.double()).norm() / wa.double().norm()) < 1e-6   # repeatable
+    # dW does not depend on lr inside one step, so the last layer's update doubles with lr (lower
+    # layers' updates sit at the fp32 resolution of W and cannot be recovered by subtraction)
+    i = len(units) - 2
+    w0 = torch.from_numpy(params["W"][i]).cuda().double()
+    da, dc = results["a"][1][i].double() - w0, results["c"][1][i].double() - w0
+    assert float(dc.norm()) > 0 and float((dc - 2 * da).norm() / dc.norm()) < 1e-3
