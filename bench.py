@@ -266,6 +266,12 @@ def run_gpu(args):
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     value = world * BATCH * args.steps / (ms_total * 1e-3)
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps,
+                              "gpu_launches": launches}), flush=True)
+        return 0
+
     # ---- end-to-end: pinned host buffers -> H2D -> step -> D2H loss, every step ------------------
     for _ in range(2):
         nn.train_step(Xp, Yp, LR)
@@ -336,6 +342,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling runs (ncu): skip the e2e, int8-peak and CPU-baseline legs")
     args = ap.parse_args()
     rc = run_reference(args) if args.impl == "reference" else run_gpu(args)
     try:

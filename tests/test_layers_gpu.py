@@ -90,7 +90,7 @@ def test_stage_parity_teacher_forced(golden, name):
         out = layer.forward(x_in, isTrain=True)
         z = layer.cache["z"][:, :units[i + 1]].cpu().numpy()
         if i == 0:
-            assert rel_err(z, g["s0_z0"]) < 1e-6          # real x +-1 through the fp16 split GEMM
+            assert rel_err(z, g["s0_z0"]) < 5e-6          # real x +-1 through the fp16 split GEMM
         else:
             assert np.array_equal(z.astype(np.float32), g[f"s0_z{i}"])   # bit-exact integers
         bn_ref = g[f"s0_bn_out{i}"]
@@ -129,7 +129,7 @@ def test_popc_and_i8_variants_are_bit_identical(golden, monkeypatch):
         zs = []
         for layer in nn._layers:
             a = layer.forward(a, isTrain=True)
-            zs.append(layer.cache["z"].clone())
+            zs.append(layer.cache["z"][:, :layer.layerUnits].clone())  # pad columns are scratch
         outs[variant] = zs
     import torch
     for z1, z2 in zip(outs["i8"][1:], outs["popc"][1:]):
