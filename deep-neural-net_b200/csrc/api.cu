@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 namespace bnn {
@@ -33,6 +34,17 @@ int sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+// K steps (of 128 bytes) per fp32 accumulation chunk of the tcgen05 GEMM; see gemm_tc.cu.
+int gemm_chunk_iters() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("BNN_GEMM_CHUNK");
+        int n = e ? atoi(e) : 16;
+        v = n < 1 ? 1 : (n > 4096 ? 4096 : n);
+    }
+    return v;
 }
 
 int gemm_tc_dispatch(const bnn_gemm_desc& g, cudaStream_t stream);

@@ -9,13 +9,24 @@
 //   * real-valued products: fp16 hi/lo split operands, kind::f16, fp32 accumulators; the passes of
 //     the split (hi*hi, hi*lo, lo*hi) are extra trips round the K loop into the SAME accumulator.
 //
-// CTA = 8 warps:  w0 lane0  TMA producer        (cp.async.bulk.tensor -> 128B-swizzled smem ring)
-//                 w1 lane0  MMA issuer          (tcgen05.mma, tcgen05.commit -> mbarriers)
-//                 w2        TMEM allocator
-//                 w4..w7    epilogue            (tcgen05.ld -> registers -> global), one TMEM lane
-//                                                quarter each, overlapped with the next tile's
-//                                                main loop through a 2-deep TMEM accumulator ring.
+// CTA = 20 warps:  w0 lane0  TMA producer       (cp.async.bulk.tensor -> 128B-swizzled smem ring)
+//                  w1 lane0  MMA issuer         (tcgen05.mma, tcgen05.commit -> mbarriers)
+//                  w2        TMEM allocator
+//                  w4..w19   epilogue           (tcgen05.ld -> registers -> global): warp w owns TMEM
+//                                                lane quarter w%4 and column quarter (w-4)/4 of the tile.
+// setmaxnreg moves registers from the role warp group to the four epilogue warp groups.
 // Tile 128 x BLOCK_N, K step = 128 bytes (one swizzle atom row), 4 UMMAs (32 bytes of K) per step.
+//
+// Chunked accumulation.  Measured on B200: the TMEM fp32 accumulator TRUNCATES on every MMA, a bias of
+// ~3e-8 (relative) per accumulation step that grows linearly with K (2.5e-5 after the 1024 steps of a
+// K = 8192, 2-pass dW product; an fp32 SGEMM is at 1e-6).  The MMA issuer therefore closes the
+// accumulator every `chunk_iters` K steps and moves to the other half of a 2-deep TMEM ring, while the
+// epilogue warps drain the finished chunk and add it to a register-resident running sum with
+// round-to-nearest fp32 adds.  Draining a chunk (128 KB of TMEM) is hidden behind the next chunk's MMAs.
+// Measured at config-2 shapes against an fp64 product (tests/test_kernels_gpu.py): chunk = 4 / 8 / 16 /
+// none -> 3.9e-7 / 7e-7 / 1.2e-6 / 2.5e-5 relative error (cuBLAS SGEMM: 1.2e-6) for +2.4 / +0.9 / +0.5 / 0 %
+// of the dominant launches' time; the default of 16 K steps matches an fp32 SGEMM.
+// Integer accumulation is exact, so kind::i8 products use a single chunk.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -24,12 +35,17 @@
 
 namespace bnn {
 
+int gemm_chunk_iters();  // api.cu: K steps per accumulation chunk (env BNN_GEMM_CHUNK, default 16)
+
 namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kKBytes = 128;   // bytes of K per pipeline stage row (= swizzle span)
 constexpr int kUmmaKBytes = 32;
-constexpr int kThreads = 256;
+constexpr int kRoleThreads = 128;       // warp group 0: TMA, MMA, TMEM alloc, idle
+constexpr int kEpiWarps = 8;            // warp groups 1-2
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = kRoleThreads + kEpiThreads;
 constexpr int kAccStages = 2;
 
 template <int BLOCK_N>
@@ -41,12 +57,16 @@ struct TileCfg {
     static constexpr int kTmemCols = (kAccStages * BLOCK_N) < 32 ? 32 : (kAccStages * BLOCK_N);
     static constexpr int kBarBytes = (2 * kStages + 2 * kAccStages) * 8 + 16;
     static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + align slack
+    static constexpr int kColsPerThread = BLOCK_N / 2;                 // per epilogue thread
+    static constexpr int kGroup = kColsPerThread < 16 ? kColsPerThread : 16;  // columns per tcgen05.ld
+    static constexpr int kGroups = kColsPerThread / kGroup;
 };
 
 struct TcParams {
     int M, N, batch;
-    int kblocks;  // K steps per pass
+    int kblocks;      // K steps per pass
     int n_pass;
+    int chunk_iters;  // K steps per accumulation chunk
     int pa[BNN_GEMM_MAX_PASS];
     int pb[BNN_GEMM_MAX_PASS];
     int m_tiles, n_tiles;
@@ -75,7 +95,72 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& b,
     n_blk = rr / gsz;
 }
 
-template <bool kI8, int BLOCK_N>
+// Store / update one group of G consecutive columns of one output row from registers.
+template <bool kI8, int EPI, int G>
+__device__ __forceinline__ void store_group(const TcParams& p, char* dbase, long long off, int col0,
+                                            const uint32_t (&v)[G], float scale) {
+    const bool full = (col0 + G <= p.N) && p.vec_ok;
+    if (EPI == BNN_EPI_STORE_S16) {
+        int16_t* d = reinterpret_cast<int16_t*>(dbase) + off;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < G; j += 8) {
+                uint4 o;
+                o.x = (v[j + 0] & 0xffffu) | (v[j + 1] << 16);
+                o.y = (v[j + 2] & 0xffffu) | (v[j + 3] << 16);
+                o.z = (v[j + 4] & 0xffffu) | (v[j + 5] << 16);
+                o.w = (v[j + 6] & 0xffffu) | (v[j + 7] << 16);
+                *reinterpret_cast<uint4*>(d + j) = o;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                if (col0 + j < p.N) d[j] = (int16_t)(int)v[j];
+        }
+    } else if (EPI == BNN_EPI_STORE_S32) {
+        int32_t* d = reinterpret_cast<int32_t*>(dbase) + off;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < G; j += 4)
+                *reinterpret_cast<uint4*>(d + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                if (col0 + j < p.N) d[j] = (int)v[j];
+        }
+    } else {
+        float* d = reinterpret_cast<float*>(dbase) + off;
+        constexpr bool sgd = EPI == BNN_EPI_SGD_F32;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < G; j += 4) {
+                float4 f;
+                f.x = __fmul_rn(kI8 ? (float)(int)v[j + 0] : __uint_as_float(v[j + 0]), scale);
+                f.y = __fmul_rn(kI8 ? (float)(int)v[j + 1] : __uint_as_float(v[j + 1]), scale);
+                f.z = __fmul_rn(kI8 ? (float)(int)v[j + 2] : __uint_as_float(v[j + 2]), scale);
+                f.w = __fmul_rn(kI8 ? (float)(int)v[j + 3] : __uint_as_float(v[j + 3]), scale);
+                if (sgd) {  // weights -= lr * dw (layers.py:268): two roundings, like NumPy
+                    const float4 w = *reinterpret_cast<const float4*>(d + j);
+                    f.x = __fsub_rn(w.x, f.x);
+                    f.y = __fsub_rn(w.y, f.y);
+                    f.z = __fsub_rn(w.z, f.z);
+                    f.w = __fsub_rn(w.w, f.w);
+                }
+                *reinterpret_cast<float4*>(d + j) = f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                if (col0 + j < p.N) {
+                    const float f = __fmul_rn(kI8 ? (float)(int)v[j] : __uint_as_float(v[j]), scale);
+                    d[j] = sgd ? __fsub_rn(d[j], f) : f;
+                }
+            }
+        }
+    }
+}
+
+template <bool kI8, int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
@@ -97,6 +182,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int total_tiles = p.batch * p.m_tiles * p.n_tiles;
     const int k_iters = p.n_pass * p.kblocks;
+    const int n_chunks = (k_iters + p.chunk_iters - 1) / p.chunk_iters;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&mapA0);
@@ -113,7 +199,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
         for (int a = 0; a < kAccStages; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
-            ptx::mbar_init(&tempty_bar[a], 128);
+            ptx::mbar_init(&tempty_bar[a], kEpiWarps);
         }
         ptx::fence_mbar_init();
         ptx::fence_proxy_async();
@@ -124,8 +210,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 0) {
-        if (lane == 0) {
+    if (warp < 4) {
+        // give the registers this warp group does not need to the epilogue warp groups.  The budget
+        // (128 x 56 + 256 x 224 = 64512) leaves 1024 registers of the SM's 64K unclaimed: asking for
+        // the full 65536 made tcgen05-era hardware spin forever in USETMAXREG.TRY_ALLOC.
+        ptx::setmaxnreg_dec<56>();
+        if (warp == 0 && lane == 0) {
             // ------------------------------------------------------------- TMA producer
             int s = 0;
             uint32_t ph = 0;
@@ -148,9 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                 }
             }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
+        } else if (warp == 1 && lane == 0) {
             // ------------------------------------------------------------- MMA issuer
             constexpr uint32_t idesc = kI8 ? ptx::umma_idesc(2u, 1u, kBlockM, BLOCK_N)
                                            : ptx::umma_idesc(1u, 0u, kBlockM, BLOCK_N);
@@ -159,34 +247,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             int acc = 0;
             uint32_t acc_ph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                ptx::mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
-                ptx::tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-                for (int it = 0; it < k_iters; ++it) {
-                    ptx::mbar_wait(&full_bar[s], ph);
+                int it = 0;
+                for (int c = 0; c < n_chunks; ++c) {
+                    ptx::mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
                     ptx::tc_fence_after_sync();
-                    const uint32_t a_addr = ptx::smem_u32(smem + s * Cfg::kStageBytes);
-                    const uint64_t da = ptx::umma_desc_k_sw128(a_addr);
-                    const uint64_t db = ptx::umma_desc_k_sw128(a_addr + Cfg::kABytes);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                    const int it_end = min(it + p.chunk_iters, k_iters);
+                    for (bool first = true; it < it_end; ++it) {
+                        ptx::mbar_wait(&full_bar[s], ph);
+                        ptx::tc_fence_after_sync();
+                        const uint32_t a_addr = ptx::smem_u32(smem + s * Cfg::kStageBytes);
+                        const uint64_t da = ptx::umma_desc_k_sw128(a_addr);
+                        const uint64_t db = ptx::umma_desc_k_sw128(a_addr + Cfg::kABytes);
 #pragma unroll
-                    for (int j = 0; j < kKBytes / kUmmaKBytes; ++j) {
-                        const uint64_t adv = (uint64_t)((j * kUmmaKBytes) >> 4);
-                        const uint32_t accum = (it > 0 || j > 0) ? 1u : 0u;
-                        if (kI8)
-                            ptx::mma_i8(d_tmem, da + adv, db + adv, idesc, accum);
-                        else
-                            ptx::mma_f16(d_tmem, da + adv, db + adv, idesc, accum);
+                        for (int j = 0; j < kKBytes / kUmmaKBytes; ++j) {
+                            const uint64_t adv = (uint64_t)((j * kUmmaKBytes) >> 4);
+                            const uint32_t accum = (!first || j > 0) ? 1u : 0u;
+                            if (kI8)
+                                ptx::mma_i8(d_tmem, da + adv, db + adv, idesc, accum);
+                            else
+                                ptx::mma_f16(d_tmem, da + adv, db + adv, idesc, accum);
+                        }
+                        first = false;
+                        ptx::mma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs retire
+                        if (++s == S) { s = 0; ph ^= 1u; }
                     }
-                    ptx::mma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs retire
-                    if (++s == S) { s = 0; ph ^= 1u; }
+                    ptx::mma_commit(&tfull_bar[acc]);  // chunk complete -> epilogue
+                    if (++acc == kAccStages) { acc = 0; acc_ph ^= 1u; }
                 }
-                ptx::mma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-                if (++acc == kAccStages) { acc = 0; acc_ph ^= 1u; }
             }
         }
-    } else if (warp >= 4) {
-        // ----------------------------------------------------------------- epilogue
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
+    } else {
+        // ----------------------------------------------------------------- epilogue (16 warps)
+        ptx::setmaxnreg_inc<224>();
+        constexpr int CPT = Cfg::kColsPerThread, G = Cfg::kGroup, NG = Cfg::kGroups;
+        const int q = warp & 3;          // TMEM lane quarter this warp may access
+        const int h = (warp - 4) >> 2;   // column quarter of the tile
         float inv = 1.0f;
         if (p.sa) inv /= __ldg(p.sa);
         if (p.sb) inv /= __ldg(p.sb);
@@ -194,91 +290,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         int acc = 0;
         uint32_t acc_ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            uint32_t sum[CPT];  // running sum of the chunks (fp32 bit patterns, or int32)
             int b, m_blk, n_blk;
             tile_coords(p, tile, b, m_blk, n_blk);
             const int row = m_blk * kBlockM + q * 32 + lane;
-            const bool row_ok = row < p.M;
-            ptx::mbar_wait(&tfull_bar[acc], acc_ph);
-            ptx::tc_fence_after_sync();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            char* dbase = reinterpret_cast<char*>(p.D);
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                const int col0 = n_blk * BLOCK_N + c * 32;
-                if (col0 >= p.N) break;  // uniform across the CTA
-                uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), v);
-                ptx::tmem_ld_wait();
-                if (!row_ok) continue;
-                const long long off = (long long)b * p.stride_d + (long long)row * p.ldd + col0;
-                const bool full = (col0 + 32 <= p.N) && p.vec_ok;
-                if (p.epilogue == BNN_EPI_STORE_S16) {
-                    int16_t* d = reinterpret_cast<int16_t*>(dbase) + off;
-                    if (full) {
+            const int colbase = n_blk * BLOCK_N + h * CPT;
+            for (int c = 0; c < n_chunks; ++c) {
+                ptx::mbar_wait(&tfull_bar[acc], acc_ph);
+                ptx::tc_fence_after_sync();
+                const uint32_t t_row =
+                    tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + h * CPT);
+                if (c == 0) {
+                    // first chunk lands directly in the running sum (columns past N hold zeros)
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 o;
-                            o.x = (v[j + 0] & 0xffffu) | (v[j + 1] << 16);
-                            o.y = (v[j + 2] & 0xffffu) | (v[j + 3] << 16);
-                            o.z = (v[j + 4] & 0xffffu) | (v[j + 5] << 16);
-                            o.w = (v[j + 6] & 0xffffu) | (v[j + 7] << 16);
-                            *reinterpret_cast<uint4*>(d + j) = o;
-                        }
-                    } else {
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N) d[j] = (int16_t)(int)v[j];
-                    }
-                } else if (p.epilogue == BNN_EPI_STORE_S32) {
-                    int32_t* d = reinterpret_cast<int32_t*>(dbase) + off;
-                    if (full) {
+                    for (int g = 0; g < NG; ++g) {
+                        uint32_t v[G];
+                        ptx::tmem_ld_cols<G>(t_row + (uint32_t)(g * G), v);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<uint4*>(d + j) =
-                                make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N) d[j] = (int)v[j];
+                        for (int j = 0; j < G; ++j) sum[g * G + j] = v[j];
                     }
+                    ptx::tmem_ld_wait();
                 } else {
-                    float f[32];
+                    // ptxas would hoist all eight tcgen05.ld's above the adds (8 x 16 temporaries on
+                    // top of the 128-register running sum spill); a data-dependent branch after each
+                    // group is a barrier for the warp-synchronous loads and keeps 16 temporaries
+                    // live at a time.  The tested bit pattern (a NaN payload no accumulator can
+                    // produce, far outside any int32 sum) never occurs.
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float a = kI8 ? (float)(int)v[j] : __uint_as_float(v[j]);
-                        f[j] = __fmul_rn(a, scale);
+                    for (int g = 0; g < NG; ++g) {
+                        uint32_t v[G];
+                        ptx::tmem_ld_cols<G>(t_row + (uint32_t)(g * G), v);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < G; ++j)
+                            sum[g * G + j] =
+                                kI8 ? sum[g * G + j] + v[j]
+                                    : __float_as_uint(__fadd_rn(__uint_as_float(sum[g * G + j]),
+                                                                __uint_as_float(v[j])));
+                        if (sum[g * G + G - 1] == 0x7FC12345u) __trap();
                     }
-                    float* d = reinterpret_cast<float*>(dbase) + off;
-                    if (p.epilogue == BNN_EPI_SGD_F32) {
-                        // weights -= lr * dw  (layers.py:268): two roundings, like NumPy
-                        if (full) {
+                }
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                if (++acc == kAccStages) { acc = 0; acc_ph ^= 1u; }
+            }
+            if (row < p.M) {
+                char* dbase = reinterpret_cast<char*>(p.D);
+                const long long rowoff = (long long)b * p.stride_d + (long long)row * p.ldd;
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                float4 w = *reinterpret_cast<float4*>(d + j);
-                                w.x = __fsub_rn(w.x, f[j + 0]);
-                                w.y = __fsub_rn(w.y, f[j + 1]);
-                                w.z = __fsub_rn(w.z, f[j + 2]);
-                                w.w = __fsub_rn(w.w, f[j + 3]);
-                                *reinterpret_cast<float4*>(d + j) = w;
-                            }
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.N) d[j] = __fsub_rn(d[j], f[j]);
-                        }
-                    } else {
-                        if (full) {
+                for (int g = 0; g < NG; ++g) {
+                    const int col0 = colbase + g * G;
+                    if (col0 < p.N) {
+                        uint32_t v[G];
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(d + j) =
-                                    make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.N) d[j] = f[j];
-                        }
+                        for (int j = 0; j < G; ++j) v[j] = sum[g * G + j];
+                        store_group<kI8, EPI, G>(p, dbase, rowoff + col0, col0, v, scale);
+                        asm volatile("" ::: "memory");  // keep the groups' live ranges disjoint
                     }
                 }
             }
-            ptx::tc_fence_before_sync();
-            ptx::mbar_arrive(&tempty_bar[acc]);
-            if (++acc == kAccStages) { acc = 0; acc_ph ^= 1u; }
         }
     }
 
@@ -336,12 +407,12 @@ int make_operand_map(CUtensorMap* map, const void* base, bool i8, long long rows
     return BNN_OK;
 }
 
-template <bool kI8, int BLOCK_N>
+template <bool kI8, int BLOCK_N, int EPI>
 int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     using Cfg = TileCfg<BLOCK_N>;
     static bool attr_set = false;
     if (!attr_set) {
-        BNN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kI8, BLOCK_N>,
+        BNN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kI8, BLOCK_N, EPI>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::kSmemBytes));
         attr_set = true;
@@ -366,6 +437,8 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     const int kelems = kI8 ? kKBytes : kKBytes / 2;
     p.kblocks = cdiv(g.K, kelems);
     p.n_pass = g.n_pass;
+    // integer accumulation is exact: one chunk; fp32 accumulation is re-rounded every chunk
+    p.chunk_iters = kI8 ? (p.kblocks * g.n_pass) : gemm_chunk_iters();
     for (int i = 0; i < BNN_GEMM_MAX_PASS; ++i) {
         p.pa[i] = g.pa[i];
         p.pb[i] = g.pb[i];
@@ -385,10 +458,24 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     p.host_scale = g.host_scale;
     const long long tiles = (long long)p.batch * p.m_tiles * p.n_tiles;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    gemm_tc_kernel<kI8, BLOCK_N><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA[0], mA[1], mB[0],
-                                                                             mB[1], p);
+    gemm_tc_kernel<kI8, BLOCK_N, EPI><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA[0], mA[1],
+                                                                                  mB[0], mB[1], p);
     BNN_LAUNCH_CHECK("gemm_tc_kernel");
     return BNN_OK;
+}
+
+template <int BLOCK_N>
+int pick_epilogue(const bnn_gemm_desc& g, bool i8, cudaStream_t stream) {
+    if (i8) {
+        switch (g.epilogue) {
+            case BNN_EPI_STORE_S16: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S16>(g, stream);
+            case BNN_EPI_STORE_S32: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S32>(g, stream);
+            case BNN_EPI_STORE_F32: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_F32>(g, stream);
+            default: return launch_tc<true, BLOCK_N, BNN_EPI_SGD_F32>(g, stream);
+        }
+    }
+    return g.epilogue == BNN_EPI_SGD_F32 ? launch_tc<false, BLOCK_N, BNN_EPI_SGD_F32>(g, stream)
+                                          : launch_tc<false, BLOCK_N, BNN_EPI_STORE_F32>(g, stream);
 }
 
 }  // namespace
@@ -406,9 +493,8 @@ int gemm_tc_dispatch(const bnn_gemm_desc& g, cudaStream_t stream) {
     BNN_CHECK_ARG((g.stride_a * es) % 16 == 0 && (g.stride_b * es) % 16 == 0,
                   "bnn_gemm: batch strides must be multiples of 16 bytes");
     BNN_CHECK_ARG(g.lda >= g.K && g.ldb >= g.K, "bnn_gemm: pitch smaller than K");
-    if (g.N <= 32) return i8 ? launch_tc<true, 32>(g, stream) : launch_tc<false, 32>(g, stream);
-    if (g.N <= 128) return i8 ? launch_tc<true, 128>(g, stream) : launch_tc<false, 128>(g, stream);
-    return i8 ? launch_tc<true, 256>(g, stream) : launch_tc<false, 256>(g, stream);
+    return g.N <= 32 ? pick_epilogue<32>(g, i8, stream)
+                     : (g.N <= 128 ? pick_epilogue<128>(g, i8, stream) : pick_epilogue<256>(g, i8, stream));
 }
 
 }  // namespace bnn
