@@ -7,6 +7,8 @@
 //   A10    cross_entropy_loss/_derivative  mlpcode/loss.py:10-36, 39-68
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace bnn {
 namespace {
 
@@ -28,40 +30,111 @@ struct ZLoad<BNN_Z_S32> {
     __device__ static float get(const void* z, long long i) { return (float)__ldg((const int32_t*)z + i); }
 };
 
-constexpr int CS_COLS = 128;  // columns per block (32 lanes x 4)
+constexpr int CS_COLS = 128;  // columns per block (16 threads x 8)
 constexpr int CS_ROWS = 256;  // rows per block
 
 // ---------------------------------------------------------------------------------------------
+// 8-column vector access.  Every HBM-bound kernel below gives a thread 8 adjacent columns of a row:
+// 16-byte loads of int16 Z, 2 x 16-byte loads of fp32, 8/16-byte stores of the int8 / fp16 outputs.
+// `vec` says the base pointer and pitch allow it; otherwise (and on ragged edges) elements are
+// touched one by one.
+// ---------------------------------------------------------------------------------------------
+template <int ZT>
+__device__ __forceinline__ void load8_z(const void* __restrict__ Z, long long off, int valid, bool vec,
+                                        float (&z)[8]) {
+    using T = typename ZLoad<ZT>::T;
+    const T* p = reinterpret_cast<const T*>(Z) + off;
+    if (vec && valid == 8) {
+        if (ZT == BNN_Z_S16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                z[2 * j] = (float)(int16_t)(w[j] & 0xffffu);
+                z[2 * j + 1] = (float)(int16_t)(w[j] >> 16);
+            }
+        } else if (ZT == BNN_Z_F32) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+            z[0] = a.x; z[1] = a.y; z[2] = a.z; z[3] = a.w;
+            z[4] = b.x; z[5] = b.y; z[6] = b.z; z[7] = b.w;
+        } else {
+            const int4 a = __ldg(reinterpret_cast<const int4*>(p));
+            const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+            z[0] = (float)a.x; z[1] = (float)a.y; z[2] = (float)a.z; z[3] = (float)a.w;
+            z[4] = (float)b.x; z[5] = (float)b.y; z[6] = (float)b.z; z[7] = (float)b.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = j < valid ? (float)__ldg(p + j) : 0.0f;
+    }
+}
+
+__device__ __forceinline__ void load8_f32(const float* __restrict__ p, int valid, bool vec,
+                                          float (&x)[8]) {
+    if (vec && valid == 8) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+        x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = j < valid ? __ldg(p + j) : 0.0f;
+    }
+}
+
+template <int ZT>
+__host__ __device__ inline bool z_vec_ok(const void* Z, long long ldz) {
+    const int es = ZT == BNN_Z_S16 ? 2 : 4;
+    return aligned16(Z) && (ldz * es) % 16 == 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Column sums / sums of squares in fp64 (exact for integer-valued Z; order independent).
-// block = (32, 8); thread owns 4 adjacent columns and every 8th row of a 256-row slab.
+// block = 256 threads = 16 column groups (8 columns each) x 16 row lanes over a 256-row slab.
 // ---------------------------------------------------------------------------------------------
 template <int ZT>
 __global__ void __launch_bounds__(256) colstats_kernel(const void* __restrict__ Z, int B, int N,
                                                        long long ldz, double* __restrict__ sums) {
     __shared__ double red[2][8][CS_COLS];
-    const int lane = threadIdx.x, y = threadIdx.y;
-    const int c0 = blockIdx.x * CS_COLS + lane * 4;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int c0 = blockIdx.x * CS_COLS + tx * 8;
+    const int valid = min(8, N - c0);
     const int r0 = blockIdx.y * CS_ROWS;
     const int r1 = min(r0 + CS_ROWS, B);
-    double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-    for (int r = r0 + y; r < r1; r += 8) {
+    const bool vec = z_vec_ok<ZT>(Z, ldz);
+    double s[8], q[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (c0 + j < N) {
-                const double v = (double)ZLoad<ZT>::get(Z, (long long)r * ldz + c0 + j);
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.0;
+    if (valid > 0) {
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += 16) {
+            float z[8];
+            load8_z<ZT>(Z, (long long)r * ldz + c0, valid, vec, z);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double v = (double)z[j];
                 s[j] += v;
-                q[j] += v * v;
+                q[j] = fma(v, v, q[j]);
             }
         }
     }
+    // lanes l and l^16 hold the same columns (rows ty and ty^1): fold, then one row per warp
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        red[0][y][lane * 4 + j] = s[j];
-        red[1][y][lane * 4 + j] = q[j];
+    for (int j = 0; j < 8; ++j) {
+        s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
+        q[j] += __shfl_xor_sync(0xffffffffu, q[j], 16);
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 16) == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            red[0][warp][tx * 8 + j] = s[j];
+            red[1][warp][tx * 8 + j] = q[j];
+        }
     }
     __syncthreads();
-    const int t = y * 32 + lane;  // 256 threads -> 2 x 128 outputs
-    const int which = t >> 7, col = t & 127;
+    const int which = threadIdx.x >> 7, col = threadIdx.x & 127;
     double a = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) a += red[which][i][col];
@@ -81,10 +154,14 @@ __global__ void bn_stats_finalize_kernel(const double* __restrict__ sums, int N,
 }
 
 // ---------------------------------------------------------------------------------------------
-// BN apply + sign, 64 x 64 tiles.  The normalisation follows the reference's fp32 operation
-// order (sub, div by sqrt(var+eps), mul gamma, add beta) with explicit round-to-nearest
-// intrinsics so no FMA contraction can change a sign decision.
+// BN apply + sign, 64 (rows) x 128 (columns) tiles, 8 columns per thread.  The normalisation follows
+// the reference's fp32 operation order (sub, div by sqrt(var+eps), mul gamma, add beta) with explicit
+// round-to-nearest intrinsics so no FMA contraction can change a sign decision.  The transposed fp16
+// copy (next layer's dW operand) goes through a shared-memory tile of sign bytes and leaves as
+// 16-byte stores of 8 consecutive batch rows.
 // ---------------------------------------------------------------------------------------------
+constexpr int AP_ROWS = 64, AP_COLS = 128;
+
 template <int ZT>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const float* __restrict__ mu,
@@ -93,46 +170,112 @@ bn_apply_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const f
                 long long ld_f32, int8_t* __restrict__ act_i8, long long ld_i8,
                 __half* __restrict__ act_t16, long long ld_t16, uint32_t* __restrict__ act_bits,
                 long long ld_bits) {
-    __shared__ uint8_t sg[64][68];
-    const int b0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-    const int tn = threadIdx.x & 63, tb = threadIdx.x >> 6;
-    const int gn = n0 + tn;
-    const bool col_ok = gn < N;
-    float m = 0.f, d = 1.f, g = 0.f, be = 0.f;
-    if (col_ok) {
-        m = __ldg(mu + gn);
-        d = __fsqrt_rn(__fadd_rn(__ldg(var + gn), eps));
-        g = __ldg(gamma + gn);
-        be = __ldg(beta + gn);
+    __shared__ __align__(16) uint8_t sg[AP_ROWS][AP_COLS + 16];
+    const int b0 = blockIdx.y * AP_ROWS, n0 = blockIdx.x * AP_COLS;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int c0 = n0 + tx * 8;
+    const int valid = max(0, min(8, N - c0));
+    const bool zvec = z_vec_ok<ZT>(Z, ldz);
+    const bool fvec = out_f32 && aligned16(out_f32) && (ld_f32 % 4 == 0);
+    const bool ivec = act_i8 && ((reinterpret_cast<uintptr_t>(act_i8) & 7u) == 0) && (ld_i8 % 8 == 0);
+    float m[8], d[8], g[8], be[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const bool ok = j < valid;
+        m[j] = ok ? __ldg(mu + c0 + j) : 0.f;
+        d[j] = ok ? __fsqrt_rn(__fadd_rn(__ldg(var + c0 + j), eps)) : 1.f;
+        g[j] = ok ? __ldg(gamma + c0 + j) : 0.f;
+        be[j] = ok ? __ldg(beta + c0 + j) : 0.f;
     }
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const int r = tb + 4 * i;
+    // issue every row's load before touching any of them: 4 x 16..32 bytes in flight per thread
+    float zall[AP_ROWS / 16][8];
+#pragma unroll
+    for (int i = 0; i < AP_ROWS / 16; ++i) {
+        const int gb = b0 + ty + 16 * i;
+        if (gb < B && valid > 0) load8_z<ZT>(Z, (long long)gb * ldz + c0, valid, zvec, zall[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < AP_ROWS / 16; ++i) {
+        const int r = ty + 16 * i;
         const int gb = b0 + r;
-        bool plus = false;
-        if (col_ok && gb < B) {
-            const float z = ZLoad<ZT>::get(Z, (long long)gb * ldz + gn);
-            const float o = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(z, m), d), g), be);
-            plus = o >= 0.0f;
-            if (out_f32) out_f32[(long long)gb * ld_f32 + gn] = o;
-            if (act_i8) act_i8[(long long)gb * ld_i8 + gn] = plus ? (int8_t)1 : (int8_t)-1;
+        uint32_t sb = 0;  // sign bits of this thread's 8 columns
+        if (gb < B && valid > 0) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                o[j] = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(zall[i][j], m[j]), d[j]), g[j]), be[j]);
+                sb |= (uint32_t)(j < valid && o[j] >= 0.0f) << j;
+            }
+            if (out_f32) {
+                float* p = out_f32 + (long long)gb * ld_f32 + c0;
+                if (fvec && valid == 8) {
+                    reinterpret_cast<float4*>(p)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                    reinterpret_cast<float4*>(p)[1] = make_float4(o[4], o[5], o[6], o[7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < valid) p[j] = o[j];
+                }
+            }
+            if (act_i8) {
+                int8_t* p = act_i8 + (long long)gb * ld_i8 + c0;
+                if (ivec && valid == 8) {
+                    uint2 w;
+                    w.x = w.y = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        w.x |= (((sb >> j) & 1u) ? 0x01u : 0xFFu) << (8 * j);
+                        w.y |= (((sb >> (j + 4)) & 1u) ? 0x01u : 0xFFu) << (8 * j);
+                    }
+                    *reinterpret_cast<uint2*>(p) = w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < valid) p[j] = ((sb >> j) & 1u) ? (int8_t)1 : (int8_t)-1;
+                }
+            }
         }
         if (act_bits) {
-            const uint32_t word = __ballot_sync(0xffffffffu, plus);
-            if ((threadIdx.x & 31) == 0 && gb < B && (n0 + (tn & 32)) < N)
-                act_bits[(long long)gb * ld_bits + ((n0 + (tn & 32)) >> 5)] = word;
+            // 4 adjacent threads own the 32 columns of one word
+            uint32_t w = sb << (8 * (tx & 3));
+            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+            if ((tx & 3) == 0 && gb < B && c0 < N) act_bits[(long long)gb * ld_bits + (c0 >> 5)] = w;
         }
-        sg[r][tn] = plus ? 1 : 0;
+        if (act_t16) {
+            uint2 w;
+            w.x = w.y = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                w.x |= ((sb >> j) & 1u) << (8 * j);
+                w.y |= ((sb >> (j + 4)) & 1u) << (8 * j);
+            }
+            *reinterpret_cast<uint2*>(&sg[r][tx * 8]) = w;
+        }
     }
     if (!act_t16) return;
     __syncthreads();
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const int c = tb + 4 * i;
-        const int gb = b0 + tn, gc = n0 + c;
-        if (gb < B && gc < N)
-            act_t16[(long long)gc * ld_t16 + gb] =
-                __ushort_as_half(sg[tn][c] ? (unsigned short)0x3C00 : (unsigned short)0xBC00);
+    const bool tvec = aligned16(act_t16) && (ld_t16 % 8 == 0);
+#pragma unroll
+    for (int k = 0; k < (AP_COLS * AP_ROWS / 8) / 256; ++k) {
+        const int item = threadIdx.x + 256 * k;
+        const int n = item & (AP_COLS - 1), bg = item >> 7;  // column, group of 8 batch rows
+        const int gn = n0 + n, gb = b0 + bg * 8;
+        if (gn >= N || gb >= B) continue;
+        uint32_t h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t lo = sg[bg * 8 + 2 * j][n] ? 0x3C00u : 0xBC00u;
+            const uint32_t hi = sg[bg * 8 + 2 * j + 1][n] ? 0x3C00u : 0xBC00u;
+            h[j] = lo | (hi << 16);
+        }
+        __half* p = act_t16 + (long long)gn * ld_t16 + gb;
+        if (tvec && gb + 8 <= B) {
+            *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+        } else {
+            for (int j = 0; j < 8 && gb + j < B; ++j)
+                p[j] = __ushort_as_half((unsigned short)(h[j >> 1] >> (16 * (j & 1))));
+        }
     }
 }
 
@@ -180,6 +323,7 @@ softmax_xent_kernel(const float* __restrict__ logits, int B, int C, long long ld
 
 // ---------------------------------------------------------------------------------------------
 // BN backward, pass 1: column reductions of delta and delta*(Z-mu) plus magnitude bounds.
+// Same 16 x 16 thread layout as colstats_kernel, 8 columns per thread.
 // ---------------------------------------------------------------------------------------------
 template <int ZT>
 __global__ void __launch_bounds__(256)
@@ -188,38 +332,56 @@ bn_bwd_reduce_kernel(const float* __restrict__ delta, long long ldd, const void*
                      double* __restrict__ red, uint32_t* __restrict__ red_max) {
     __shared__ double sred[2][8][CS_COLS];
     __shared__ float smax[2][8][CS_COLS];
-    const int lane = threadIdx.x, y = threadIdx.y;
-    const int c0 = blockIdx.x * CS_COLS + lane * 4;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int c0 = blockIdx.x * CS_COLS + tx * 8;
+    const int valid = max(0, min(8, N - c0));
     const int r0 = blockIdx.y * CS_ROWS;
     const int r1 = min(r0 + CS_ROWS, B);
-    float m[4];
+    const bool zvec = z_vec_ok<ZT>(Z, ldz);
+    const bool dvec = aligned16(delta) && (ldd % 4 == 0);
+    float m[8], md[8], mx[8];
+    double s1[8], s2[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) m[j] = (c0 + j < N) ? __ldg(mu + c0 + j) : 0.f;
-    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-    float md[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};
-    for (int r = r0 + y; r < r1; r += 8) {
+    for (int j = 0; j < 8; ++j) {
+        m[j] = j < valid ? __ldg(mu + c0 + j) : 0.f;
+        md[j] = mx[j] = 0.f;
+        s1[j] = s2[j] = 0.0;
+    }
+    if (valid > 0) {
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += 16) {
+            float z[8], dl[8];
+            load8_f32(delta + (long long)r * ldd + c0, valid, dvec, dl);
+            load8_z<ZT>(Z, (long long)r * ldz + c0, valid, zvec, z);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (c0 + j < N) {
-                const float dl = __ldg(delta + (long long)r * ldd + c0 + j);
-                const float xm = ZLoad<ZT>::get(Z, (long long)r * ldz + c0 + j) - m[j];
-                s1[j] += (double)dl;
-                s2[j] += (double)dl * (double)xm;
-                md[j] = fmaxf(md[j], fabsf(dl));
-                mx[j] = fmaxf(mx[j], fabsf(xm));
+            for (int j = 0; j < 8; ++j) {
+                const float xm = z[j] - m[j];
+                s1[j] += (double)dl[j];
+                s2[j] = fma((double)dl[j], (double)xm, s2[j]);
+                md[j] = fmaxf(md[j], fabsf(dl[j]));
+                mx[j] = fmaxf(mx[j], j < valid ? fabsf(xm) : 0.f);
             }
         }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        sred[0][y][lane * 4 + j] = s1[j];
-        sred[1][y][lane * 4 + j] = s2[j];
-        smax[0][y][lane * 4 + j] = md[j];
-        smax[1][y][lane * 4 + j] = mx[j];
+    for (int j = 0; j < 8; ++j) {
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+        md[j] = fmaxf(md[j], __shfl_xor_sync(0xffffffffu, md[j], 16));
+        mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], 16));
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 16) == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sred[0][warp][tx * 8 + j] = s1[j];
+            sred[1][warp][tx * 8 + j] = s2[j];
+            smax[0][warp][tx * 8 + j] = md[j];
+            smax[1][warp][tx * 8 + j] = mx[j];
+        }
     }
     __syncthreads();
-    const int t = y * 32 + lane;
-    const int which = t >> 7, col = t & 127;
+    const int which = threadIdx.x >> 7, col = threadIdx.x & 127;
     double a = 0;
     float mm = 0.f;
 #pragma unroll
@@ -282,8 +444,50 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ red,
 }
 
 // ---------------------------------------------------------------------------------------------
-// BN backward, pass 2: delta' and its fp16 hi/lo split in both operand layouts (64 x 64 tiles).
+// BN backward, pass 2: delta' and its fp16 hi/lo split in both operand layouts.  64 x 128 tiles,
+// 8 columns per thread; the transposed pieces go through shared memory and leave as 16-byte stores.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 pack8_half(const __half (&h)[8]) {
+    uint4 v;
+    v.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+    v.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    v.z = (uint32_t)__half_as_ushort(h[4]) | ((uint32_t)__half_as_ushort(h[5]) << 16);
+    v.w = (uint32_t)__half_as_ushort(h[6]) | ((uint32_t)__half_as_ushort(h[7]) << 16);
+    return v;
+}
+
+// Shared tail of bn_bwd_apply_kernel and (pack.cu) split: write a tile's transposed pieces.
+__device__ __forceinline__ void store_transposed_pieces(const __half (*sh)[AP_COLS + 8],
+                                                        const __half (*sl)[AP_COLS + 8], int b0, int n0,
+                                                        int B, int N, __half* __restrict__ dt_hi,
+                                                        __half* __restrict__ dt_lo, long long ld_t) {
+    const bool tvec = aligned16(dt_hi) && aligned16(dt_lo) && (ld_t % 8 == 0);
+#pragma unroll
+    for (int k = 0; k < (AP_COLS * AP_ROWS / 8) / 256; ++k) {
+        const int item = threadIdx.x + 256 * k;
+        const int n = item & (AP_COLS - 1), bg = item >> 7;
+        const int gn = n0 + n, gb = b0 + bg * 8;
+        if (gn >= N || gb >= B) continue;
+        __half h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            h[j] = sh[bg * 8 + j][n];
+            l[j] = sl[bg * 8 + j][n];
+        }
+        __half* ph = dt_hi + (long long)gn * ld_t + gb;
+        __half* pl = dt_lo + (long long)gn * ld_t + gb;
+        if (tvec && gb + 8 <= B) {
+            *reinterpret_cast<uint4*>(ph) = pack8_half(h);
+            *reinterpret_cast<uint4*>(pl) = pack8_half(l);
+        } else {
+            for (int j = 0; j < 8 && gb + j < B; ++j) {
+                ph[j] = h[j];
+                pl[j] = l[j];
+            }
+        }
+    }
+}
+
 template <int ZT>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ delta, long long ldd, const void* __restrict__ Z,
@@ -292,51 +496,83 @@ bn_bwd_apply_kernel(const float* __restrict__ delta, long long ldd, const void* 
                     float* __restrict__ out_f32, long long ld_f32, __half* __restrict__ d_hi,
                     __half* __restrict__ d_lo, long long ld_rm, __half* __restrict__ dt_hi,
                     __half* __restrict__ dt_lo, long long ld_t, float* __restrict__ scale_out) {
-    __shared__ __half sh[64][66];
-    __shared__ __half sl[64][66];
+    __shared__ __align__(16) __half sh[AP_ROWS][AP_COLS + 8];
+    __shared__ __align__(16) __half sl[AP_ROWS][AP_COLS + 8];
     const float s = split_scale_from_bound(__ldg(bound));
     if (scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *scale_out = s;
-    const int b0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-    const int tn = threadIdx.x & 63, tb = threadIdx.x >> 6;
-    const int gn = n0 + tn;
-    const bool col_ok = gn < N;
-    float m = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-    if (col_ok) {
-        m = __ldg(mu + gn);
-        c0 = __ldg(coef + gn);
-        c1 = __ldg(coef + N + gn);
-        c2 = __ldg(coef + 2 * N + gn);
+    const int b0 = blockIdx.y * AP_ROWS, n0 = blockIdx.x * AP_COLS;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int c0 = n0 + tx * 8;
+    const int valid = max(0, min(8, N - c0));
+    const bool zvec = z_vec_ok<ZT>(Z, ldz);
+    const bool dvec = aligned16(delta) && (ldd % 4 == 0);
+    const bool fvec = out_f32 && aligned16(out_f32) && (ld_f32 % 4 == 0);
+    const bool rvec = d_hi && aligned16(d_hi) && aligned16(d_lo) && (ld_rm % 8 == 0);
+    float m[8], k0[8], k1[8], k2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const bool ok = j < valid;
+        m[j] = ok ? __ldg(mu + c0 + j) : 0.f;
+        k0[j] = ok ? __ldg(coef + c0 + j) : 0.f;
+        k1[j] = ok ? __ldg(coef + N + c0 + j) : 0.f;
+        k2[j] = ok ? __ldg(coef + 2 * N + c0 + j) : 0.f;
     }
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const int r = tb + 4 * i;
+    // issue every row's loads first (4 x 48 bytes in flight per thread), then compute and store
+    float zall[AP_ROWS / 16][8], dall[AP_ROWS / 16][8];
+#pragma unroll
+    for (int i = 0; i < AP_ROWS / 16; ++i) {
+        const int gb = b0 + ty + 16 * i;
+        if (gb < B && valid > 0) {
+            load8_f32(delta + (long long)gb * ldd + c0, valid, dvec, dall[i]);
+            load8_z<ZT>(Z, (long long)gb * ldz + c0, valid, zvec, zall[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < AP_ROWS / 16; ++i) {
+        const int r = ty + 16 * i;
         const int gb = b0 + r;
-        __half h = __ushort_as_half(0), l = __ushort_as_half(0);
-        if (col_ok && gb < B) {
-            const float dl = __ldg(delta + (long long)gb * ldd + gn);
-            const float xm = ZLoad<ZT>::get(Z, (long long)gb * ldz + gn) - m;
-            const float nd = fmaf(c0, dl, fmaf(c1, xm, c2));
-            if (out_f32) out_f32[(long long)gb * ld_f32 + gn] = nd;
-            split_f16(nd * s, h, l);
+        __half h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = l[j] = __ushort_as_half(0);
+        if (gb < B && valid > 0) {
+            float nd[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                nd[j] = fmaf(k0[j], dall[i][j], fmaf(k1[j], zall[i][j] - m[j], k2[j]));
+                split_f16(nd[j] * s, h[j], l[j]);
+            }
+            if (out_f32) {
+                float* p = out_f32 + (long long)gb * ld_f32 + c0;
+                if (fvec && valid == 8) {
+                    reinterpret_cast<float4*>(p)[0] = make_float4(nd[0], nd[1], nd[2], nd[3]);
+                    reinterpret_cast<float4*>(p)[1] = make_float4(nd[4], nd[5], nd[6], nd[7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < valid) p[j] = nd[j];
+                }
+            }
             if (d_hi) {
-                d_hi[(long long)gb * ld_rm + gn] = h;
-                d_lo[(long long)gb * ld_rm + gn] = l;
+                __half* ph = d_hi + (long long)gb * ld_rm + c0;
+                __half* pl = d_lo + (long long)gb * ld_rm + c0;
+                if (rvec && valid == 8) {
+                    *reinterpret_cast<uint4*>(ph) = pack8_half(h);
+                    *reinterpret_cast<uint4*>(pl) = pack8_half(l);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < valid) { ph[j] = h[j]; pl[j] = l[j]; }
+                }
             }
         }
-        sh[r][tn] = h;
-        sl[r][tn] = l;
+        if (dt_hi) {
+            *reinterpret_cast<uint4*>(&sh[r][tx * 8]) = pack8_half(h);
+            *reinterpret_cast<uint4*>(&sl[r][tx * 8]) = pack8_half(l);
+        }
     }
     if (!dt_hi) return;
     __syncthreads();
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const int c = tb + 4 * i;
-        const int gb = b0 + tn, gc = n0 + c;
-        if (gb < B && gc < N) {
-            dt_hi[(long long)gc * ld_t + gb] = sh[tn][c];
-            dt_lo[(long long)gc * ld_t + gb] = sl[tn][c];
-        }
-    }
+    store_transposed_pieces(sh, sl, b0, n0, B, N, dt_hi, dt_lo, ld_t);
 }
 
 __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -346,23 +582,37 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
         p[i] = __fsub_rn(p[i], __fmul_rn(lr, __ldg(g + i)));
 }
 
+// rows are grouped: row r belongs to group r / B and is compared with labels[r % B] (one group per
+// fault trial, all trials sharing the evaluation labels); correct[group] += hits.
 __global__ void __launch_bounds__(256) count_correct_kernel(const float* __restrict__ scores, int B,
                                                             int C, long long lds,
                                                             const int32_t* __restrict__ labels,
-                                                            int32_t* __restrict__ correct) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    int hit = 0;
-    if (b < B) {
+                                                            int32_t* __restrict__ correct, int groups) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long rows = (long long)B * groups;
+    int hit = 0, grp = 0;
+    if (r < rows) {
+        grp = (int)(r / B);
         int best = 0;
-        float bv = scores[(long long)b * lds];
+        float bv = scores[r * lds];
         for (int c = 1; c < C; ++c) {
-            const float v = scores[(long long)b * lds + c];
+            const float v = scores[r * lds + c];
             if (v > bv) { bv = v; best = c; }
         }
-        hit = (best == labels[b]) ? 1 : 0;
+        hit = (best == labels[r % B]) ? 1 : 0;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(correct, __popc(m));
+    // a warp can straddle two groups: count per group with two ballots
+    const int g0 = __shfl_sync(0xffffffffu, grp, 0);
+    const unsigned m0 = __ballot_sync(0xffffffffu, hit && grp == g0);
+    const unsigned m1 = __ballot_sync(0xffffffffu, hit && grp != g0);
+    if ((threadIdx.x & 31) == 0) {
+        if (m0) atomicAdd(correct + g0, __popc(m0));
+    }
+    if (m1) {
+        const int src = __ffs(m1) - 1;
+        const int g1 = __shfl_sync(0xffffffffu, grp, src);
+        if ((threadIdx.x & 31) == 0) atomicAdd(correct + g1, __popc(m1));
+    }
 }
 
 template <typename F>
@@ -386,10 +636,10 @@ extern "C" int bnn_colstats(const void* Z, int z_dtype, int B, int N, int64_t ld
     BNN_CHECK_ARG(Z && sums && B > 0 && N > 0 && ldz >= N, "bnn_colstats: bad input");
     cudaStream_t s = (cudaStream_t)stream;
     if (!accumulate) BNN_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * N, s));
-    dim3 grid(cdiv(N, CS_COLS), cdiv(B, CS_ROWS)), block(32, 8);
+    dim3 grid(cdiv(N, CS_COLS), cdiv(B, CS_ROWS));
     BNN_CHECK_ARG(grid.y <= 65535, "bnn_colstats: B too large");
     return dispatch_z(z_dtype, [&](auto zt) {
-        colstats_kernel<decltype(zt)::value><<<grid, block, 0, s>>>(Z, B, N, ldz, sums);
+        colstats_kernel<decltype(zt)::value><<<grid, 256, 0, s>>>(Z, B, N, ldz, sums);
         BNN_LAUNCH_CHECK("colstats_kernel");
         return (int)BNN_OK;
     });
@@ -414,7 +664,7 @@ extern "C" int bnn_bn_apply(const void* Z, int z_dtype, int B, int N, int64_t ld
     BNN_CHECK_ARG(!act_i8 || ld_i8 >= N, "bnn_bn_apply: ld_i8 < N");
     BNN_CHECK_ARG(!act_t16 || ld_t16 >= B, "bnn_bn_apply: ld_t16 < B");
     BNN_CHECK_ARG(!act_bits || ld_bits >= (N + 31) / 32, "bnn_bn_apply: ld_bits too small");
-    dim3 grid(cdiv(N, 64), cdiv(B, 64));
+    dim3 grid(cdiv(N, AP_COLS), cdiv(B, AP_ROWS));
     BNN_CHECK_ARG(grid.y <= 65535, "bnn_bn_apply: B too large");
     cudaStream_t s = (cudaStream_t)stream;
     return dispatch_z(z_dtype, [&](auto zt) {
@@ -450,10 +700,10 @@ extern "C" int bnn_bn_bwd_reduce(const float* delta, int64_t ldd, const void* Z,
         BNN_CUDA(cudaMemsetAsync(red, 0, sizeof(double) * 2 * N, s));
         BNN_CUDA(cudaMemsetAsync(red_max, 0, sizeof(uint32_t) * 2 * N, s));
     }
-    dim3 grid(cdiv(N, CS_COLS), cdiv(B, CS_ROWS)), block(32, 8);
+    dim3 grid(cdiv(N, CS_COLS), cdiv(B, CS_ROWS));
     BNN_CHECK_ARG(grid.y <= 65535, "bnn_bn_bwd_reduce: B too large");
     return dispatch_z(z_dtype, [&](auto zt) {
-        bn_bwd_reduce_kernel<decltype(zt)::value><<<grid, block, 0, s>>>(delta, ldd, Z, ldz, B, N,
+        bn_bwd_reduce_kernel<decltype(zt)::value><<<grid, 256, 0, s>>>(delta, ldd, Z, ldz, B, N,
                                                                          mu, red, red_max);
         BNN_LAUNCH_CHECK("bn_bwd_reduce_kernel");
         return (int)BNN_OK;
@@ -492,7 +742,7 @@ extern "C" int bnn_bn_bwd_apply(const float* delta, int64_t ldd, const void* Z, 
     BNN_CHECK_ARG(!d_hi || ld_rm >= N, "bnn_bn_bwd_apply: ld_rm < N");
     BNN_CHECK_ARG(!dt_hi || ld_t >= B, "bnn_bn_bwd_apply: ld_t < B");
     BNN_CHECK_ARG(!out_f32 || ld_f32 >= N, "bnn_bn_bwd_apply: ld_f32 < N");
-    dim3 grid(cdiv(N, 64), cdiv(B, 64));
+    dim3 grid(cdiv(N, AP_COLS), cdiv(B, AP_ROWS));
     BNN_CHECK_ARG(grid.y <= 65535, "bnn_bn_bwd_apply: B too large");
     cudaStream_t s = (cudaStream_t)stream;
     return dispatch_z(z_dtype, [&](auto zt) {
@@ -516,11 +766,13 @@ extern "C" int bnn_sgd_update(float* p, const float* g, int64_t n, float lr, bnn
 }
 
 extern "C" int bnn_count_correct(const float* scores, int B, int C, int64_t lds,
-                                 const int32_t* labels, int32_t* correct, bnn_stream_t stream) {
-    BNN_CHECK_ARG(scores && labels && correct && B > 0 && C > 0 && lds >= C,
+                                 const int32_t* labels, int32_t* correct, int groups,
+                                 bnn_stream_t stream) {
+    BNN_CHECK_ARG(scores && labels && correct && B > 0 && C > 0 && lds >= C && groups >= 1,
                   "bnn_count_correct: bad input");
-    count_correct_kernel<<<cdiv(B, 256), 256, 0, (cudaStream_t)stream>>>(scores, B, C, lds, labels,
-                                                                         correct);
+    BNN_CHECK_ARG(B >= 32 || groups == 1, "bnn_count_correct: grouped mode needs B >= 32");
+    count_correct_kernel<<<cdiv((long)B * groups, 256), 256, 0, (cudaStream_t)stream>>>(
+        scores, B, C, lds, labels, correct, groups);
     BNN_LAUNCH_CHECK("count_correct_kernel");
     return BNN_OK;
 }

@@ -47,7 +47,7 @@ flip_bernoulli_kernel(const int8_t* __restrict__ wt_i8, long long ld_i8,
         uint32_t mask = 0;
         const unsigned long long e0 = (unsigned long long)n * (unsigned long long)K + kbase;
         U4 rnd = {0, 0, 0, 0};
-        for (int j = 0; j < cnt; ++j) {
+        for (int j = 0; j < (threshold ? cnt : 0); ++j) {  // threshold 0: plain replication
             const unsigned long long e = e0 + j;
             if (j == 0 || (e & 3ull) == 0) {
                 const unsigned long long q = e >> 2;

@@ -42,17 +42,28 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
 __global__ void __launch_bounds__(256)
 binarize_t_kernel(const float* __restrict__ W, int K, int N, int8_t* __restrict__ wt_i8,
                   long long ld_i8, __half* __restrict__ wt_f16, long long ld_f16,
-                  uint32_t* __restrict__ wt_bits, long long ld_bits) {
+                  uint32_t* __restrict__ wt_bits, long long ld_bits,
+                  uint32_t* __restrict__ absmax_bits) {
     __shared__ uint32_t s[128][33];
     const int k0 = blockIdx.y * 128, n0 = blockIdx.x * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float amax = 0.0f;
 #pragma unroll 4
     for (int i = 0; i < 16; ++i) {
         const int k = warp + 8 * i;
         const int gk = k0 + k, gn = n0 + lane;
         float v = -1.0f;
-        if (gk < K && gn < N) v = __ldg(W + (long long)gk * N + gn);
+        if (gk < K && gn < N) {
+            v = __ldg(W + (long long)gk * N + gn);
+            amax = fmaxf(amax, fabsf(v));
+        }
         s[k][lane] = sign_bit_ge0(v);
+    }
+    if (absmax_bits) {  // max|W| for the backward split comes for free with this read of W
+        amax = warp_max(amax);
+        // one atomic per warp only while it can still raise the maximum (plain read as a filter)
+        if (lane == 0 && __float_as_uint(amax) > *reinterpret_cast<volatile uint32_t*>(absmax_bits))
+            atomicMax(absmax_bits, __float_as_uint(amax));
     }
     __syncthreads();
 #pragma unroll
@@ -110,47 +121,102 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
     }
     for (long long j = n4 * 4 + i; j < n; j += stride) m = fmaxf(m, fabsf(__ldg(x + j)));
     m = warp_max(m);
-    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0 && __float_as_uint(m) > *reinterpret_cast<volatile uint32_t*>(out))
+        atomicMax(out, __float_as_uint(m));
 }
 
 // ---------------------------------------------------------------------------------------------
-// fp32 -> fp16 hi/lo split, row-major and transposed (64 x 64 tiles through shared memory).
+// fp32 -> fp16 hi/lo split, row-major and transposed.  64 x 128 tiles, 8 columns per thread: two
+// 16-byte loads, 16-byte stores of each piece; the transposed pieces go through shared memory and
+// leave as 16-byte stores of 8 consecutive rows.
 // ---------------------------------------------------------------------------------------------
+constexpr int SP_ROWS = 64, SP_COLS = 128;
+
+__device__ __forceinline__ uint4 pack8(const __half (&h)[8]) {
+    uint4 v;
+    v.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+    v.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    v.z = (uint32_t)__half_as_ushort(h[4]) | ((uint32_t)__half_as_ushort(h[5]) << 16);
+    v.w = (uint32_t)__half_as_ushort(h[6]) | ((uint32_t)__half_as_ushort(h[7]) << 16);
+    return v;
+}
+
 __global__ void __launch_bounds__(256)
 split_f16_kernel(const float* __restrict__ x, int R, int C, long long ldx,
                  const float* __restrict__ bound, __half* __restrict__ hi, __half* __restrict__ lo,
                  long long ld_rm, __half* __restrict__ hi_t, __half* __restrict__ lo_t,
                  long long ld_t, float* __restrict__ scale_out) {
-    __shared__ __half sh[64][66];
-    __shared__ __half sl[64][66];
+    __shared__ __align__(16) __half sh[SP_ROWS][SP_COLS + 8];
+    __shared__ __align__(16) __half sl[SP_ROWS][SP_COLS + 8];
     const float s = split_scale_from_bound(__ldg(bound));
     if (scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *scale_out = s;
-    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-    const int tc = threadIdx.x & 63, tr = threadIdx.x >> 6;
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const int r = tr + 4 * i;
-        const int gr = r0 + r, gc = c0 + tc;
-        __half h = __ushort_as_half(0), l = __ushort_as_half(0);
-        if (gr < R && gc < C) {
-            split_f16(__ldg(x + (long long)gr * ldx + gc) * s, h, l);
+    const int r0 = blockIdx.y * SP_ROWS, c0 = blockIdx.x * SP_COLS + (threadIdx.x & 15) * 8;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int valid = max(0, min(8, C - c0));
+    const bool xvec = aligned16(x) && (ldx % 4 == 0);
+    const bool rvec = hi && aligned16(hi) && aligned16(lo) && (ld_rm % 8 == 0);
+#pragma unroll
+    for (int i = 0; i < SP_ROWS / 16; ++i) {
+        const int r = ty + 16 * i;
+        const int gr = r0 + r;
+        __half h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = l[j] = __ushort_as_half(0);
+        if (gr < R && valid > 0) {
+            const float* p = x + (long long)gr * ldx + c0;
+            float v[8];
+            if (xvec && valid == 8) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = j < valid ? __ldg(p + j) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split_f16(v[j] * s, h[j], l[j]);
             if (hi) {
-                hi[(long long)gr * ld_rm + gc] = h;
-                lo[(long long)gr * ld_rm + gc] = l;
+                __half* ph = hi + (long long)gr * ld_rm + c0;
+                __half* pl = lo + (long long)gr * ld_rm + c0;
+                if (rvec && valid == 8) {
+                    *reinterpret_cast<uint4*>(ph) = pack8(h);
+                    *reinterpret_cast<uint4*>(pl) = pack8(l);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < valid) { ph[j] = h[j]; pl[j] = l[j]; }
+                }
             }
         }
-        sh[r][tc] = h;
-        sl[r][tc] = l;
+        if (hi_t) {
+            *reinterpret_cast<uint4*>(&sh[r][tx * 8]) = pack8(h);
+            *reinterpret_cast<uint4*>(&sl[r][tx * 8]) = pack8(l);
+        }
     }
     if (!hi_t) return;
     __syncthreads();
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const int c = tr + 4 * i;
-        const int gr = r0 + tc, gc = c0 + c;
-        if (gr < R && gc < C) {
-            hi_t[(long long)gc * ld_t + gr] = sh[tc][c];
-            lo_t[(long long)gc * ld_t + gr] = sl[tc][c];
+    const int n0 = blockIdx.x * SP_COLS;
+    const bool tvec = aligned16(hi_t) && aligned16(lo_t) && (ld_t % 8 == 0);
+#pragma unroll
+    for (int k = 0; k < (SP_COLS * SP_ROWS / 8) / 256; ++k) {
+        const int item = threadIdx.x + 256 * k;
+        const int n = item & (SP_COLS - 1), rg = item >> 7;
+        const int gc = n0 + n, gr = r0 + rg * 8;
+        if (gc >= C || gr >= R) continue;
+        __half h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            h[j] = sh[rg * 8 + j][n];
+            l[j] = sl[rg * 8 + j][n];
+        }
+        __half* ph = hi_t + (long long)gc * ld_t + gr;
+        __half* pl = lo_t + (long long)gc * ld_t + gr;
+        if (tvec && gr + 8 <= R) {
+            *reinterpret_cast<uint4*>(ph) = pack8(h);
+            *reinterpret_cast<uint4*>(pl) = pack8(l);
+        } else {
+            for (int j = 0; j < 8 && gr + j < R; ++j) { ph[j] = h[j]; pl[j] = l[j]; }
         }
     }
 }
@@ -188,15 +254,17 @@ extern "C" int bnn_pack_i8_rows(const int8_t* x, int R, int C, int64_t ldx, uint
 
 extern "C" int bnn_binarize_weights_t(const float* W, int K, int N, int8_t* wt_i8, int64_t ld_i8,
                                       void* wt_f16, int64_t ld_f16, uint32_t* wt_bits,
-                                      int64_t ld_bits, bnn_stream_t stream) {
+                                      int64_t ld_bits, uint32_t* absmax_bits, bnn_stream_t stream) {
     BNN_CHECK_ARG(W && K > 0 && N > 0, "bnn_binarize_weights_t: bad input");
     BNN_CHECK_ARG(!wt_i8 || ld_i8 >= K, "bnn_binarize_weights_t: ld_i8 < K");
     BNN_CHECK_ARG(!wt_f16 || ld_f16 >= K, "bnn_binarize_weights_t: ld_f16 < K");
     BNN_CHECK_ARG(!wt_bits || ld_bits >= (K + 31) / 32, "bnn_binarize_weights_t: ld_bits too small");
     dim3 grid(cdiv(N, 32), cdiv(K, 128));
     BNN_CHECK_ARG(grid.y <= 65535, "bnn_binarize_weights_t: K too large");
+    if (absmax_bits)
+        BNN_CUDA(cudaMemsetAsync(absmax_bits, 0, sizeof(uint32_t), (cudaStream_t)stream));
     binarize_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        W, K, N, wt_i8, ld_i8, static_cast<__half*>(wt_f16), ld_f16, wt_bits, ld_bits);
+        W, K, N, wt_i8, ld_i8, static_cast<__half*>(wt_f16), ld_f16, wt_bits, ld_bits, absmax_bits);
     BNN_LAUNCH_CHECK("binarize_t_kernel");
     return BNN_OK;
 }
@@ -234,7 +302,7 @@ extern "C" int bnn_split_f16(const float* x, int R, int C, int64_t ldx, const fl
                   "bnn_split_f16: hi/lo must be given in pairs");
     BNN_CHECK_ARG(!hi || ld_rm >= C, "bnn_split_f16: ld_rm < C");
     BNN_CHECK_ARG(!hi_t || ld_t >= R, "bnn_split_f16: ld_t < R");
-    dim3 grid(cdiv(C, 64), cdiv(R, 64));
+    dim3 grid(cdiv(C, SP_COLS), cdiv(R, SP_ROWS));
     BNN_CHECK_ARG(grid.y <= 65535, "bnn_split_f16: R too large");
     split_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         x, R, C, ldx, bound, static_cast<__half*>(hi), static_cast<__half*>(lo), ld_rm,

@@ -55,7 +55,7 @@ PROTOTYPES = {
     "bnn_device_query": [C.POINTER(C.c_int)] * 3,
     "bnn_pack_sign_rows": [_p, _i, _i, _i64, _p, _i64, _p],
     "bnn_pack_i8_rows": [_p, _i, _i, _i64, _p, _i64, _p],
-    "bnn_binarize_weights_t": [_p, _i, _i, _p, _i64, _p, _i64, _p, _i64, _p],
+    "bnn_binarize_weights_t": [_p, _i, _i, _p, _i64, _p, _i64, _p, _i64, _p, _p],
     "bnn_unpack_bits": [_p, _i, _i, _i64, _p, _i64, _p, _i64, _p],
     "bnn_absmax_f32": [_p, _i64, _p, _i, _p],
     "bnn_split_f16": [_p, _i, _i, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p, _p],
@@ -80,7 +80,7 @@ PROTOTYPES = {
     "bnn_flip_images": [_p, _i, _i, _i, _i, _u64, _u32, _i, _p, _p],
     "bnn_normalize_u8": [_p, _i64, _p, _p, _f, _f, _p, _p],
     "bnn_minmax_u8": [_p, _i64, _p, _p, _p],
-    "bnn_count_correct": [_p, _i, _i, _i64, _p, _p, _p],
+    "bnn_count_correct": [_p, _i, _i, _i64, _p, _p, _i, _p],
 }
 _RESTYPE = {"bnn_last_error": C.c_char_p}
 

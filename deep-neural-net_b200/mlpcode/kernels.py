@@ -52,13 +52,13 @@ def pack_i8_rows(x: torch.Tensor, C_: int, bits: torch.Tensor) -> None:
     _call("bnn_pack_i8_rows", ptr(x), x.shape[0], C_, _ld(x), ptr(bits), _ld(bits))
 
 
-def binarize_weights_t(W: torch.Tensor, wt_i8=None, wt_f16=None, wt_bits=None) -> None:
+def binarize_weights_t(W: torch.Tensor, wt_i8=None, wt_f16=None, wt_bits=None, absmax=None) -> None:
     K, N = W.shape
     assert W.is_contiguous()
     _call("bnn_binarize_weights_t", ptr(W), K, N,
           ptr(wt_i8), _ld(wt_i8) if wt_i8 is not None else 0,
           ptr(wt_f16), _ld(wt_f16) if wt_f16 is not None else 0,
-          ptr(wt_bits), _ld(wt_bits) if wt_bits is not None else 0)
+          ptr(wt_bits), _ld(wt_bits) if wt_bits is not None else 0, ptr(absmax))
 
 
 def unpack_bits(bits: torch.Tensor, C_: int, out_i8=None, out_f16=None) -> None:
@@ -167,8 +167,9 @@ def sgd_update(p, g, lr) -> None:
     _call("bnn_sgd_update", ptr(p), ptr(g), p.numel(), lr)
 
 
-def count_correct(scores, B, Cc, labels_i32, correct_i32) -> None:
-    _call("bnn_count_correct", ptr(scores), B, Cc, _ld(scores), ptr(labels_i32), ptr(correct_i32))
+def count_correct(scores, B, Cc, labels_i32, correct_i32, groups=1) -> None:
+    _call("bnn_count_correct", ptr(scores), B, Cc, _ld(scores), ptr(labels_i32), ptr(correct_i32),
+          groups)
 
 
 # ------------------------------------------------------------------------------- fault injection

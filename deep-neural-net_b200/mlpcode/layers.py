@@ -328,8 +328,10 @@ class BinaryLayer(LinearLayer):
             ops["f16"] = ws.get("wt_f16", (N, pad_to(Kd, 8)), torch.float16, zero=True)
         else:
             ops["i8"] = ws.get("wt_i8", (N, pad_to(Kd, 16)), torch.int8, zero=True)
+        # the same pass over W yields max|W|, the bound of the backward pass's fp16 split of W
+        ops["amax"] = ws.get("w_amax", (1,), torch.float32)
         K_.binarize_weights_t(self.weights.t, wt_i8=ops.get("i8"), wt_f16=ops.get("f16"),
-                              wt_bits=ops["bits"])
+                              wt_bits=ops["bits"], absmax=ops["amax"])
         return ops
 
     def _real_input_operands(self, Xt, train: bool):
@@ -470,7 +472,7 @@ class BinaryLayer(LinearLayer):
             w_scale = ws.get("w_scale", (1,), torch.float32)
             w_hi = ws.get("w_hi", (Kd, Np), torch.float16, zero=True)
             w_lo = ws.get("w_lo", (Kd, Np), torch.float16, zero=True)
-            K_.absmax_f32(self.weights.t, w_amax)
+            # W has not changed since this step's forward, whose binarize pass left max|W| in w_amax
             K_.split_f16(self.weights.t, w_amax, hi=w_hi, lo=w_lo, scale_out=w_scale)
             dX = empty((B, pad_to(Kd, 4)))
             K_.gemm(M=B, N=Kd, K=N, A=(d_hi, d_lo), B=(w_hi, w_lo), lda=Np, ldb=Np, D=dX,

@@ -1,0 +1,208 @@
+"""Fault-injection sweeps: many trials per kernel launch, trials sharded across GPUs.
+
+The reference runs one trial at a time: attach an `ErrorCallback` to every layer, call
+`get_accuracy` (weightsErrorInjectionv2.py:23-32), or corrupt the test images and evaluate
+(imageBitflipTrainModelSel.py:19-32) — a fresh host-RNG mask per layer per forward and a full
+evaluation per trial.  Here T trials advance together:
+
+  * the clean K-major binarized weights are packed once per sweep (latent weights are never touched,
+    layers.py:286 / SURVEY Q9);
+  * one bnn_flip_weights_* launch writes the T corrupted copies of a layer ([T, N, K] int8 or fp16);
+  * one batched bnn_gemm (batch = T) evaluates the layer for all trials — layer 0 shares the split
+    input across trials (stride 0), deeper layers read the trial's own activations;
+  * batch-norm (running statistics) + sign run on the [T*R, N] stack, and one grouped
+    bnn_count_correct yields T correct-counts.
+
+Mask definition (in-kernel RNG; restated bit-exactly on the CPU by the test oracle):
+  Bernoulli(p):  trial t, layer i  ->  Philox key = seed, stream id = i, trial = t
+  exact-k:       trial t flips the first k_t outputs of the keyed bijection over ALL weights of the
+                 network (layer-major, K-major within a layer), distinct by construction.
+Trials are independent units: `trial_range` shards them over ranks with no communication until the
+final gather of accuracies.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import kernels as K_
+from .activation import ActivationFuncs as af
+from .device import empty, pad_to, to_tensor, zeros
+from .parallel import shard_range
+
+
+class WeightFaultSweep:
+    def __init__(self, nn, X, labels, trials_per_launch: int = 8):
+        assert nn.isCompiled and nn.isBinarized and nn.useBatchNorm
+        self.nn = nn
+        self.T = int(trials_per_launch)
+        self.layers = nn._layers
+        X = to_tensor(X, torch.float32)
+        self.R, self.F = X.shape
+        assert self.R >= 32, "grouped accuracy counting needs at least 32 evaluation rows"
+        self.labels = to_tensor(labels).reshape(-1).to(torch.int32).contiguous()
+        assert self.labels.numel() == self.R
+        self.units = nn.unitList
+        self.total_weights = sum(k * n for k, n in zip(self.units[:-1], self.units[1:]))
+        self.offsets = np.cumsum([0] + [k * n for k, n in zip(self.units[:-1], self.units[1:])])[:-1]
+
+        # ---- once per sweep: split input, clean packed weights -------------------------------
+        Fp = pad_to(self.F, 8)
+        self.x_amax = zeros((1,), torch.float32)
+        self.x_scale = zeros((1,), torch.float32)
+        self.x_hi = zeros((self.R, Fp), torch.float16)
+        self.x_lo = zeros((self.R, Fp), torch.float16)
+        K_.absmax_f32(X, self.x_amax)
+        K_.split_f16(X, self.x_amax, hi=self.x_hi, lo=self.x_lo, scale_out=self.x_scale)
+        self.clean_bits, self.w, self.z, self.act = [], [], [], []
+        T, R = self.T, self.R
+        for i, layer in enumerate(self.layers):
+            Kd, N = layer.weights_shape
+            bits = zeros((N, pad_to(Kd, 32) // 32), torch.int32)
+            K_.binarize_weights_t(layer.weights.t, wt_bits=bits)
+            self.clean_bits.append(bits)
+            if i == 0:
+                self.w.append(zeros((T, N, pad_to(Kd, 8)), torch.float16))
+                self.z.append(empty((T * R, pad_to(N, 4)), torch.float32))
+            else:
+                self.w.append(zeros((T, N, pad_to(Kd, 16)), torch.int8))
+                zdt = torch.int16 if Kd < 32768 else torch.int32
+                self.z.append(empty((T * R, pad_to(N, 8)), zdt))
+            last = i == len(self.layers) - 1
+            self.act.append(empty((T * R, N)) if last else zeros((T * R, pad_to(N, 16)), torch.int8))
+        self.correct = zeros((T,), torch.int32)
+
+    # ------------------------------------------------------------------ one launch group
+    def _forward_group(self, n_live: int) -> torch.Tensor:
+        """Evaluate trials 0..n_live-1 of the current corrupted weights; returns correct counts."""
+        T, R = n_live, self.R
+        for i, layer in enumerate(self.layers):
+            Kd, N = layer.weights_shape
+            bn = layer.batchNormLayer
+            w, Z = self.w[i], self.z[i]
+            if i == 0:
+                K_.gemm(M=R, N=N, K=Kd, A=(self.x_hi, self.x_lo), B=(w,), lda=self.x_hi.stride(0),
+                        ldb=w.stride(1), D=Z, ldd=Z.stride(0), in_dtype=nat.DT_F16,
+                        epilogue=nat.EPI_STORE_F32, passes=((0, 0), (1, 0)), sa=self.x_scale,
+                        batch=T, stride_a=0, stride_b=w.stride(0), stride_d=R * Z.stride(0))
+            else:
+                a = self.act[i - 1]
+                epi = nat.EPI_STORE_S16 if Z.dtype == torch.int16 else nat.EPI_STORE_S32
+                K_.gemm(M=R, N=N, K=Kd, A=(a,), B=(w,), lda=a.stride(0), ldb=w.stride(1), D=Z,
+                        ldd=Z.stride(0), in_dtype=nat.DT_I8, epilogue=epi, batch=T,
+                        stride_a=R * a.stride(0), stride_b=w.stride(0), stride_d=R * Z.stride(0))
+            out = self.act[i]
+            if i < len(self.layers) - 1:
+                K_.bn_apply(Z, T * R, N, bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON,
+                            act_i8=out)
+            else:
+                # softmax is monotone per row: the argmax of the BN output decides the class
+                K_.bn_apply(Z, T * R, N, bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON,
+                            out_f32=out)
+        self.correct.zero_()
+        K_.count_correct(self.act[-1], R, self.units[-1], self.labels, self.correct, groups=T)
+        return self.correct[:T].clone()
+
+    def _flip_bernoulli(self, p: float, seed: int, trial0: int, n_live: int) -> None:
+        for i, layer in enumerate(self.layers):
+            Kd, N = layer.weights_shape
+            w = self.w[i][:n_live]
+            K_.flip_weights_bernoulli(N=N, K=Kd, p=p, seed=seed, stream_id=i, trial0=trial0,
+                                      n_trials=n_live, wt_bits=self.clean_bits[i],
+                                      out_f16=w if i == 0 else None, out_i8=None if i == 0 else w)
+
+    def _flip_exactk(self, ks: torch.Tensor, k_max: int, seed: int, trial0: int) -> None:
+        n_live = ks.numel()
+        for i, layer in enumerate(self.layers):
+            Kd, N = layer.weights_shape
+            w = self.w[i][:n_live]
+            # replicate the clean weights (p = 0), then scatter this layer's share of the flips
+            K_.flip_weights_bernoulli(N=N, K=Kd, p=0.0, seed=0, stream_id=0, trial0=0, n_trials=n_live,
+                                      wt_bits=self.clean_bits[i], out_f16=w if i == 0 else None,
+                                      out_i8=None if i == 0 else w)
+            K_.flip_weights_exactk(N=N, K=Kd, total=self.total_weights, offset=int(self.offsets[i]),
+                                   seed=seed, trial0=trial0, k_per_trial=ks, k_max=k_max,
+                                   io_f16=w if i == 0 else None, io_i8=None if i == 0 else w)
+
+    # ------------------------------------------------------------------ public sweeps
+    def trial_range(self, n_trials: int, comm=None):
+        return shard_range(n_trials, comm.rank, comm.world) if comm else (0, n_trials)
+
+    def run_bernoulli(self, p: float, n_trials: int, seed: int, comm=None) -> np.ndarray:
+        """Accuracy (%) of trials [0, n_trials) with i.i.d. Bernoulli(p) sign flips on every layer —
+        the reference's BNN fault model (callbacks.py:79-83)."""
+        lo, hi = self.trial_range(n_trials, comm)
+        counts = []
+        for t0 in range(lo, hi, self.T):
+            n_live = min(self.T, hi - t0)
+            self._flip_bernoulli(float(p), seed, t0, n_live)
+            counts.append(self._forward_group(n_live))
+        return self._gather(counts, n_trials, lo, hi, comm)
+
+    def run_exactk(self, k_of_trial, n_trials: int, seed: int, comm=None) -> np.ndarray:
+        """Accuracy (%) of trials whose trial t flips exactly k_of_trial(t) distinct weights of the
+        whole network (BASELINE config 4: k swept over 1..1000)."""
+        lo, hi = self.trial_range(n_trials, comm)
+        counts = []
+        for t0 in range(lo, hi, self.T):
+            n_live = min(self.T, hi - t0)
+            ks_host = np.array([int(k_of_trial(t)) for t in range(t0, t0 + n_live)], np.int32)
+            self._flip_exactk(to_tensor(ks_host), int(ks_host.max()), seed, t0)
+            counts.append(self._forward_group(n_live))
+        return self._gather(counts, n_trials, lo, hi, comm)
+
+    def clean_accuracy(self) -> float:
+        self._flip_bernoulli(0.0, 0, 0, 1)
+        return float(self._forward_group(1)[0].item()) * 100.0 / self.R
+
+    def _gather(self, counts, n_trials, lo, hi, comm) -> np.ndarray:
+        mine = torch.cat(counts) if counts else zeros((0,), torch.int32)
+        if comm is None or comm.world == 1:
+            return mine.cpu().numpy().astype(np.float64) * 100.0 / self.R
+        # the only communication of a sweep: one gather of the per-trial counts
+        width = (n_trials + comm.world - 1) // comm.world
+        padded = torch.full((width,), -1, dtype=torch.int32, device=mine.device)
+        padded[: hi - lo] = mine
+        allc = comm.allgather(padded).cpu().numpy()
+        out = np.concatenate([row[row >= 0] for row in allc])
+        return out.astype(np.float64) * 100.0 / self.R
+
+
+class ImageFaultSweep:
+    """imageBitflipTrainModelSel.py:19-32: corrupt the uint8 test images (exactly round(p*8F) bit flips
+    per image), normalize to [-1, 1] with the corrupted set's own min/max, evaluate; repeat."""
+
+    def __init__(self, nn, images_u8, labels, trials_per_launch: int = 8):
+        from .callbacks import ImageErrorCallback  # noqa: F401 (documented entry point)
+        self.nn = nn
+        self.images = to_tensor(images_u8)
+        assert self.images.dtype == torch.uint8 and self.images.ndim == 2
+        self.labels = to_tensor(labels).reshape(-1).to(torch.int32).contiguous()
+        self.T = int(trials_per_launch)
+        self.R, self.F = self.images.shape
+        self.flipped = empty((self.T, self.R, self.F), torch.uint8)
+        self.xf = empty((self.R, self.F), torch.float32)
+        self.mm_u32 = zeros((2,), torch.int32)
+        self.mm_f32 = zeros((2,), torch.float32)
+
+    def run(self, p: float, n_trials: int, seed: int, mode: int = 2, comm=None) -> np.ndarray:
+        k = int(round(p * self.F * 8))
+        lo, hi = shard_range(n_trials, comm.rank, comm.world) if comm else (0, n_trials)
+        accs = []
+        for t0 in range(lo, hi, self.T):
+            n_live = min(self.T, hi - t0)
+            K_.flip_images(self.images, k, mode, seed, t0, n_live, self.flipped[:n_live])
+            for t in range(n_live):
+                img = self.flipped[t]
+                K_.minmax_u8(img, self.mm_u32, self.mm_f32)
+                K_.normalize_u8(img, self.mm_f32[0:1], self.mm_f32[1:2], -1.0, 1.0, self.xf)
+                accs.append(self.nn.get_accuracy(self.xf, self.labels))
+        mine = np.array(accs, np.float64)
+        if comm is None or comm.world == 1:
+            return mine
+        width = (n_trials + comm.world - 1) // comm.world
+        padded = torch.full((width,), -1.0, dtype=torch.float64, device=self.images.device)
+        padded[: hi - lo] = torch.from_numpy(mine).to(padded.device)
+        allc = comm.allgather(padded).cpu().numpy()
+        return np.concatenate([row[row >= 0] for row in allc])

@@ -67,10 +67,12 @@ int bnn_pack_i8_rows(const int8_t* x, int R, int C, int64_t ldx, uint32_t* bits,
  *   wt_i8  [N, ld_i8 ]  int8  +-1                 (tcgen05 kind::i8 operand)
  *   wt_f16 [N, ld_f16]  fp16  +-1                 (tcgen05 kind::f16 operand, real-input layer 0)
  *   wt_bits[N, ld_bits] uint32, bit j of word w = (W[32w+j, n] >= 0), pad bits 0 (XOR+popc operand,
- *                       and the "packed weights" the fault kernels mutate) */
+ *                       and the "packed weights" the fault kernels mutate)
+ *   absmax_bits         device uint32 <- bits(max|W|): the bound the backward fp16 split of W needs,
+ *                       obtained from the same read of W (see bnn_absmax_f32) */
 int bnn_binarize_weights_t(const float* W, int K, int N, int8_t* wt_i8, int64_t ld_i8,
                            void* wt_f16, int64_t ld_f16, uint32_t* wt_bits, int64_t ld_bits,
-                           bnn_stream_t stream);
+                           uint32_t* absmax_bits, bnn_stream_t stream);
 
 /* Expand packed sign bits [R, ldw] back to int8 +-1 [R, C] (pitch ldo) and/or fp16 +-1. */
 int bnn_unpack_bits(const uint32_t* bits, int R, int C, int64_t ldw, int8_t* out_i8, int64_t ld_i8,
@@ -288,10 +290,12 @@ int bnn_minmax_u8(const uint8_t* in, int64_t n, uint32_t* minmax, float* minmax_
 /* ---------------------------------------------------------------------------------------------
  * A13  evaluation helper                                (predict_classes network.py:401-404,
  *                                                        evaluate :406-421)
- * correct += #{ b : argmax_c scores[b, c] == labels[b] } (first maximum wins, as ndarray.argmax).
+ * correct[g] += #{ b : argmax_c scores[g*B + b, c] == labels[b] } for g < groups (first maximum
+ * wins, as ndarray.argmax).  groups > 1 evaluates several fault trials stacked along the rows
+ * against one set of labels; it needs B >= 32.
  * ------------------------------------------------------------------------------------------- */
 int bnn_count_correct(const float* scores, int B, int C, int64_t lds, const int32_t* labels,
-                      int32_t* correct, bnn_stream_t stream);
+                      int32_t* correct, int groups, bnn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -260,3 +260,99 @@ def test_config2_step_properties():
     w0 = torch.from_numpy(params["W"][i]).cuda().double()
     da, dc = results["a"][1][i].double() - w0, results["c"][1][i].double() - w0
     assert float(dc.norm()) > 0 and float((dc - 2 * da).norm() / dc.norm()) < 1e-3
+
+
+# ------------------------------------------------------------------------------------- sweeps
+def _tiled_eval_set(g, reps=2):
+    return np.tile(g["X"], (reps, 1)), np.tile(g["labels"], reps)
+
+
+def test_weight_fault_sweep_bernoulli_matches_oracle(golden, oracle):
+    from mlpcode.sweep import WeightFaultSweep
+    g = golden("weight_faults")
+    units = [int(u) for u in g["units"]]
+    n = len(units) - 1
+    params = params_from_golden(g, "", n)
+    nn = build_net(units, params)
+    X, labels = _tiled_eval_set(g)
+    sweep = WeightFaultSweep(nn, X, labels, trials_per_launch=2)
+    assert sweep.clean_accuracy() == oracle.accuracy(params, X.copy(), labels)
+    p, seed, n_trials = 0.15, 20251, 5                     # 5 trials, 2 per launch: ragged last group
+    got = sweep.run_bernoulli(p, n_trials, seed)
+    want = []
+    for t in range(n_trials):
+        masks = [oracle.c_bernoulli_mask(units[i], units[i + 1], p, seed, i, t) for i in range(n)]
+        hooks = [(lambda m: (lambda W: oracle.flip_bnn_mask(W, m)))(m) for m in masks]
+        want.append(oracle.accuracy(params, X.copy(), labels, weight_hooks=hooks))
+    assert np.array_equal(got, np.array(want))
+    assert len(set(got)) > 1                                # the faults actually change the outcome
+    assert np.array_equal(sweep.run_bernoulli(p, n_trials, seed), got)   # reproducible
+
+
+def test_weight_fault_sweep_exactk_matches_oracle(golden, oracle):
+    from mlpcode.sweep import WeightFaultSweep
+    g = golden("weight_faults")
+    units = [int(u) for u in g["units"]]
+    n = len(units) - 1
+    params = params_from_golden(g, "", n)
+    nn = build_net(units, params)
+    X, labels = _tiled_eval_set(g)
+    sweep = WeightFaultSweep(nn, X, labels, trials_per_launch=3)
+    ks = [0, 1, 40, 400, 1200]
+    total = sum(units[i] * units[i + 1] for i in range(n))
+    assert sweep.total_weights == total == 1200
+    seed = 77
+    got = sweep.run_exactk(lambda t: ks[t], len(ks), seed)
+    offs = np.cumsum([0] + [units[i] * units[i + 1] for i in range(n)])
+    want = []
+    for t, k in enumerate(ks):
+        pos = oracle.c_exactk_positions(total, seed, t, k).astype(np.int64)
+        hooks = []
+        for i in range(n):
+            Kd, N = units[i], units[i + 1]
+            mine = pos[(pos >= offs[i]) & (pos < offs[i + 1])] - offs[i]
+            mask = np.zeros((Kd, N), bool)
+            mask[mine % Kd, mine // Kd] = True             # e = n*K + k  ->  W[k, n]
+            hooks.append((lambda m: (lambda W: oracle.flip_bnn_mask(W, m)))(mask))
+        want.append(oracle.accuracy(params, X.copy(), labels, weight_hooks=hooks))
+    assert np.array_equal(got, np.array(want))
+    assert got[0] == sweep.clean_accuracy()                 # k = 0 is the clean network
+    # k = total flips every weight: every hidden sign and the logits negate
+    assert got[-1] != got[0]
+
+
+def test_image_fault_sweep_matches_oracle(golden, oracle):
+    from mlpcode.sweep import ImageFaultSweep
+    g = golden("train_tiny")
+    units = [int(u) for u in g["units"]]
+    n = len(units) - 1
+    params = params_from_golden(g, "after2_", n)
+    nn = build_net(units, params, out="identity")
+    rng = np.random.default_rng(8)
+    imgs = rng.integers(0, 256, (40, units[0]), dtype=np.uint8)
+    labels = rng.integers(0, 10, 40).astype(np.uint8)
+    sweep = ImageFaultSweep(nn, imgs, labels, trials_per_launch=2)
+    p, seed = 0.14, 99
+    got = sweep.run(p, 3, seed)
+    k = int(round(p * units[0] * 8))
+    want = []
+    for t in range(3):
+        x = oracle.normalize(oracle.c_flip_image_rows(imgs, k, 2, seed, t), -1, 1)
+        want.append(oracle.accuracy(params, x, labels, out_af="identity"))
+    assert np.array_equal(got, np.array(want))
+
+
+def test_data_parallel_two_gpus_equal_reference():
+    """N-GPU == 1-GPU == reference (needs 2 GPUs: `gpurun --gpus 2`)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from conftest import REPO
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+                          "29611", str(REPO / "tools" / "dp_check.py")], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "dp_check ok" in out.stdout
