@@ -114,6 +114,12 @@ class _NoComm:
     def allreduce_sum(self, t):
         return None
 
+    def global_rows(self, local_rows):
+        return local_rows
+
+    def allreduce_sum_async(self, t):
+        return None
+
 
 class Layer:
     def __init__(self, layerUnits: int, gpu=False):
@@ -180,7 +186,7 @@ class BatchNormLayer(Layer):
         var = self._ws.get("var_b", (n,), torch.float32)
         K_.colstats(Z, B, n, sums)
         self.comm.allreduce_sum(sums)  # sync-BN: exact (integer-valued fp64 sums) for +-1 layers
-        K_.bn_stats_finalize(sums, n, B * self.comm.world, mu, var)
+        K_.bn_stats_finalize(sums, n, self.comm.global_rows(B), mu, var)
         return sums, mu, var
 
     def backward_kernels(self, delta, Z, B, sums, mu, var, lr, want_f32, d_rm, d_t, scale):
@@ -191,7 +197,7 @@ class BatchNormLayer(Layer):
         bound = self._ws.get("bound", (1,), torch.float32)  # written as uint32 bits of a float
         K_.bn_bwd_reduce(delta, Z, B, n, mu, red, red_max)
         self.comm.allreduce_sum(red)
-        K_.bn_bwd_finalize(red, red_max, n, B * self.comm.world, mu, var, self.EPSILON,
+        K_.bn_bwd_finalize(red, red_max, n, self.comm.global_rows(B), mu, var, self.EPSILON,
                            self.gamma.t, self.beta.t, self.mu.t, self.sigma.t, lr, self.MA_BETA,
                            sums, coef, bound)
         out = empty((B, n)) if want_f32 else None
@@ -239,6 +245,7 @@ class LinearLayer(Layer):
         self.callbacks = []
         self.comm = _NoComm()
         self.skip_input_grad = False  # set on the first layer: its dX is discarded (network.py:389-390)
+        self._pending_update = None   # (all-reduce handle, dW, lr) of a data-parallel step in flight
         self._ws = _Workspace()
         if batchNorm:
             self.batchNormLayer = BatchNormLayer(layerUnits, gpu=gpu)
@@ -361,9 +368,19 @@ class BinaryLayer(LinearLayer):
         K_.binarize_weights_t(new_w, wt_i8=wops.get("i8"), wt_f16=wops.get("f16"),
                               wt_bits=wops["bits"])
 
+    def finish_update(self) -> None:
+        """Apply `W -= lr * dW` of a data-parallel step once its all-reduce has landed."""
+        if self._pending_update is not None:
+            work, dW, lr = self._pending_update
+            self._pending_update = None
+            if work is not None:
+                work.wait()  # stream-side wait: the update kernel queues behind the collective
+            K_.sgd_update(self.weights.t, dW, lr)
+
     # ------------------------------------------------------------------ forward
     def forward(self, X, isTrain=True):
         assert self.isBuilt
+        self.finish_update()
         Kd, N = self.weights_shape
         ws = self._ws
         bn = self.batchNormLayer
@@ -495,8 +512,9 @@ class BinaryLayer(LinearLayer):
             K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=dW, ldd=N,
                     in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32, passes=passes, sa=sa,
                     sb=d_scale)
-            self.comm.allreduce_sum(dW)  # batch-sharded dW -> global dW (NCCL over NVLink)
-            K_.sgd_update(Wt, dW, lr)
+            # batch-sharded dW -> global dW over NCCL/NVLink, started now and awaited only when the
+            # weights are next needed, so it overlaps the lower layers' backward kernels
+            self._pending_update = (self.comm.allreduce_sum_async(dW), dW, lr)
 
         self.cache.clear()
         return DeviceArray(dX) if dX is not None else None

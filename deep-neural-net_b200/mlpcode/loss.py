@@ -26,8 +26,8 @@ class LossFuncs(Enum):
         return self.value
 
 
-GLOBAL_BATCH_SCALE = 1  # data-parallel runs set this to world_size: loss.py:66 divides by the
-                        # GLOBAL batch when the batch is sharded over ranks
+GLOBAL_BATCH_ROWS = None  # data-parallel runs set this: loss.py:66 divides by the GLOBAL batch
+                          # when the batch is sharded over ranks (None: the local batch)
 
 
 def _fused(ypred, y):
@@ -41,7 +41,7 @@ def _fused(ypred, y):
         loss_sum = zeros((1,), torch.float64)
         # probabilities are rewritten clipped, which is the in-place np.clip of loss.py:32
         K_.softmax_xent(logits, B, C, onehot=yt, probs=ypred.t, loss_rows=loss_rows, grad=grad,
-                        count=B * GLOBAL_BATCH_SCALE, loss_sum=loss_sum)
+                        count=GLOBAL_BATCH_ROWS or B, loss_sum=loss_sum)
         ypred.fused = (loss_rows, grad, loss_sum)
     return ypred.fused
 

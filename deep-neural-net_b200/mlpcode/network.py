@@ -245,22 +245,27 @@ class Network(object):
             history["val_accuracy"] = val_accs
         return history
 
-    def train_step_async(self, X, y, lr: float = None):
+    def train_step_async(self, X, y, lr: float = None, global_batch: int = None):
         """One SGD step on one batch (the body of `__updateBatch`, network.py:372-392) without the
-        host read of the loss; returns the device array of per-sample losses."""
+        host read of the loss; returns the device array of per-sample losses.  Data-parallel runs
+        with unequal shards pass the global batch size."""
         lr = self._lr.value if lr is None else lr
+        if self._comm.world > 1:
+            self._comm.global_batch = global_batch
         output = self.predict(X, isTraining=True)
-        loss_mod.GLOBAL_BATCH_SCALE = self._comm.world
+        loss_mod.GLOBAL_BATCH_ROWS = self._comm.global_rows(X.shape[0])
         cost = LOSS_FUNCS[self._lossF](output, y)
         fused = self._lossF == lf.cross_entropy and self._outAf in (af.softmax, af.sigmoid)
         delta = LOSS_DERIVATES[self._lossF](output, y, with_softmax=fused)
         delta = self._layers[-1].backwards(delta, lr, activDeriv=not fused)
         for layer in reversed(self._layers[:-1]):
             delta = layer.backwards(delta, lr)
+        for layer in self._layers:  # data-parallel: dW all-reduces overlapped the backward pass
+            layer.finish_update()
         return cost
 
-    def train_step(self, X, y, lr: float = None) -> float:
-        return float(self.train_step_async(X, y, lr).mean())
+    def train_step(self, X, y, lr: float = None, global_batch: int = None) -> float:
+        return float(self.train_step_async(X, y, lr, global_batch).mean())
 
     _Network__updateBatch = lambda self, batch, lr: self.train_step(batch[0], batch[1], lr)  # noqa: E731
 

@@ -29,12 +29,26 @@ class Comm:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.collectives = 0
+        self.global_batch = None  # rows of the current step over all ranks (None: local * world)
+
+    def global_rows(self, local_rows: int) -> int:
+        """Batch-norm statistics and the loss gradient divide by the GLOBAL batch (layers.py:81-82,
+        loss.py:66).  Equal shards are assumed unless the driver states the global batch."""
+        return self.global_batch if self.global_batch is not None else local_rows * self.world
 
     def allreduce_sum(self, t: torch.Tensor):
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
             self.collectives += 1
         return t
+
+    def allreduce_sum_async(self, t: torch.Tensor):
+        """Start the all-reduce on the communication stream and return a handle whose `.wait()` makes
+        the CURRENT stream wait for it (no host block), so the next layers' kernels overlap it."""
+        if self.world == 1:
+            return None
+        self.collectives += 1
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def allgather(self, t: torch.Tensor) -> torch.Tensor:
         out = [torch.empty_like(t) for _ in range(self.world)]

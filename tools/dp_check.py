@@ -34,12 +34,15 @@ def main():
         for s in range(g["X"].shape[0]):
             Bg = g["X"].shape[1]
             lo, hi = parallel.shard_range(Bg, comm.rank, comm.world)
-            nn.train_step(g["X"][s][lo:hi], g["Y"][s][lo:hi], float(g["lr"]))
+            nn.train_step(g["X"][s][lo:hi], g["Y"][s][lo:hi], float(g["lr"]), global_batch=Bg)
             gam, bet, mus, sig = nn.batchNormParams
             for i in range(n):
-                worst = max(worst, rel_err(nn.weights[i].get(), g[f"after{s}_W{i}"]))
+                errs = {"W": rel_err(nn.weights[i].get(), g[f"after{s}_W{i}"])}
                 for key, arr in (("gamma", gam), ("beta", bet), ("mu", mus), ("sigma", sig)):
-                    worst = max(worst, rel_err(arr[i].get(), g[f"after{s}_{key}{i}"]))
+                    errs[key] = rel_err(arr[i].get(), g[f"after{s}_{key}{i}"])
+                if comm.rank == 0:
+                    print(name, "step", s, "layer", i, {k: f"{v:.2e}" for k, v in errs.items()})
+                worst = max(worst, max(errs.values()))
     t = torch.tensor([worst], device="cuda")
     torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     if comm.rank == 0:
