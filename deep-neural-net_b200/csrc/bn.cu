@@ -39,9 +39,16 @@ constexpr int CS_ROWS = 256;  // rows per block
 // `vec` says the base pointer and pitch allow it; otherwise (and on ragged edges) elements are
 // touched one by one.
 // ---------------------------------------------------------------------------------------------
+// int -> float without the conversion (XU) pipe: 0x4B400000 is 12582912.0f = 1.5 * 2^23, whose ulp is 1,
+// so adding a small integer to its bit pattern adds it to its value exactly (|v| < 2^22).
+__device__ __forceinline__ float int_to_float_exact(int v) {
+    return __int_as_float(0x4B400000 + v) - 12582912.0f;
+}
+
+// Raw integer view of 8 adjacent columns (int16 / int32 Z only).
 template <int ZT>
-__device__ __forceinline__ void load8_z(const void* __restrict__ Z, long long off, int valid, bool vec,
-                                        float (&z)[8]) {
+__device__ __forceinline__ void load8_zi(const void* __restrict__ Z, long long off, int valid, bool vec,
+                                         int (&z)[8]) {
     using T = typename ZLoad<ZT>::T;
     const T* p = reinterpret_cast<const T*>(Z) + off;
     if (vec && valid == 8) {
@@ -50,23 +57,45 @@ __device__ __forceinline__ void load8_z(const void* __restrict__ Z, long long of
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                z[2 * j] = (float)(int16_t)(w[j] & 0xffffu);
-                z[2 * j + 1] = (float)(int16_t)(w[j] >> 16);
+                z[2 * j] = (int)(short)(w[j] & 0xffffu);
+                z[2 * j + 1] = (int)w[j] >> 16;
             }
-        } else if (ZT == BNN_Z_F32) {
+        } else {
+            const int4 a = __ldg(reinterpret_cast<const int4*>(p));
+            const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+            z[0] = a.x; z[1] = a.y; z[2] = a.z; z[3] = a.w;
+            z[4] = b.x; z[5] = b.y; z[6] = b.z; z[7] = b.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = j < valid ? (int)__ldg(p + j) : 0;
+    }
+}
+
+template <int ZT>
+__device__ __forceinline__ void load8_z(const void* __restrict__ Z, long long off, int valid, bool vec,
+                                        float (&z)[8]) {
+    if (ZT == BNN_Z_F32) {
+        const float* p = reinterpret_cast<const float*>(Z) + off;
+        if (vec && valid == 8) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(p));
             const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
             z[0] = a.x; z[1] = a.y; z[2] = a.z; z[3] = a.w;
             z[4] = b.x; z[5] = b.y; z[6] = b.z; z[7] = b.w;
         } else {
-            const int4 a = __ldg(reinterpret_cast<const int4*>(p));
-            const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
-            z[0] = (float)a.x; z[1] = (float)a.y; z[2] = (float)a.z; z[3] = (float)a.w;
-            z[4] = (float)b.x; z[5] = (float)b.y; z[6] = (float)b.z; z[7] = (float)b.w;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) z[j] = j < valid ? __ldg(p + j) : 0.0f;
         }
     } else {
+        int zi[8];
+        load8_zi < ZT == BNN_Z_F32 ? BNN_Z_S32 : ZT > (Z, off, valid, vec, zi);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = j < valid ? (float)__ldg(p + j) : 0.0f;
+        for (int j = 0; j < 8; ++j) {
+            // |z| <= K: exact through the magic constant below 2^22, a plain convert above
+            z[j] = (ZT == BNN_Z_S16) ? int_to_float_exact(zi[j])
+                                     : ((zi[j] > -4194304 && zi[j] < 4194304) ? int_to_float_exact(zi[j])
+                                                                              : (float)zi[j]);
+        }
     }
 }
 
@@ -103,21 +132,47 @@ __global__ void __launch_bounds__(256) colstats_kernel(const void* __restrict__ 
     const int r0 = blockIdx.y * CS_ROWS;
     const int r1 = min(r0 + CS_ROWS, B);
     const bool vec = z_vec_ok<ZT>(Z, ldz);
+    // Per-thread partials over <= 16 rows stay off the fp64 / conversion pipes: integers for the
+    // integer-valued Z (exact: |sum| < 2^20, sum of squares in 64 bits), fp32 for the fp32 Z of
+    // layer 0 (16 terms).  Only the cross-thread reduction below is fp64.
     double s[8], q[8];
+    if (ZT == BNN_Z_F32) {
+        float sf[8], qf[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.0;
-    if (valid > 0) {
+        for (int j = 0; j < 8; ++j) sf[j] = qf[j] = 0.f;
+        if (valid > 0) {
 #pragma unroll 4
-        for (int r = r0 + ty; r < r1; r += 16) {
-            float z[8];
-            load8_z<ZT>(Z, (long long)r * ldz + c0, valid, vec, z);
+            for (int r = r0 + ty; r < r1; r += 16) {
+                float z[8];
+                load8_z<ZT>(Z, (long long)r * ldz + c0, valid, vec, z);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const double v = (double)z[j];
-                s[j] += v;
-                q[j] = fma(v, v, q[j]);
+                for (int j = 0; j < 8; ++j) {
+                    sf[j] += z[j];
+                    qf[j] = fmaf(z[j], z[j], qf[j]);
+                }
             }
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] = (double)sf[j]; q[j] = (double)qf[j]; }
+    } else {
+        int si[8];
+        unsigned long long qi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { si[j] = 0; qi[j] = 0ull; }
+        if (valid > 0) {
+#pragma unroll 4
+            for (int r = r0 + ty; r < r1; r += 16) {
+                int z[8];
+                load8_zi < ZT == BNN_Z_F32 ? BNN_Z_S32 : ZT > (Z, (long long)r * ldz + c0, valid, vec, z);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    si[j] += z[j];
+                    qi[j] += (unsigned long long)((long long)z[j] * (long long)z[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] = (double)si[j]; q[j] = (double)qi[j]; }
     }
     // lanes l and l^16 hold the same columns (rows ty and ty^1): fold, then one row per warp
 #pragma unroll
@@ -153,6 +208,10 @@ __global__ void bn_stats_finalize_kernel(const double* __restrict__ sums, int N,
     var[n] = (float)v;
 }
 
+// IEEE division kept out of line so the common path below stays a handful of FMAs (inlined, ptxas
+// if-converts it and every element pays for it).
+__device__ __noinline__ float ieee_div_slow_path(float x, float d) { return __fdiv_rn(x, d); }
+
 // ---------------------------------------------------------------------------------------------
 // BN apply + sign, 64 (rows) x 128 (columns) tiles, 8 columns per thread.  The normalisation follows
 // the reference's fp32 operation order (sub, div by sqrt(var+eps), mul gamma, add beta) with explicit
@@ -170,7 +229,9 @@ bn_apply_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const f
                 long long ld_f32, int8_t* __restrict__ act_i8, long long ld_i8,
                 __half* __restrict__ act_t16, long long ld_t16, uint32_t* __restrict__ act_bits,
                 long long ld_bits) {
-    __shared__ __align__(16) uint8_t sg[AP_ROWS][AP_COLS + 16];
+    // sign bytes [row][column]; the 4-byte word index of a row is XOR-ed with (row / 8) so that the
+    // transposed read below (8 rows apart, same column) hits 8 different banks
+    __shared__ __align__(16) uint32_t sg[AP_ROWS][AP_COLS / 4];
     const int b0 = blockIdx.y * AP_ROWS, n0 = blockIdx.x * AP_COLS;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int c0 = n0 + tx * 8;
@@ -178,12 +239,21 @@ bn_apply_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const f
     const bool zvec = z_vec_ok<ZT>(Z, ldz);
     const bool fvec = out_f32 && aligned16(out_f32) && (ld_f32 % 4 == 0);
     const bool ivec = act_i8 && ((reinterpret_cast<uintptr_t>(act_i8) & 7u) == 0) && (ld_i8 % 8 == 0);
-    float m[8], d[8], g[8], be[8];
+    // (z - mu) / d with d = sqrt(var + eps) constant per column: q0 = x * RN(1/d), one FMA residual
+    // correction gives the correctly rounded quotient (Markstein) unless d's significand is all ones,
+    // in which case the column falls back to the IEEE division.  Bit-identical to NumPy's divide.
+    float m[8], d[8], rd[8], g[8], be[8];
+    uint32_t slow = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const bool ok = j < valid;
         m[j] = ok ? __ldg(mu + c0 + j) : 0.f;
         d[j] = ok ? __fsqrt_rn(__fadd_rn(__ldg(var + c0 + j), eps)) : 1.f;
+        rd[j] = __frcp_rn(d[j]);
+        const uint32_t bits = __float_as_uint(d[j]);
+        const uint32_t ex = (bits >> 23) & 0xffu;
+        // all-ones significand, or anything that is not a comfortably normal positive number
+        if ((bits & 0x7fffffu) == 0x7fffffu || (bits >> 31) || ex < 32u || ex > 222u) slow |= 1u << j;
         g[j] = ok ? __ldg(gamma + c0 + j) : 0.f;
         be[j] = ok ? __ldg(beta + c0 + j) : 0.f;
     }
@@ -203,7 +273,14 @@ bn_apply_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const f
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                o[j] = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(zall[i][j], m[j]), d[j]), g[j]), be[j]);
+                const float x = __fsub_rn(zall[i][j], m[j]);
+                float q = __fmul_rn(x, rd[j]);
+                q = __fmaf_rn(__fmaf_rn(-q, d[j], x), rd[j], q);
+                // the shortcut is valid for normal-range operands; tiny / huge x take the slow path too
+                const uint32_t ax = __float_as_uint(x) & 0x7fffffffu;
+                if (((slow >> j) & 1u) || (ax != 0u && (ax < 0x10000000u || ax > 0x6f000000u)))
+                    q = ieee_div_slow_path(x, d[j]);
+                o[j] = __fadd_rn(__fmul_rn(q, g[j]), be[j]);
                 sb |= (uint32_t)(j < valid && o[j] >= 0.0f) << j;
             }
             if (out_f32) {
@@ -243,30 +320,34 @@ bn_apply_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const f
             if ((tx & 3) == 0 && gb < B && c0 < N) act_bits[(long long)gb * ld_bits + (c0 >> 5)] = w;
         }
         if (act_t16) {
-            uint2 w;
-            w.x = w.y = 0;
+            uint32_t w0 = 0, w1 = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                w.x |= ((sb >> j) & 1u) << (8 * j);
-                w.y |= ((sb >> (j + 4)) & 1u) << (8 * j);
+                w0 |= ((sb >> j) & 1u) << (8 * j);
+                w1 |= ((sb >> (j + 4)) & 1u) << (8 * j);
             }
-            *reinterpret_cast<uint2*>(&sg[r][tx * 8]) = w;
+            const int sw = (r >> 3) & 7;
+            sg[r][(2 * tx) ^ sw] = w0;
+            sg[r][(2 * tx + 1) ^ sw] = w1;
         }
     }
     if (!act_t16) return;
     __syncthreads();
     const bool tvec = aligned16(act_t16) && (ld_t16 % 8 == 0);
+    const uint8_t* sgb = reinterpret_cast<const uint8_t*>(&sg[0][0]);
 #pragma unroll
     for (int k = 0; k < (AP_COLS * AP_ROWS / 8) / 256; ++k) {
+        // 8 adjacent lanes write the 8 x 16 bytes of one output row: full 128-byte lines
         const int item = threadIdx.x + 256 * k;
-        const int n = item & (AP_COLS - 1), bg = item >> 7;  // column, group of 8 batch rows
+        const int bg = item & 7, n = item >> 3;  // group of 8 batch rows, column
         const int gn = n0 + n, gb = b0 + bg * 8;
         if (gn >= N || gb >= B) continue;
+        const int word = (n >> 2) ^ bg, byte = n & 3;
         uint32_t h[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t lo = sg[bg * 8 + 2 * j][n] ? 0x3C00u : 0xBC00u;
-            const uint32_t hi = sg[bg * 8 + 2 * j + 1][n] ? 0x3C00u : 0xBC00u;
+            const uint32_t lo = sgb[(bg * 8 + 2 * j) * AP_COLS + word * 4 + byte] ? 0x3C00u : 0xBC00u;
+            const uint32_t hi = sgb[(bg * 8 + 2 * j + 1) * AP_COLS + word * 4 + byte] ? 0x3C00u : 0xBC00u;
             h[j] = lo | (hi << 16);
         }
         __half* p = act_t16 + (long long)gn * ld_t16 + gb;
@@ -339,15 +420,15 @@ bn_bwd_reduce_kernel(const float* __restrict__ delta, long long ldd, const void*
     const int r1 = min(r0 + CS_ROWS, B);
     const bool zvec = z_vec_ok<ZT>(Z, ldz);
     const bool dvec = aligned16(delta) && (ldd % 4 == 0);
-    float m[8], md[8], mx[8];
-    double s1[8], s2[8];
+    float m[8], md[8], mx[8], f1[8], f2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         m[j] = j < valid ? __ldg(mu + c0 + j) : 0.f;
-        md[j] = mx[j] = 0.f;
-        s1[j] = s2[j] = 0.0;
+        md[j] = mx[j] = f1[j] = f2[j] = 0.f;
     }
     if (valid > 0) {
+        // <= 16 rows per thread: fp32 partials (no fp64 / conversion-pipe work per element); the
+        // cross-thread and cross-block reduction below is fp64
 #pragma unroll 4
         for (int r = r0 + ty; r < r1; r += 16) {
             float z[8], dl[8];
@@ -356,13 +437,16 @@ bn_bwd_reduce_kernel(const float* __restrict__ delta, long long ldd, const void*
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float xm = z[j] - m[j];
-                s1[j] += (double)dl[j];
-                s2[j] = fma((double)dl[j], (double)xm, s2[j]);
+                f1[j] += dl[j];
+                f2[j] = fmaf(dl[j], xm, f2[j]);
                 md[j] = fmaxf(md[j], fabsf(dl[j]));
                 mx[j] = fmaxf(mx[j], j < valid ? fabsf(xm) : 0.f);
             }
         }
     }
+    double s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = (double)f1[j]; s2[j] = (double)f2[j]; }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
@@ -456,23 +540,29 @@ __device__ __forceinline__ uint4 pack8_half(const __half (&h)[8]) {
     return v;
 }
 
-// Shared tail of bn_bwd_apply_kernel and (pack.cu) split: write a tile's transposed pieces.
-__device__ __forceinline__ void store_transposed_pieces(const __half (*sh)[AP_COLS + 8],
-                                                        const __half (*sl)[AP_COLS + 8], int b0, int n0,
-                                                        int B, int N, __half* __restrict__ dt_hi,
+// Tile of fp16 pieces [row][column] in shared memory; the 16-byte chunk index of a row is XOR-ed with
+// (row / 8) & 7 so the transposed read (8 rows apart, same column) is bank-conflict free.
+__device__ __forceinline__ int piece_index(int row, int col) {
+    return row * AP_COLS + ((((col >> 3) ^ (row >> 3)) & 15) << 3) + (col & 7);
+}
+
+// Write a tile's transposed pieces: 8 adjacent lanes cover the 8 x 16 bytes of one output row.
+__device__ __forceinline__ void store_transposed_pieces(const __half* sh, const __half* sl, int b0,
+                                                        int n0, int B, int N, __half* __restrict__ dt_hi,
                                                         __half* __restrict__ dt_lo, long long ld_t) {
     const bool tvec = aligned16(dt_hi) && aligned16(dt_lo) && (ld_t % 8 == 0);
 #pragma unroll
     for (int k = 0; k < (AP_COLS * AP_ROWS / 8) / 256; ++k) {
         const int item = threadIdx.x + 256 * k;
-        const int n = item & (AP_COLS - 1), bg = item >> 7;
+        const int bg = item & 7, n = item >> 3;
         const int gn = n0 + n, gb = b0 + bg * 8;
         if (gn >= N || gb >= B) continue;
         __half h[8], l[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            h[j] = sh[bg * 8 + j][n];
-            l[j] = sl[bg * 8 + j][n];
+            const int idx = piece_index(bg * 8 + j, n);
+            h[j] = sh[idx];
+            l[j] = sl[idx];
         }
         __half* ph = dt_hi + (long long)gn * ld_t + gb;
         __half* pl = dt_lo + (long long)gn * ld_t + gb;
@@ -496,8 +586,8 @@ bn_bwd_apply_kernel(const float* __restrict__ delta, long long ldd, const void* 
                     float* __restrict__ out_f32, long long ld_f32, __half* __restrict__ d_hi,
                     __half* __restrict__ d_lo, long long ld_rm, __half* __restrict__ dt_hi,
                     __half* __restrict__ dt_lo, long long ld_t, float* __restrict__ scale_out) {
-    __shared__ __align__(16) __half sh[AP_ROWS][AP_COLS + 8];
-    __shared__ __align__(16) __half sl[AP_ROWS][AP_COLS + 8];
+    __shared__ __align__(16) __half sh[AP_ROWS * AP_COLS];
+    __shared__ __align__(16) __half sl[AP_ROWS * AP_COLS];
     const float s = split_scale_from_bound(__ldg(bound));
     if (scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *scale_out = s;
     const int b0 = blockIdx.y * AP_ROWS, n0 = blockIdx.x * AP_COLS;
@@ -566,8 +656,8 @@ bn_bwd_apply_kernel(const float* __restrict__ delta, long long ldd, const void* 
             }
         }
         if (dt_hi) {
-            *reinterpret_cast<uint4*>(&sh[r][tx * 8]) = pack8_half(h);
-            *reinterpret_cast<uint4*>(&sl[r][tx * 8]) = pack8_half(l);
+            *reinterpret_cast<uint4*>(&sh[piece_index(r, tx * 8)]) = pack8_half(h);
+            *reinterpret_cast<uint4*>(&sl[piece_index(r, tx * 8)]) = pack8_half(l);
         }
     }
     if (!dt_hi) return;

@@ -146,8 +146,12 @@ split_f16_kernel(const float* __restrict__ x, int R, int C, long long ldx,
                  const float* __restrict__ bound, __half* __restrict__ hi, __half* __restrict__ lo,
                  long long ld_rm, __half* __restrict__ hi_t, __half* __restrict__ lo_t,
                  long long ld_t, float* __restrict__ scale_out) {
-    __shared__ __align__(16) __half sh[SP_ROWS][SP_COLS + 8];
-    __shared__ __align__(16) __half sl[SP_ROWS][SP_COLS + 8];
+    // 16-byte chunk index XOR-ed with (row / 8): conflict-free transposed reads (see bn.cu)
+    __shared__ __align__(16) __half sh[SP_ROWS * SP_COLS];
+    __shared__ __align__(16) __half sl[SP_ROWS * SP_COLS];
+    auto pidx = [](int row, int col) {
+        return row * SP_COLS + ((((col >> 3) ^ (row >> 3)) & 15) << 3) + (col & 7);
+    };
     const float s = split_scale_from_bound(__ldg(bound));
     if (scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *scale_out = s;
     const int r0 = blockIdx.y * SP_ROWS, c0 = blockIdx.x * SP_COLS + (threadIdx.x & 15) * 8;
@@ -190,8 +194,8 @@ split_f16_kernel(const float* __restrict__ x, int R, int C, long long ldx,
             }
         }
         if (hi_t) {
-            *reinterpret_cast<uint4*>(&sh[r][tx * 8]) = pack8(h);
-            *reinterpret_cast<uint4*>(&sl[r][tx * 8]) = pack8(l);
+            *reinterpret_cast<uint4*>(&sh[pidx(r, tx * 8)]) = pack8(h);
+            *reinterpret_cast<uint4*>(&sl[pidx(r, tx * 8)]) = pack8(l);
         }
     }
     if (!hi_t) return;
@@ -200,15 +204,16 @@ split_f16_kernel(const float* __restrict__ x, int R, int C, long long ldx,
     const bool tvec = aligned16(hi_t) && aligned16(lo_t) && (ld_t % 8 == 0);
 #pragma unroll
     for (int k = 0; k < (SP_COLS * SP_ROWS / 8) / 256; ++k) {
+        // 8 adjacent lanes write the 8 x 16 bytes of one transposed row: full 128-byte lines
         const int item = threadIdx.x + 256 * k;
-        const int n = item & (SP_COLS - 1), rg = item >> 7;
+        const int rg = item & 7, n = item >> 3;
         const int gc = n0 + n, gr = r0 + rg * 8;
         if (gc >= C || gr >= R) continue;
         __half h[8], l[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            h[j] = sh[rg * 8 + j][n];
-            l[j] = sl[rg * 8 + j][n];
+            h[j] = sh[pidx(rg * 8 + j, n)];
+            l[j] = sl[pidx(rg * 8 + j, n)];
         }
         __half* ph = hi_t + (long long)gc * ld_t + gr;
         __half* pl = lo_t + (long long)gc * ld_t + gr;

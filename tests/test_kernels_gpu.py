@@ -313,8 +313,8 @@ def test_colstats_and_bn_apply(T, oracle, B, N, zdt):
     K.colstats(Zd, B, N, sums)
     z64 = Z.astype(np.float64)
     s = sums.cpu().numpy()
-    if zdt == "f32":
-        assert rel_err(s[0], z64.sum(0)) < 1e-12 and rel_err(s[1], (z64 ** 2).sum(0)) < 1e-12
+    if zdt == "f32":   # fp32 partial sums over <= 16 rows per thread, fp64 across threads
+        assert rel_err(s[0], z64.sum(0)) < 1e-6 and rel_err(s[1], (z64 ** 2).sum(0)) < 1e-6
     else:
         assert np.array_equal(s[0], z64.sum(0)) and np.array_equal(s[1], (z64 ** 2).sum(0))
     K.bn_stats_finalize(sums, N, B, mu, var)

@@ -10,3 +10,8 @@ run k_gemm      200 $PT tests/test_kernels_gpu.py -k "gemm or variants or precis
 run l_all       300 $PT tests/test_layers_gpu.py
 run smoke       120 python -c "import __graft_entry__ as g; g.smoke()"
 run bench       300 python bench.py --steps 20 --warmup 5
+CMD="python bench.py --steps 2 --warmup 3 --profile"
+$CMD > gpurun_out/profile_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+    --log-file gpurun_out/launches.csv $CMD > gpurun_out/profile_ncu1.log 2>&1
+echo "launch list rc=$?"
