@@ -34,6 +34,7 @@ UNITS = [784, 4096, 4096, 4096, 10]
 BATCH = 8192
 LR = 0.01
 METRIC, UNIT = "BNN MLP train samples/s", "samples/s"
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 540.9e6  # profiles/r01_gemm_full_raw.csv (see profiles/r01_summary.md)
 
 
 def workload_config(n_gpus):
@@ -299,7 +300,11 @@ def run_gpu(args):
         roofline = {
             "kernel": "gemm_tc_kernel<f16 split> (dW + dX + layer-0 forward)", "bound": "tensor",
             "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
-            "traffic": None, "peak_source": f"bf16_tflops_sustained of {peak_kind}",
+            "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+            "traffic_source": "profiles/r01_summary.md section 2: dram__bytes_read+write, average over the "
+                              "7 launches/step of this kernel in one ncu --set full capture "
+                              "(algorithmic: 320e6 for a 4096-wide dX or dW)",
+            "peak_source": f"bf16_tflops_sustained of {peak_kind}",
             "executed_tflops": split["exec"] / (split["ms"] * 1e-3) / 1e12,
             "executed_frac": split["exec"] / (split["ms"] * 1e-3) / 1e12 / tensor_peak,
             "avg_launch_ms": split["ms"] / split["n"], "launches": split["n"],
