@@ -77,8 +77,13 @@ extern "C" int bnn_gemm(const bnn_gemm_desc* g, int impl, bnn_stream_t stream) {
                   "bnn_gemm: empty shape M=%d N=%d K=%d batch=%d", g->M, g->N, g->K, g->batch);
     BNN_CHECK_ARG(g->in_dtype == BNN_DT_I8 || g->in_dtype == BNN_DT_F16, "bnn_gemm: bad in_dtype %d",
                   g->in_dtype);
-    BNN_CHECK_ARG(g->epilogue >= BNN_EPI_STORE_F32 && g->epilogue <= BNN_EPI_SGD_F32,
+    BNN_CHECK_ARG(g->epilogue >= BNN_EPI_STORE_F32 && g->epilogue <= BNN_EPI_SIGN_I8,
                   "bnn_gemm: bad epilogue %d", g->epilogue);
+    BNN_CHECK_ARG(g->epilogue != BNN_EPI_SIGN_I8 || (g->epi_thr && g->epi_sgn),
+                  "bnn_gemm: BNN_EPI_SIGN_I8 needs epi_thr and epi_sgn");
+    BNN_CHECK_ARG(g->epilogue != BNN_EPI_SIGN_I8 ||
+                      (aligned16(g->epi_thr) && aligned16(g->epi_sgn)),
+                  "bnn_gemm: epi_thr / epi_sgn must be 16-byte aligned");
     BNN_CHECK_ARG(g->in_dtype == BNN_DT_I8 ||
                       (g->epilogue != BNN_EPI_STORE_S32 && g->epilogue != BNN_EPI_STORE_S16),
                   "bnn_gemm: integer stores need int8 operands");

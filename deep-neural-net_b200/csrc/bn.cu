@@ -361,6 +361,154 @@ bn_apply_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const f
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sign thresholds.  out(z) = ((z - mu) / sqrt(var + eps)) * gamma + beta is a composition of
+// correctly rounded monotone fp32 operations, hence monotone in z (non-decreasing for gamma >= 0,
+// non-increasing otherwise).  So sign(out(z)) == +1  <=>  z * sgn >= thr for a per-column float
+// threshold found by bisection over the ordered float bit patterns, evaluating exactly the
+// reference's operation sequence.  The sign pass and the fused GEMM epilogue then need one multiply
+// and one compare per element and stay bit-identical to evaluating the formula (layers.py:84-86,
+// 94-97 followed by activation.py:106-113).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_to_key(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void bn_sign_thresholds_kernel(const float* __restrict__ mu, const float* __restrict__ var,
+                                          const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, float eps, int N,
+                                          float* __restrict__ thr, float* __restrict__ sgn) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float m = mu[n], d = __fsqrt_rn(__fadd_rn(var[n], eps)), g = gamma[n], be = beta[n];
+    const float s = g < 0.0f ? -1.0f : 1.0f;
+    auto plus = [&](float w) {  // w = z * s, so this predicate is non-decreasing in w
+        const float z = w * s;
+        const float o = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(z, m), d), g), be);
+        return o >= 0.0f;
+    };
+    // search domain |z| <= 2^40: far beyond any pre-activation (|z| <= K for +-1 layers) and small
+    // enough that (z - mu) / d * gamma cannot overflow to inf and turn inf * 0 into NaN
+    uint32_t lo = float_to_key(-1.099511627776e12f), hi = float_to_key(1.099511627776e12f);
+    float t;
+    if (!plus(key_to_float(hi))) {
+        t = INFINITY;  // never +1 (includes NaN parameters: NaN >= 0 is false, like the reference)
+    } else if (plus(key_to_float(lo))) {
+        t = -INFINITY;  // always +1
+    } else {
+        while (hi - lo > 1u) {  // invariant: !plus(lo), plus(hi)
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (plus(key_to_float(mid))) hi = mid; else lo = mid;
+        }
+        t = key_to_float(hi);
+    }
+    thr[n] = t;
+    sgn[n] = s;
+}
+
+// Sign pass on thresholds: Z -> int8 +-1, transposed fp16 +-1, packed bits.  64 x 128 tiles, 8 columns
+// per thread, few registers (the normalisation constants collapse into thr / sgn).
+template <int ZT>
+__global__ void __launch_bounds__(256, 3)
+bn_sign_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const float* __restrict__ thr,
+               const float* __restrict__ sgn, int8_t* __restrict__ act_i8, long long ld_i8,
+               __half* __restrict__ act_t16, long long ld_t16, uint32_t* __restrict__ act_bits,
+               long long ld_bits) {
+    __shared__ __align__(16) uint32_t sg[AP_ROWS][AP_COLS / 4];
+    const int b0 = blockIdx.y * AP_ROWS, n0 = blockIdx.x * AP_COLS;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int c0 = n0 + tx * 8;
+    const int valid = max(0, min(8, N - c0));
+    const bool zvec = z_vec_ok<ZT>(Z, ldz);
+    const bool ivec = act_i8 && ((reinterpret_cast<uintptr_t>(act_i8) & 7u) == 0) && (ld_i8 % 8 == 0);
+    float t[8], s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        t[j] = j < valid ? __ldg(thr + c0 + j) : INFINITY;
+        s[j] = j < valid ? __ldg(sgn + c0 + j) : 1.0f;
+    }
+    float zall[AP_ROWS / 16][8];
+#pragma unroll
+    for (int i = 0; i < AP_ROWS / 16; ++i) {
+        const int gb = b0 + ty + 16 * i;
+        if (gb < B && valid > 0) load8_z<ZT>(Z, (long long)gb * ldz + c0, valid, zvec, zall[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < AP_ROWS / 16; ++i) {
+        const int r = ty + 16 * i;
+        const int gb = b0 + r;
+        uint32_t sb = 0;
+        if (gb < B && valid > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sb |= (uint32_t)(__fmul_rn(zall[i][j], s[j]) >= t[j]) << j;
+            if (act_i8) {
+                int8_t* p = act_i8 + (long long)gb * ld_i8 + c0;
+                if (ivec && valid == 8) {
+                    uint2 w;
+                    w.x = w.y = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        w.x |= (((sb >> j) & 1u) ? 0x01u : 0xFFu) << (8 * j);
+                        w.y |= (((sb >> (j + 4)) & 1u) ? 0x01u : 0xFFu) << (8 * j);
+                    }
+                    *reinterpret_cast<uint2*>(p) = w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < valid) p[j] = ((sb >> j) & 1u) ? (int8_t)1 : (int8_t)-1;
+                }
+            }
+        }
+        if (act_bits) {
+            uint32_t w = sb << (8 * (tx & 3));
+            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+            if ((tx & 3) == 0 && gb < B && c0 < N) act_bits[(long long)gb * ld_bits + (c0 >> 5)] = w;
+        }
+        if (act_t16) {
+            uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                w0 |= ((sb >> j) & 1u) << (8 * j);
+                w1 |= ((sb >> (j + 4)) & 1u) << (8 * j);
+            }
+            const int sw = (r >> 3) & 7;
+            sg[r][(2 * tx) ^ sw] = w0;
+            sg[r][(2 * tx + 1) ^ sw] = w1;
+        }
+    }
+    if (!act_t16) return;
+    __syncthreads();
+    const bool tvec = aligned16(act_t16) && (ld_t16 % 8 == 0);
+    const uint8_t* sgb = reinterpret_cast<const uint8_t*>(&sg[0][0]);
+#pragma unroll
+    for (int k = 0; k < (AP_COLS * AP_ROWS / 8) / 256; ++k) {
+        const int item = threadIdx.x + 256 * k;
+        const int bg = item & 7, n = item >> 3;
+        const int gn = n0 + n, gb = b0 + bg * 8;
+        if (gn >= N || gb >= B) continue;
+        const int word = (n >> 2) ^ bg, byte = n & 3;
+        uint32_t h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t lo = sgb[(bg * 8 + 2 * j) * AP_COLS + word * 4 + byte] ? 0x3C00u : 0xBC00u;
+            const uint32_t hi = sgb[(bg * 8 + 2 * j + 1) * AP_COLS + word * 4 + byte] ? 0x3C00u : 0xBC00u;
+            h[j] = lo | (hi << 16);
+        }
+        __half* p = act_t16 + (long long)gn * ld_t16 + gb;
+        if (tvec && gb + 8 <= B) {
+            *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+        } else {
+            for (int j = 0; j < 8 && gb + j < B; ++j)
+                p[j] = __ushort_as_half((unsigned short)(h[j >> 1] >> (16 * (j & 1))));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // softmax + clipped cross-entropy + (p - y)/count, one thread per row (C <= 32).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -762,6 +910,35 @@ extern "C" int bnn_bn_apply(const void* Z, int z_dtype, int B, int N, int64_t ld
             Z, B, N, ldz, mu, var, gamma, beta, eps, out_f32, ld_f32, act_i8, ld_i8,
             static_cast<__half*>(act_t16), ld_t16, act_bits, ld_bits);
         BNN_LAUNCH_CHECK("bn_apply_kernel");
+        return (int)BNN_OK;
+    });
+}
+
+extern "C" int bnn_bn_sign_thresholds(const float* mu, const float* var, const float* gamma,
+                                      const float* beta, float eps, int N, float* thr, float* sgn,
+                                      bnn_stream_t stream) {
+    BNN_CHECK_ARG(mu && var && gamma && beta && thr && sgn && N > 0, "bnn_bn_sign_thresholds: bad input");
+    bn_sign_thresholds_kernel<<<cdiv(N, 128), 128, 0, (cudaStream_t)stream>>>(mu, var, gamma, beta, eps,
+                                                                              N, thr, sgn);
+    BNN_LAUNCH_CHECK("bn_sign_thresholds_kernel");
+    return BNN_OK;
+}
+
+extern "C" int bnn_bn_sign(const void* Z, int z_dtype, int B, int N, int64_t ldz, const float* thr,
+                           const float* sgn, int8_t* act_i8, int64_t ld_i8, void* act_t16,
+                           int64_t ld_t16, uint32_t* act_bits, int64_t ld_bits, bnn_stream_t stream) {
+    BNN_CHECK_ARG(Z && thr && sgn && B > 0 && N > 0 && ldz >= N, "bnn_bn_sign: bad input");
+    BNN_CHECK_ARG(!act_i8 || ld_i8 >= N, "bnn_bn_sign: ld_i8 < N");
+    BNN_CHECK_ARG(!act_t16 || ld_t16 >= B, "bnn_bn_sign: ld_t16 < B");
+    BNN_CHECK_ARG(!act_bits || ld_bits >= (N + 31) / 32, "bnn_bn_sign: ld_bits too small");
+    dim3 grid(cdiv(N, AP_COLS), cdiv(B, AP_ROWS));
+    BNN_CHECK_ARG(grid.y <= 65535, "bnn_bn_sign: B too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    return dispatch_z(z_dtype, [&](auto zt) {
+        bn_sign_kernel<decltype(zt)::value><<<grid, 256, 0, s>>>(
+            Z, B, N, ldz, thr, sgn, act_i8, ld_i8, static_cast<__half*>(act_t16), ld_t16, act_bits,
+            ld_bits);
+        BNN_LAUNCH_CHECK("bn_sign_kernel");
         return (int)BNN_OK;
     });
 }

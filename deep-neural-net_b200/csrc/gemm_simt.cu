@@ -36,6 +36,8 @@ struct SimtParams {
     const float* sb;
     float host_scale;
     int epilogue;
+    const float* thr;
+    const float* sgn;
 };
 
 template <bool kI8>
@@ -101,6 +103,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
                 case BNN_EPI_STORE_S32:
                     reinterpret_cast<int32_t*>(p.D)[off] = (int)acc[i][j];
                     break;
+                case BNN_EPI_SIGN_I8: {
+                    const float a = kI8 ? (float)acc[i][j] : __fmul_rn((float)acc[i][j], scale);
+                    reinterpret_cast<int8_t*>(p.D)[off] =
+                        (__fmul_rn(a, p.sgn[gn]) >= p.thr[gn]) ? (int8_t)1 : (int8_t)-1;
+                } break;
                 case BNN_EPI_SGD_F32: {
                     float* d = reinterpret_cast<float*>(p.D) + off;
                     *d = __fsub_rn(*d, __fmul_rn((float)acc[i][j], scale));
@@ -123,6 +130,7 @@ int gemm_simt_dispatch(const bnn_gemm_desc& g, cudaStream_t stream) {
     p.lda = g.lda; p.ldb = g.ldb; p.stride_a = g.stride_a; p.stride_b = g.stride_b;
     p.D = g.D; p.ldd = g.ldd; p.stride_d = g.stride_d;
     p.sa = g.sa; p.sb = g.sb; p.host_scale = g.host_scale; p.epilogue = g.epilogue;
+    p.thr = g.epi_thr; p.sgn = g.epi_sgn;
     dim3 grid(cdiv(g.N, TN), cdiv(g.M, TM), g.batch);
     BNN_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "bnn_gemm(simt): grid too large");
     if (g.in_dtype == BNN_DT_I8)

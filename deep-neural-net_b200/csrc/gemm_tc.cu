@@ -78,6 +78,8 @@ struct TcParams {
     const float* sa;
     const float* sb;
     float host_scale;
+    const float* thr;  // BNN_EPI_SIGN_I8
+    const float* sgn;
 };
 
 __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& b, int& m_blk,
@@ -100,7 +102,51 @@ template <bool kI8, int EPI, int G>
 __device__ __forceinline__ void store_group(const TcParams& p, char* dbase, long long off, int col0,
                                             const uint32_t (&v)[G], float scale) {
     const bool full = (col0 + G <= p.N) && p.vec_ok;
-    if (EPI == BNN_EPI_STORE_S16) {
+    if (EPI == BNN_EPI_SIGN_I8) {
+        // batch-norm + sign as one compare against the per-column threshold (bn.cu)
+        int8_t* d = reinterpret_cast<int8_t*>(dbase) + off;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < G; j += 4) {
+            float t[4], s[4];
+            if (col0 + j + 4 <= p.N) {
+                const float4 tv = __ldg(reinterpret_cast<const float4*>(p.thr + col0 + j));
+                const float4 sv = __ldg(reinterpret_cast<const float4*>(p.sgn + col0 + j));
+                t[0] = tv.x; t[1] = tv.y; t[2] = tv.z; t[3] = tv.w;
+                s[0] = sv.x; s[1] = sv.y; s[2] = sv.z; s[3] = sv.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool ok = col0 + j + q < p.N;
+                    t[q] = ok ? __ldg(p.thr + col0 + j + q) : INFINITY;
+                    s[q] = ok ? __ldg(p.sgn + col0 + j + q) : 1.0f;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float a = kI8 ? (float)(int)v[j + q] : __fmul_rn(__uint_as_float(v[j + q]), scale);
+                bits |= (uint32_t)(__fmul_rn(a, s[q]) >= t[q]) << (j + q);
+            }
+        }
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < G; j += 16) {
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    w[q] = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        w[q] |= (((bits >> (j + 4 * q + b)) & 1u) ? 0x01u : 0xFFu) << (8 * b);
+                }
+                *reinterpret_cast<uint4*>(d + j) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                if (col0 + j < p.N) d[j] = ((bits >> j) & 1u) ? (int8_t)1 : (int8_t)-1;
+        }
+    } else if (EPI == BNN_EPI_STORE_S16) {
         int16_t* d = reinterpret_cast<int16_t*>(dbase) + off;
         if (full) {
 #pragma unroll
@@ -446,7 +492,7 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     p.m_tiles = cdiv(g.M, kBlockM);
     p.n_tiles = cdiv(g.N, BLOCK_N);
     p.epilogue = g.epilogue;
-    const int esz = (g.epilogue == BNN_EPI_STORE_S16) ? 2 : 4;
+    const int esz = (g.epilogue == BNN_EPI_STORE_S16) ? 2 : (g.epilogue == BNN_EPI_SIGN_I8 ? 1 : 4);
     p.vec_ok = aligned16(g.D) && ((g.ldd * esz) % 16 == 0) && ((g.stride_d * esz) % 16 == 0);
     p.a_batched = g.stride_a != 0;
     p.b_batched = g.stride_b != 0;
@@ -456,6 +502,8 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     p.sa = g.sa;
     p.sb = g.sb;
     p.host_scale = g.host_scale;
+    p.thr = g.epi_thr;
+    p.sgn = g.epi_sgn;
     const long long tiles = (long long)p.batch * p.m_tiles * p.n_tiles;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
     gemm_tc_kernel<kI8, BLOCK_N, EPI><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA[0], mA[1],
@@ -471,11 +519,15 @@ int pick_epilogue(const bnn_gemm_desc& g, bool i8, cudaStream_t stream) {
             case BNN_EPI_STORE_S16: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S16>(g, stream);
             case BNN_EPI_STORE_S32: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S32>(g, stream);
             case BNN_EPI_STORE_F32: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_F32>(g, stream);
+            case BNN_EPI_SIGN_I8: return launch_tc<true, BLOCK_N, BNN_EPI_SIGN_I8>(g, stream);
             default: return launch_tc<true, BLOCK_N, BNN_EPI_SGD_F32>(g, stream);
         }
     }
-    return g.epilogue == BNN_EPI_SGD_F32 ? launch_tc<false, BLOCK_N, BNN_EPI_SGD_F32>(g, stream)
-                                          : launch_tc<false, BLOCK_N, BNN_EPI_STORE_F32>(g, stream);
+    switch (g.epilogue) {
+        case BNN_EPI_SGD_F32: return launch_tc<false, BLOCK_N, BNN_EPI_SGD_F32>(g, stream);
+        case BNN_EPI_SIGN_I8: return launch_tc<false, BLOCK_N, BNN_EPI_SIGN_I8>(g, stream);
+        default: return launch_tc<false, BLOCK_N, BNN_EPI_STORE_F32>(g, stream);
+    }
 }
 
 }  // namespace

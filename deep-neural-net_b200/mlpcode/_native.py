@@ -15,7 +15,7 @@ LIB_PATH = Path(os.environ.get("BNN_B200_LIB", _PKG.parent / "lib" / "libbnn_b20
 
 BNN_OK, BNN_ERR_ARG, BNN_ERR_CUDA, BNN_ERR_UNSUPPORTED = 0, -1, -2, -3
 DT_I8, DT_F16 = 0, 1
-EPI_STORE_F32, EPI_STORE_S32, EPI_STORE_S16, EPI_SGD_F32 = 0, 1, 2, 3
+EPI_STORE_F32, EPI_STORE_S32, EPI_STORE_S16, EPI_SGD_F32, EPI_SIGN_I8 = 0, 1, 2, 3, 4
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
 Z_F32, Z_S16, Z_S32 = 0, 1, 2
 GEMM_MAX_PASS = 4
@@ -43,6 +43,7 @@ class GemmDesc(C.Structure):
         ("D", C.c_void_p), ("ldd", C.c_int64), ("stride_d", C.c_int64),
         ("sa", C.c_void_p), ("sb", C.c_void_p),
         ("host_scale", C.c_float), ("reserved", C.c_int32),
+        ("epi_thr", C.c_void_p), ("epi_sgn", C.c_void_p),
     ]
 
 
@@ -65,6 +66,8 @@ PROTOTYPES = {
     "bnn_bn_stats_finalize": [_p, _i, _d, _p, _p, _p],
     "bnn_bn_apply": [_p, _i, _i, _i, _i64, _p, _p, _p, _p, _f, _p, _i64, _p, _i64, _p, _i64, _p,
                      _i64, _p],
+    "bnn_bn_sign_thresholds": [_p, _p, _p, _p, _f, _i, _p, _p, _p],
+    "bnn_bn_sign": [_p, _i, _i, _i, _i64, _p, _p, _p, _i64, _p, _i64, _p, _i64, _p],
     "bnn_softmax_xent": [_p, _i, _i, _i64, _p, _p, _p, _p, _d, _p, _p],
     "bnn_bn_bwd_reduce": [_p, _i64, _p, _i, _i64, _i, _i, _p, _p, _p, _i, _p],
     "bnn_bn_bwd_finalize": [_p, _p, _i, _d, _p, _p, _f, _p, _p, _p, _p, _f, _d, _p, _p, _p, _p, _p,

@@ -82,7 +82,8 @@ def split_f16(x: torch.Tensor, bound: torch.Tensor, hi=None, lo=None, hi_t=None,
 
 # ------------------------------------------------------------------------------- GEMMs
 def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),), sa=None,
-         sb=None, host_scale=1.0, batch=1, stride_a=0, stride_b=0, stride_d=0, impl=None) -> None:
+         sb=None, host_scale=1.0, batch=1, stride_a=0, stride_b=0, stride_d=0, impl=None,
+         epi_thr=None, epi_sgn=None) -> None:
     """D = epi(sum_p A[pa] @ B[pb]^T); A/B are sequences of 1..2 operand-piece tensors."""
     d = nat.GemmDesc()
     d.M, d.N, d.K, d.batch = M, N, K, batch
@@ -96,6 +97,7 @@ def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),
     d.D, d.ldd, d.stride_d = ptr(D), ldd, stride_d
     d.sa, d.sb = ptr(sa), ptr(sb)
     d.host_scale = host_scale
+    d.epi_thr, d.epi_sgn = ptr(epi_thr), ptr(epi_sgn)
     if gemm_events is None:
         _call("bnn_gemm", C.byref(d), gemm_impl() if impl is None else impl)
         return
@@ -130,6 +132,18 @@ def bn_apply(Z, B, N, mu, var, gamma, beta, eps, out_f32=None, act_i8=None, act_
     _call("bnn_bn_apply", ptr(Z), z_dtype_of(Z), B, N, _ld(Z), ptr(mu), ptr(var), ptr(gamma),
           ptr(beta), eps,
           ptr(out_f32), _ld(out_f32) if out_f32 is not None else 0,
+          ptr(act_i8), _ld(act_i8) if act_i8 is not None else 0,
+          ptr(act_t16), _ld(act_t16) if act_t16 is not None else 0,
+          ptr(act_bits), _ld(act_bits) if act_bits is not None else 0)
+
+
+def bn_sign_thresholds(mu, var, gamma, beta, eps, N, thr, sgn) -> None:
+    _call("bnn_bn_sign_thresholds", ptr(mu), ptr(var), ptr(gamma), ptr(beta), eps, N, ptr(thr),
+          ptr(sgn))
+
+
+def bn_sign(Z, B, N, thr, sgn, act_i8=None, act_t16=None, act_bits=None) -> None:
+    _call("bnn_bn_sign", ptr(Z), z_dtype_of(Z), B, N, _ld(Z), ptr(thr), ptr(sgn),
           ptr(act_i8), _ld(act_i8) if act_i8 is not None else 0,
           ptr(act_t16), _ld(act_t16) if act_t16 is not None else 0,
           ptr(act_bits), _ld(act_bits) if act_bits is not None else 0)

@@ -404,27 +404,50 @@ class BinaryLayer(LinearLayer):
                 else:
                     self._apply_foreign_callback(cb, wops)
 
+        sign_out = self.activation == af.sign
+        popc = binary_gemm_variant() == "popc"
+        # eval mode: running statistics are known before the GEMM, so batch-norm + sign collapse into
+        # per-column thresholds applied in the GEMM epilogue and Z never reaches HBM
+        fuse_sign = sign_out and not isTrain and not (popc and not real_input)
+        thr = ws.get("thr", (N,), torch.float32)
+        sgn = ws.get("sgn", (N,), torch.float32)
+        act_i8 = None
+        if sign_out:
+            act_i8 = ws.get(f"a_i8_{B}", (B, pad_to(N, 16)), torch.int8, zero=True)
+        if fuse_sign:
+            K_.bn_sign_thresholds(bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
+
         # ---- z = X . sign(W)
+        Z = None
         if real_input:
             xin = self._real_input_operands(Xt, isTrain)
-            Z = ws.get(f"z_f32_{B}", (B, pad_to(N, 4)), torch.float32)
+            if fuse_sign:
+                D, ldd, epi = act_i8, act_i8.stride(0), nat.EPI_SIGN_I8
+            else:
+                Z = ws.get(f"z_f32_{B}", (B, pad_to(N, 4)), torch.float32)
+                D, ldd, epi = Z, Z.stride(0), nat.EPI_STORE_F32
             K_.gemm(M=B, N=N, K=Kd, A=(xin["hi"], xin["lo"]), B=(wops["f16"],),
-                    lda=xin["hi"].stride(0), ldb=wops["f16"].stride(0), D=Z, ldd=Z.stride(0),
-                    in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32, passes=((0, 0), (1, 0)),
-                    sa=xin["scale"])
+                    lda=xin["hi"].stride(0), ldb=wops["f16"].stride(0), D=D, ldd=ldd,
+                    in_dtype=nat.DT_F16, epilogue=epi, passes=((0, 0), (1, 0)), sa=xin["scale"],
+                    epi_thr=thr, epi_sgn=sgn)
         else:
             xin = X
             s16 = Kd < 32768
-            Z = ws.get(f"z_int_{B}", (B, pad_to(N, 8)), torch.int16 if s16 else torch.int32)
-            if binary_gemm_variant() == "popc":
-                if X.bits is None:
-                    X.bits = ws.get(f"x_bits{B}", (B, pad_to(Kd, 32) // 32), torch.int32, zero=True)
-                    K_.pack_i8_rows(X.i8, Kd, X.bits)
-                K_.gemm_popc(X.bits, wops["bits"], B, N, Kd, Z, out_s16=s16)
-            else:
+            if fuse_sign:
                 K_.gemm(M=B, N=N, K=Kd, A=(X.i8,), B=(wops["i8"],), lda=X.i8.stride(0),
-                        ldb=wops["i8"].stride(0), D=Z, ldd=Z.stride(0), in_dtype=nat.DT_I8,
-                        epilogue=nat.EPI_STORE_S16 if s16 else nat.EPI_STORE_S32)
+                        ldb=wops["i8"].stride(0), D=act_i8, ldd=act_i8.stride(0), in_dtype=nat.DT_I8,
+                        epilogue=nat.EPI_SIGN_I8, epi_thr=thr, epi_sgn=sgn)
+            else:
+                Z = ws.get(f"z_int_{B}", (B, pad_to(N, 8)), torch.int16 if s16 else torch.int32)
+                if popc:
+                    if X.bits is None:
+                        X.bits = ws.get(f"x_bits{B}", (B, pad_to(Kd, 32) // 32), torch.int32, zero=True)
+                        K_.pack_i8_rows(X.i8, Kd, X.bits)
+                    K_.gemm_popc(X.bits, wops["bits"], B, N, Kd, Z, out_s16=s16)
+                else:
+                    K_.gemm(M=B, N=N, K=Kd, A=(X.i8,), B=(wops["i8"],), lda=X.i8.stride(0),
+                            ldb=wops["i8"].stride(0), D=Z, ldd=Z.stride(0), in_dtype=nat.DT_I8,
+                            epilogue=nat.EPI_STORE_S16 if s16 else nat.EPI_STORE_S32)
 
         # ---- batch-norm statistics
         if isTrain:
@@ -433,14 +456,16 @@ class BinaryLayer(LinearLayer):
             sums, mu, var = None, bn.mu.t, bn.sigma.t
 
         # ---- BN + activation
-        if self.activation == af.sign:
-            act_i8 = ws.get(f"a_i8_{B}", (B, pad_to(N, 16)), torch.int8, zero=True)
+        if sign_out:
             act_t16 = ws.get(f"a_t16_{B}", (N, pad_to(B, 8)), torch.float16, zero=True) if isTrain else None
-            act_bits = None
-            if binary_gemm_variant() == "popc":
-                act_bits = ws.get(f"a_bits{B}", (B, pad_to(N, 32) // 32), torch.int32, zero=True)
-            K_.bn_apply(Z, B, N, mu, var, bn.gamma.t, bn.beta.t, bn.EPSILON, act_i8=act_i8,
-                        act_t16=act_t16, act_bits=act_bits)
+            act_bits = ws.get(f"a_bits{B}", (B, pad_to(N, 32) // 32), torch.int32, zero=True) if popc else None
+            if not fuse_sign:
+                # sign(BN(z)) through the per-column thresholds: one compare per element, bit-identical
+                # to evaluating gamma*((z-mu)/sqrt(var+eps))+beta and taking the sign
+                K_.bn_sign_thresholds(mu, var, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
+                K_.bn_sign(Z, B, N, thr, sgn, act_i8=act_i8, act_t16=act_t16, act_bits=act_bits)
+            elif act_bits is not None:
+                K_.pack_i8_rows(act_i8, N, act_bits)
             out = SignActivation(act_i8, N, t16=act_t16, bits=act_bits)
         else:
             logits = empty((B, N))

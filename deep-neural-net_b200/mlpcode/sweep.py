@@ -55,21 +55,28 @@ class WeightFaultSweep:
         self.x_lo = zeros((self.R, Fp), torch.float16)
         K_.absmax_f32(X, self.x_amax)
         K_.split_f16(X, self.x_amax, hi=self.x_hi, lo=self.x_lo, scale_out=self.x_scale)
-        self.clean_bits, self.w, self.z, self.act = [], [], [], []
+        self.clean_bits, self.w, self.z, self.act, self.thr = [], [], [], [], []
         T, R = self.T, self.R
         for i, layer in enumerate(self.layers):
             Kd, N = layer.weights_shape
+            bn = layer.batchNormLayer
+            last = i == len(self.layers) - 1
             bits = zeros((N, pad_to(Kd, 32) // 32), torch.int32)
             K_.binarize_weights_t(layer.weights.t, wt_bits=bits)
             self.clean_bits.append(bits)
             if i == 0:
                 self.w.append(zeros((T, N, pad_to(Kd, 8)), torch.float16))
-                self.z.append(empty((T * R, pad_to(N, 4)), torch.float32))
             else:
                 self.w.append(zeros((T, N, pad_to(Kd, 16)), torch.int8))
-                zdt = torch.int16 if Kd < 32768 else torch.int32
+            if last:   # the output layer keeps its pre-activation: Z -> batch-norm -> scores
+                zdt = torch.float32 if i == 0 else (torch.int16 if Kd < 32768 else torch.int32)
                 self.z.append(empty((T * R, pad_to(N, 8)), zdt))
-            last = i == len(self.layers) - 1
+                self.thr.append(None)
+            else:      # hidden layers: running-statistic batch-norm + sign fused into the GEMM epilogue
+                self.z.append(None)
+                thr, sgn = zeros((N,), torch.float32), zeros((N,), torch.float32)
+                K_.bn_sign_thresholds(bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
+                self.thr.append((thr, sgn))
             self.act.append(empty((T * R, N)) if last else zeros((T * R, pad_to(N, 16)), torch.int8))
         self.correct = zeros((T,), torch.int32)
 
@@ -80,23 +87,26 @@ class WeightFaultSweep:
         for i, layer in enumerate(self.layers):
             Kd, N = layer.weights_shape
             bn = layer.batchNormLayer
-            w, Z = self.w[i], self.z[i]
+            w, Z, out = self.w[i], self.z[i], self.act[i]
+            last = i == len(self.layers) - 1
+            if last:
+                D, ldd, thr, sgn = Z, Z.stride(0), None, None
+                epi = (nat.EPI_STORE_F32 if i == 0 else
+                       (nat.EPI_STORE_S16 if Z.dtype == torch.int16 else nat.EPI_STORE_S32))
+            else:
+                D, ldd, epi = out, out.stride(0), nat.EPI_SIGN_I8
+                thr, sgn = self.thr[i]
             if i == 0:
                 K_.gemm(M=R, N=N, K=Kd, A=(self.x_hi, self.x_lo), B=(w,), lda=self.x_hi.stride(0),
-                        ldb=w.stride(1), D=Z, ldd=Z.stride(0), in_dtype=nat.DT_F16,
-                        epilogue=nat.EPI_STORE_F32, passes=((0, 0), (1, 0)), sa=self.x_scale,
-                        batch=T, stride_a=0, stride_b=w.stride(0), stride_d=R * Z.stride(0))
+                        ldb=w.stride(1), D=D, ldd=ldd, in_dtype=nat.DT_F16, epilogue=epi,
+                        passes=((0, 0), (1, 0)), sa=self.x_scale, batch=T, stride_a=0,
+                        stride_b=w.stride(0), stride_d=R * ldd, epi_thr=thr, epi_sgn=sgn)
             else:
                 a = self.act[i - 1]
-                epi = nat.EPI_STORE_S16 if Z.dtype == torch.int16 else nat.EPI_STORE_S32
-                K_.gemm(M=R, N=N, K=Kd, A=(a,), B=(w,), lda=a.stride(0), ldb=w.stride(1), D=Z,
-                        ldd=Z.stride(0), in_dtype=nat.DT_I8, epilogue=epi, batch=T,
-                        stride_a=R * a.stride(0), stride_b=w.stride(0), stride_d=R * Z.stride(0))
-            out = self.act[i]
-            if i < len(self.layers) - 1:
-                K_.bn_apply(Z, T * R, N, bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON,
-                            act_i8=out)
-            else:
+                K_.gemm(M=R, N=N, K=Kd, A=(a,), B=(w,), lda=a.stride(0), ldb=w.stride(1), D=D, ldd=ldd,
+                        in_dtype=nat.DT_I8, epilogue=epi, batch=T, stride_a=R * a.stride(0),
+                        stride_b=w.stride(0), stride_d=R * ldd, epi_thr=thr, epi_sgn=sgn)
+            if last:
                 # softmax is monotone per row: the argmax of the BN output decides the class
                 K_.bn_apply(Z, T * R, N, bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON,
                             out_f32=out)

@@ -110,7 +110,10 @@ enum {
     BNN_EPI_STORE_F32 = 0, /* D fp32  = acc * host_scale / (sa*sb)                       */
     BNN_EPI_STORE_S32 = 1, /* D int32 = acc                      (I8 only)               */
     BNN_EPI_STORE_S16 = 2, /* D int16 = acc                      (I8 only, |acc| < 2^15) */
-    BNN_EPI_SGD_F32 = 3    /* D fp32 -= acc * host_scale / (sa*sb)   (fused SGD update)  */
+    BNN_EPI_SGD_F32 = 3,   /* D fp32 -= acc * host_scale / (sa*sb)   (fused SGD update)  */
+    BNN_EPI_SIGN_I8 = 4    /* D int8 = +1 if acc*host_scale/(sa*sb) * epi_sgn[n] >= epi_thr[n] else -1:
+                              batch-norm + sign fused into the GEMM (thresholds from
+                              bnn_bn_sign_thresholds); Z never reaches HBM (eval mode)           */
 };
 enum {
     BNN_GEMM_TCGEN05 = 0, /* TMA + tcgen05.mma + TMEM accumulators (product path)          */
@@ -136,6 +139,8 @@ typedef struct bnn_gemm_desc {
     const float* sb;
     float host_scale; /* 1 for plain stores, lr for BNN_EPI_SGD_F32 */
     int32_t reserved;
+    const float* epi_thr; /* BNN_EPI_SIGN_I8: per-column threshold and orientation (device, [N]) */
+    const float* epi_sgn;
 } bnn_gemm_desc;
 
 int bnn_gemm(const bnn_gemm_desc* desc_host, int impl, bnn_stream_t stream);
@@ -177,6 +182,18 @@ int bnn_bn_apply(const void* Z, int z_dtype, int B, int N, int64_t ldz, const fl
                  const float* var, const float* gamma, const float* beta, float eps,
                  float* out_f32, int64_t ld_f32, int8_t* act_i8, int64_t ld_i8, void* act_t16,
                  int64_t ld_t16, uint32_t* act_bits, int64_t ld_bits, bnn_stream_t stream);
+
+/* Per-column sign thresholds of the batch-norm + sign pair: out(z) is monotone in z, so
+ * sign(out(z)) = +1  <=>  z * sgn[n] >= thr[n]; thr is found by bisection over float bit patterns
+ * with exactly the operation sequence above, so decisions are bit-identical to bnn_bn_apply for
+ * |z| <= 2^40 (pre-activations of a K-input +-1 layer satisfy |z| <= K). */
+int bnn_bn_sign_thresholds(const float* mu, const float* var, const float* gamma, const float* beta,
+                           float eps, int N, float* thr, float* sgn, bnn_stream_t stream);
+
+/* The sign-only form of bnn_bn_apply on those thresholds (same outputs, no out_f32). */
+int bnn_bn_sign(const void* Z, int z_dtype, int B, int N, int64_t ldz, const float* thr,
+                const float* sgn, int8_t* act_i8, int64_t ld_i8, void* act_t16, int64_t ld_t16,
+                uint32_t* act_bits, int64_t ld_bits, bnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * A6/A10  output activation, loss and its gradient   (softmax activation.py:44-53;

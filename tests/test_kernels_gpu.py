@@ -341,6 +341,49 @@ def test_colstats_and_bn_apply(T, oracle, B, N, zdt):
     assert np.array_equal(i8.cpu().numpy()[:, :N], sgn.astype(np.int8))
     assert np.array_equal(t16.cpu().numpy()[:, :B].astype(np.float32), sgn.T)
     assert np.array_equal(bits.cpu().numpy().view(np.uint32), oracle.pack_sign_rows(ref))
+    # the threshold form of batch-norm + sign (one compare per element) decides identically, also
+    # for gamma < 0 (column 0), gamma == 0 and a beta that pins the sign
+    for variant in range(2):
+        gam = gamma.copy()
+        if variant == 1 and N > 2:
+            gam[1], beta[1] = 0.0, -0.25
+            gam[2], beta[2] = 0.0, 0.0
+        ref_v = oracle.bn_forward_eval(Z.copy(), gam, beta, mu_h, var_h)
+        thr, sg = (T.zeros(N, dtype=T.float32, device="cuda") for _ in range(2))
+        K.bn_sign_thresholds(mu, var, dev(gam), dev(beta), 1e-4, N, thr, sg)
+        i8b, t16b, bitsb = T.zeros_like(i8), T.zeros_like(t16), T.zeros_like(bits)
+        K.bn_sign(Zd, B, N, thr, sg, act_i8=i8b, act_t16=t16b, act_bits=bitsb)
+        want = oracle.unitstep(ref_v)
+        assert np.array_equal(i8b.cpu().numpy()[:, :N], want.astype(np.int8))
+        assert np.array_equal(t16b.cpu().numpy()[:, :B].astype(np.float32), want.T)
+        assert np.array_equal(bitsb.cpu().numpy().view(np.uint32), oracle.pack_sign_rows(ref_v))
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+@pytest.mark.parametrize("M,N,K_", [(128, 256, 128), (300, 130, 784), (64, 40, 4096), (1000, 520, 256)])
+def test_gemm_fused_bn_sign_epilogue(T, oracle, impl, M, N, K_):
+    """BNN_EPI_SIGN_I8: the +-1 GEMM writing sign(BN(z)) directly equals GEMM -> Z -> BN -> sign."""
+    from mlpcode import _native as nat, kernels as K
+    rng = np.random.default_rng(M + N + K_)
+    a, b = pm1(rng, (M, K_)), pm1(rng, (N, K_))
+    z = (a.astype(np.int32) @ b.astype(np.int32).T).astype(np.float32)
+    mu = (rng.standard_normal(N) * 3).astype(np.float32)
+    var = (rng.random(N) * K_ + 1).astype(np.float32)
+    gamma = (rng.random(N) + 0.5).astype(np.float32)
+    gamma[::7] *= -1
+    beta = (rng.standard_normal(N) * 0.3).astype(np.float32)
+    want = oracle.unitstep(oracle.bn_forward_eval(z.copy(), gamma, beta, mu, var)).astype(np.int8)
+    thr, sg = (T.zeros(N, dtype=T.float32, device="cuda") for _ in range(2))
+    K.bn_sign_thresholds(dev(mu), dev(var), dev(gamma), dev(beta), 1e-4, N, thr, sg)
+    A, Bm = padded(a, 16), padded(b, 16)
+    Np = (N + 15) // 16 * 16
+    out = T.full((M, Np), 7, dtype=T.int8, device="cuda")
+    K.gemm(M=M, N=N, K=K_, A=(A,), B=(Bm,), lda=A.stride(0), ldb=Bm.stride(0), D=out, ldd=Np,
+           in_dtype=nat.DT_I8, epilogue=nat.EPI_SIGN_I8, epi_thr=thr, epi_sgn=sg,
+           impl=nat.GEMM_TCGEN05 if impl == "tcgen05" else nat.GEMM_SIMT)
+    got = out.cpu().numpy()
+    assert np.array_equal(got[:, :N], want)
+    assert np.all(got[:, N:] == 7)
 
 
 def test_softmax_xent(T, golden, oracle):

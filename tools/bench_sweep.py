@@ -1,0 +1,106 @@
+"""Fault-sweep and inference throughput (BASELINE configs[3] and [4]) on this rank's GPU(s).
+    python tools/bench_sweep.py [--trials 64] [--cpu-trials 1]
+    torchrun --nproc-per-node N tools/bench_sweep.py ...       # trials sharded over ranks, no comm
+Prints one JSON line on rank 0: weight-fault trials/s (Bernoulli p=0.1 and exact-k 1..1000 on the
+784-4096^3-10 BNN, 10 000 evaluation rows), inference samples/s (3072-8192-8192-10, batch 65536), and the
+NumPy oracle port of one reference trial timed on the host cores."""
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(REPO / "deep-neural-net_b200"), str(REPO / "oracle")]
+
+
+def build(units, seed=0):
+    import bnn_oracle as O
+    from mlpcode.activation import ActivationFuncs as af
+    from mlpcode.network import Network
+    params = O.new_params(units, np.random.default_rng(seed))
+    nn = Network(units, useGpu=True, binarized=True, useBatchNorm=True)
+    nn.compile(lr=0.01, hiddenAf=af.sign, outAf=af.softmax)
+    nn.load_weights(params["W"])
+    return nn, params
+
+
+def main():
+    import torch
+    from mlpcode import parallel
+    from mlpcode.sweep import WeightFaultSweep
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--trials", type=int, default=64)
+    ap.add_argument("--cpu-trials", type=int, default=1)
+    ap.add_argument("--per-launch", type=int, default=8)
+    args = ap.parse_args()
+    comm = parallel.init_from_env("nccl")
+    rank = comm.rank if comm else 0
+    world = comm.world if comm else 1
+
+    def sync():
+        torch.cuda.synchronize()
+        if comm:
+            comm.barrier()
+            torch.cuda.synchronize()
+
+    out = {"n_gpus": world}
+    # ---- config 4: weight-fault sweep -----------------------------------------------------------
+    units = [784, 4096, 4096, 4096, 10]
+    nn, params = build(units)
+    rng = np.random.default_rng(1)
+    X = rng.random((10000, 784), dtype=np.float32) * 2 - 1
+    labels = rng.integers(0, 10, 10000).astype(np.uint8)
+    sweep = WeightFaultSweep(nn, X, labels, trials_per_launch=args.per_launch)
+    out["clean_accuracy"] = sweep.clean_accuracy()
+    n_trials = args.trials * world
+    for name, fn in (("bernoulli_p0.1", lambda: sweep.run_bernoulli(0.1, n_trials, 7, comm)),
+                     ("exactk_1..1000", lambda: sweep.run_exactk(lambda t: 1 + (t % 1000), n_trials, 7, comm))):
+        fn()                                                  # warm-up (allocations, first launches)
+        sync()
+        t0 = time.perf_counter()
+        acc = fn()
+        sync()
+        dt = time.perf_counter() - t0
+        out[name] = {"trials": n_trials, "seconds": dt, "trials_per_s": n_trials / dt,
+                     "mean_accuracy": float(np.mean(acc)),
+                     "flop_equiv_per_trial": 2.0 * 10000 * sum(a * b for a, b in zip(units[:-1], units[1:]))}
+    # ---- config 5: large-batch inference --------------------------------------------------------
+    del sweep, nn
+    torch.cuda.empty_cache()
+    units5 = [3072, 8192, 8192, 10]
+    nn5, _ = build(units5, seed=2)
+    B5 = 65536
+    X5 = torch.rand((B5, 3072), device="cuda") * 2 - 1
+    for _ in range(2):
+        nn5.predict(X5)
+    sync()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        nn5.predict(X5)
+    sync()
+    dt = time.perf_counter() - t0
+    out["inference_3072-8192-8192-10"] = {"batch_per_gpu": B5, "samples_per_s": world * B5 * reps / dt,
+                                          "ms_per_batch": 1e3 * dt / reps}
+    # ---- CPU baseline: the oracle port of one reference trial (callbacks.py:79-83 + get_accuracy) --
+    if rank == 0 and args.cpu_trials > 0:
+        import bnn_oracle as O
+        t0 = time.perf_counter()
+        for t in range(args.cpu_trials):
+            np.random.seed(t)
+            hooks = [(lambda W: O.flip_bnn_mask(W, np.random.uniform(size=W.shape) < 0.1))] * 4
+            O.accuracy(params, X.copy(), labels, weight_hooks=hooks)
+        dt = (time.perf_counter() - t0) / args.cpu_trials
+        out["cpu_reference_port"] = {"seconds_per_trial": dt, "trials_per_s": 1.0 / dt,
+                                     "sample": f"{args.cpu_trials} Bernoulli(0.1) trial(s), 10 000 rows"}
+    if rank == 0:
+        print(json.dumps(out))
+    if comm:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
