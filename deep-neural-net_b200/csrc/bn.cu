@@ -99,6 +99,43 @@ __device__ __forceinline__ void load8_z(const void* __restrict__ Z, long long of
     }
 }
 
+// Two-step form of load8_z for kernels that keep several rows in flight: the raw 16 / 32 bytes stay
+// packed in registers until they are needed (vector path only; valid == 8).
+struct Raw8 {
+    uint4 a, b;
+};
+template <int ZT>
+__device__ __forceinline__ Raw8 load8_raw(const void* __restrict__ Z, long long off) {
+    using T = typename ZLoad<ZT>::T;
+    const T* p = reinterpret_cast<const T*>(Z) + off;
+    Raw8 r;
+    r.a = __ldg(reinterpret_cast<const uint4*>(p));
+    r.b = (ZT == BNN_Z_S16) ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    return r;
+}
+template <int ZT>
+__device__ __forceinline__ void cvt8_raw(const Raw8& r, float (&z)[8]) {
+    if (ZT == BNN_Z_S16) {
+        const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            z[2 * j] = int_to_float_exact((int)(short)(w[j] & 0xffffu));
+            z[2 * j + 1] = int_to_float_exact((int)w[j] >> 16);
+        }
+    } else {
+        const uint32_t w[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (ZT == BNN_Z_F32) {
+                z[j] = __uint_as_float(w[j]);
+            } else {
+                const int v = (int)w[j];
+                z[j] = (v > -4194304 && v < 4194304) ? int_to_float_exact(v) : (float)v;
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void load8_f32(const float* __restrict__ p, int valid, bool vec,
                                           float (&x)[8]) {
     if (vec && valid == 8) {
@@ -654,9 +691,10 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ red,
         const double resid = sums ? (sums[n] / count - (double)mu[n]) : 0.0;
         const double dMu = -g * sinv * S1 + dVar * (-2.0 * resid);
         const double c0 = g * sinv, c1 = 2.0 * dVar / count, c2 = dMu / count;
+        // delta' = c0*delta + c1*(Z - mu) + c2 is applied as c0*delta + c1*Z + (c2 - c1*mu)
         coef[n] = (float)c0;
         coef[N + n] = (float)c1;
-        coef[2 * N + n] = (float)c2;
+        coef[2 * N + n] = (float)(c2 - c1 * (double)mu[n]);
         const float dGamma = (float)(S2 * sinv);  // sum(delta * znorm)
         const float dBeta = (float)S1;
         if (dgamma_out) dgamma_out[n] = dGamma;
@@ -727,7 +765,7 @@ __device__ __forceinline__ void store_transposed_pieces(const __half* sh, const 
 }
 
 template <int ZT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const float* __restrict__ delta, long long ldd, const void* __restrict__ Z,
                     long long ldz, int B, int N, const float* __restrict__ mu,
                     const float* __restrict__ coef, const float* __restrict__ bound,
@@ -746,66 +784,77 @@ bn_bwd_apply_kernel(const float* __restrict__ delta, long long ldd, const void* 
     const bool dvec = aligned16(delta) && (ldd % 4 == 0);
     const bool fvec = out_f32 && aligned16(out_f32) && (ld_f32 % 4 == 0);
     const bool rvec = d_hi && aligned16(d_hi) && aligned16(d_lo) && (ld_rm % 8 == 0);
-    float m[8], k0[8], k1[8], k2[8];
+    float k0[8], k1[8], k2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const bool ok = j < valid;
-        m[j] = ok ? __ldg(mu + c0 + j) : 0.f;
         k0[j] = ok ? __ldg(coef + c0 + j) : 0.f;
         k1[j] = ok ? __ldg(coef + N + c0 + j) : 0.f;
         k2[j] = ok ? __ldg(coef + 2 * N + c0 + j) : 0.f;
     }
-    // issue every row's loads first (4 x 48 bytes in flight per thread), then compute and store
-    float zall[AP_ROWS / 16][8], dall[AP_ROWS / 16][8];
+    // two rows at a time: 2 x 48 bytes of loads in flight per thread at 3 blocks per SM; Z stays
+    // packed (4 registers per row) until it is used
+    const bool fast = zvec && dvec && valid == 8;
 #pragma unroll
-    for (int i = 0; i < AP_ROWS / 16; ++i) {
-        const int gb = b0 + ty + 16 * i;
-        if (gb < B && valid > 0) {
-            load8_f32(delta + (long long)gb * ldd + c0, valid, dvec, dall[i]);
-            load8_z<ZT>(Z, (long long)gb * ldz + c0, valid, zvec, zall[i]);
-        }
-    }
+    for (int i0 = 0; i0 < AP_ROWS / 16; i0 += 2) {
+        Raw8 zraw[2];
+        float dall[2][8];
 #pragma unroll
-    for (int i = 0; i < AP_ROWS / 16; ++i) {
-        const int r = ty + 16 * i;
-        const int gb = b0 + r;
-        __half h[8], l[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) h[j] = l[j] = __ushort_as_half(0);
-        if (gb < B && valid > 0) {
-            float nd[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                nd[j] = fmaf(k0[j], dall[i][j], fmaf(k1[j], zall[i][j] - m[j], k2[j]));
-                split_f16(nd[j] * s, h[j], l[j]);
-            }
-            if (out_f32) {
-                float* p = out_f32 + (long long)gb * ld_f32 + c0;
-                if (fvec && valid == 8) {
-                    reinterpret_cast<float4*>(p)[0] = make_float4(nd[0], nd[1], nd[2], nd[3]);
-                    reinterpret_cast<float4*>(p)[1] = make_float4(nd[4], nd[5], nd[6], nd[7]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < valid) p[j] = nd[j];
-                }
-            }
-            if (d_hi) {
-                __half* ph = d_hi + (long long)gb * ld_rm + c0;
-                __half* pl = d_lo + (long long)gb * ld_rm + c0;
-                if (rvec && valid == 8) {
-                    *reinterpret_cast<uint4*>(ph) = pack8_half(h);
-                    *reinterpret_cast<uint4*>(pl) = pack8_half(l);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < valid) { ph[j] = h[j]; pl[j] = l[j]; }
-                }
+        for (int u = 0; u < 2; ++u) {
+            const int gb = b0 + ty + 16 * (i0 + u);
+            if (fast && gb < B) {
+                load8_f32(delta + (long long)gb * ldd + c0, 8, true, dall[u]);
+                zraw[u] = load8_raw<ZT>(Z, (long long)gb * ldz + c0);
             }
         }
-        if (dt_hi) {
-            *reinterpret_cast<uint4*>(&sh[piece_index(r, tx * 8)]) = pack8_half(h);
-            *reinterpret_cast<uint4*>(&sl[piece_index(r, tx * 8)]) = pack8_half(l);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int r = ty + 16 * (i0 + u);
+            const int gb = b0 + r;
+            __half h[8], l[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = l[j] = __ushort_as_half(0);
+            if (gb < B && valid > 0) {
+                float nd[8], z[8];
+                if (fast) {
+                    cvt8_raw<ZT>(zraw[u], z);
+                } else {  // ragged edge / unaligned pitch
+                    load8_f32(delta + (long long)gb * ldd + c0, valid, false, dall[u]);
+                    load8_z<ZT>(Z, (long long)gb * ldz + c0, valid, false, z);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    nd[j] = fmaf(k0[j], dall[u][j], fmaf(k1[j], z[j], k2[j]));
+                    split_f16(nd[j] * s, h[j], l[j]);
+                }
+                if (out_f32) {
+                    float* p = out_f32 + (long long)gb * ld_f32 + c0;
+                    if (fvec && valid == 8) {
+                        reinterpret_cast<float4*>(p)[0] = make_float4(nd[0], nd[1], nd[2], nd[3]);
+                        reinterpret_cast<float4*>(p)[1] = make_float4(nd[4], nd[5], nd[6], nd[7]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < valid) p[j] = nd[j];
+                    }
+                }
+                if (d_hi) {
+                    __half* ph = d_hi + (long long)gb * ld_rm + c0;
+                    __half* pl = d_lo + (long long)gb * ld_rm + c0;
+                    if (rvec && valid == 8) {
+                        *reinterpret_cast<uint4*>(ph) = pack8_half(h);
+                        *reinterpret_cast<uint4*>(pl) = pack8_half(l);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < valid) { ph[j] = h[j]; pl[j] = l[j]; }
+                    }
+                }
+            }
+            if (dt_hi) {
+                *reinterpret_cast<uint4*>(&sh[piece_index(r, tx * 8)]) = pack8_half(h);
+                *reinterpret_cast<uint4*>(&sl[piece_index(r, tx * 8)]) = pack8_half(l);
+            }
         }
     }
     if (!dt_hi) return;
@@ -814,10 +863,13 @@ bn_bwd_apply_kernel(const float* __restrict__ delta, long long ldd, const void* 
 }
 
 __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                                  long long n, float lr) {
+                                                  long long n, float lr, int parts, long long part_stride) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        p[i] = __fsub_rn(p[i], __fmul_rn(lr, __ldg(g + i)));
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float sum = __ldg(g + i);
+        for (int s = 1; s < parts; ++s) sum = __fadd_rn(sum, __ldg(g + s * part_stride + i));
+        p[i] = __fsub_rn(p[i], __fmul_rn(lr, sum));
+    }
 }
 
 // rows are grouped: row r belongs to group r / B and is compared with labels[r % B] (one group per
@@ -1022,12 +1074,14 @@ extern "C" int bnn_bn_bwd_apply(const float* delta, int64_t ldd, const void* Z, 
     });
 }
 
-extern "C" int bnn_sgd_update(float* p, const float* g, int64_t n, float lr, bnn_stream_t stream) {
-    BNN_CHECK_ARG(p && g && n >= 0, "bnn_sgd_update: bad input");
+extern "C" int bnn_sgd_update(float* p, const float* g, int64_t n, float lr, int parts,
+                              int64_t part_stride, bnn_stream_t stream) {
+    BNN_CHECK_ARG(p && g && n >= 0 && parts >= 1, "bnn_sgd_update: bad input");
+    BNN_CHECK_ARG(parts == 1 || part_stride >= n, "bnn_sgd_update: part_stride < n");
     if (n == 0) return BNN_OK;
     const long long blocks = (n + 255) / 256;
     const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
-    sgd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, n, lr);
+    sgd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, n, lr, parts, part_stride);
     BNN_LAUNCH_CHECK("sgd_kernel");
     return BNN_OK;
 }

@@ -176,9 +176,10 @@ def bn_bwd_apply(delta, Z, B, N, mu, coef, bound, out_f32=None, d_hi=None, d_lo=
           ptr(dt_hi), ptr(dt_lo), _ld(dt_hi) if dt_hi is not None else 0, ptr(scale_out))
 
 
-def sgd_update(p, g, lr) -> None:
-    assert p.is_contiguous() and g.is_contiguous() and p.numel() == g.numel()
-    _call("bnn_sgd_update", ptr(p), ptr(g), p.numel(), lr)
+def sgd_update(p, g, lr, parts=1) -> None:
+    """p -= lr * sum over the `parts` leading slices of g (g: [parts, *p.shape] or p.shape)."""
+    assert p.is_contiguous() and g.is_contiguous() and p.numel() * parts == g.numel()
+    _call("bnn_sgd_update", ptr(p), ptr(g), p.numel(), lr, parts, p.numel())
 
 
 def count_correct(scores, B, Cc, labels_i32, correct_i32, groups=1) -> None:

@@ -528,7 +528,18 @@ class BinaryLayer(LinearLayer):
         else:
             A, passes, sa = (xin.t16,), ((0, 0), (0, 1)), None
         Wt = self.weights.t
-        if self.comm.world == 1:
+        split = 4 if (N <= 32 and Kd >= 1024 and B % 256 == 0 and self.comm.world == 1) else 1
+        if split > 1:
+            # narrow layer (the 10-unit output): a 128 x 32 tile grid has only Kd/128 CTAs, so the
+            # contraction over the batch is cut into `split` slices run as GEMM batches (operand
+            # slices are column ranges: batch stride = slice length), summed by the update kernel
+            Ks = B // split
+            parts = ws.get("dW_parts", (split, Kd, N), torch.float32)
+            K_.gemm(M=Kd, N=N, K=Ks, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=parts, ldd=N,
+                    in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32, passes=passes, sa=sa, sb=d_scale,
+                    batch=split, stride_a=Ks, stride_b=Ks, stride_d=Kd * N)
+            K_.sgd_update(Wt, parts, lr, parts=split)
+        elif self.comm.world == 1:
             K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=Wt, ldd=N,
                     in_dtype=nat.DT_F16, epilogue=nat.EPI_SGD_F32, passes=passes, sa=sa, sb=d_scale,
                     host_scale=lr)

@@ -242,9 +242,10 @@ int bnn_bn_bwd_apply(const float* delta, int64_t ldd, const void* Z, int z_dtype
                      int64_t ld_rm, void* dt_hi, void* dt_lo, int64_t ld_t, float* scale_out,
                      bnn_stream_t stream);
 
-/* p[i] -= lr * g[i]     (weights -= lr*dw, layers.py:268, for the data-parallel path where dW is
- * all-reduced before the update). */
-int bnn_sgd_update(float* p, const float* g, int64_t n, float lr, bnn_stream_t stream);
+/* p[i] -= lr * sum_s g[s*part_stride + i]     (weights -= lr*dw, layers.py:268): the data-parallel path
+ * (dW all-reduced before the update, parts = 1) and split-K dW products of narrow layers (parts > 1). */
+int bnn_sgd_update(float* p, const float* g, int64_t n, float lr, int parts, int64_t part_stride,
+                   bnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * A11  weight fault injection                          (ErrorCallback._flipBNNMask

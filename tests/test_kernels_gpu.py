@@ -462,6 +462,10 @@ def test_sgd_and_count_correct(T):
     pd = dev(p).clone()
     K.sgd_update(pd, dev(g), np.float32(0.01))
     assert np.array_equal(pd.cpu().numpy(), p - np.float32(0.01) * g)     # weights -= lr*dw, exact
+    g3 = rng.standard_normal((3, 10007)).astype(np.float32)               # split-K partial sums
+    pd = dev(p).clone()
+    K.sgd_update(pd, dev(g3), np.float32(0.01), parts=3)
+    assert np.array_equal(pd.cpu().numpy(), p - np.float32(0.01) * ((g3[0] + g3[1]) + g3[2]))
     scores = rng.standard_normal((1000, 10)).astype(np.float32)
     scores[5, 2] = scores[5, 7] = 99.0                                     # tie: first maximum wins
     labels = rng.integers(0, 10, 1000).astype(np.int32)

@@ -354,3 +354,25 @@ def test_data_parallel_two_gpus_equal_reference():
                          timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "dp_check ok" in out.stdout
+
+
+def test_narrow_output_layer_split_k_matches_oracle(oracle):
+    """A net whose 10-unit output layer takes the split-K dW route (K >= 1024, batch % 256 == 0)."""
+    units, B = [64, 1024, 10], 256
+    rng = np.random.default_rng(5)
+    params = oracle.new_params(units, rng)
+    X = rng.random((B, units[0]), dtype=np.float32) * 2 - 1
+    Y = np.eye(10, dtype=np.int8)[rng.integers(0, 10, B)]
+    nn = build_net(units, params)
+    ref = oracle.copy_params(params)
+    for _ in range(2):
+        cost = nn.train_step(X, Y, 0.01)
+        cost_ref = oracle.train_step(ref, X.copy(), Y, 0.01)
+        assert abs(cost - cost_ref) <= TOL * abs(cost_ref)
+    st = state_of(nn)
+    for i in range(2):
+        assert rel_err(st["W"][i], ref["W"][i]) < TOL
+        upd, upd_ref = st["W"][i] - params["W"][i], ref["W"][i] - params["W"][i]
+        assert rel_err(upd, upd_ref) < 2e-2, i
+        for k in ("gamma", "mu", "sigma"):
+            assert rel_err(st["bn"][i][k], ref["bn"][i][k]) < TOL, (i, k)
