@@ -127,6 +127,22 @@ def bn_stats_finalize(sums, N, count, mu, var) -> None:
     _call("bnn_bn_stats_finalize", ptr(sums), N, float(count), ptr(mu), ptr(var))
 
 
+def _peer_arrays(call):
+    n = call["world"]
+    return (C.c_uint64 * n)(*call["data"]), (C.c_uint64 * n)(*call["flags"])
+
+
+def bn_stats_finalize_p2p(call, N, count, mu, var, sums_total) -> None:
+    data, flags = _peer_arrays(call)
+    _call("bnn_bn_stats_finalize_p2p", data, flags, call["rank"], call["world"], call["epoch"], N,
+          float(count), ptr(mu), ptr(var), ptr(sums_total))
+
+
+def allreduce_f64_p2p(call, n, out) -> None:
+    data, flags = _peer_arrays(call)
+    _call("bnn_allreduce_f64_p2p", data, flags, call["rank"], call["world"], call["epoch"], n, ptr(out))
+
+
 def bn_apply(Z, B, N, mu, var, gamma, beta, eps, out_f32=None, act_i8=None, act_t16=None,
              act_bits=None) -> None:
     _call("bnn_bn_apply", ptr(Z), z_dtype_of(Z), B, N, _ld(Z), ptr(mu), ptr(var), ptr(gamma),

@@ -120,6 +120,8 @@ class _NoComm:
     def allreduce_sum_async(self, t):
         return None
 
+    peer_exchange = None
+
 
 class Layer:
     def __init__(self, layerUnits: int, gpu=False):
@@ -184,6 +186,14 @@ class BatchNormLayer(Layer):
         sums = self._ws.get("sums", (2, n), torch.float64)
         mu = self._ws.get("mu_b", (n,), torch.float32)
         var = self._ws.get("var_b", (n,), torch.float32)
+        px = self.comm.peer_exchange
+        if px is not None and n <= px.max_cols:
+            # sync-BN over NVLink peer memory: partial sums land in this rank's symmetric slot and the
+            # finalize kernel itself gathers every rank's slot (one launch, no NCCL call)
+            slot, call = px.begin(2 * n)
+            K_.colstats(Z, B, n, slot.view(2, n))
+            K_.bn_stats_finalize_p2p(call, n, self.comm.global_rows(B), mu, var, sums)
+            return sums, mu, var
         K_.colstats(Z, B, n, sums)
         self.comm.allreduce_sum(sums)  # sync-BN: exact (integer-valued fp64 sums) for +-1 layers
         K_.bn_stats_finalize(sums, n, self.comm.global_rows(B), mu, var)
@@ -195,8 +205,14 @@ class BatchNormLayer(Layer):
         red_max = self._ws.get("red_max", (2, n), torch.int32)
         coef = self._ws.get("coef", (3, n), torch.float32)
         bound = self._ws.get("bound", (1,), torch.float32)  # written as uint32 bits of a float
-        K_.bn_bwd_reduce(delta, Z, B, n, mu, red, red_max)
-        self.comm.allreduce_sum(red)
+        px = self.comm.peer_exchange
+        if px is not None and n <= px.max_cols:
+            slot, call = px.begin(2 * n)
+            K_.bn_bwd_reduce(delta, Z, B, n, mu, slot.view(2, n), red_max)
+            K_.allreduce_f64_p2p(call, 2 * n, red)
+        else:
+            K_.bn_bwd_reduce(delta, Z, B, n, mu, red, red_max)
+            self.comm.allreduce_sum(red)
         K_.bn_bwd_finalize(red, red_max, n, self.comm.global_rows(B), mu, var, self.EPSILON,
                            self.gamma.t, self.beta.t, self.mu.t, self.sigma.t, lr, self.MA_BETA,
                            sums, coef, bound)

@@ -127,6 +127,8 @@ class Network(object):
     def set_data_parallel(self, comm) -> None:
         """comm: object with `.world` and `.allreduce_sum(tensor)` (see mlpcode.parallel)."""
         self._comm = comm
+        if hasattr(comm, "enable_peer_exchange"):
+            comm.enable_peer_exchange(max(self.unitList[1:]))
         for layer in self._layers:
             layer.set_comm(comm)
 

@@ -19,6 +19,48 @@ import torch
 import torch.distributed as dist
 
 
+class PeerExchange:
+    """Symmetric buffer (torch symmetric memory: the same allocation mapped into every rank over
+    NVLink / NVSwitch) for the batch-norm exchanges that libbnn_b200 fuses into its finalize kernels
+    (bnn_bn_stats_finalize_p2p, bnn_allreduce_f64_p2p).  Layout, identical on every rank:
+        [0, 256)            flag pad  uint32[2][16]   (parity of the call counter, sending rank)
+        [256, ...)          two slots of `slot_doubles` fp64 each, selected by the same parity
+    PyTorch only allocates and exchanges the mappings; the kernels do the signalling and the sums."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, comm: "Comm", max_cols: int):
+        import torch.distributed._symmetric_memory as symm
+        self.comm = comm
+        self.slot_doubles = 2 * max_cols
+        self.max_cols = max_cols
+        nbytes = self.FLAG_BYTES + 2 * self.slot_doubles * 8
+        group = comm.group if comm.group is not None else dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group)
+        self.base = [int(p) for p in self.handle.buffer_ptrs]
+        assert len(self.base) == comm.world and self.base[comm.rank] == self.buf.data_ptr()
+        self.epoch = 0
+        torch.cuda.synchronize()
+        comm.barrier()  # every pad is zero before anyone signals
+
+    def begin(self, n_doubles: int):
+        """Advance the call counter; returns (this rank's slot as an fp64 tensor, call descriptor)."""
+        assert n_doubles <= self.slot_doubles
+        self.epoch += 1
+        off = self.FLAG_BYTES + (self.epoch & 1) * self.slot_doubles * 8
+        slot = self.buf[off: off + n_doubles * 8].view(torch.float64)
+        call = dict(data=[b + off for b in self.base], flags=list(self.base), rank=self.comm.rank,
+                    world=self.comm.world, epoch=self.epoch & 0xFFFFFFFF or 1)
+        self.comm.collectives += 1
+        return slot, call
+
+
 class Comm:
     """Sum all-reduce over a torch.distributed process group (any backend: nccl on GPUs, gloo in
     the CPU tests of the host-side logic)."""
@@ -30,6 +72,26 @@ class Comm:
         self.rank = dist.get_rank(group)
         self.collectives = 0
         self.global_batch = None  # rows of the current step over all ranks (None: local * world)
+        self.peer_exchange = None  # PeerExchange once enable_peer_exchange() succeeded
+
+    def enable_peer_exchange(self, max_cols: int) -> bool:
+        """Route the small batch-norm exchanges through NVLink peer memory instead of NCCL.  Returns
+        False (and keeps NCCL) where symmetric memory is unavailable; BNN_P2P=0 disables it."""
+        if self.world == 1 or os.environ.get("BNN_P2P", "1") == "0" or not torch.cuda.is_available():
+            return False
+        if dist.get_backend(self.group) != "nccl":
+            return False
+        try:
+            self.peer_exchange = PeerExchange(self, max_cols)
+        except Exception as exc:  # pragma: no cover - depends on the platform
+            print(f"[mlpcode.parallel] peer exchange unavailable, staying on NCCL: {exc}")
+            self.peer_exchange = None
+        # all ranks must agree, or the kernels would wait for peers that never signal
+        ok = torch.tensor([1 if self.peer_exchange is not None else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            self.peer_exchange = None
+        return self.peer_exchange is not None
 
     def global_rows(self, local_rows: int) -> int:
         """Batch-norm statistics and the loss gradient divide by the GLOBAL batch (layers.py:81-82,

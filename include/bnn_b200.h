@@ -248,6 +248,27 @@ int bnn_sgd_update(float* p, const float* g, int64_t n, float lr, int parts, int
                    bnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Data-parallel exchange fused into the finalize kernels (new in this build; the reference is
+ * single-process).  The producers (bnn_colstats / bnn_bn_bwd_reduce) write this rank's [2, N] fp64
+ * partial sums into its slot of a symmetric buffer; these kernels signal every peer, wait for every
+ * peer (bounded spin on a flag pad, st.release.sys / ld.acquire.sys), read all ranks' slots over
+ * NVLink peer mappings in rank order and finalize on the totals — one launch instead of an NCCL
+ * all-reduce plus a finalize.
+ *   peer_data_host[r]  (host array of `world` device addresses) rank r's slot for THIS call
+ *   peer_flags_host[r] rank r's flag pad, uint32[2][16], zero-initialised once
+ *   epoch              call counter (>= 1) advanced identically on every rank; slots and flags are
+ *                      double-buffered on its parity by the caller
+ * ------------------------------------------------------------------------------------------- */
+int bnn_bn_stats_finalize_p2p(const uint64_t* peer_data_host, const uint64_t* peer_flags_host, int rank,
+                              int world, uint32_t epoch, int N, double count, float* mu, float* var,
+                              double* sums_total, bnn_stream_t stream);
+
+/* The same exchange without the finalize arithmetic: out[i] = sum_r slot_r[i], i < n (used for the
+ * batch-norm backward reductions, whose finalize is bnn_bn_bwd_finalize). */
+int bnn_allreduce_f64_p2p(const uint64_t* peer_data_host, const uint64_t* peer_flags_host, int rank,
+                          int world, uint32_t epoch, int n, double* out, bnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * A11  weight fault injection                          (ErrorCallback._flipBNNMask
  *                                                       callbacks.py:79-83, dispatch :94-98)
  * Flips act on the K-major binarized copy WbT[N, K]; element (n, k) has linear index e = n*K + k.
