@@ -271,6 +271,70 @@ class Network(object):
 
     _Network__updateBatch = lambda self, batch, lr: self.train_step(batch[0], batch[1], lr)  # noqa: E731
 
+    def train_stream(self, batches, lr: float = None, global_batch: int = None) -> List[float]:
+        """Run one SGD step per (X, y) host batch and return the per-batch mean losses, pipelined:
+        the host->device copy of batch i+1 (from pinned memory, on a copy stream, into the other of two
+        device buffers) overlaps the kernels of batch i, and the loss of batch i is read back while
+        batch i+1 runs.  Every batch is still copied in and every loss still copied out; only the
+        serialisation of `train_step` (copy, compute, blocking read) is removed."""
+        compute = torch.cuda.current_stream()
+        st = getattr(self, "_stream_state", None)
+        if st is None:  # created once: stream, events, pinned loss words and device buffers are reused
+            st = dict(copier=torch.cuda.Stream(), ready=[torch.cuda.Event(), torch.cuda.Event()],
+                      freed=[torch.cuda.Event(), torch.cuda.Event()],
+                      loss_done=[torch.cuda.Event(), torch.cuda.Event()], dev=[None, None],
+                      loss_host=[torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)])
+            self._stream_state = st
+        copier, ready, freed, loss_done = st["copier"], st["ready"], st["freed"], st["loss_done"]
+        dev, loss_host = st["dev"], st["loss_host"]
+        for e in freed:
+            e.record(compute)
+        rows = [0, 0]
+        losses: List[float] = []
+
+        def stage(slot, batch):
+            X, y = batch
+            X = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X))
+            y = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(y))
+            with torch.cuda.stream(copier):
+                copier.wait_event(freed[slot])  # the step that last read this buffer has finished
+                if dev[slot] is None or dev[slot][0].shape != X.shape or dev[slot][1].shape != y.shape:
+                    dev[slot] = (torch.empty(X.shape, dtype=torch.float32, device="cuda"),
+                                 torch.empty(y.shape, dtype=torch.int8, device="cuda"))
+                dev[slot][0].copy_(X, non_blocking=True)
+                dev[slot][1].copy_(y, non_blocking=True)
+                ready[slot].record(copier)
+
+        it = iter(batches)
+        try:
+            stage(0, next(it))
+        except StopIteration:
+            return losses
+        i = 0
+        more = True
+        while more:
+            slot = i & 1
+            try:
+                stage(slot ^ 1, next(it))  # queued before this step's kernels so the two overlap
+            except StopIteration:
+                more = False
+            compute.wait_event(ready[slot])
+            Xd, Yd = dev[slot]
+            cost = self.train_step_async(Xd, Yd, lr, global_batch)
+            freed[slot].record(compute)
+            loss_host[slot].copy_(cost._sum, non_blocking=True)
+            loss_done[slot].record(compute)
+            rows[slot] = Xd.shape[0]
+            if i > 0:  # read the previous step's loss while this one runs
+                prev = slot ^ 1
+                loss_done[prev].synchronize()
+                losses.append(float(loss_host[prev][0]) / rows[prev])
+            i += 1
+        last = (i - 1) & 1
+        loss_done[last].synchronize()
+        losses.append(float(loss_host[last][0]) / rows[last])
+        return losses
+
     # ------------------------------------------------------------------ inference
     def predict(self, X, isTraining=False):
         a = X

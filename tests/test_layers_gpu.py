@@ -376,3 +376,39 @@ def test_narrow_output_layer_split_k_matches_oracle(oracle):
         assert rel_err(upd, upd_ref) < 2e-2, i
         for k in ("gamma", "mu", "sigma"):
             assert rel_err(st["bn"][i][k], ref["bn"][i][k]) < TOL, (i, k)
+
+
+def test_train_stream_equals_stepwise_training(golden):
+    """The pipelined host-batch API (copies overlapped with compute) gives the reference's losses and state."""
+    g = golden("train_tiny")
+    units = [int(u) for u in g["units"]]
+    n = len(units) - 1
+    nn = build_net(units, params_from_golden(g, "init_", n), lr=float(g["lr"]))
+    steps = g["X"].shape[0]
+    losses = nn.train_stream([(g["X"][s], g["Y"][s]) for s in range(steps)], float(g["lr"]))
+    assert len(losses) == steps
+    for s in range(steps):
+        assert abs(losses[s] - g["costs"][s]) <= TOL * abs(g["costs"][s])
+    st = state_of(nn)
+    for i in range(n):
+        assert rel_err(st["W"][i], g[f"after{steps - 1}_W{i}"]) < TOL
+        for k in ("gamma", "beta", "mu", "sigma"):
+            assert rel_err(st["bn"][i][k], g[f"after{steps - 1}_{k}{i}"]) < TOL
+    assert nn.train_stream([], 0.01) == []
+
+
+def test_int32_preactivations_for_very_wide_layers(oracle):
+    """K >= 32768 inputs: z no longer fits int16, the layer switches to int32 Z."""
+    units, B = [64, 33000, 10], 64
+    rng = np.random.default_rng(9)
+    params = oracle.new_params(units, rng)
+    X = rng.random((B, units[0]), dtype=np.float32) * 2 - 1
+    nn = build_net(units, params)
+    got = nn.predict(X).get()
+    want = oracle.predict(params, X.copy())
+    assert rel_err(got, want) < TOL
+    Y = np.eye(10, dtype=np.int8)[rng.integers(0, 10, B)]
+    ref = oracle.copy_params(params)
+    cost, cost_ref = nn.train_step(X, Y, 0.01), oracle.train_step(ref, X.copy(), Y, 0.01)
+    assert abs(cost - cost_ref) <= TOL * abs(cost_ref)
+    assert rel_err(nn.weights[1].get(), ref["W"][1]) < TOL
