@@ -237,13 +237,18 @@ def run_gpu(args):
             comm.barrier()
             torch.cuda.synchronize()
 
-    def timed(step_fn, steps):
+    host_ms = {}
+
+    def timed(step_fn, steps, tag=None):
         fence()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0 = time.perf_counter()
         s.record()
         for _ in range(steps):
             step_fn()
         e.record()
+        if tag:  # host time to ENQUEUE the steps (before waiting for the device)
+            host_ms[tag] = 1e3 * (time.perf_counter() - h0) / steps
         fence()
         ms = torch.tensor([s.elapsed_time(e)], device="cuda", dtype=torch.float64)
         if comm:
@@ -260,7 +265,7 @@ def run_gpu(args):
     K.gemm_events = []
     launches0 = K.launch_count
     t0 = time.perf_counter()
-    ms_total = timed(lambda: nn.train_step_async(Xd, Yd, LR), args.steps)
+    ms_total = timed(lambda: nn.train_step_async(Xd, Yd, LR), args.steps, "device_resident")
     t1 = time.perf_counter()
     launches = K.launch_count - launches0
     events, K.gemm_events = K.gemm_events, None
@@ -347,6 +352,7 @@ def run_gpu(args):
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "binary_gemm": binary,
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": host_threads(), "kind": "port",
                          "sample": cpu_sample},
+        "host_enqueue_ms_per_step": host_ms.get("device_resident"),
         "collectives_per_step": (comm.collectives / (args.steps * 2 + max(args.warmup, 3) + 2))
         if comm else 0,
     }

@@ -77,8 +77,23 @@ extern "C" int bnn_gemm(const bnn_gemm_desc* g, int impl, bnn_stream_t stream) {
                   "bnn_gemm: empty shape M=%d N=%d K=%d batch=%d", g->M, g->N, g->K, g->batch);
     BNN_CHECK_ARG(g->in_dtype == BNN_DT_I8 || g->in_dtype == BNN_DT_F16, "bnn_gemm: bad in_dtype %d",
                   g->in_dtype);
-    BNN_CHECK_ARG(g->epilogue >= BNN_EPI_STORE_F32 && g->epilogue <= BNN_EPI_SIGN_I8,
+    BNN_CHECK_ARG(g->epilogue >= BNN_EPI_STORE_F32 && g->epilogue <= BNN_EPI_SCATTER_F32,
                   "bnn_gemm: bad epilogue %d", g->epilogue);
+    if (g->epilogue == BNN_EPI_SCATTER_F32) {
+        const bnn_peer_scatter* sc = g->scatter;
+        BNN_CHECK_ARG(sc != nullptr, "bnn_gemm: BNN_EPI_SCATTER_F32 needs desc.scatter");
+        BNN_CHECK_ARG(sc->world >= 1 && sc->world <= BNN_MAX_RANKS && sc->rank >= 0 &&
+                          sc->rank < sc->world,
+                      "bnn_gemm: scatter world %d / rank %d out of range", sc->world, sc->rank);
+        BNN_CHECK_ARG(sc->rows_per_owner > 0 && sc->rows_per_owner % 128 == 0 &&
+                          (int64_t)sc->rows_per_owner * sc->world >= g->M,
+                      "bnn_gemm: scatter rows_per_owner %d must be a multiple of 128 covering M=%d",
+                      sc->rows_per_owner, g->M);
+        for (int r = 0; r < sc->world; ++r)
+            BNN_CHECK_ARG(sc->stage[r] != 0, "bnn_gemm: scatter stage[%d] is null", r);
+        BNN_CHECK_ARG(g->batch == 1 && g->in_dtype == BNN_DT_F16 && impl == BNN_GEMM_TCGEN05,
+                      "bnn_gemm: BNN_EPI_SCATTER_F32 is a single fp16-split tcgen05 product");
+    }
     BNN_CHECK_ARG(g->epilogue != BNN_EPI_SIGN_I8 || (g->epi_thr && g->epi_sgn),
                   "bnn_gemm: BNN_EPI_SIGN_I8 needs epi_thr and epi_sgn");
     BNN_CHECK_ARG(g->epilogue != BNN_EPI_SIGN_I8 ||
@@ -91,7 +106,8 @@ extern "C" int bnn_gemm(const bnn_gemm_desc* g, int impl, bnn_stream_t stream) {
                   "bnn_gemm: K too large for an int16 result");
     BNN_CHECK_ARG(g->n_pass >= 1 && g->n_pass <= BNN_GEMM_MAX_PASS, "bnn_gemm: n_pass %d out of range",
                   g->n_pass);
-    BNN_CHECK_ARG(g->A[0] && g->B[0] && g->D, "bnn_gemm: null operand");
+    BNN_CHECK_ARG(g->A[0] && g->B[0] && (g->D || g->epilogue == BNN_EPI_SCATTER_F32),
+                  "bnn_gemm: null operand");
     for (int p = 0; p < g->n_pass; ++p) {
         BNN_CHECK_ARG(g->pa[p] >= 0 && g->pa[p] <= 1 && g->pb[p] >= 0 && g->pb[p] <= 1,
                       "bnn_gemm: pass %d refers to a piece outside {0,1}", p);

@@ -47,6 +47,11 @@ constexpr int kEpiWarps = 8;            // warp groups 1-2
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kRoleThreads + kEpiThreads;
 constexpr int kAccStages = 2;
+// fp32 results leave through a per-warp shared-memory transpose so that every store instruction
+// writes whole 128-byte row segments (the TMEM layout gives each lane one ROW, and row-per-lane
+// stores are 32 scattered 16-byte pieces: tolerable into local L2, crippling over NVLink).
+constexpr int kXposeRows = 16;    // half a warp's rows per phase
+constexpr int kXposeStride = 36;  // floats per staged row (32 + 4: conflict-free 128-bit access)
 
 template <int BLOCK_N>
 struct TileCfg {
@@ -56,7 +61,9 @@ struct TileCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = (kAccStages * BLOCK_N) < 32 ? 32 : (kAccStages * BLOCK_N);
     static constexpr int kBarBytes = (2 * kStages + 2 * kAccStages) * 8 + 16;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + align slack
+    static constexpr int kXposeBytes = kEpiWarps * kXposeRows * kXposeStride * 4;  // fp32 store staging
+    static constexpr int kSmemBytes =
+        kStages * kStageBytes + kBarBytes + 16 + kXposeBytes + 1024;  // + align slack
     static constexpr int kColsPerThread = BLOCK_N / 2;                 // per epilogue thread
     static constexpr int kGroup = kColsPerThread < 16 ? kColsPerThread : 16;  // columns per tcgen05.ld
     static constexpr int kGroups = kColsPerThread / kGroup;
@@ -80,6 +87,11 @@ struct TcParams {
     float host_scale;
     const float* thr;  // BNN_EPI_SIGN_I8
     const float* sgn;
+    // BNN_EPI_SCATTER_F32: row tiles go to the staging buffer of the rank that owns them
+    unsigned long long peer[BNN_MAX_RANKS];
+    int rows_per_owner;
+    int rank;
+    int m_rot;  // row-tile rotation: this rank starts with the tiles it owns itself
 };
 
 __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& b, int& m_blk,
@@ -95,6 +107,10 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& b,
     const int rr = r - g * group;
     m_blk = first_m + rr % gsz;
     n_blk = rr / gsz;
+    if (p.m_rot) {  // ranks of a data-parallel group walk the row tiles from different starting points
+        m_blk += p.m_rot;
+        if (m_blk >= p.m_tiles) m_blk -= p.m_tiles;
+    }
 }
 
 // Store / update one group of G consecutive columns of one output row from registers.
@@ -206,6 +222,58 @@ __device__ __forceinline__ void store_group(const TcParams& p, char* dbase, long
     }
 }
 
+// Coalesced fp32 store of one warp's 32 rows x CPT columns (registers: lane = row) through the warp's
+// transpose buffer.  Two phases of 16 rows; per phase and 32-column group the 16 source lanes write
+// their 8 float4, then all 32 lanes read 4 float4 each so that 8 adjacent lanes cover the 128 bytes
+// of one row segment.  EPI: STORE_F32 / SCATTER_F32 store, SGD_F32 subtracts from the destination.
+template <bool kI8, int EPI, int CPT>
+__device__ __forceinline__ void store_rows_coalesced(const TcParams& p, float* xbuf, float* dst_row0,
+                                                     int rows_valid, const uint32_t (&sum)[CPT],
+                                                     float scale, int lane) {
+    constexpr int GC = CPT < 32 ? CPT : 32;   // columns per group
+    constexpr int LPR = GC / 4;               // lanes per row segment
+    constexpr int RPI = 32 / LPR;             // rows per store instruction
+    constexpr bool sgd = EPI == BNN_EPI_SGD_F32;
+#pragma unroll
+    for (int g = 0; g < CPT / GC; ++g) {
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+            if ((lane >> 4) == ph) {
+                float* w = xbuf + (lane & 15) * kXposeStride;
+#pragma unroll
+                for (int j = 0; j < GC; j += 4) {
+                    float4 f;
+                    f.x = __fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 0] : __uint_as_float(sum[g * GC + j + 0]), scale);
+                    f.y = __fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 1] : __uint_as_float(sum[g * GC + j + 1]), scale);
+                    f.z = __fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 2] : __uint_as_float(sum[g * GC + j + 2]), scale);
+                    f.w = __fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 3] : __uint_as_float(sum[g * GC + j + 3]), scale);
+                    *reinterpret_cast<float4*>(w + j) = f;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < kXposeRows / RPI; ++i) {
+                const int r = lane / LPR + RPI * i;       // row within the phase
+                const int c = (lane % LPR) * 4;           // column within the group
+                const int row = ph * kXposeRows + r;      // row within the warp's 32
+                float4 f = *reinterpret_cast<const float4*>(xbuf + r * kXposeStride + c);
+                if (row < rows_valid) {
+                    float* d = dst_row0 + (long long)row * p.ldd + g * GC + c;
+                    if (sgd) {  // weights -= lr * dw (layers.py:268): two roundings, like NumPy
+                        const float4 wv = *reinterpret_cast<const float4*>(d);
+                        f.x = __fsub_rn(wv.x, f.x);
+                        f.y = __fsub_rn(wv.y, f.y);
+                        f.z = __fsub_rn(wv.z, f.z);
+                        f.w = __fsub_rn(wv.w, f.w);
+                    }
+                    *reinterpret_cast<float4*>(d) = f;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 template <bool kI8, int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -223,6 +291,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     uint64_t* tfull_bar = empty_bar + S;
     uint64_t* tempty_bar = tfull_bar + kAccStages;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
+    float* xpose = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + Cfg::kBarBytes + 16 -
+                                            ((S * Cfg::kStageBytes + Cfg::kBarBytes) & 15));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -381,9 +451,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
                 if (++acc == kAccStages) { acc = 0; acc_ph ^= 1u; }
             }
-            if (row < p.M) {
-                char* dbase = reinterpret_cast<char*>(p.D);
-                const long long rowoff = (long long)b * p.stride_d + (long long)row * p.ldd;
+            constexpr bool kF32Out = EPI == BNN_EPI_STORE_F32 || EPI == BNN_EPI_SGD_F32 ||
+                                     EPI == BNN_EPI_SCATTER_F32;
+            char* dbase = reinterpret_cast<char*>(p.D);
+            long long rowoff = (long long)b * p.stride_d + (long long)row * p.ldd;
+            if (EPI == BNN_EPI_SCATTER_F32) {
+                // reduce-scatter fused into the epilogue: this partial tile is stored straight
+                // into slice `rank` of the owner's staging buffer (peer memory over NVLink)
+                const int owner = (m_blk * kBlockM) / p.rows_per_owner;
+                dbase = reinterpret_cast<char*>(p.peer[owner]);
+                rowoff = ((long long)p.rank * p.rows_per_owner +
+                          (row - owner * p.rows_per_owner)) * p.ldd;
+            }
+            if (kF32Out && p.vec_ok && colbase + CPT <= p.N) {
+                // full-width tile: whole 128-byte row segments per store instruction
+                const int row_w0 = m_blk * kBlockM + q * 32;  // first row of this warp
+                float* dst = reinterpret_cast<float*>(dbase) + (rowoff - (long long)lane * p.ldd) + colbase;
+                store_rows_coalesced<kI8, EPI, CPT>(p, xpose + (warp - 4) * kXposeRows * kXposeStride,
+                                                    dst, p.M - row_w0, sum, scale, lane);
+            } else if (row < p.M) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     const int col0 = colbase + g * G;
@@ -504,6 +590,23 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     p.host_scale = g.host_scale;
     p.thr = g.epi_thr;
     p.sgn = g.epi_sgn;
+    p.rows_per_owner = 0;
+    p.rank = 0;
+    p.m_rot = 0;
+    for (int r = 0; r < BNN_MAX_RANKS; ++r) p.peer[r] = 0;
+    if (EPI == BNN_EPI_SCATTER_F32) {
+        const bnn_peer_scatter& sc = *g.scatter;
+        p.rows_per_owner = sc.rows_per_owner;
+        p.rank = sc.rank;
+        p.m_rot = (int)(((long long)sc.rank * (sc.rows_per_owner / kBlockM)) % p.m_tiles);
+        p.vec_ok = (g.ldd * 4) % 16 == 0;
+        for (int r = 0; r < sc.world; ++r) {
+            p.peer[r] = sc.stage[r];
+            p.vec_ok = p.vec_ok && (sc.stage[r] % 16 == 0);
+        }
+        p.D = nullptr;
+        p.stride_d = 0;
+    }
     const long long tiles = (long long)p.batch * p.m_tiles * p.n_tiles;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
     gemm_tc_kernel<kI8, BLOCK_N, EPI><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA[0], mA[1],
@@ -526,6 +629,7 @@ int pick_epilogue(const bnn_gemm_desc& g, bool i8, cudaStream_t stream) {
     switch (g.epilogue) {
         case BNN_EPI_SGD_F32: return launch_tc<false, BLOCK_N, BNN_EPI_SGD_F32>(g, stream);
         case BNN_EPI_SIGN_I8: return launch_tc<false, BLOCK_N, BNN_EPI_SIGN_I8>(g, stream);
+        case BNN_EPI_SCATTER_F32: return launch_tc<false, BLOCK_N, BNN_EPI_SCATTER_F32>(g, stream);
         default: return launch_tc<false, BLOCK_N, BNN_EPI_STORE_F32>(g, stream);
     }
 }

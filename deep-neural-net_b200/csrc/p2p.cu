@@ -99,10 +99,226 @@ allreduce_f64_p2p_kernel(const PeerTable t, int rank, int world, uint32_t epoch,
     out[n] = s;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Data-parallel dW: the all-gather half.  The dW GEMM (gemm_tc.cu, BNN_EPI_SCATTER_F32) has pushed
+// every rank's partial rows into the owner's staging buffer; the owner sums them in rank order,
+// applies W -= lr * dW (layers.py:268) and stores the new rows into every rank's W.
+// Flags are uint32[n_slots][kMaxRanks] of monotonically increasing epochs.
+// ---------------------------------------------------------------------------------------------
+struct FlagTable {
+    uint32_t* flags[kMaxRanks];
+};
+struct WTable {
+    float* w[kMaxRanks];
+};
+
+__device__ void spin_until(const uint32_t* f, uint32_t epoch, int rank, int peer, const char* what) {
+    unsigned long long t0 = 0;
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+        if ((++spins & 0xfffu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 10000000000ull) {
+                printf("bnn_b200: %s timed out (rank %d waiting for rank %d, epoch %u, saw %u)\n", what,
+                       rank, peer, epoch, ld_acquire_sys(f));
+                __trap();
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32)
+peer_signal_kernel(const FlagTable t, int slot, int rank, int world, uint32_t epoch) {
+    // every earlier kernel of this stream has completed, so its peer stores are performed; the fence
+    // orders them before the flag for observers on other GPUs
+    if (threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(t.flags[threadIdx.x] + slot * kMaxRanks + rank, epoch);
+    }
+}
+
+__global__ void __launch_bounds__(32)
+peer_wait_kernel(const uint32_t* __restrict__ flags_local, int slot, int rank, int world,
+                 uint32_t epoch) {
+    if (threadIdx.x < world)
+        spin_until(flags_local + slot * kMaxRanks + threadIdx.x, epoch, rank, threadIdx.x, "peer wait");
+}
+
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 v;
+    // L2-only load: the staging rows were written by peers while this kernel may already have been
+    // resident, so nothing may be served from a non-coherent path
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+template <int VEC>
+struct Pack;
+template <>
+struct Pack<4> {
+    float v[4];
+    __device__ static Pack load_stream(const float* p) {
+        const float4 f = ld_stream_f4(reinterpret_cast<const float4*>(p));
+        return Pack{{f.x, f.y, f.z, f.w}};
+    }
+    __device__ static Pack load(const float* p) {
+        const float4 f = *reinterpret_cast<const float4*>(p);
+        return Pack{{f.x, f.y, f.z, f.w}};
+    }
+    __device__ void store(float* p) const {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <>
+struct Pack<1> {
+    float v[1];
+    __device__ static Pack load_stream(const float* p) {
+        float f;
+        asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(f) : "l"(p));
+        return Pack{{f}};
+    }
+    __device__ static Pack load(const float* p) { return Pack{{*p}}; }
+    __device__ void store(float* p) const { *p = v[0]; }
+};
+
+template <int WORLD, int VEC>  // WORLD 0 = run-time world; VEC floats per thread and access
+__global__ void __launch_bounds__(256)
+dw_reduce_sgd_p2p_kernel(const float* __restrict__ stage, const WTable wt, const FlagTable ft,
+                         int slot_pushed, int slot_landed, int rank, int world_rt, uint32_t epoch,
+                         int rows, int N, int rows_per_owner, float lr, int broadcast,
+                         uint32_t* __restrict__ counter, uint32_t* __restrict__ epoch_word) {
+    const int world = WORLD ? WORLD : world_rt;
+    if (epoch_word && blockIdx.x == 0 && threadIdx.x == 0) *epoch_word = epoch;
+    // wait for every rank's partial rows of this epoch (bounded)
+    if (threadIdx.x < world)
+        spin_until(ft.flags[rank] + slot_pushed * kMaxRanks + threadIdx.x, epoch, rank, threadIdx.x,
+                   "dW reduce");
+    __syncthreads();
+    const long long first = (long long)rank * rows_per_owner * N;  // first owned element of W
+    const long long slice = (long long)rows_per_owner * N;  // one source rank's slice of the staging
+    const long long total = (long long)rows * N;
+    const long long stride = (long long)gridDim.x * blockDim.x * VEC;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < total; i += stride) {
+        Pack<VEC> acc = Pack<VEC>::load_stream(stage + i);
+#pragma unroll 4
+        for (int r = 1; r < world; ++r) {  // fixed rank order: the owner alone forms the sum
+            const Pack<VEC> v = Pack<VEC>::load_stream(stage + r * slice + i);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc.v[j] = __fadd_rn(acc.v[j], v.v[j]);
+        }
+        Pack<VEC> w = Pack<VEC>::load(wt.w[rank] + first + i);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) w.v[j] = __fsub_rn(w.v[j], __fmul_rn(lr, acc.v[j]));
+        if (broadcast) {
+#pragma unroll 4
+            for (int r = 0; r < world; ++r) {
+                int dst = rank + r;  // start with the local copy, then walk the peers
+                if (dst >= world) dst -= world;
+                w.store(wt.w[dst] + first + i);
+            }
+        } else {
+            w.store(wt.w[rank] + first + i);
+        }
+    }
+    if (!broadcast) return;
+    // the last block to finish publishes "my rows have landed" to every rank
+    __threadfence_system();
+    __syncthreads();
+    __shared__ uint32_t last;
+    if (threadIdx.x == 0) last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(ft.flags[threadIdx.x] + slot_landed * kMaxRanks + rank, epoch);
+    }
+}
+
 }  // namespace
 }  // namespace bnn
 
 using namespace bnn;
+
+static int fill_flags(FlagTable& t, const uint64_t* peer_flags_host, int world) {
+    BNN_CHECK_ARG(world >= 1 && world <= kMaxRanks, "p2p: world %d out of range (max %d)", world,
+                  kMaxRanks);
+    for (int r = 0; r < kMaxRanks; ++r)
+        t.flags[r] = r < world ? reinterpret_cast<uint32_t*>(peer_flags_host[r]) : nullptr;
+    return BNN_OK;
+}
+
+extern "C" int bnn_peer_signal(const uint64_t* peer_flags_host, int slot, int rank, int world,
+                               uint32_t epoch, bnn_stream_t stream) {
+    BNN_CHECK_ARG(peer_flags_host && slot >= 0 && rank >= 0 && rank < world && epoch > 0,
+                  "bnn_peer_signal: bad input");
+    FlagTable t;
+    int rc = fill_flags(t, peer_flags_host, world);
+    if (rc) return rc;
+    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(t, slot, rank, world, epoch);
+    BNN_LAUNCH_CHECK("peer_signal_kernel");
+    return BNN_OK;
+}
+
+extern "C" int bnn_peer_wait(const uint32_t* flags_local, int slot, int rank, int world, uint32_t epoch,
+                             bnn_stream_t stream) {
+    BNN_CHECK_ARG(flags_local && slot >= 0 && rank >= 0 && rank < world && world <= kMaxRanks &&
+                      epoch > 0,
+                  "bnn_peer_wait: bad input");
+    peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags_local, slot, rank, world, epoch);
+    BNN_LAUNCH_CHECK("peer_wait_kernel");
+    return BNN_OK;
+}
+
+extern "C" int bnn_dw_reduce_sgd_p2p(const float* stage_local, const uint64_t* peer_w_host,
+                                     const uint64_t* peer_flags_host, int slot_pushed, int slot_landed,
+                                     int rank, int world, uint32_t epoch, int K, int N,
+                                     int rows_per_owner, float lr, int broadcast, uint32_t* counter,
+                                     uint32_t* epoch_word, bnn_stream_t stream) {
+    BNN_CHECK_ARG(stage_local && peer_w_host && peer_flags_host && counter && K > 0 && N > 0 &&
+                      rank >= 0 && rank < world && epoch > 0 && slot_pushed >= 0 && slot_landed >= 0,
+                  "bnn_dw_reduce_sgd_p2p: bad input");
+    BNN_CHECK_ARG(rows_per_owner > 0 && (long long)rows_per_owner * world >= K,
+                  "bnn_dw_reduce_sgd_p2p: rows_per_owner %d does not cover K=%d", rows_per_owner, K);
+    FlagTable ft;
+    int rc = fill_flags(ft, peer_flags_host, world);
+    if (rc) return rc;
+    WTable wt;
+    bool vec = aligned16(stage_local) && ((long long)rows_per_owner * N) % 4 == 0;
+    for (int r = 0; r < kMaxRanks; ++r)
+        wt.w[r] = r < world ? reinterpret_cast<float*>(peer_w_host[r]) : nullptr;
+    for (int r = 0; r < world; ++r) {
+        BNN_CHECK_ARG(wt.w[r], "bnn_dw_reduce_sgd_p2p: W of rank %d is null", r);
+        vec = vec && aligned16(wt.w[r]);
+    }
+    // rows this rank owns (the last owners of a short matrix may own fewer, or none)
+    const long long first = (long long)rank * rows_per_owner;
+    const int rows = (int)(first >= K ? 0 : (K - first < rows_per_owner ? K - first : rows_per_owner));
+    vec = vec && ((long long)rows * N) % 4 == 0;
+    const long long items = ((long long)rows * N + (vec ? 3 : 0)) / (vec ? 4 : 1);
+    const long long want = (items + 255) / 256;
+    const int cap = sm_count() * 8;
+    const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    cudaStream_t s = (cudaStream_t)stream;
+#define BNN_DW_LAUNCH(W, V)                                                                          \
+    dw_reduce_sgd_p2p_kernel<W, V><<<grid, 256, 0, s>>>(stage_local, wt, ft, slot_pushed, slot_landed, \
+                                                        rank, world, epoch, rows, N, rows_per_owner,  \
+                                                        lr, broadcast, counter, epoch_word)
+    if (vec) {
+        switch (world) {
+            case 2: BNN_DW_LAUNCH(2, 4); break;
+            case 4: BNN_DW_LAUNCH(4, 4); break;
+            case 8: BNN_DW_LAUNCH(8, 4); break;
+            default: BNN_DW_LAUNCH(0, 4); break;
+        }
+    } else {
+        BNN_DW_LAUNCH(0, 1);
+    }
+#undef BNN_DW_LAUNCH
+    BNN_LAUNCH_CHECK("dw_reduce_sgd_p2p_kernel");
+    return BNN_OK;
+}
 
 static int fill_table(PeerTable& t, const uint64_t* peer_data_host, const uint64_t* peer_flags_host,
                       int world) {
@@ -143,5 +359,30 @@ extern "C" int bnn_allreduce_f64_p2p(const uint64_t* peer_data_host, const uint6
     allreduce_f64_p2p_kernel<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(t, rank, world, epoch, n,
                                                                             out);
     BNN_LAUNCH_CHECK("allreduce_f64_p2p_kernel");
+    return BNN_OK;
+}
+
+extern "C" int bnn_peer_broadcast_rows(const uint64_t* peer_w_host, const uint64_t* peer_flags_host,
+                                       int slot_landed, int rank, int world, int K, int N,
+                                       int rows_per_owner, const uint32_t* epoch_word,
+                                       bnn_stream_t stream) {
+    BNN_CHECK_ARG(peer_w_host && peer_flags_host && epoch_word && K > 0 && N > 0 && rank >= 0 &&
+                      rank < world && world <= kMaxRanks && slot_landed >= 0 && rows_per_owner > 0,
+                  "bnn_peer_broadcast_rows: bad input");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long first = (long long)rank * rows_per_owner;
+    const long long rows = first >= K ? 0 : (K - first < rows_per_owner ? K - first : rows_per_owner);
+    const size_t off = (size_t)first * N * sizeof(float), bytes = (size_t)rows * N * sizeof(float);
+    const char* src = reinterpret_cast<const char*>(peer_w_host[rank]) + off;
+    for (int i = 1; i < world && bytes > 0; ++i) {
+        const int p = (rank + i) % world;  // every rank starts with a different peer
+        BNN_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(peer_w_host[p]) + off, src, bytes,
+                                 cudaMemcpyDeviceToDevice, s));
+    }
+    for (int i = 0; i < world; ++i) {
+        const int p = (rank + i) % world;
+        uint32_t* flag = reinterpret_cast<uint32_t*>(peer_flags_host[p]) + slot_landed * kMaxRanks + rank;
+        BNN_CUDA(cudaMemcpyAsync(flag, epoch_word, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    }
     return BNN_OK;
 }

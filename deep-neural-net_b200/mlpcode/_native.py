@@ -15,7 +15,8 @@ LIB_PATH = Path(os.environ.get("BNN_B200_LIB", _PKG.parent / "lib" / "libbnn_b20
 
 BNN_OK, BNN_ERR_ARG, BNN_ERR_CUDA, BNN_ERR_UNSUPPORTED = 0, -1, -2, -3
 DT_I8, DT_F16 = 0, 1
-EPI_STORE_F32, EPI_STORE_S32, EPI_STORE_S16, EPI_SGD_F32, EPI_SIGN_I8 = 0, 1, 2, 3, 4
+EPI_STORE_F32, EPI_STORE_S32, EPI_STORE_S16, EPI_SGD_F32, EPI_SIGN_I8, EPI_SCATTER_F32 = 0, 1, 2, 3, 4, 5
+MAX_RANKS = 16
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
 Z_F32, Z_S16, Z_S32 = 0, 1, 2
 GEMM_MAX_PASS = 4
@@ -27,6 +28,13 @@ class BnnError(RuntimeError):
     def __init__(self, fn: str, code: int, text: str):
         super().__init__(f"{fn} failed ({code}): {text}")
         self.code = code
+
+
+class PeerScatter(C.Structure):
+    """Mirror of `struct bnn_peer_scatter`."""
+
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("rows_per_owner", C.c_int32),
+                ("reserved", C.c_int32), ("stage", C.c_uint64 * MAX_RANKS)]
 
 
 class GemmDesc(C.Structure):
@@ -44,6 +52,7 @@ class GemmDesc(C.Structure):
         ("sa", C.c_void_p), ("sb", C.c_void_p),
         ("host_scale", C.c_float), ("reserved", C.c_int32),
         ("epi_thr", C.c_void_p), ("epi_sgn", C.c_void_p),
+        ("scatter", C.POINTER(PeerScatter)),
     ]
 
 
@@ -77,6 +86,10 @@ PROTOTYPES = {
     "bnn_bn_stats_finalize_p2p": [_p, _p, _i, _i, _u32, _i, _d, _p, _p, _p, _p],
     "bnn_allreduce_f64_p2p": [_p, _p, _i, _i, _u32, _i, _p, _p],
     "bnn_sgd_update": [_p, _p, _i64, _f, _i, _i64, _p],
+    "bnn_peer_signal": [_p, _i, _i, _i, _u32, _p],
+    "bnn_peer_wait": [_p, _i, _i, _i, _u32, _p],
+    "bnn_dw_reduce_sgd_p2p": [_p, _p, _p, _i, _i, _i, _i, _u32, _i, _i, _i, _f, _i, _p, _p, _p],
+    "bnn_peer_broadcast_rows": [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p],
     "bnn_flip_weights_bernoulli": [_p, _i64, _p, _i64, _i, _i, _u64, _u64, _u32, _u32, _i, _p, _i64,
                                    _p, _i64, _i64, _p, _i64, _p, _i64, _p],
     "bnn_flip_weights_exactk": [_i, _i, _u64, _u64, _u64, _u32, _i, _p, _i, _p, _i64, _i64, _p, _i64,

@@ -18,7 +18,7 @@ launch_count = 0  # kernels launched through this module (bench.py reports it as
 gemm_events = None  # bench.py sets this to a list to collect (start, end, kind, 2MNK, passes) per GEMM
 
 # launches (kernels + memsets are not counted) issued per C call
-_LAUNCHES = {"bnn_minmax_u8": 2}
+_LAUNCHES = {"bnn_minmax_u8": 2, "bnn_peer_broadcast_rows": 0}
 
 
 def _call(name, *args):
@@ -83,8 +83,9 @@ def split_f16(x: torch.Tensor, bound: torch.Tensor, hi=None, lo=None, hi_t=None,
 # ------------------------------------------------------------------------------- GEMMs
 def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),), sa=None,
          sb=None, host_scale=1.0, batch=1, stride_a=0, stride_b=0, stride_d=0, impl=None,
-         epi_thr=None, epi_sgn=None) -> None:
-    """D = epi(sum_p A[pa] @ B[pb]^T); A/B are sequences of 1..2 operand-piece tensors."""
+         epi_thr=None, epi_sgn=None, scatter=None) -> None:
+    """D = epi(sum_p A[pa] @ B[pb]^T); A/B are sequences of 1..2 operand-piece tensors.
+    scatter (EPI_SCATTER_F32): dict(world, rank, rows_per_owner, stage=[address per rank])."""
     d = nat.GemmDesc()
     d.M, d.N, d.K, d.batch = M, N, K, batch
     d.in_dtype, d.epilogue, d.n_pass = in_dtype, epilogue, len(passes)
@@ -98,6 +99,12 @@ def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),
     d.sa, d.sb = ptr(sa), ptr(sb)
     d.host_scale = host_scale
     d.epi_thr, d.epi_sgn = ptr(epi_thr), ptr(epi_sgn)
+    if scatter is not None:
+        sc = nat.PeerScatter()
+        sc.world, sc.rank, sc.rows_per_owner = scatter["world"], scatter["rank"], scatter["rows_per_owner"]
+        for r, a in enumerate(scatter["stage"]):
+            sc.stage[r] = a
+        d.scatter = C.pointer(sc)  # keeps `sc` alive for the duration of the call
     if gemm_events is None:
         _call("bnn_gemm", C.byref(d), gemm_impl() if impl is None else impl)
         return
@@ -141,6 +148,32 @@ def bn_stats_finalize_p2p(call, N, count, mu, var, sums_total) -> None:
 def allreduce_f64_p2p(call, n, out) -> None:
     data, flags = _peer_arrays(call)
     _call("bnn_allreduce_f64_p2p", data, flags, call["rank"], call["world"], call["epoch"], n, ptr(out))
+
+
+def _u64_array(values):
+    return (C.c_uint64 * len(values))(*values)
+
+
+def peer_signal(peer_flags, slot, rank, world, epoch) -> None:
+    _call("bnn_peer_signal", _u64_array(peer_flags), slot, rank, world, epoch)
+
+
+def peer_wait(flags_local_ptr, slot, rank, world, epoch) -> None:
+    _call("bnn_peer_wait", C.c_void_p(flags_local_ptr), slot, rank, world, epoch)
+
+
+def dw_reduce_sgd_p2p(stage_local_ptr, peer_w, peer_flags, slot_pushed, slot_landed, rank, world, epoch,
+                      K, N, rows_per_owner, lr, broadcast, counter, epoch_word=None) -> None:
+    _call("bnn_dw_reduce_sgd_p2p", C.c_void_p(stage_local_ptr), _u64_array(peer_w),
+          _u64_array(peer_flags), slot_pushed, slot_landed, rank, world, epoch, K, N, rows_per_owner,
+          lr, int(broadcast), ptr(counter), ptr(epoch_word))
+
+
+def peer_broadcast_rows(peer_w, peer_flags, slot_landed, rank, world, K, N, rows_per_owner,
+                        epoch_word) -> None:
+    """Copy-engine all-gather of this rank's rows of W (no kernel); runs on torch's current stream."""
+    _call("bnn_peer_broadcast_rows", _u64_array(peer_w), _u64_array(peer_flags), slot_landed, rank,
+          world, K, N, rows_per_owner, ptr(epoch_word))
 
 
 def bn_apply(Z, B, N, mu, var, gamma, beta, eps, out_f32=None, act_i8=None, act_t16=None,

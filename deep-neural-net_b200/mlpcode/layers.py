@@ -254,6 +254,7 @@ class LinearLayer(Layer):
         super().__init__(layerUnits, gpu=gpu)
         self.inputUnits = inputUnits
         self.useBias = useBias
+        self._pending_update = None   # weight update of a data-parallel step still in flight
         self.weights = None
         self.bias = None
         self.activation = None
@@ -261,10 +262,25 @@ class LinearLayer(Layer):
         self.callbacks = []
         self.comm = _NoComm()
         self.skip_input_grad = False  # set on the first layer: its dX is discarded (network.py:389-390)
-        self._pending_update = None   # (all-reduce handle, dW, lr) of a data-parallel step in flight
+        self._dwx = None              # (parallel.DwExchange, layer index): fused dW exchange over NVLink
         self._ws = _Workspace()
         if batchNorm:
             self.batchNormLayer = BatchNormLayer(layerUnits, gpu=gpu)
+
+    @property
+    def weights(self):
+        """Latent fp32 [K, N] weights (layers.py:191-194).  A data-parallel update still in flight
+        (all-reduce / peer rows on their way) is completed before the array is handed out."""
+        if self._pending_update is not None:
+            self.finish_update()
+        return self._weights
+
+    @weights.setter
+    def weights(self, value):
+        self._weights = value
+
+    def finish_update(self) -> None:
+        self._pending_update = None
 
     @property
     def weights_shape(self):
@@ -285,6 +301,23 @@ class LinearLayer(Layer):
         if self.useBias:
             raise NotImplementedError("bias is outside the B200 hot path (batch-norm nets drop it, "
                                       "network.py:37-41)")
+        self._home_weights()
+
+    def attach_dw_exchange(self, dwx, index: int) -> None:
+        """Data-parallel runs keep W in the exchange's symmetric arena so that the owner of a row block
+        can store its updated rows into every rank's copy (parallel.DwExchange)."""
+        self._dwx = (dwx, index) if dwx is not None else None
+        self._home_weights()
+
+    def _home_weights(self) -> None:
+        if self._dwx is None or self.weights is None:
+            return
+        dwx, li = self._dwx
+        view = dwx.weight_view(li)
+        if self.weights.t.data_ptr() != view.data_ptr():
+            assert tuple(self.weights.shape) == tuple(view.shape)
+            view.copy_(self.weights.t)
+            self.weights = DeviceArray(view)
 
     def loadBatchNormParams(self, gamma, beta, mu, sigma):
         assert self.batchNorm
@@ -386,17 +419,35 @@ class BinaryLayer(LinearLayer):
 
     def finish_update(self) -> None:
         """Apply `W -= lr * dW` of a data-parallel step once its all-reduce has landed."""
-        if self._pending_update is not None:
-            work, dW, lr = self._pending_update
-            self._pending_update = None
-            if work is not None:
-                work.wait()  # stream-side wait: the update kernel queues behind the collective
-            K_.sgd_update(self.weights.t, dW, lr)
+        if self._pending_update is None:
+            return
+        work, dW, lr = self._pending_update
+        self._pending_update = None
+        if work in ("p2p", "p2p-ce"):
+            dwx, li = self._dwx
+            epoch = dW
+            if work == "p2p":
+                # the dW GEMM pushed every rank's partial rows to their owners; sum + update the rows
+                # this rank owns and store them into every rank's W from the kernel itself
+                self._dw_reduce(epoch, lr, broadcast=True)
+            # every rank's rows of this step must have landed in the local W before it is read
+            K_.peer_wait(dwx.flag_ptrs()[dwx.rank], 2 * li + 1, dwx.rank, dwx.world, epoch)
+            return
+        if work is not None:
+            work.wait()  # stream-side wait: the update kernel queues behind the collective
+        K_.sgd_update(self.weights.t, dW, lr)
+
+    def _dw_reduce(self, epoch: int, lr: float, broadcast: bool) -> None:
+        dwx, li = self._dwx
+        L = dwx.layout[li]
+        K_.dw_reduce_sgd_p2p(dwx.stage_ptrs(li)[dwx.rank], dwx.w_ptrs(li), dwx.flag_ptrs(), 2 * li,
+                             2 * li + 1, dwx.rank, dwx.world, epoch, L["K"], L["N"],
+                             L["rows_per_owner"], lr, broadcast, dwx.counters[li:li + 1],
+                             epoch_word=dwx.epoch_words[li:li + 1])
 
     # ------------------------------------------------------------------ forward
     def forward(self, X, isTrain=True):
         assert self.isBuilt
-        self.finish_update()
         Kd, N = self.weights_shape
         ws = self._ws
         bn = self.batchNormLayer
@@ -411,6 +462,9 @@ class BinaryLayer(LinearLayer):
             assert X.n == Kd
             B = X.i8.shape[0]
 
+        # operand preparation of a real-valued input does not depend on W: queue it before the weight
+        # read, which in data-parallel runs first waits for the peers' updated rows to land
+        xin = self._real_input_operands(Xt, isTrain) if real_input else X
         wops = self._weight_operands(real_input)
         # fault-injection hooks act on the already-binarized weight, eval mode only (layers.py:215-218)
         if not isTrain:
@@ -436,7 +490,6 @@ class BinaryLayer(LinearLayer):
         # ---- z = X . sign(W)
         Z = None
         if real_input:
-            xin = self._real_input_operands(Xt, isTrain)
             if fuse_sign:
                 D, ldd, epi = act_i8, act_i8.stride(0), nat.EPI_SIGN_I8
             else:
@@ -447,7 +500,6 @@ class BinaryLayer(LinearLayer):
                     in_dtype=nat.DT_F16, epilogue=epi, passes=((0, 0), (1, 0)), sa=xin["scale"],
                     epi_thr=thr, epi_sgn=sgn)
         else:
-            xin = X
             s16 = Kd < 32768
             if fuse_sign:
                 K_.gemm(M=B, N=N, K=Kd, A=(X.i8,), B=(wops["i8"],), lda=X.i8.stride(0),
@@ -559,6 +611,45 @@ class BinaryLayer(LinearLayer):
             K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=Wt, ldd=N,
                     in_dtype=nat.DT_F16, epilogue=nat.EPI_SGD_F32, passes=passes, sa=sa, sb=d_scale,
                     host_scale=lr)
+        elif self._dwx is not None:
+            # reduce-scatter fused into the GEMM epilogue: each 128-row tile of this rank's partial dW
+            # is stored over NVLink into the staging buffer of the rank that owns those rows
+            self._home_weights()
+            dwx, li = self._dwx
+            epoch = dwx.next_epoch(li)
+            K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=None, ldd=N,
+                    in_dtype=nat.DT_F16, epilogue=nat.EPI_SCATTER_F32, passes=passes, sa=sa,
+                    sb=d_scale,
+                    scatter=dict(world=dwx.world, rank=dwx.rank,
+                                 rows_per_owner=dwx.layout[li]["rows_per_owner"],
+                                 stage=dwx.stage_ptrs(li)))
+            K_.peer_signal(dwx.flag_ptrs(), 2 * li, dwx.rank, dwx.world, epoch)
+            if dwx.copy_engine_broadcast and not self.skip_input_grad:
+                # owner update now (local rows only); the rows then travel to the peers on the copy
+                # engines, on a side stream, while this stream carries on with the backward pass
+                main = torch.cuda.current_stream()
+                if dwx.copied[li] is not None:
+                    main.wait_event(dwx.copied[li])  # last step's copies have finished reading W
+                self._dw_reduce(epoch, lr, broadcast=False)
+                dwx.reduced[li].record(main)
+                with torch.cuda.stream(dwx.side):
+                    dwx.side.wait_event(dwx.reduced[li])
+                    L = dwx.layout[li]
+                    K_.peer_broadcast_rows(dwx.w_ptrs(li), dwx.flag_ptrs(), 2 * li + 1, dwx.rank,
+                                           dwx.world, L["K"], L["N"], L["rows_per_owner"],
+                                           dwx.epoch_words[li:li + 1])
+                    if dwx.copied[li] is None:
+                        dwx.copied[li] = torch.cuda.Event()
+                    dwx.copied[li].record(dwx.side)
+                self._pending_update = ("p2p-ce", epoch, lr)
+            elif self.skip_input_grad:
+                # first layer: its dW GEMM ends the step and its weights open the next one, so nothing
+                # is left to overlap the copies with — the owner-update kernel stores the (small) row
+                # blocks into the peers itself, which is quicker than a train of copy-engine calls
+                self._dw_reduce(epoch, lr, broadcast=True)
+                self._pending_update = ("p2p-ce", epoch, lr)
+            else:
+                self._pending_update = ("p2p", epoch, lr)
         else:
             dW = ws.get("dW", (Kd, N), torch.float32)
             K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=dW, ldd=N,

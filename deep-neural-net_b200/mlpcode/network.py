@@ -131,6 +131,10 @@ class Network(object):
             comm.enable_peer_exchange(max(self.unitList[1:]))
         for layer in self._layers:
             layer.set_comm(comm)
+        if hasattr(comm, "enable_dw_exchange") and comm.enable_dw_exchange(
+                [layer.weights_shape for layer in self._layers]):
+            for i, layer in enumerate(self._layers):
+                layer.attach_dw_exchange(comm.dw_exchange, i)
 
     # ------------------------------------------------------------------ checkpoints (.npz bridge)
     @staticmethod
@@ -262,8 +266,8 @@ class Network(object):
         delta = self._layers[-1].backwards(delta, lr, activDeriv=not fused)
         for layer in reversed(self._layers[:-1]):
             delta = layer.backwards(delta, lr)
-        for layer in self._layers:  # data-parallel: dW all-reduces overlapped the backward pass
-            layer.finish_update()
+        # data-parallel: each layer's weight update (all-reduce / peer rows in flight) is completed
+        # lazily, when that layer's weights are next read — normally its next forward
         return cost
 
     def train_step(self, X, y, lr: float = None, global_batch: int = None) -> float:

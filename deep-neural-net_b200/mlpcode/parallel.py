@@ -61,6 +61,90 @@ class PeerExchange:
         return slot, call
 
 
+def _symmetric_buffer(comm: "Comm", nbytes: int):
+    """(local uint8 tensor, [address of every rank's copy as mapped into this process])."""
+    import torch.distributed._symmetric_memory as symm
+    group = comm.group if comm.group is not None else dist.group.WORLD
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            symm.enable_symm_mem_for_group(group.group_name)
+    except Exception:
+        pass
+    buf = symm.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+    buf.zero_()
+    handle = symm.rendezvous(buf, group)
+    base = [int(p) for p in handle.buffer_ptrs]
+    assert len(base) == comm.world and base[comm.rank] == buf.data_ptr()
+    return buf, base, handle
+
+
+class DwExchange:
+    """Symmetric arena for the dW all-reduce that libbnn_b200 fuses into its own kernels
+    (`dW` all-reduce-sum before `W -= lr*dW`, layers.py:268).
+
+    Per layer the arena holds, at the same offset on every rank,
+        W      fp32 [K, N]                      the layer's latent weights (re-homed here)
+        stage  fp32 [world, rows_per_owner, N]  partial dW rows pushed by every rank's dW GEMM
+    and a flag pad uint32[2 * n_layers][16] at offset 0 (slot 2l: "rank r has pushed its partial dW of
+    layer l", slot 2l+1: "rank r's updated rows of W_l have landed").  Rank r owns rows
+    [r*rows_per_owner, (r+1)*rows_per_owner) of every layer's W (rows_per_owner a multiple of the
+    GEMM's 128-row tile): the dW GEMM's epilogue stores each row tile into its owner's stage over
+    NVLink (reduce-scatter), the owner sums, updates and stores the new rows into every rank's W
+    (all-gather).  PyTorch allocates and maps the arena; the kernels move and synchronise the data."""
+
+    ALIGN = 1024
+
+    def __init__(self, comm: "Comm", shapes):
+        self.comm = comm
+        self.world, self.rank = comm.world, comm.rank
+        self.shapes = [(int(k), int(n)) for k, n in shapes]
+        n_layers = len(self.shapes)
+        self.flag_bytes = -(-(2 * n_layers * 16 * 4) // self.ALIGN) * self.ALIGN
+        off = self.flag_bytes
+        self.layout = []
+        for (k, n) in self.shapes:
+            tiles = -(-k // 128)
+            rpo = -(-tiles // self.world) * 128
+            w_off = off
+            off += -(-(k * n * 4) // self.ALIGN) * self.ALIGN
+            s_off = off
+            off += -(-(self.world * rpo * n * 4) // self.ALIGN) * self.ALIGN
+            self.layout.append(dict(K=k, N=n, rows_per_owner=rpo, w_off=w_off, stage_off=s_off))
+        self.nbytes = off
+        self.buf, self.base, self.handle = _symmetric_buffer(comm, self.nbytes)
+        self.epochs = [0] * n_layers
+        self.counters = torch.zeros(n_layers, dtype=torch.int32, device=self.buf.device)
+        # all-gather half: "ce" = copy engines on a side stream (overlaps the backward pass),
+        # "kernel" = peer stores from the owner-update kernel itself
+        self.copy_engine_broadcast = os.environ.get("BNN_DW_BCAST", "ce").lower() != "kernel"
+        self.epoch_words = torch.zeros(n_layers, dtype=torch.int32, device=self.buf.device)
+        self.side = torch.cuda.Stream()
+        self.reduced = [torch.cuda.Event() for _ in range(n_layers)]
+        self.copied = [None] * n_layers
+        torch.cuda.synchronize()
+        comm.barrier()  # every flag pad is zero before anyone signals
+
+    def weight_view(self, layer: int) -> torch.Tensor:
+        L = self.layout[layer]
+        return self.buf[L["w_off"]: L["w_off"] + L["K"] * L["N"] * 4].view(torch.float32).view(L["K"], L["N"])
+
+    def w_ptrs(self, layer: int):
+        return [b + self.layout[layer]["w_off"] for b in self.base]
+
+    def stage_ptrs(self, layer: int):
+        return [b + self.layout[layer]["stage_off"] for b in self.base]
+
+    def flag_ptrs(self):
+        return list(self.base)
+
+    def next_epoch(self, layer: int) -> int:
+        self.epochs[layer] += 1
+        self.comm.collectives += 1
+        return self.epochs[layer]
+
+
 class Comm:
     """Sum all-reduce over a torch.distributed process group (any backend: nccl on GPUs, gloo in
     the CPU tests of the host-side logic)."""
@@ -73,6 +157,7 @@ class Comm:
         self.collectives = 0
         self.global_batch = None  # rows of the current step over all ranks (None: local * world)
         self.peer_exchange = None  # PeerExchange once enable_peer_exchange() succeeded
+        self.dw_exchange = None    # DwExchange once enable_dw_exchange() succeeded
 
     def enable_peer_exchange(self, max_cols: int) -> bool:
         """Route the small batch-norm exchanges through NVLink peer memory instead of NCCL.  Returns
@@ -92,6 +177,26 @@ class Comm:
         if int(ok.item()) == 0:
             self.peer_exchange = None
         return self.peer_exchange is not None
+
+    def _all_agree(self, ok: bool) -> bool:
+        t = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return int(t.item()) == 1
+
+    def enable_dw_exchange(self, shapes) -> bool:
+        """Route the dW all-reduce through the fused reduce-scatter epilogue + owner update over NVLink
+        peer memory.  BNN_DW_P2P=0 keeps the NCCL all-reduce."""
+        if (self.world == 1 or os.environ.get("BNN_DW_P2P", "1") == "0" or not torch.cuda.is_available()
+                or dist.get_backend(self.group) != "nccl" or self.world > 16):
+            return False
+        try:
+            self.dw_exchange = DwExchange(self, shapes)
+        except Exception as exc:  # pragma: no cover - depends on the platform
+            print(f"[mlpcode.parallel] dW peer exchange unavailable, staying on NCCL: {exc}")
+            self.dw_exchange = None
+        if not self._all_agree(self.dw_exchange is not None):
+            self.dw_exchange = None
+        return self.dw_exchange is not None
 
     def global_rows(self, local_rows: int) -> int:
         """Batch-norm statistics and the loss gradient divide by the GLOBAL batch (layers.py:81-82,

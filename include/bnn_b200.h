@@ -111,10 +111,28 @@ enum {
     BNN_EPI_STORE_S32 = 1, /* D int32 = acc                      (I8 only)               */
     BNN_EPI_STORE_S16 = 2, /* D int16 = acc                      (I8 only, |acc| < 2^15) */
     BNN_EPI_SGD_F32 = 3,   /* D fp32 -= acc * host_scale / (sa*sb)   (fused SGD update)  */
-    BNN_EPI_SIGN_I8 = 4    /* D int8 = +1 if acc*host_scale/(sa*sb) * epi_sgn[n] >= epi_thr[n] else -1:
+    BNN_EPI_SIGN_I8 = 4,   /* D int8 = +1 if acc*host_scale/(sa*sb) * epi_sgn[n] >= epi_thr[n] else -1:
                               batch-norm + sign fused into the GEMM (thresholds from
                               bnn_bn_sign_thresholds); Z never reaches HBM (eval mode)           */
+    BNN_EPI_SCATTER_F32 = 5 /* like STORE_F32, but every 128-row tile is stored over NVLink into the
+                              staging buffer of the rank that owns those rows (desc.scatter): the
+                              reduce-scatter half of the data-parallel dW all-reduce, fused into the
+                              GEMM epilogue.  D / stride_d are ignored, ldd is the staging pitch.   */
 };
+#define BNN_MAX_RANKS 16
+
+/* Row ownership and peer mappings for BNN_EPI_SCATTER_F32.  Rank r owns output rows
+ * [r*rows_per_owner, (r+1)*rows_per_owner) (rows_per_owner a multiple of 128).  Every rank holds a
+ * staging buffer float[world][rows_per_owner][ldd]; stage[o] is the address of rank o's buffer as
+ * mapped into THIS process (symmetric memory).  Rank `rank` stores row m of its partial product at
+ * stage[o][rank][m - o*rows_per_owner][.] with o = m / rows_per_owner, and visits the row tiles
+ * starting from its own, so that at any moment the ranks write to different owners. */
+typedef struct bnn_peer_scatter {
+    int32_t world, rank;
+    int32_t rows_per_owner;
+    int32_t reserved;
+    uint64_t stage[BNN_MAX_RANKS];
+} bnn_peer_scatter;
 enum {
     BNN_GEMM_TCGEN05 = 0, /* TMA + tcgen05.mma + TMEM accumulators (product path)          */
     BNN_GEMM_SIMT = 1     /* plain fp32/int32 CUDA-core kernel: cross-check + tiny shapes */
@@ -141,6 +159,7 @@ typedef struct bnn_gemm_desc {
     int32_t reserved;
     const float* epi_thr; /* BNN_EPI_SIGN_I8: per-column threshold and orientation (device, [N]) */
     const float* epi_sgn;
+    const bnn_peer_scatter* scatter; /* BNN_EPI_SCATTER_F32 (host pointer), else NULL */
 } bnn_gemm_desc;
 
 int bnn_gemm(const bnn_gemm_desc* desc_host, int impl, bnn_stream_t stream);
@@ -267,6 +286,40 @@ int bnn_bn_stats_finalize_p2p(const uint64_t* peer_data_host, const uint64_t* pe
  * batch-norm backward reductions, whose finalize is bnn_bn_bwd_finalize). */
 int bnn_allreduce_f64_p2p(const uint64_t* peer_data_host, const uint64_t* peer_flags_host, int rank,
                           int world, uint32_t epoch, int n, double* out, bnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel dW: reduce-scatter fused into the dW GEMM (BNN_EPI_SCATTER_F32 above), then the owner
+ * of each row block sums the `world` partial products in rank order, applies `W -= lr * dW`
+ * (layers.py:268) and writes the updated rows into every rank's copy of W over NVLink — the
+ * all-gather half.  Synchronisation is by monotonically increasing epochs in flag pads
+ * uint32[n_slots][BNN_MAX_RANKS] that live in symmetric memory (zero-initialised once):
+ *   bnn_peer_signal   after this rank's GEMM: flags_of_peer[p][slot][rank] = epoch for every p
+ *   bnn_dw_reduce_sgd_p2p   waits until local flags[slot_pushed][*] >= epoch, reduces + updates + broadcasts
+ *                     its rows, then (last block) sets flags_of_peer[p][slot_landed][rank] = epoch
+ *   bnn_peer_wait     spins until local flags[slot][r] >= epoch for all r (before W is next read)
+ * All waits are bounded (10 s -> trap).  peer_*_host are host arrays of `world` device addresses.
+ * ------------------------------------------------------------------------------------------- */
+int bnn_peer_signal(const uint64_t* peer_flags_host, int slot, int rank, int world, uint32_t epoch,
+                    bnn_stream_t stream);
+int bnn_peer_wait(const uint32_t* flags_local, int slot, int rank, int world, uint32_t epoch,
+                  bnn_stream_t stream);
+/* stage_local: this rank's staging buffer float[world][rows_per_owner][ld]; W: [K, N] fp32 row-major
+ * with pitch ld == N on every rank (peer_w_host[r] = rank r's W as mapped here; may alias W for
+ * r == rank).  counter: device uint32, zero-initialised once (self-resetting block counter).
+ * broadcast = 0 updates only the local rows and writes `epoch` to *epoch_word (device uint32): the
+ * caller then runs bnn_peer_broadcast_rows on another stream, which moves the rows with the copy
+ * engines while the compute stream carries on with the backward pass. */
+int bnn_dw_reduce_sgd_p2p(const float* stage_local, const uint64_t* peer_w_host,
+                          const uint64_t* peer_flags_host, int slot_pushed, int slot_landed, int rank,
+                          int world, uint32_t epoch, int K, int N, int rows_per_owner, float lr,
+                          int broadcast, uint32_t* counter, uint32_t* epoch_word, bnn_stream_t stream);
+
+/* All-gather by copy engine: for every rank p, cudaMemcpyAsync of this rank's owned rows of W into
+ * rank p's W, followed by a 4-byte copy of *epoch_word into flags_of_peer[p][slot_landed][rank] (also
+ * for p == rank).  Stream order makes the flag land after the rows.  No kernel is launched. */
+int bnn_peer_broadcast_rows(const uint64_t* peer_w_host, const uint64_t* peer_flags_host,
+                            int slot_landed, int rank, int world, int K, int N, int rows_per_owner,
+                            const uint32_t* epoch_word, bnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * A11  weight fault injection                          (ErrorCallback._flipBNNMask
