@@ -10,8 +10,11 @@
 //   2. waits until every peer's flag for this epoch has arrived in its own pad (ld.acquire.sys, bounded),
 //   3. reads all ranks' slots through the peer pointers in rank order (so every rank forms bit-identical
 //      totals) and runs the finalize arithmetic on the totals.
-// Slots and flags are double-buffered on the parity of a call counter that all ranks advance in lock
-// step: a rank can run at most one call ahead of its slowest peer, so two buffers suffice.
+// Every exchange call site (layer x direction) has its own slot and its own flag row, and the epoch is
+// the training-step counter that all ranks advance in lock step.  The counter lives in device memory
+// (bnn_step_tick increments it) and the kernels read it through a pointer, so a whole training step can
+// be captured into a CUDA graph and replayed.  A rank cannot overwrite a slot that a peer is still
+// reading: between two uses of one call site every rank passes another site's barrier.
 #include "common.cuh"
 
 namespace bnn {
@@ -22,8 +25,13 @@ constexpr int kMaxRanks = 16;
 
 struct PeerTable {
     const double* data[kMaxRanks];  // every rank's slot for this call (device-mapped peer pointers)
-    uint32_t* flags[kMaxRanks];     // every rank's flag pad: uint32[2][kMaxRanks]
+    uint32_t* flags[kMaxRanks];     // every rank's flag row for this call site: uint32[kMaxRanks]
 };
+
+// epoch operand of every exchange kernel: the device-resident step counter when given, else immediate
+__device__ __forceinline__ uint32_t resolve_epoch(const uint32_t* epoch_ptr, uint32_t epoch_imm) {
+    return epoch_ptr ? *reinterpret_cast<const volatile uint32_t*>(epoch_ptr) : epoch_imm;
+}
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -42,13 +50,12 @@ __device__ __forceinline__ double ld_peer_f64(const double* p) {
 // Cross-rank barrier executed by every block: block 0 publishes this rank's arrival to all peers, every
 // block waits on the local pad.  Bounded: a missing peer is a trapped launch, not a hung GPU.
 __device__ void peer_barrier(const PeerTable& t, int rank, int world, uint32_t epoch) {
-    const int parity = epoch & 1u;
     if (blockIdx.x == 0 && threadIdx.x < world) {
         __threadfence_system();
-        st_release_sys(t.flags[threadIdx.x] + parity * kMaxRanks + rank, epoch);
+        st_release_sys(t.flags[threadIdx.x] + rank, epoch);
     }
     if (threadIdx.x < world) {
-        const uint32_t* f = t.flags[rank] + parity * kMaxRanks + threadIdx.x;
+        const uint32_t* f = t.flags[rank] + threadIdx.x;
         unsigned long long t0 = 0;
         uint32_t spins = 0;
         while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
@@ -68,10 +75,11 @@ __device__ void peer_barrier(const PeerTable& t, int rank, int world, uint32_t e
 }
 
 __global__ void __launch_bounds__(128)
-bn_stats_finalize_p2p_kernel(const PeerTable t, int rank, int world, uint32_t epoch, int N, double count,
+bn_stats_finalize_p2p_kernel(const PeerTable t, int rank, int world, uint32_t epoch_imm,
+                             const uint32_t* __restrict__ epoch_ptr, int N, double count,
                              float* __restrict__ mu, float* __restrict__ var,
                              double* __restrict__ sums_total) {
-    peer_barrier(t, rank, world, epoch);
+    peer_barrier(t, rank, world, resolve_epoch(epoch_ptr, epoch_imm));
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     double s = 0.0, q = 0.0;
@@ -89,9 +97,9 @@ bn_stats_finalize_p2p_kernel(const PeerTable t, int rank, int world, uint32_t ep
 }
 
 __global__ void __launch_bounds__(128)
-allreduce_f64_p2p_kernel(const PeerTable t, int rank, int world, uint32_t epoch, int n_total,
-                         double* __restrict__ out) {
-    peer_barrier(t, rank, world, epoch);
+allreduce_f64_p2p_kernel(const PeerTable t, int rank, int world, uint32_t epoch_imm,
+                         const uint32_t* __restrict__ epoch_ptr, int n_total, double* __restrict__ out) {
+    peer_barrier(t, rank, world, resolve_epoch(epoch_ptr, epoch_imm));
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n_total) return;
     double s = 0.0;
@@ -130,7 +138,9 @@ __device__ void spin_until(const uint32_t* f, uint32_t epoch, int rank, int peer
 }
 
 __global__ void __launch_bounds__(32)
-peer_signal_kernel(const FlagTable t, int slot, int rank, int world, uint32_t epoch) {
+peer_signal_kernel(const FlagTable t, int slot, int rank, int world, uint32_t epoch_imm,
+                   const uint32_t* __restrict__ epoch_ptr) {
+    const uint32_t epoch = resolve_epoch(epoch_ptr, epoch_imm);
     // every earlier kernel of this stream has completed, so its peer stores are performed; the fence
     // orders them before the flag for observers on other GPUs
     if (threadIdx.x < world) {
@@ -139,12 +149,18 @@ peer_signal_kernel(const FlagTable t, int slot, int rank, int world, uint32_t ep
     }
 }
 
+// waits on n_slots flag rows: slot, slot + slot_stride, ...
 __global__ void __launch_bounds__(32)
-peer_wait_kernel(const uint32_t* __restrict__ flags_local, int slot, int rank, int world,
-                 uint32_t epoch) {
+peer_wait_kernel(const uint32_t* __restrict__ flags_local, int slot, int slot_stride, int n_slots,
+                 int rank, int world, uint32_t epoch_imm, const uint32_t* __restrict__ epoch_ptr) {
+    const uint32_t epoch = resolve_epoch(epoch_ptr, epoch_imm);
     if (threadIdx.x < world)
-        spin_until(flags_local + slot * kMaxRanks + threadIdx.x, epoch, rank, threadIdx.x, "peer wait");
+        for (int i = 0; i < n_slots; ++i)
+            spin_until(flags_local + (slot + i * slot_stride) * kMaxRanks + threadIdx.x, epoch, rank,
+                       threadIdx.x, "peer wait");
 }
+
+__global__ void step_tick_kernel(uint32_t* __restrict__ step) { *step += 1u; }
 
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
     float4 v;
@@ -187,10 +203,12 @@ struct Pack<1> {
 template <int WORLD, int VEC>  // WORLD 0 = run-time world; VEC floats per thread and access
 __global__ void __launch_bounds__(256)
 dw_reduce_sgd_p2p_kernel(const float* __restrict__ stage, const WTable wt, const FlagTable ft,
-                         int slot_pushed, int slot_landed, int rank, int world_rt, uint32_t epoch,
-                         int rows, int N, int rows_per_owner, float lr, int broadcast,
-                         uint32_t* __restrict__ counter, uint32_t* __restrict__ epoch_word) {
+                         int slot_pushed, int slot_landed, int rank, int world_rt, uint32_t epoch_imm,
+                         const uint32_t* __restrict__ epoch_ptr, int rows, int N, int rows_per_owner,
+                         float lr, int broadcast, uint32_t* __restrict__ counter,
+                         uint32_t* __restrict__ epoch_word) {
     const int world = WORLD ? WORLD : world_rt;
+    const uint32_t epoch = resolve_epoch(epoch_ptr, epoch_imm);
     if (epoch_word && blockIdx.x == 0 && threadIdx.x == 0) *epoch_word = epoch;
     // wait for every rank's partial rows of this epoch (bounded)
     if (threadIdx.x < world)
@@ -249,35 +267,45 @@ static int fill_flags(FlagTable& t, const uint64_t* peer_flags_host, int world) 
     return BNN_OK;
 }
 
+extern "C" int bnn_step_tick(uint32_t* step_dev, bnn_stream_t stream) {
+    BNN_CHECK_ARG(step_dev, "bnn_step_tick: null counter");
+    step_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    BNN_LAUNCH_CHECK("step_tick_kernel");
+    return BNN_OK;
+}
+
 extern "C" int bnn_peer_signal(const uint64_t* peer_flags_host, int slot, int rank, int world,
-                               uint32_t epoch, bnn_stream_t stream) {
-    BNN_CHECK_ARG(peer_flags_host && slot >= 0 && rank >= 0 && rank < world && epoch > 0,
+                               uint32_t epoch, const uint32_t* epoch_ptr, bnn_stream_t stream) {
+    BNN_CHECK_ARG(peer_flags_host && slot >= 0 && rank >= 0 && rank < world && (epoch > 0 || epoch_ptr),
                   "bnn_peer_signal: bad input");
     FlagTable t;
     int rc = fill_flags(t, peer_flags_host, world);
     if (rc) return rc;
-    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(t, slot, rank, world, epoch);
+    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(t, slot, rank, world, epoch, epoch_ptr);
     BNN_LAUNCH_CHECK("peer_signal_kernel");
     return BNN_OK;
 }
 
-extern "C" int bnn_peer_wait(const uint32_t* flags_local, int slot, int rank, int world, uint32_t epoch,
+extern "C" int bnn_peer_wait(const uint32_t* flags_local, int slot, int slot_stride, int n_slots,
+                             int rank, int world, uint32_t epoch, const uint32_t* epoch_ptr,
                              bnn_stream_t stream) {
-    BNN_CHECK_ARG(flags_local && slot >= 0 && rank >= 0 && rank < world && world <= kMaxRanks &&
-                      epoch > 0,
+    BNN_CHECK_ARG(flags_local && slot >= 0 && n_slots >= 1 && rank >= 0 && rank < world &&
+                      world <= kMaxRanks && (epoch > 0 || epoch_ptr),
                   "bnn_peer_wait: bad input");
-    peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags_local, slot, rank, world, epoch);
+    peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags_local, slot, slot_stride, n_slots, rank,
+                                                         world, epoch, epoch_ptr);
     BNN_LAUNCH_CHECK("peer_wait_kernel");
     return BNN_OK;
 }
 
 extern "C" int bnn_dw_reduce_sgd_p2p(const float* stage_local, const uint64_t* peer_w_host,
                                      const uint64_t* peer_flags_host, int slot_pushed, int slot_landed,
-                                     int rank, int world, uint32_t epoch, int K, int N,
-                                     int rows_per_owner, float lr, int broadcast, uint32_t* counter,
-                                     uint32_t* epoch_word, bnn_stream_t stream) {
+                                     int rank, int world, uint32_t epoch, const uint32_t* epoch_ptr,
+                                     int K, int N, int rows_per_owner, float lr, int broadcast,
+                                     uint32_t* counter, uint32_t* epoch_word, bnn_stream_t stream) {
     BNN_CHECK_ARG(stage_local && peer_w_host && peer_flags_host && counter && K > 0 && N > 0 &&
-                      rank >= 0 && rank < world && epoch > 0 && slot_pushed >= 0 && slot_landed >= 0,
+                      rank >= 0 && rank < world && (epoch > 0 || epoch_ptr) && slot_pushed >= 0 &&
+                      slot_landed >= 0,
                   "bnn_dw_reduce_sgd_p2p: bad input");
     BNN_CHECK_ARG(rows_per_owner > 0 && (long long)rows_per_owner * world >= K,
                   "bnn_dw_reduce_sgd_p2p: rows_per_owner %d does not cover K=%d", rows_per_owner, K);
@@ -303,7 +331,8 @@ extern "C" int bnn_dw_reduce_sgd_p2p(const float* stage_local, const uint64_t* p
     cudaStream_t s = (cudaStream_t)stream;
 #define BNN_DW_LAUNCH(W, V)                                                                          \
     dw_reduce_sgd_p2p_kernel<W, V><<<grid, 256, 0, s>>>(stage_local, wt, ft, slot_pushed, slot_landed, \
-                                                        rank, world, epoch, rows, N, rows_per_owner,  \
+                                                        rank, world, epoch, epoch_ptr, rows, N,        \
+                                                        rows_per_owner,                               \
                                                         lr, broadcast, counter, epoch_word)
     if (vec) {
         switch (world) {
@@ -332,32 +361,32 @@ static int fill_table(PeerTable& t, const uint64_t* peer_data_host, const uint64
 }
 
 extern "C" int bnn_bn_stats_finalize_p2p(const uint64_t* peer_data_host, const uint64_t* peer_flags_host,
-                                         int rank, int world, uint32_t epoch, int N, double count,
-                                         float* mu, float* var, double* sums_total,
+                                         int rank, int world, uint32_t epoch, const uint32_t* epoch_ptr,
+                                         int N, double count, float* mu, float* var, double* sums_total,
                                          bnn_stream_t stream) {
     BNN_CHECK_ARG(peer_data_host && peer_flags_host && mu && var && sums_total && N > 0 && count > 0 &&
-                      rank >= 0 && rank < world && epoch > 0,
+                      rank >= 0 && rank < world && (epoch > 0 || epoch_ptr),
                   "bnn_bn_stats_finalize_p2p: bad input");
     PeerTable t;
     int rc = fill_table(t, peer_data_host, peer_flags_host, world);
     if (rc) return rc;
     bn_stats_finalize_p2p_kernel<<<cdiv(N, 128), 128, 0, (cudaStream_t)stream>>>(
-        t, rank, world, epoch, N, count, mu, var, sums_total);
+        t, rank, world, epoch, epoch_ptr, N, count, mu, var, sums_total);
     BNN_LAUNCH_CHECK("bn_stats_finalize_p2p_kernel");
     return BNN_OK;
 }
 
 extern "C" int bnn_allreduce_f64_p2p(const uint64_t* peer_data_host, const uint64_t* peer_flags_host,
-                                     int rank, int world, uint32_t epoch, int n, double* out,
-                                     bnn_stream_t stream) {
+                                     int rank, int world, uint32_t epoch, const uint32_t* epoch_ptr, int n,
+                                     double* out, bnn_stream_t stream) {
     BNN_CHECK_ARG(peer_data_host && peer_flags_host && out && n > 0 && rank >= 0 && rank < world &&
-                      epoch > 0,
+                      (epoch > 0 || epoch_ptr),
                   "bnn_allreduce_f64_p2p: bad input");
     PeerTable t;
     int rc = fill_table(t, peer_data_host, peer_flags_host, world);
     if (rc) return rc;
-    allreduce_f64_p2p_kernel<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(t, rank, world, epoch, n,
-                                                                            out);
+    allreduce_f64_p2p_kernel<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(t, rank, world, epoch,
+                                                                            epoch_ptr, n, out);
     BNN_LAUNCH_CHECK("allreduce_f64_p2p_kernel");
     return BNN_OK;
 }

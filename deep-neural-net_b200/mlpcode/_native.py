@@ -83,12 +83,13 @@ PROTOTYPES = {
                             _p],
     "bnn_bn_bwd_apply": [_p, _i64, _p, _i, _i64, _i, _i, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _p,
                          _i64, _p, _p],
-    "bnn_bn_stats_finalize_p2p": [_p, _p, _i, _i, _u32, _i, _d, _p, _p, _p, _p],
-    "bnn_allreduce_f64_p2p": [_p, _p, _i, _i, _u32, _i, _p, _p],
+    "bnn_step_tick": [_p, _p],
+    "bnn_bn_stats_finalize_p2p": [_p, _p, _i, _i, _u32, _p, _i, _d, _p, _p, _p, _p],
+    "bnn_allreduce_f64_p2p": [_p, _p, _i, _i, _u32, _p, _i, _p, _p],
     "bnn_sgd_update": [_p, _p, _i64, _f, _i, _i64, _p],
-    "bnn_peer_signal": [_p, _i, _i, _i, _u32, _p],
-    "bnn_peer_wait": [_p, _i, _i, _i, _u32, _p],
-    "bnn_dw_reduce_sgd_p2p": [_p, _p, _p, _i, _i, _i, _i, _u32, _i, _i, _i, _f, _i, _p, _p, _p],
+    "bnn_peer_signal": [_p, _i, _i, _i, _u32, _p, _p],
+    "bnn_peer_wait": [_p, _i, _i, _i, _i, _i, _u32, _p, _p],
+    "bnn_dw_reduce_sgd_p2p": [_p, _p, _p, _i, _i, _i, _i, _u32, _p, _i, _i, _i, _f, _i, _p, _p, _p],
     "bnn_peer_broadcast_rows": [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p],
     "bnn_flip_weights_bernoulli": [_p, _i64, _p, _i64, _i, _i, _u64, _u64, _u32, _u32, _i, _p, _i64,
                                    _p, _i64, _i64, _p, _i64, _p, _i64, _p],

@@ -139,34 +139,40 @@ def _peer_arrays(call):
     return (C.c_uint64 * n)(*call["data"]), (C.c_uint64 * n)(*call["flags"])
 
 
+def step_tick(step_dev) -> None:
+    _call("bnn_step_tick", ptr(step_dev))
+
+
 def bn_stats_finalize_p2p(call, N, count, mu, var, sums_total) -> None:
     data, flags = _peer_arrays(call)
-    _call("bnn_bn_stats_finalize_p2p", data, flags, call["rank"], call["world"], call["epoch"], N,
+    _call("bnn_bn_stats_finalize_p2p", data, flags, call["rank"], call["world"], 0, ptr(call["step"]), N,
           float(count), ptr(mu), ptr(var), ptr(sums_total))
 
 
 def allreduce_f64_p2p(call, n, out) -> None:
     data, flags = _peer_arrays(call)
-    _call("bnn_allreduce_f64_p2p", data, flags, call["rank"], call["world"], call["epoch"], n, ptr(out))
+    _call("bnn_allreduce_f64_p2p", data, flags, call["rank"], call["world"], 0, ptr(call["step"]), n,
+          ptr(out))
 
 
 def _u64_array(values):
     return (C.c_uint64 * len(values))(*values)
 
 
-def peer_signal(peer_flags, slot, rank, world, epoch) -> None:
-    _call("bnn_peer_signal", _u64_array(peer_flags), slot, rank, world, epoch)
+def peer_signal(peer_flags, slot, rank, world, step_dev) -> None:
+    _call("bnn_peer_signal", _u64_array(peer_flags), slot, rank, world, 0, ptr(step_dev))
 
 
-def peer_wait(flags_local_ptr, slot, rank, world, epoch) -> None:
-    _call("bnn_peer_wait", C.c_void_p(flags_local_ptr), slot, rank, world, epoch)
+def peer_wait(flags_local_ptr, slot, slot_stride, n_slots, rank, world, step_dev) -> None:
+    _call("bnn_peer_wait", C.c_void_p(flags_local_ptr), slot, slot_stride, n_slots, rank, world, 0,
+          ptr(step_dev))
 
 
-def dw_reduce_sgd_p2p(stage_local_ptr, peer_w, peer_flags, slot_pushed, slot_landed, rank, world, epoch,
-                      K, N, rows_per_owner, lr, broadcast, counter, epoch_word=None) -> None:
+def dw_reduce_sgd_p2p(stage_local_ptr, peer_w, peer_flags, slot_pushed, slot_landed, rank, world,
+                      step_dev, K, N, rows_per_owner, lr, broadcast, counter) -> None:
     _call("bnn_dw_reduce_sgd_p2p", C.c_void_p(stage_local_ptr), _u64_array(peer_w),
-          _u64_array(peer_flags), slot_pushed, slot_landed, rank, world, epoch, K, N, rows_per_owner,
-          lr, int(broadcast), ptr(counter), ptr(epoch_word))
+          _u64_array(peer_flags), slot_pushed, slot_landed, rank, world, 0, ptr(step_dev), K, N,
+          rows_per_owner, lr, int(broadcast), ptr(counter), None)
 
 
 def peer_broadcast_rows(peer_w, peer_flags, slot_landed, rank, world, K, N, rows_per_owner,

@@ -111,6 +111,12 @@ class _Workspace:
 class _NoComm:
     world = 1
 
+    def begin_step(self):
+        pass
+
+    def finish_step(self):
+        pass
+
     def allreduce_sum(self, t):
         return None
 
@@ -146,6 +152,7 @@ class BatchNormLayer(Layer):
         self.sigma = None  # running VARIANCE (layers.py:121-123), despite the name
         self._ws = _Workspace()
         self.comm = _NoComm()
+        self.exchange_site = 0  # call-site base of this layer's peer exchanges (2 per layer)
 
     @property
     def parameter_shape(self):
@@ -157,6 +164,7 @@ class BatchNormLayer(Layer):
         return (self.gamma, self.beta, self.mu, self.sigma)
 
     def loadBatchNormParams(self, gamma, beta, mu, sigma):
+        self.version = getattr(self, "version", 0) + 1
         shp = self.parameter_shape
         for a in (gamma, beta, mu, sigma):
             assert tuple(a.shape) == shp
@@ -190,7 +198,7 @@ class BatchNormLayer(Layer):
         if px is not None and n <= px.max_cols:
             # sync-BN over NVLink peer memory: partial sums land in this rank's symmetric slot and the
             # finalize kernel itself gathers every rank's slot (one launch, no NCCL call)
-            slot, call = px.begin(2 * n)
+            slot, call = px.begin(self.exchange_site, 2 * n)
             K_.colstats(Z, B, n, slot.view(2, n))
             K_.bn_stats_finalize_p2p(call, n, self.comm.global_rows(B), mu, var, sums)
             return sums, mu, var
@@ -207,7 +215,7 @@ class BatchNormLayer(Layer):
         bound = self._ws.get("bound", (1,), torch.float32)  # written as uint32 bits of a float
         px = self.comm.peer_exchange
         if px is not None and n <= px.max_cols:
-            slot, call = px.begin(2 * n)
+            slot, call = px.begin(self.exchange_site + 1, 2 * n)
             K_.bn_bwd_reduce(delta, Z, B, n, mu, slot.view(2, n), red_max)
             K_.allreduce_f64_p2p(call, 2 * n, red)
         else:
@@ -255,6 +263,7 @@ class LinearLayer(Layer):
         self.inputUnits = inputUnits
         self.useBias = useBias
         self._pending_update = None   # weight update of a data-parallel step still in flight
+        self._dwx = None              # (parallel.DwExchange, layer index): fused dW exchange over NVLink
         self.weights = None
         self.bias = None
         self.activation = None
@@ -262,7 +271,6 @@ class LinearLayer(Layer):
         self.callbacks = []
         self.comm = _NoComm()
         self.skip_input_grad = False  # set on the first layer: its dX is discarded (network.py:389-390)
-        self._dwx = None              # (parallel.DwExchange, layer index): fused dW exchange over NVLink
         self._ws = _Workspace()
         if batchNorm:
             self.batchNormLayer = BatchNormLayer(layerUnits, gpu=gpu)
@@ -273,11 +281,14 @@ class LinearLayer(Layer):
         (all-reduce / peer rows on their way) is completed before the array is handed out."""
         if self._pending_update is not None:
             self.finish_update()
+        if self._dwx is not None and self._dwx[1] in self._dwx[0].pending:
+            self._dwx[0].finish_step()  # a step driven layer by layer, outside Network.train_step
         return self._weights
 
     @weights.setter
     def weights(self, value):
         self._weights = value
+        self.version = getattr(self, "version", 0) + 1  # invalidates captured step graphs
 
     def finish_update(self) -> None:
         self._pending_update = None
@@ -310,13 +321,13 @@ class LinearLayer(Layer):
         self._home_weights()
 
     def _home_weights(self) -> None:
-        if self._dwx is None or self.weights is None:
+        if self._dwx is None or self._weights is None:
             return
         dwx, li = self._dwx
         view = dwx.weight_view(li)
-        if self.weights.t.data_ptr() != view.data_ptr():
-            assert tuple(self.weights.shape) == tuple(view.shape)
-            view.copy_(self.weights.t)
+        if self._weights.t.data_ptr() != view.data_ptr():
+            assert tuple(self._weights.shape) == tuple(view.shape)
+            view.copy_(self._weights.t)
             self.weights = DeviceArray(view)
 
     def loadBatchNormParams(self, gamma, beta, mu, sigma):
@@ -330,6 +341,7 @@ class LinearLayer(Layer):
         self.callbacks.clear()
 
     def set_comm(self, comm):
+        self.version = getattr(self, "version", 0) + 1
         self.comm = comm
         if self.batchNorm:
             self.batchNormLayer.comm = comm
@@ -423,27 +435,16 @@ class BinaryLayer(LinearLayer):
             return
         work, dW, lr = self._pending_update
         self._pending_update = None
-        if work in ("p2p", "p2p-ce"):
-            dwx, li = self._dwx
-            epoch = dW
-            if work == "p2p":
-                # the dW GEMM pushed every rank's partial rows to their owners; sum + update the rows
-                # this rank owns and store them into every rank's W from the kernel itself
-                self._dw_reduce(epoch, lr, broadcast=True)
-            # every rank's rows of this step must have landed in the local W before it is read
-            K_.peer_wait(dwx.flag_ptrs()[dwx.rank], 2 * li + 1, dwx.rank, dwx.world, epoch)
-            return
         if work is not None:
             work.wait()  # stream-side wait: the update kernel queues behind the collective
         K_.sgd_update(self.weights.t, dW, lr)
 
-    def _dw_reduce(self, epoch: int, lr: float, broadcast: bool) -> None:
+    def _dw_reduce(self, lr: float, broadcast: bool) -> None:
         dwx, li = self._dwx
         L = dwx.layout[li]
         K_.dw_reduce_sgd_p2p(dwx.stage_ptrs(li)[dwx.rank], dwx.w_ptrs(li), dwx.flag_ptrs(), 2 * li,
-                             2 * li + 1, dwx.rank, dwx.world, epoch, L["K"], L["N"],
-                             L["rows_per_owner"], lr, broadcast, dwx.counters[li:li + 1],
-                             epoch_word=dwx.epoch_words[li:li + 1])
+                             2 * li + 1, dwx.rank, dwx.world, dwx.comm.step_dev, L["K"], L["N"],
+                             L["rows_per_owner"], lr, broadcast, dwx.counters[li:li + 1])
 
     # ------------------------------------------------------------------ forward
     def forward(self, X, isTrain=True):
@@ -583,7 +584,7 @@ class BinaryLayer(LinearLayer):
             w_hi = ws.get("w_hi", (Kd, Np), torch.float16, zero=True)
             w_lo = ws.get("w_lo", (Kd, Np), torch.float16, zero=True)
             # W has not changed since this step's forward, whose binarize pass left max|W| in w_amax
-            K_.split_f16(self.weights.t, w_amax, hi=w_hi, lo=w_lo, scale_out=w_scale)
+            K_.split_f16(self._weights.t, w_amax, hi=w_hi, lo=w_lo, scale_out=w_scale)
             dX = empty((B, pad_to(Kd, 4)))
             K_.gemm(M=B, N=Kd, K=N, A=(d_hi, d_lo), B=(w_hi, w_lo), lda=Np, ldb=Np, D=dX,
                     ldd=dX.stride(0), in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32,
@@ -595,7 +596,7 @@ class BinaryLayer(LinearLayer):
             A, passes, sa = (xin["hi_t"], xin["lo_t"]), ((0, 0), (0, 1), (1, 0)), xin["scale"]
         else:
             A, passes, sa = (xin.t16,), ((0, 0), (0, 1)), None
-        Wt = self.weights.t
+        Wt = self._weights.t
         split = 4 if (N <= 32 and Kd >= 1024 and B % 256 == 0 and self.comm.world == 1) else 1
         if split > 1:
             # narrow layer (the 10-unit output): a 128 x 32 tile grid has only Kd/128 CTAs, so the
@@ -616,40 +617,34 @@ class BinaryLayer(LinearLayer):
             # is stored over NVLink into the staging buffer of the rank that owns those rows
             self._home_weights()
             dwx, li = self._dwx
-            epoch = dwx.next_epoch(li)
+            step_dev = dwx.comm.step_dev
+            dwx.comm.collectives += 1
             K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=None, ldd=N,
                     in_dtype=nat.DT_F16, epilogue=nat.EPI_SCATTER_F32, passes=passes, sa=sa,
                     sb=d_scale,
                     scatter=dict(world=dwx.world, rank=dwx.rank,
                                  rows_per_owner=dwx.layout[li]["rows_per_owner"],
                                  stage=dwx.stage_ptrs(li)))
-            K_.peer_signal(dwx.flag_ptrs(), 2 * li, dwx.rank, dwx.world, epoch)
+            K_.peer_signal(dwx.flag_ptrs(), 2 * li, dwx.rank, dwx.world, step_dev)
             if dwx.copy_engine_broadcast and not self.skip_input_grad:
                 # owner update now (local rows only); the rows then travel to the peers on the copy
                 # engines, on a side stream, while this stream carries on with the backward pass
                 main = torch.cuda.current_stream()
-                if dwx.copied[li] is not None:
-                    main.wait_event(dwx.copied[li])  # last step's copies have finished reading W
-                self._dw_reduce(epoch, lr, broadcast=False)
+                self._dw_reduce(lr, broadcast=False)
                 dwx.reduced[li].record(main)
                 with torch.cuda.stream(dwx.side):
                     dwx.side.wait_event(dwx.reduced[li])
                     L = dwx.layout[li]
                     K_.peer_broadcast_rows(dwx.w_ptrs(li), dwx.flag_ptrs(), 2 * li + 1, dwx.rank,
-                                           dwx.world, L["K"], L["N"], L["rows_per_owner"],
-                                           dwx.epoch_words[li:li + 1])
-                    if dwx.copied[li] is None:
-                        dwx.copied[li] = torch.cuda.Event()
+                                           dwx.world, L["K"], L["N"], L["rows_per_owner"], step_dev)
                     dwx.copied[li].record(dwx.side)
-                self._pending_update = ("p2p-ce", epoch, lr)
-            elif self.skip_input_grad:
-                # first layer: its dW GEMM ends the step and its weights open the next one, so nothing
-                # is left to overlap the copies with — the owner-update kernel stores the (small) row
-                # blocks into the peers itself, which is quicker than a train of copy-engine calls
-                self._dw_reduce(epoch, lr, broadcast=True)
-                self._pending_update = ("p2p-ce", epoch, lr)
+                dwx.in_flight.append(li)
             else:
-                self._pending_update = ("p2p", epoch, lr)
+                # first layer (its dW GEMM ends the step and its weights open the next one, so there
+                # is nothing left to overlap copies with) or BNN_DW_BCAST=kernel: the owner-update
+                # kernel stores the row blocks into the peers itself
+                self._dw_reduce(lr, broadcast=True)
+            dwx.pending.append(li)  # awaited by comm.finish_step() at the end of the training step
         else:
             dW = ws.get("dW", (Kd, N), torch.float32)
             K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=dW, ldd=N,

@@ -62,6 +62,8 @@ class Network(object):
         self._lr: LRScheduler = None
         self._compiled = False
         self._comm = _NoComm()
+        self._graph_on = False
+        self._graphs = {}
 
     # ------------------------------------------------------------------ parameters
     @property
@@ -128,9 +130,11 @@ class Network(object):
         """comm: object with `.world` and `.allreduce_sum(tensor)` (see mlpcode.parallel)."""
         self._comm = comm
         if hasattr(comm, "enable_peer_exchange"):
-            comm.enable_peer_exchange(max(self.unitList[1:]))
-        for layer in self._layers:
+            comm.enable_peer_exchange(max(self.unitList[1:]), n_sites=2 * len(self._layers))
+        for i, layer in enumerate(self._layers):
             layer.set_comm(comm)
+            if getattr(layer, "batchNorm", False):
+                layer.batchNormLayer.exchange_site = 2 * i
         if hasattr(comm, "enable_dw_exchange") and comm.enable_dw_exchange(
                 [layer.weights_shape for layer in self._layers]):
             for i, layer in enumerate(self._layers):
@@ -251,13 +255,72 @@ class Network(object):
             history["val_accuracy"] = val_accs
         return history
 
+    # ------------------------------------------------------------------ CUDA-graph replay of a step
+    def enable_step_graph(self, on: bool = True) -> None:
+        """Replay each training step as ONE CUDA graph launch instead of ~90 kernel launches.
+
+        A step is a fixed sequence of libbnn_b200 kernels over fixed buffers; the only things that
+        vary are the batch (copied into static device buffers) and, in data-parallel runs, the
+        exchange epoch (a device word the kernels read).  The first two steps of a given (batch shape,
+        lr, global batch, parameter identity) run eagerly to populate the workspaces, the third is
+        captured (copy-engine all-gather on its side stream included) and every later one is a
+        replay.  Loading new parameters or changing lr re-captures.  Results are identical to eager
+        execution: the same kernels with the same arguments."""
+        self._graph_on = bool(on)
+        self._graphs = {}
+
+    def _param_version(self) -> int:
+        v = 0
+        for layer in self._layers:
+            v += getattr(layer, "version", 0)
+            if getattr(layer, "batchNorm", False):
+                v += getattr(layer.batchNormLayer, "version", 0)
+        return v
+
+    def _graph_step(self, X, y, lr, global_batch):
+        if self._comm.world > 1 and (getattr(self._comm, "dw_exchange", None) is None
+                                     or getattr(self._comm, "peer_exchange", None) is None):
+            return None  # NCCL collectives in the step: stay eager
+        Xt, yt = to_tensor(X, torch.float32), to_tensor(y)
+        key = (tuple(Xt.shape), tuple(yt.shape), yt.dtype, float(lr), global_batch, self._param_version())
+        st = self._graphs.get(key)
+        if st is None:
+            self._graphs = {k: v for k, v in self._graphs.items() if k[-1] == key[-1]}
+            st = self._graphs[key] = {"warm": 0}
+        if st["warm"] < 2:
+            st["warm"] += 1
+            return None
+        if "graph" not in st:
+            st["X"], st["y"] = Xt.clone(), yt.clone()
+            launches0 = K_.launch_count
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                st["cost"] = self._train_step_eager(DeviceArray(st["X"]), DeviceArray(st["y"]), lr,
+                                                    global_batch)
+            st["graph"], st["launches"] = g, K_.launch_count - launches0
+            K_.launch_count = launches0
+        else:
+            st["X"].copy_(Xt, non_blocking=True)
+            st["y"].copy_(yt, non_blocking=True)
+        st["graph"].replay()
+        K_.launch_count += st["launches"]
+        return st["cost"]
+
     def train_step_async(self, X, y, lr: float = None, global_batch: int = None):
         """One SGD step on one batch (the body of `__updateBatch`, network.py:372-392) without the
         host read of the loss; returns the device array of per-sample losses.  Data-parallel runs
         with unequal shards pass the global batch size."""
         lr = self._lr.value if lr is None else lr
+        if self._graph_on and K_.gemm_events is None:
+            cost = self._graph_step(X, y, lr, global_batch)
+            if cost is not None:
+                return cost
+        return self._train_step_eager(X, y, lr, global_batch)
+
+    def _train_step_eager(self, X, y, lr: float, global_batch: int = None):
         if self._comm.world > 1:
             self._comm.global_batch = global_batch
+        self._comm.begin_step()
         output = self.predict(X, isTraining=True)
         loss_mod.GLOBAL_BATCH_ROWS = self._comm.global_rows(X.shape[0])
         cost = LOSS_FUNCS[self._lossF](output, y)
@@ -266,8 +329,10 @@ class Network(object):
         delta = self._layers[-1].backwards(delta, lr, activDeriv=not fused)
         for layer in reversed(self._layers[:-1]):
             delta = layer.backwards(delta, lr)
-        # data-parallel: each layer's weight update (all-reduce / peer rows in flight) is completed
-        # lazily, when that layer's weights are next read — normally its next forward
+        # data-parallel: the peer-memory exchange is completed here (copy-engine stream joined, every
+        # rank's rows landed); an NCCL all-reduce still in flight is completed lazily, when that
+        # layer's weights are next read
+        self._comm.finish_step()
         return cost
 
     def train_step(self, X, y, lr: float = None, global_batch: int = None) -> float:

@@ -22,41 +22,38 @@ import torch.distributed as dist
 class PeerExchange:
     """Symmetric buffer (torch symmetric memory: the same allocation mapped into every rank over
     NVLink / NVSwitch) for the batch-norm exchanges that libbnn_b200 fuses into its finalize kernels
-    (bnn_bn_stats_finalize_p2p, bnn_allreduce_f64_p2p).  Layout, identical on every rank:
-        [0, 256)            flag pad  uint32[2][16]   (parity of the call counter, sending rank)
-        [256, ...)          two slots of `slot_doubles` fp64 each, selected by the same parity
-    PyTorch only allocates and exchanges the mappings; the kernels do the signalling and the sums."""
+    (bnn_bn_stats_finalize_p2p, bnn_allreduce_f64_p2p).  Every call site (layer x direction) owns a
+    flag row and a data slot; layout, identical on every rank:
+        [0, 64 * n_sites)   flag rows  uint32[n_sites][16]   (row = call site, column = sending rank)
+        then n_sites slots of `slot_doubles` fp64 each
+    The epoch of every exchange is the training-step counter `comm.step_dev`, a device word that the
+    kernels read themselves.  PyTorch only allocates and exchanges the mappings; the kernels do the
+    signalling and the sums."""
 
-    FLAG_BYTES = 256
-
-    def __init__(self, comm: "Comm", max_cols: int):
-        import torch.distributed._symmetric_memory as symm
+    def __init__(self, comm: "Comm", max_cols: int, n_sites: int):
         self.comm = comm
         self.slot_doubles = 2 * max_cols
         self.max_cols = max_cols
-        nbytes = self.FLAG_BYTES + 2 * self.slot_doubles * 8
-        group = comm.group if comm.group is not None else dist.group.WORLD
-        try:
-            symm.enable_symm_mem_for_group(group.group_name)
-        except Exception:
-            pass
-        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
-        self.buf.zero_()
-        self.handle = symm.rendezvous(self.buf, group)
-        self.base = [int(p) for p in self.handle.buffer_ptrs]
-        assert len(self.base) == comm.world and self.base[comm.rank] == self.buf.data_ptr()
-        self.epoch = 0
+        self.n_sites = n_sites
+        self.flag_bytes = -(-(64 * n_sites) // 256) * 256
+        nbytes = self.flag_bytes + n_sites * self.slot_doubles * 8
+        self.buf, self.base, self.handle = _symmetric_buffer(comm, nbytes)
+        self.last_step = [0] * n_sites
         torch.cuda.synchronize()
-        comm.barrier()  # every pad is zero before anyone signals
+        comm.barrier()  # every flag row is zero before anyone signals
 
-    def begin(self, n_doubles: int):
-        """Advance the call counter; returns (this rank's slot as an fp64 tensor, call descriptor)."""
-        assert n_doubles <= self.slot_doubles
-        self.epoch += 1
-        off = self.FLAG_BYTES + (self.epoch & 1) * self.slot_doubles * 8
+    def begin(self, site: int, n_doubles: int):
+        """Returns (this rank's slot of call site `site` as an fp64 tensor, call descriptor)."""
+        assert n_doubles <= self.slot_doubles and 0 <= site < self.n_sites
+        # a call site is used once per step; code that drives a layer outside Network.train_step
+        # (several forwards in a row) advances the step itself, identically on every rank
+        if self.last_step[site] == self.comm.step:
+            self.comm.begin_step()
+        self.last_step[site] = self.comm.step
+        off = self.flag_bytes + site * self.slot_doubles * 8
         slot = self.buf[off: off + n_doubles * 8].view(torch.float64)
-        call = dict(data=[b + off for b in self.base], flags=list(self.base), rank=self.comm.rank,
-                    world=self.comm.world, epoch=self.epoch & 0xFFFFFFFF or 1)
+        call = dict(data=[b + off for b in self.base], flags=[b + 64 * site for b in self.base],
+                    rank=self.comm.rank, world=self.comm.world, step=self.comm.step_dev)
         self.comm.collectives += 1
         return slot, call
 
@@ -114,15 +111,15 @@ class DwExchange:
             self.layout.append(dict(K=k, N=n, rows_per_owner=rpo, w_off=w_off, stage_off=s_off))
         self.nbytes = off
         self.buf, self.base, self.handle = _symmetric_buffer(comm, self.nbytes)
-        self.epochs = [0] * n_layers
         self.counters = torch.zeros(n_layers, dtype=torch.int32, device=self.buf.device)
         # all-gather half: "ce" = copy engines on a side stream (overlaps the backward pass),
         # "kernel" = peer stores from the owner-update kernel itself
         self.copy_engine_broadcast = os.environ.get("BNN_DW_BCAST", "ce").lower() != "kernel"
-        self.epoch_words = torch.zeros(n_layers, dtype=torch.int32, device=self.buf.device)
         self.side = torch.cuda.Stream()
         self.reduced = [torch.cuda.Event() for _ in range(n_layers)]
-        self.copied = [None] * n_layers
+        self.copied = [torch.cuda.Event() for _ in range(n_layers)]
+        self.in_flight = []   # layers whose rows are on their way to the peers (this step)
+        self.pending = []     # layers whose updated rows have not been awaited yet (this step)
         torch.cuda.synchronize()
         comm.barrier()  # every flag pad is zero before anyone signals
 
@@ -139,10 +136,20 @@ class DwExchange:
     def flag_ptrs(self):
         return list(self.base)
 
-    def next_epoch(self, layer: int) -> int:
-        self.epochs[layer] += 1
-        self.comm.collectives += 1
-        return self.epochs[layer]
+    def finish_step(self) -> None:
+        """End of a training step: join the copy-engine stream, then ONE kernel waits until every
+        rank's updated rows of every layer exchanged this step have landed in the local W."""
+        main = torch.cuda.current_stream()
+        for li in self.in_flight:
+            main.wait_event(self.copied[li])
+        self.in_flight.clear()
+        if self.pending:
+            from . import kernels as K_
+            lo, n = min(self.pending), len(self.pending)
+            assert sorted(self.pending) == list(range(lo, lo + n))
+            K_.peer_wait(self.base[self.rank], 2 * lo + 1, 2, n, self.rank, self.world,
+                         self.comm.step_dev)
+            self.pending.clear()
 
 
 class Comm:
@@ -158,8 +165,27 @@ class Comm:
         self.global_batch = None  # rows of the current step over all ranks (None: local * world)
         self.peer_exchange = None  # PeerExchange once enable_peer_exchange() succeeded
         self.dw_exchange = None    # DwExchange once enable_dw_exchange() succeeded
+        # training-step counter: the epoch of every peer-memory exchange.  The device word is what
+        # the kernels read (so a captured step replays correctly); `step` mirrors it on the host.
+        self.step = 0
+        self.step_dev = None
 
-    def enable_peer_exchange(self, max_cols: int) -> bool:
+    def begin_step(self) -> None:
+        """Advance the step counter (host mirror + device word); called once per training step by
+        Network.train_step_async on every rank."""
+        if self.peer_exchange is None and self.dw_exchange is None:
+            return
+        if self.step_dev is None:
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
+        from . import kernels as K_
+        self.step += 1
+        K_.step_tick(self.step_dev)
+
+    def finish_step(self) -> None:
+        if self.dw_exchange is not None:
+            self.dw_exchange.finish_step()
+
+    def enable_peer_exchange(self, max_cols: int, n_sites: int = 2) -> bool:
         """Route the small batch-norm exchanges through NVLink peer memory instead of NCCL.  Returns
         False (and keeps NCCL) where symmetric memory is unavailable; BNN_P2P=0 disables it."""
         if self.world == 1 or os.environ.get("BNN_P2P", "1") == "0" or not torch.cuda.is_available():
@@ -167,15 +193,15 @@ class Comm:
         if dist.get_backend(self.group) != "nccl":
             return False
         try:
-            self.peer_exchange = PeerExchange(self, max_cols)
+            self.peer_exchange = PeerExchange(self, max_cols, n_sites)
         except Exception as exc:  # pragma: no cover - depends on the platform
             print(f"[mlpcode.parallel] peer exchange unavailable, staying on NCCL: {exc}")
             self.peer_exchange = None
         # all ranks must agree, or the kernels would wait for peers that never signal
-        ok = torch.tensor([1 if self.peer_exchange is not None else 0], device="cuda")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
-        if int(ok.item()) == 0:
+        if not self._all_agree(self.peer_exchange is not None):
             self.peer_exchange = None
+        if self.peer_exchange is not None and self.step_dev is None:
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
         return self.peer_exchange is not None
 
     def _all_agree(self, ok: bool) -> bool:
@@ -196,6 +222,8 @@ class Comm:
             self.dw_exchange = None
         if not self._all_agree(self.dw_exchange is not None):
             self.dw_exchange = None
+        if self.dw_exchange is not None and self.step_dev is None:
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
         return self.dw_exchange is not None
 
     def global_rows(self, local_rows: int) -> int:

@@ -270,22 +270,27 @@ int bnn_sgd_update(float* p, const float* g, int64_t n, float lr, int parts, int
  * Data-parallel exchange fused into the finalize kernels (new in this build; the reference is
  * single-process).  The producers (bnn_colstats / bnn_bn_bwd_reduce) write this rank's [2, N] fp64
  * partial sums into its slot of a symmetric buffer; these kernels signal every peer, wait for every
- * peer (bounded spin on a flag pad, st.release.sys / ld.acquire.sys), read all ranks' slots over
+ * peer (bounded spin on a flag row, st.release.sys / ld.acquire.sys), read all ranks' slots over
  * NVLink peer mappings in rank order and finalize on the totals — one launch instead of an NCCL
- * all-reduce plus a finalize.
- *   peer_data_host[r]  (host array of `world` device addresses) rank r's slot for THIS call
- *   peer_flags_host[r] rank r's flag pad, uint32[2][16], zero-initialised once
- *   epoch              call counter (>= 1) advanced identically on every rank; slots and flags are
- *                      double-buffered on its parity by the caller
+ * all-reduce plus a finalize.  Every call site (layer x direction) owns one slot and one flag row.
+ *   peer_data_host[r]  (host array of `world` device addresses) rank r's slot of this call site
+ *   peer_flags_host[r] rank r's flag row of this call site, uint32[BNN_MAX_RANKS], zeroed once
+ *   epoch / epoch_ptr  the training-step counter, advanced identically on every rank: either an
+ *                      immediate (epoch >= 1, epoch_ptr NULL) or a device word read by the kernel
+ *                      (bnn_step_tick increments it), which lets a whole step be replayed as a CUDA
+ *                      graph.  The same convention holds for every *_p2p / bnn_peer_* call below.
  * ------------------------------------------------------------------------------------------- */
+int bnn_step_tick(uint32_t* step_dev, bnn_stream_t stream);
+
 int bnn_bn_stats_finalize_p2p(const uint64_t* peer_data_host, const uint64_t* peer_flags_host, int rank,
-                              int world, uint32_t epoch, int N, double count, float* mu, float* var,
-                              double* sums_total, bnn_stream_t stream);
+                              int world, uint32_t epoch, const uint32_t* epoch_ptr, int N, double count,
+                              float* mu, float* var, double* sums_total, bnn_stream_t stream);
 
 /* The same exchange without the finalize arithmetic: out[i] = sum_r slot_r[i], i < n (used for the
  * batch-norm backward reductions, whose finalize is bnn_bn_bwd_finalize). */
 int bnn_allreduce_f64_p2p(const uint64_t* peer_data_host, const uint64_t* peer_flags_host, int rank,
-                          int world, uint32_t epoch, int n, double* out, bnn_stream_t stream);
+                          int world, uint32_t epoch, const uint32_t* epoch_ptr, int n, double* out,
+                          bnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Data-parallel dW: reduce-scatter fused into the dW GEMM (BNN_EPI_SCATTER_F32 above), then the owner
@@ -297,12 +302,14 @@ int bnn_allreduce_f64_p2p(const uint64_t* peer_data_host, const uint64_t* peer_f
  *   bnn_dw_reduce_sgd_p2p   waits until local flags[slot_pushed][*] >= epoch, reduces + updates + broadcasts
  *                     its rows, then (last block) sets flags_of_peer[p][slot_landed][rank] = epoch
  *   bnn_peer_wait     spins until local flags[slot][r] >= epoch for all r (before W is next read)
+ *   bnn_peer_broadcast_rows   the copy-engine form of the all-gather
  * All waits are bounded (10 s -> trap).  peer_*_host are host arrays of `world` device addresses.
  * ------------------------------------------------------------------------------------------- */
 int bnn_peer_signal(const uint64_t* peer_flags_host, int slot, int rank, int world, uint32_t epoch,
-                    bnn_stream_t stream);
-int bnn_peer_wait(const uint32_t* flags_local, int slot, int rank, int world, uint32_t epoch,
-                  bnn_stream_t stream);
+                    const uint32_t* epoch_ptr, bnn_stream_t stream);
+/* waits on the n_slots flag rows slot, slot + slot_stride, ... in one launch */
+int bnn_peer_wait(const uint32_t* flags_local, int slot, int slot_stride, int n_slots, int rank,
+                  int world, uint32_t epoch, const uint32_t* epoch_ptr, bnn_stream_t stream);
 /* stage_local: this rank's staging buffer float[world][rows_per_owner][ld]; W: [K, N] fp32 row-major
  * with pitch ld == N on every rank (peer_w_host[r] = rank r's W as mapped here; may alias W for
  * r == rank).  counter: device uint32, zero-initialised once (self-resetting block counter).
@@ -311,8 +318,9 @@ int bnn_peer_wait(const uint32_t* flags_local, int slot, int rank, int world, ui
  * engines while the compute stream carries on with the backward pass. */
 int bnn_dw_reduce_sgd_p2p(const float* stage_local, const uint64_t* peer_w_host,
                           const uint64_t* peer_flags_host, int slot_pushed, int slot_landed, int rank,
-                          int world, uint32_t epoch, int K, int N, int rows_per_owner, float lr,
-                          int broadcast, uint32_t* counter, uint32_t* epoch_word, bnn_stream_t stream);
+                          int world, uint32_t epoch, const uint32_t* epoch_ptr, int K, int N,
+                          int rows_per_owner, float lr, int broadcast, uint32_t* counter,
+                          uint32_t* epoch_word, bnn_stream_t stream);
 
 /* All-gather by copy engine: for every rank p, cudaMemcpyAsync of this rank's owned rows of W into
  * rank p's W, followed by a 4-byte copy of *epoch_word into flags_of_peer[p][slot_landed][rank] (also
