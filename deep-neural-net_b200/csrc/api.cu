@@ -113,6 +113,18 @@ extern "C" int bnn_gemm(const bnn_gemm_desc* g, int impl, bnn_stream_t stream) {
                       "bnn_gemm: pass %d refers to a piece outside {0,1}", p);
         BNN_CHECK_ARG(g->A[g->pa[p]] && g->B[g->pb[p]], "bnn_gemm: pass %d uses a null piece", p);
     }
+    BNN_CHECK_ARG(g->stats >= BNN_STATS_NONE && g->stats <= BNN_STATS_BN_BWD, "bnn_gemm: bad stats %d",
+                  g->stats);
+    if (g->stats != BNN_STATS_NONE) {
+        BNN_CHECK_ARG(impl == BNN_GEMM_TCGEN05, "bnn_gemm: fused column statistics are a tcgen05 epilogue");
+        BNN_CHECK_ARG(g->stats_sums != nullptr, "bnn_gemm: stats_sums is null");
+        if (g->stats == BNN_STATS_BN_BWD) {
+            BNN_CHECK_ARG(g->stats_max && g->stats_z && g->stats_mu && g->stats_ldz >= g->N,
+                          "bnn_gemm: BNN_STATS_BN_BWD needs stats_max, stats_z (ldz >= N) and stats_mu");
+            BNN_CHECK_ARG(g->stats_z_dtype >= BNN_Z_F32 && g->stats_z_dtype <= BNN_Z_S32,
+                          "bnn_gemm: bad stats_z_dtype %d", g->stats_z_dtype);
+        }
+    }
     BNN_CHECK_ARG(g->ldd >= g->N, "bnn_gemm: ldd < N");
     BNN_CHECK_ARG(g->batch == 1 || g->stride_d >= (int64_t)g->M * g->ldd,
                   "bnn_gemm: batched output needs stride_d >= M*ldd");

@@ -92,6 +92,13 @@ struct TcParams {
     int rows_per_owner;
     int rank;
     int m_rot;  // row-tile rotation: this rank starts with the tiles it owns itself
+    // column reductions fused into the epilogue (BNN_STATS_*)
+    double* st_sums;       // [2, N] fp64 accumulators (pre-zeroed by the caller)
+    uint32_t* st_max;      // [2, N] float bit patterns (BNN_STATS_BN_BWD)
+    const void* st_Z;      // BNN_STATS_BN_BWD: pre-activations [M, st_ldz] of the batch-norm layer
+    long long st_ldz;
+    int st_zdtype;
+    const float* st_mu;
 };
 
 __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& b, int& m_blk,
@@ -222,59 +229,177 @@ __device__ __forceinline__ void store_group(const TcParams& p, char* dbase, long
     }
 }
 
-// Coalesced fp32 store of one warp's 32 rows x CPT columns (registers: lane = row) through the warp's
-// transpose buffer.  Two phases of 16 rows; per phase and 32-column group the 16 source lanes write
-// their 8 float4, then all 32 lanes read 4 float4 each so that 8 adjacent lanes cover the 128 bytes
-// of one row segment.  EPI: STORE_F32 / SCATTER_F32 store, SGD_F32 subtracts from the destination.
-template <bool kI8, int EPI, int CPT>
-__device__ __forceinline__ void store_rows_coalesced(const TcParams& p, float* xbuf, float* dst_row0,
-                                                     int rows_valid, const uint32_t (&sum)[CPT],
-                                                     float scale, int lane) {
+// One warp's 32 rows x CPT columns (registers: lane = row) pass through the warp's transpose buffer:
+// two phases of 16 rows; per phase and 32-column group the 16 source lanes write their 8 float4, then
+//   * kStore: all 32 lanes read 4 float4 each so that 8 adjacent lanes cover the 128 bytes of one row
+//     segment (EPI: STORE_F32 / SCATTER_F32 store, SGD_F32 subtracts from the destination);
+//   * STATS: lane c reads column c of the staged rows and accumulates the column reductions that
+//     the batch-norm kernels would otherwise re-read the whole matrix for:
+//       BNN_STATS_COLSUM  sum v, sum v^2                       (bnn_colstats,      layers.py:81-82)
+//       BNN_STATS_BN_BWD  sum v, sum v*(Z-mu), max|v|, max|Z-mu| (bnn_bn_bwd_reduce, layers.py:107-115)
+//     32-row partials (exact integers for int8 products, fp32 otherwise) go to the fp64 column
+//     accumulators with one atomicAdd per column and warp.
+// The value v is what the epilogue stores: acc * scale for fp32 outputs, the raw int32 sum for
+// integer outputs.
+template <bool kI8, int EPI, int CPT, int STATS, bool kStore>
+__device__ __forceinline__ void staged_rows(const TcParams& p, uint32_t xbuf, float* dst_row0,
+                                            int row_w0, int col_w0, const uint32_t (&sum)[CPT],
+                                            float scale, int lane) {
     constexpr int GC = CPT < 32 ? CPT : 32;   // columns per group
     constexpr int LPR = GC / 4;               // lanes per row segment
     constexpr int RPI = 32 / LPR;             // rows per store instruction
     constexpr bool sgd = EPI == BNN_EPI_SGD_F32;
+    constexpr bool kIntVal = EPI == BNN_EPI_STORE_S16 || EPI == BNN_EPI_STORE_S32;  // v is an integer
+    const int rows_valid = p.M - row_w0;
 #pragma unroll
     for (int g = 0; g < CPT / GC; ++g) {
+        // per-group column accumulators of lane c (STATS only)
+        int si = 0;
+        unsigned long long qi = 0ull;
+        float f1 = 0.f, f2 = 0.f, md = 0.f, mx = 0.f;
+        const int col = col_w0 + g * GC + lane;  // this lane's column in the stats phase
+        float mu = 0.f;
+        if (STATS == BNN_STATS_BN_BWD && lane < GC && col < p.N) mu = __ldg(p.st_mu + col);
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {
+            // BN_BWD: this lane's column of Z for the 16 rows of the phase is requested first, so the
+            // loads are in flight while the tile is staged and stored
+            // (raw bits only: converting here would make every load wait for the one before it).
+            // Code size matters — this function is unrolled 8 times per tile and the kernel must stay
+            // within the instruction cache — so the fast path assumes 16 valid rows and a valid
+            // column (pointer increments, no predicates); ragged bottom tiles take a rolled loop.
+            int zr[kXposeRows];
+            bool zfast = false;
+            int rmax = 0;
+            const char* zp = nullptr;
+            long long zstride = 0;
+            if (STATS == BNN_STATS_BN_BWD) {
+                const bool colok = lane < GC && col < p.N;
+                rmax = colok ? max(0, min(kXposeRows, rows_valid - ph * kXposeRows)) : 0;
+                const int esz = p.st_zdtype == BNN_Z_S16 ? 2 : 4;
+                zstride = p.st_ldz * esz;
+                zp = reinterpret_cast<const char*>(p.st_Z) +
+                     ((long long)(row_w0 + ph * kXposeRows) * p.st_ldz + col) * esz;
+                zfast = __all_sync(0xffffffffu, rmax == kXposeRows);
+                if (zfast) {
+                    const char* q = zp;
+                    if (esz == 2) {
+#pragma unroll
+                        for (int r = 0; r < kXposeRows; ++r, q += zstride)
+                            zr[r] = (int)__ldg(reinterpret_cast<const int16_t*>(q));
+                    } else {  // int32 and fp32 travel as 32-bit patterns
+#pragma unroll
+                        for (int r = 0; r < kXposeRows; ++r, q += zstride)
+                            zr[r] = __ldg(reinterpret_cast<const int32_t*>(q));
+                    }
+                }
+            }
             if ((lane >> 4) == ph) {
-                float* w = xbuf + (lane & 15) * kXposeStride;
+                const uint32_t w = xbuf + (uint32_t)((lane & 15) * kXposeStride * 4);
 #pragma unroll
                 for (int j = 0; j < GC; j += 4) {
-                    float4 f;
-                    f.x = __fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 0] : __uint_as_float(sum[g * GC + j + 0]), scale);
-                    f.y = __fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 1] : __uint_as_float(sum[g * GC + j + 1]), scale);
-                    f.z = __fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 2] : __uint_as_float(sum[g * GC + j + 2]), scale);
-                    f.w = __fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 3] : __uint_as_float(sum[g * GC + j + 3]), scale);
-                    *reinterpret_cast<float4*>(w + j) = f;
+                    uint4 u;
+                    if (kIntVal) {
+                        u = make_uint4(sum[g * GC + j], sum[g * GC + j + 1], sum[g * GC + j + 2],
+                                       sum[g * GC + j + 3]);
+                    } else {
+                        u.x = __float_as_uint(__fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 0] : __uint_as_float(sum[g * GC + j + 0]), scale));
+                        u.y = __float_as_uint(__fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 1] : __uint_as_float(sum[g * GC + j + 1]), scale));
+                        u.z = __float_as_uint(__fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 2] : __uint_as_float(sum[g * GC + j + 2]), scale));
+                        u.w = __float_as_uint(__fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 3] : __uint_as_float(sum[g * GC + j + 3]), scale));
+                    }
+                    ptx::sts_v4(w + (uint32_t)(j * 4), u.x, u.y, u.z, u.w);
                 }
             }
             __syncwarp();
+            if (kStore) {
 #pragma unroll
-            for (int i = 0; i < kXposeRows / RPI; ++i) {
-                const int r = lane / LPR + RPI * i;       // row within the phase
-                const int c = (lane % LPR) * 4;           // column within the group
-                const int row = ph * kXposeRows + r;      // row within the warp's 32
-                float4 f = *reinterpret_cast<const float4*>(xbuf + r * kXposeStride + c);
-                if (row < rows_valid) {
-                    float* d = dst_row0 + (long long)row * p.ldd + g * GC + c;
-                    if (sgd) {  // weights -= lr * dw (layers.py:268): two roundings, like NumPy
-                        const float4 wv = *reinterpret_cast<const float4*>(d);
-                        f.x = __fsub_rn(wv.x, f.x);
-                        f.y = __fsub_rn(wv.y, f.y);
-                        f.z = __fsub_rn(wv.z, f.z);
-                        f.w = __fsub_rn(wv.w, f.w);
+                for (int i = 0; i < kXposeRows / RPI; ++i) {
+                    const int r = lane / LPR + RPI * i;       // row within the phase
+                    const int c = (lane % LPR) * 4;           // column within the group
+                    const int row = ph * kXposeRows + r;      // row within the warp's 32
+                    const uint4 fu = ptx::lds_v4(xbuf + (uint32_t)((r * kXposeStride + c) * 4));
+                    float4 f = make_float4(__uint_as_float(fu.x), __uint_as_float(fu.y),
+                                           __uint_as_float(fu.z), __uint_as_float(fu.w));
+                    if (row < rows_valid) {
+                        float* d = dst_row0 + (long long)row * p.ldd + g * GC + c;
+                        if (sgd) {  // weights -= lr * dw (layers.py:268): two roundings, like NumPy
+                            const float4 wv = *reinterpret_cast<const float4*>(d);
+                            f.x = __fsub_rn(wv.x, f.x);
+                            f.y = __fsub_rn(wv.y, f.y);
+                            f.z = __fsub_rn(wv.z, f.z);
+                            f.w = __fsub_rn(wv.w, f.w);
+                        }
+                        *reinterpret_cast<float4*>(d) = f;
                     }
-                    *reinterpret_cast<float4*>(d) = f;
+                }
+            }
+            if (STATS != BNN_STATS_NONE && lane < GC && col < p.N) {
+                if (STATS == BNN_STATS_COLSUM) {
+                    // rows past M hold zeros (TMA zero-fill), so no row guard is needed for the sums
+#pragma unroll
+                    for (int r = 0; r < kXposeRows; ++r) {
+                        const uint32_t u = ptx::lds_b32(xbuf + (uint32_t)((r * kXposeStride + lane) * 4));
+                        if (kIntVal) {
+                            const int v = (int)u;
+                            si += v;
+                            qi += (unsigned long long)((long long)v * (long long)v);
+                        } else {
+                            const float v = __uint_as_float(u);
+                            f1 += v;
+                            f2 = fmaf(v, v, f2);
+                        }
+                    }
+                } else {
+                    const bool zfloat = p.st_zdtype == BNN_Z_F32;
+                    if (zfast) {
+#pragma unroll
+                        for (int r = 0; r < kXposeRows; ++r) {
+                            const float d = __uint_as_float(
+                                ptx::lds_b32(xbuf + (uint32_t)((r * kXposeStride + lane) * 4)));
+                            const float z = zfloat ? __int_as_float(zr[r]) : (float)zr[r];
+                            const float xm = z - mu;
+                            f1 += d;
+                            f2 = fmaf(d, xm, f2);
+                            md = fmaxf(md, fabsf(d));
+                            mx = fmaxf(mx, fabsf(xm));
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int r = 0; r < rmax; ++r) {
+                            const char* q = zp + (long long)r * zstride;
+                            float z;
+                            if (p.st_zdtype == BNN_Z_S16) z = (float)__ldg(reinterpret_cast<const int16_t*>(q));
+                            else if (zfloat) z = __ldg(reinterpret_cast<const float*>(q));
+                            else z = (float)__ldg(reinterpret_cast<const int32_t*>(q));
+                            const float d = __uint_as_float(
+                                ptx::lds_b32(xbuf + (uint32_t)((r * kXposeStride + lane) * 4)));
+                            const float xm = z - mu;
+                            f1 += d;
+                            f2 = fmaf(d, xm, f2);
+                            md = fmaxf(md, fabsf(d));
+                            mx = fmaxf(mx, fabsf(xm));
+                        }
+                    }
                 }
             }
             __syncwarp();
         }
+        if (STATS != BNN_STATS_NONE && lane < GC && col < p.N) {
+            double a, b;
+            if (STATS == BNN_STATS_COLSUM && kIntVal) { a = (double)si; b = (double)qi; }
+            else { a = (double)f1; b = (double)f2; }
+            atomicAdd(p.st_sums + col, a);
+            atomicAdd(p.st_sums + p.N + col, b);
+            if (STATS == BNN_STATS_BN_BWD) {
+                if (md > 0.f) atomicMax(p.st_max + col, __float_as_uint(md));
+                if (mx > 0.f) atomicMax(p.st_max + p.N + col, __float_as_uint(mx));
+            }
+        }
     }
 }
 
-template <bool kI8, int BLOCK_N, int EPI>
+template <bool kI8, int BLOCK_N, int EPI, int STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
@@ -412,6 +537,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int row = m_blk * kBlockM + q * 32 + lane;
             const int colbase = n_blk * BLOCK_N + h * CPT;
             for (int c = 0; c < n_chunks; ++c) {
+                if (STATS == BNN_STATS_BN_BWD && c == n_chunks - 1 && row < p.M) {
+                    // pull this row's slice of Z into L2 one chunk ahead of the statistics phase,
+                    // whose column-wise reads would otherwise each pay a DRAM round trip
+                    const int esz = p.st_zdtype == BNN_Z_S16 ? 2 : 4;
+                    const char* zrow = reinterpret_cast<const char*>(p.st_Z) +
+                                       ((long long)row * p.st_ldz + colbase) * esz;
+                    for (int o = 0; o < CPT * esz; o += 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(zrow + o));
+                }
                 ptx::mbar_wait(&tfull_bar[acc], acc_ph);
                 ptx::tc_fence_after_sync();
                 const uint32_t t_row =
@@ -463,12 +597,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 rowoff = ((long long)p.rank * p.rows_per_owner +
                           (row - owner * p.rows_per_owner)) * p.ldd;
             }
-            if (kF32Out && p.vec_ok && colbase + CPT <= p.N) {
+            const int row_w0 = m_blk * kBlockM + q * 32;  // first row of this warp
+            const uint32_t xbuf = ptx::smem_u32(xpose) + (uint32_t)((warp - 4) * kXposeRows * kXposeStride * 4);
+            // the host only asks for STATS on shapes where every tile is full-width and vector-aligned
+            if (kF32Out && ((p.vec_ok && colbase + CPT <= p.N) || STATS != BNN_STATS_NONE)) {
                 // full-width tile: whole 128-byte row segments per store instruction
-                const int row_w0 = m_blk * kBlockM + q * 32;  // first row of this warp
                 float* dst = reinterpret_cast<float*>(dbase) + (rowoff - (long long)lane * p.ldd) + colbase;
-                store_rows_coalesced<kI8, EPI, CPT>(p, xpose + (warp - 4) * kXposeRows * kXposeStride,
-                                                    dst, p.M - row_w0, sum, scale, lane);
+                staged_rows<kI8, EPI, CPT, STATS, true>(p, xbuf, dst, row_w0, colbase, sum, scale, lane);
             } else if (row < p.M) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
@@ -481,6 +616,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         asm volatile("" ::: "memory");  // keep the groups' live ranges disjoint
                     }
                 }
+            }
+            if (!kF32Out && STATS != BNN_STATS_NONE) {
+                // integer outputs keep their direct stores; the column sums take the staged route
+                __syncwarp();
+                staged_rows<kI8, EPI, CPT, STATS, false>(p, xbuf, nullptr, row_w0, colbase, sum, scale, lane);
             }
         }
     }
@@ -539,12 +679,12 @@ int make_operand_map(CUtensorMap* map, const void* base, bool i8, long long rows
     return BNN_OK;
 }
 
-template <bool kI8, int BLOCK_N, int EPI>
+template <bool kI8, int BLOCK_N, int EPI, int STATS = BNN_STATS_NONE>
 int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     using Cfg = TileCfg<BLOCK_N>;
     static bool attr_set = false;
     if (!attr_set) {
-        BNN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kI8, BLOCK_N, EPI>,
+        BNN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kI8, BLOCK_N, EPI, STATS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::kSmemBytes));
         attr_set = true;
@@ -609,14 +749,44 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     }
     const long long tiles = (long long)p.batch * p.m_tiles * p.n_tiles;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    gemm_tc_kernel<kI8, BLOCK_N, EPI><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA[0], mA[1],
-                                                                                  mB[0], mB[1], p);
+    p.st_sums = g.stats_sums;
+    p.st_max = g.stats_max;
+    p.st_Z = g.stats_z;
+    p.st_ldz = g.stats_ldz;
+    p.st_zdtype = g.stats_z_dtype;
+    p.st_mu = g.stats_mu;
+    if (STATS != BNN_STATS_NONE) {
+        // every tile must take the staged full-width path
+        if (!(p.vec_ok && g.N % BLOCK_N == 0 && g.batch == 1)) {
+            set_error("bnn_gemm: fused column statistics need N %% %d == 0, a 16-byte aligned output "
+                      "and batch == 1 (N=%d)", BLOCK_N, g.N);
+            return BNN_ERR_UNSUPPORTED;
+        }
+    }
+    gemm_tc_kernel<kI8, BLOCK_N, EPI, STATS><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(
+        mA[0], mA[1], mB[0], mB[1], p);
     BNN_LAUNCH_CHECK("gemm_tc_kernel");
     return BNN_OK;
 }
 
 template <int BLOCK_N>
 int pick_epilogue(const bnn_gemm_desc& g, bool i8, cudaStream_t stream) {
+    if (g.stats == BNN_STATS_COLSUM) {
+        if (i8 && g.epilogue == BNN_EPI_STORE_S16)
+            return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S16, BNN_STATS_COLSUM>(g, stream);
+        if (i8 && g.epilogue == BNN_EPI_STORE_S32)
+            return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S32, BNN_STATS_COLSUM>(g, stream);
+        if (!i8 && g.epilogue == BNN_EPI_STORE_F32)
+            return launch_tc<false, BLOCK_N, BNN_EPI_STORE_F32, BNN_STATS_COLSUM>(g, stream);
+        set_error("bnn_gemm: BNN_STATS_COLSUM goes with int8 S16/S32 or fp16 F32 stores");
+        return BNN_ERR_UNSUPPORTED;
+    }
+    if (g.stats == BNN_STATS_BN_BWD) {
+        if (!i8 && g.epilogue == BNN_EPI_STORE_F32)
+            return launch_tc<false, BLOCK_N, BNN_EPI_STORE_F32, BNN_STATS_BN_BWD>(g, stream);
+        set_error("bnn_gemm: BNN_STATS_BN_BWD goes with fp16 operands and BNN_EPI_STORE_F32");
+        return BNN_ERR_UNSUPPORTED;
+    }
     if (i8) {
         switch (g.epilogue) {
             case BNN_EPI_STORE_S16: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S16>(g, stream);

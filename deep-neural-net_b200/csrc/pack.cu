@@ -36,28 +36,59 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Transposing weight binarization: W[K,N] fp32 -> K-major +-1 copies [N, K].
-// Tile = 128 (k) x 32 (n): reads are 128-byte row segments, writes are 128 consecutive k per n.
+// Transposing weight binarization: W[K,N] fp32 -> K-major +-1 copies [N, K] and packed bits.
+// A warp owns 32 (k) x 128 (n): every row is read as one 512-byte segment (float4 per lane), and
+// each lane folds the sign of its 4 columns into four 32-bit masks over k — which ARE the packed
+// words wt_bits[n][k/32].  No transpose through shared memory is needed: the masks are expanded in
+// registers into the 32 consecutive int8 / fp16 values of output row n and leave as 16-byte stores.
+// Block = 8 warps = 128 (k) x 256 (n).
 // ---------------------------------------------------------------------------------------------
+constexpr int BT_K = 128, BT_N = 256;
+
+// 4 mask bits -> 4 bytes of +-1 (bit ? 0x01 : 0xFF)
+__device__ __forceinline__ uint32_t nibble_to_pm1_bytes(uint32_t nib) {
+    const uint32_t spread = ((nib & 0xFu) * 0x00204081u) & 0x01010101u;
+    return 0xFFFFFFFFu ^ (spread * 0xFEu);
+}
+// 2 mask bits -> 2 halves of +-1.0 (bit ? 0x3C00 : 0xBC00)
+__device__ __forceinline__ uint32_t pair_to_pm1_halves(uint32_t two) {
+    return 0x3C003C00u | ((~two & 1u) << 15) | ((~two & 2u) << 30);
+}
+
 __global__ void __launch_bounds__(256)
 binarize_t_kernel(const float* __restrict__ W, int K, int N, int8_t* __restrict__ wt_i8,
                   long long ld_i8, __half* __restrict__ wt_f16, long long ld_f16,
                   uint32_t* __restrict__ wt_bits, long long ld_bits,
                   uint32_t* __restrict__ absmax_bits) {
-    __shared__ uint32_t s[128][33];
-    const int k0 = blockIdx.y * 128, n0 = blockIdx.x * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k0 = blockIdx.y * BT_K + (warp & 3) * 32;
+    const int n0 = blockIdx.x * BT_N + (warp >> 2) * 128 + lane * 4;
+    if (k0 >= K) return;  // warp-uniform
+    const bool vec = (N % 4 == 0) && aligned16(W);
+    const int nvalid = max(0, min(4, N - n0));
+    const int kvalid = min(32, K - k0);
+    uint32_t m[4] = {0u, 0u, 0u, 0u};
     float amax = 0.0f;
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const int k = warp + 8 * i;
-        const int gk = k0 + k, gn = n0 + lane;
-        float v = -1.0f;
-        if (gk < K && gn < N) {
-            v = __ldg(W + (long long)gk * N + gn);
-            amax = fmaxf(amax, fabsf(v));
+    if (nvalid > 0) {
+        const float* base = W + (long long)k0 * N + n0;
+        if (vec && nvalid == 4 && kvalid == 32) {
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(base + (long long)k * N));
+                m[0] |= sign_bit_ge0(v.x) << k;
+                m[1] |= sign_bit_ge0(v.y) << k;
+                m[2] |= sign_bit_ge0(v.z) << k;
+                m[3] |= sign_bit_ge0(v.w) << k;
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            }
+        } else {
+            for (int k = 0; k < kvalid; ++k)
+                for (int j = 0; j < nvalid; ++j) {
+                    const float v = __ldg(base + (long long)k * N + j);
+                    m[j] |= sign_bit_ge0(v) << k;
+                    amax = fmaxf(amax, fabsf(v));
+                }
         }
-        s[k][lane] = sign_bit_ge0(v);
     }
     if (absmax_bits) {  // max|W| for the backward split comes for free with this read of W
         amax = warp_max(amax);
@@ -65,25 +96,42 @@ binarize_t_kernel(const float* __restrict__ W, int K, int N, int8_t* __restrict_
         if (lane == 0 && __float_as_uint(amax) > *reinterpret_cast<volatile uint32_t*>(absmax_bits))
             atomicMax(absmax_bits, __float_as_uint(amax));
     }
-    __syncthreads();
+    const bool i8vec = wt_i8 && aligned16(wt_i8) && (ld_i8 % 16 == 0) && kvalid == 32;
+    const bool f16vec = wt_f16 && aligned16(wt_f16) && (ld_f16 % 8 == 0) && kvalid == 32;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int n = warp * 4 + i;
-        const int gn = n0 + n;
-        if (gn >= N) continue;  // warp-uniform
+    for (int j = 0; j < 4; ++j) {
+        if (j >= nvalid) break;
+        const long long n = n0 + j;
+        const uint32_t bits = m[j];
+        if (wt_bits) wt_bits[n * ld_bits + (k0 >> 5)] = bits;
+        if (wt_i8) {
+            int8_t* d = wt_i8 + n * ld_i8 + k0;
+            if (i8vec) {
+                uint4 a, b;
+                a.x = nibble_to_pm1_bytes(bits);       a.y = nibble_to_pm1_bytes(bits >> 4);
+                a.z = nibble_to_pm1_bytes(bits >> 8);  a.w = nibble_to_pm1_bytes(bits >> 12);
+                b.x = nibble_to_pm1_bytes(bits >> 16); b.y = nibble_to_pm1_bytes(bits >> 20);
+                b.z = nibble_to_pm1_bytes(bits >> 24); b.w = nibble_to_pm1_bytes(bits >> 28);
+                reinterpret_cast<uint4*>(d)[0] = a;
+                reinterpret_cast<uint4*>(d)[1] = b;
+            } else {
+                for (int k = 0; k < kvalid; ++k) d[k] = ((bits >> k) & 1u) ? (int8_t)1 : (int8_t)-1;
+            }
+        }
+        if (wt_f16) {
+            __half* d = wt_f16 + n * ld_f16 + k0;
+            if (f16vec) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const int gk = k0 + kk * 32 + lane;
-            const bool valid = gk < K;
-            const uint32_t bit = valid ? s[kk * 32 + lane][n] : 0u;
-            const uint32_t word = __ballot_sync(0xffffffffu, bit != 0u);
-            if (wt_bits && lane == 0 && (k0 + kk * 32) < K)
-                wt_bits[(long long)gn * ld_bits + ((k0 + kk * 32) >> 5)] = word;
-            if (valid) {
-                if (wt_i8) wt_i8[(long long)gn * ld_i8 + gk] = bit ? (int8_t)1 : (int8_t)-1;
-                if (wt_f16)
-                    wt_f16[(long long)gn * ld_f16 + gk] =
-                        __ushort_as_half(bit ? (unsigned short)0x3C00 : (unsigned short)0xBC00);
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t b8 = bits >> (8 * q);
+                    reinterpret_cast<uint4*>(d)[q] =
+                        make_uint4(pair_to_pm1_halves(b8), pair_to_pm1_halves(b8 >> 2),
+                                   pair_to_pm1_halves(b8 >> 4), pair_to_pm1_halves(b8 >> 6));
+                }
+            } else {
+                for (int k = 0; k < kvalid; ++k)
+                    d[k] = __ushort_as_half(((bits >> k) & 1u) ? (unsigned short)0x3C00
+                                                               : (unsigned short)0xBC00);
             }
         }
     }
@@ -264,7 +312,7 @@ extern "C" int bnn_binarize_weights_t(const float* W, int K, int N, int8_t* wt_i
     BNN_CHECK_ARG(!wt_i8 || ld_i8 >= K, "bnn_binarize_weights_t: ld_i8 < K");
     BNN_CHECK_ARG(!wt_f16 || ld_f16 >= K, "bnn_binarize_weights_t: ld_f16 < K");
     BNN_CHECK_ARG(!wt_bits || ld_bits >= (K + 31) / 32, "bnn_binarize_weights_t: ld_bits too small");
-    dim3 grid(cdiv(N, 32), cdiv(K, 128));
+    dim3 grid(cdiv(N, BT_N), cdiv(K, BT_K));
     BNN_CHECK_ARG(grid.y <= 65535, "bnn_binarize_weights_t: K too large");
     if (absmax_bits)
         BNN_CUDA(cudaMemsetAsync(absmax_bits, 0, sizeof(uint32_t), (cudaStream_t)stream));

@@ -17,6 +17,7 @@ BNN_OK, BNN_ERR_ARG, BNN_ERR_CUDA, BNN_ERR_UNSUPPORTED = 0, -1, -2, -3
 DT_I8, DT_F16 = 0, 1
 EPI_STORE_F32, EPI_STORE_S32, EPI_STORE_S16, EPI_SGD_F32, EPI_SIGN_I8, EPI_SCATTER_F32 = 0, 1, 2, 3, 4, 5
 MAX_RANKS = 16
+STATS_NONE, STATS_COLSUM, STATS_BN_BWD = 0, 1, 2
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
 Z_F32, Z_S16, Z_S32 = 0, 1, 2
 GEMM_MAX_PASS = 4
@@ -53,6 +54,9 @@ class GemmDesc(C.Structure):
         ("host_scale", C.c_float), ("reserved", C.c_int32),
         ("epi_thr", C.c_void_p), ("epi_sgn", C.c_void_p),
         ("scatter", C.POINTER(PeerScatter)),
+        ("stats", C.c_int32), ("stats_z_dtype", C.c_int32),
+        ("stats_sums", C.c_void_p), ("stats_max", C.c_void_p), ("stats_z", C.c_void_p),
+        ("stats_ldz", C.c_int64), ("stats_mu", C.c_void_p),
     ]
 
 

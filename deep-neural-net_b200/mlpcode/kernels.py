@@ -83,9 +83,11 @@ def split_f16(x: torch.Tensor, bound: torch.Tensor, hi=None, lo=None, hi_t=None,
 # ------------------------------------------------------------------------------- GEMMs
 def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),), sa=None,
          sb=None, host_scale=1.0, batch=1, stride_a=0, stride_b=0, stride_d=0, impl=None,
-         epi_thr=None, epi_sgn=None, scatter=None) -> None:
+         epi_thr=None, epi_sgn=None, scatter=None, stats=None) -> None:
     """D = epi(sum_p A[pa] @ B[pb]^T); A/B are sequences of 1..2 operand-piece tensors.
-    scatter (EPI_SCATTER_F32): dict(world, rank, rows_per_owner, stage=[address per rank])."""
+    scatter (EPI_SCATTER_F32): dict(world, rank, rows_per_owner, stage=[address per rank]).
+    stats: dict(mode=STATS_COLSUM, sums) or dict(mode=STATS_BN_BWD, sums, max, Z, mu) — column
+    reductions of the result accumulated by the epilogue (see fused_stats_ok)."""
     d = nat.GemmDesc()
     d.M, d.N, d.K, d.batch = M, N, K, batch
     d.in_dtype, d.epilogue, d.n_pass = in_dtype, epilogue, len(passes)
@@ -99,6 +101,12 @@ def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),
     d.sa, d.sb = ptr(sa), ptr(sb)
     d.host_scale = host_scale
     d.epi_thr, d.epi_sgn = ptr(epi_thr), ptr(epi_sgn)
+    if stats is not None:
+        d.stats, d.stats_sums = stats["mode"], ptr(stats["sums"])
+        if stats["mode"] == nat.STATS_BN_BWD:
+            Zs = stats["Z"]
+            d.stats_max, d.stats_z, d.stats_mu = ptr(stats["max"]), ptr(Zs), ptr(stats["mu"])
+            d.stats_ldz, d.stats_z_dtype = _ld(Zs), z_dtype_of(Zs)
     if scatter is not None:
         sc = nat.PeerScatter()
         sc.world, sc.rank, sc.rows_per_owner = scatter["world"], scatter["rank"], scatter["rows_per_owner"]
@@ -114,6 +122,17 @@ def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),
     end.record()
     gemm_events.append((start, end, "i8" if in_dtype == nat.DT_I8 else "f16",
                         2.0 * M * N * K * batch, len(passes)))
+
+
+def fused_stats_ok(N: int, impl=None) -> bool:
+    """Shapes on which the tcgen05 epilogue can carry the column reductions: every tile full-width
+    (tile = 256 columns for N > 128, 128 for N > 32, else 32)."""
+    if (gemm_impl() if impl is None else impl) != nat.GEMM_TCGEN05:
+        return False
+    if os.environ.get("BNN_FUSE_STATS", "1") == "0":
+        return False
+    tile = 256 if N > 128 else (128 if N > 32 else 32)
+    return N % tile == 0
 
 
 def gemm_popc(a_bits, b_bits, M, N, K, D, out_s16=True) -> None:

@@ -188,8 +188,24 @@ class BatchNormLayer(Layer):
         super().build()
 
     # -- device primitives shared with BinaryLayer ----------------------------------------
-    def batch_stats(self, Z, B):
-        """Column mean / population variance of Z over the GLOBAL batch (layers.py:81-82)."""
+    def stats_target(self):
+        """Zeroed [2, n] fp64 accumulator for (sum z, sum z^2) that a GEMM epilogue may fill
+        (BNN_STATS_COLSUM) instead of a bnn_colstats pass; hand it back to batch_stats()."""
+        n = self.layerUnits
+        px = self.comm.peer_exchange
+        if px is not None and n <= px.max_cols:
+            slot, call = px.begin(self.exchange_site, 2 * n)
+            acc = slot.view(2, n)
+            self._stats_call = call
+        else:
+            acc = self._ws.get("sums", (2, n), torch.float64)
+            self._stats_call = None
+        acc.zero_()
+        return acc
+
+    def batch_stats(self, Z, B, filled=None):
+        """Column mean / population variance of Z over the GLOBAL batch (layers.py:81-82).
+        filled: the accumulator from stats_target() if the producing GEMM already summed the columns."""
         n = self.layerUnits
         sums = self._ws.get("sums", (2, n), torch.float64)
         mu = self._ws.get("mu_b", (n,), torch.float32)
@@ -198,16 +214,40 @@ class BatchNormLayer(Layer):
         if px is not None and n <= px.max_cols:
             # sync-BN over NVLink peer memory: partial sums land in this rank's symmetric slot and the
             # finalize kernel itself gathers every rank's slot (one launch, no NCCL call)
-            slot, call = px.begin(self.exchange_site, 2 * n)
-            K_.colstats(Z, B, n, slot.view(2, n))
+            if filled is None:
+                slot, call = px.begin(self.exchange_site, 2 * n)
+                K_.colstats(Z, B, n, slot.view(2, n))
+            else:
+                call = self._stats_call
             K_.bn_stats_finalize_p2p(call, n, self.comm.global_rows(B), mu, var, sums)
             return sums, mu, var
-        K_.colstats(Z, B, n, sums)
+        if filled is None:
+            K_.colstats(Z, B, n, sums)
         self.comm.allreduce_sum(sums)  # sync-BN: exact (integer-valued fp64 sums) for +-1 layers
         K_.bn_stats_finalize(sums, n, self.comm.global_rows(B), mu, var)
         return sums, mu, var
 
-    def backward_kernels(self, delta, Z, B, sums, mu, var, lr, want_f32, d_rm, d_t, scale):
+    def bwd_reduce_target(self, Z, mu):
+        """Zeroed accumulators for the batch-norm backward reductions of THIS layer, to be filled by
+        the epilogue of the dX GEMM that produces its incoming delta (BNN_STATS_BN_BWD)."""
+        n = self.layerUnits
+        red_max = self._ws.get("red_max", (2, n), torch.int32)
+        px = self.comm.peer_exchange
+        if px is not None and n <= px.max_cols:
+            slot, call = px.begin(self.exchange_site + 1, 2 * n)
+            red = slot.view(2, n)
+            self._red_call = call
+        else:
+            red = self._ws.get("red", (2, n), torch.float64)
+            self._red_call = None
+        red.zero_()
+        red_max.zero_()
+        return dict(mode=nat.STATS_BN_BWD, sums=red, max=red_max, Z=Z, mu=mu)
+
+    def backward_kernels(self, delta, Z, B, sums, mu, var, lr, want_f32, d_rm, d_t, scale,
+                         reduced=False):
+        """reduced: the reductions were already accumulated into bwd_reduce_target() by the GEMM that
+        produced `delta`."""
         n = self.layerUnits
         red = self._ws.get("red", (2, n), torch.float64)
         red_max = self._ws.get("red_max", (2, n), torch.int32)
@@ -215,11 +255,15 @@ class BatchNormLayer(Layer):
         bound = self._ws.get("bound", (1,), torch.float32)  # written as uint32 bits of a float
         px = self.comm.peer_exchange
         if px is not None and n <= px.max_cols:
-            slot, call = px.begin(self.exchange_site + 1, 2 * n)
-            K_.bn_bwd_reduce(delta, Z, B, n, mu, slot.view(2, n), red_max)
+            if reduced:
+                call = self._red_call
+            else:
+                slot, call = px.begin(self.exchange_site + 1, 2 * n)
+                K_.bn_bwd_reduce(delta, Z, B, n, mu, slot.view(2, n), red_max)
             K_.allreduce_f64_p2p(call, 2 * n, red)
         else:
-            K_.bn_bwd_reduce(delta, Z, B, n, mu, red, red_max)
+            if not reduced:
+                K_.bn_bwd_reduce(delta, Z, B, n, mu, red, red_max)
             self.comm.allreduce_sum(red)
         K_.bn_bwd_finalize(red, red_max, n, self.comm.global_rows(B), mu, var, self.EPSILON,
                            self.gamma.t, self.beta.t, self.mu.t, self.sigma.t, lr, self.MA_BETA,
@@ -488,6 +532,13 @@ class BinaryLayer(LinearLayer):
         if fuse_sign:
             K_.bn_sign_thresholds(bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
 
+        # training: the GEMM epilogue also accumulates the batch-norm column sums (sum z, sum z^2), so
+        # Z is not re-read for them (shapes the epilogue cannot cover use the bnn_colstats pass)
+        acc = None
+        if isTrain and not (popc and not real_input) and K_.fused_stats_ok(N):
+            acc = bn.stats_target()
+        stats = dict(mode=nat.STATS_COLSUM, sums=acc) if acc is not None else None
+
         # ---- z = X . sign(W)
         Z = None
         if real_input:
@@ -499,7 +550,7 @@ class BinaryLayer(LinearLayer):
             K_.gemm(M=B, N=N, K=Kd, A=(xin["hi"], xin["lo"]), B=(wops["f16"],),
                     lda=xin["hi"].stride(0), ldb=wops["f16"].stride(0), D=D, ldd=ldd,
                     in_dtype=nat.DT_F16, epilogue=epi, passes=((0, 0), (1, 0)), sa=xin["scale"],
-                    epi_thr=thr, epi_sgn=sgn)
+                    epi_thr=thr, epi_sgn=sgn, stats=stats)
         else:
             s16 = Kd < 32768
             if fuse_sign:
@@ -516,11 +567,11 @@ class BinaryLayer(LinearLayer):
                 else:
                     K_.gemm(M=B, N=N, K=Kd, A=(X.i8,), B=(wops["i8"],), lda=X.i8.stride(0),
                             ldb=wops["i8"].stride(0), D=Z, ldd=Z.stride(0), in_dtype=nat.DT_I8,
-                            epilogue=nat.EPI_STORE_S16 if s16 else nat.EPI_STORE_S32)
+                            epilogue=nat.EPI_STORE_S16 if s16 else nat.EPI_STORE_S32, stats=stats)
 
         # ---- batch-norm statistics
         if isTrain:
-            sums, mu, var = bn.batch_stats(Z, B)
+            sums, mu, var = bn.batch_stats(Z, B, filled=acc)
         else:
             sums, mu, var = None, bn.mu.t, bn.sigma.t
 
@@ -564,6 +615,9 @@ class BinaryLayer(LinearLayer):
         # (activation.py:122-131 via layers.py:252-254), and softmax+CE arrives pre-differentiated.
         delta = to_tensor(dA, torch.float32)
         assert tuple(delta.shape) == (B, N)
+        # the layer above may already have summed this layer's batch-norm reductions in the epilogue
+        # of the GEMM that produced dA
+        reduced = getattr(dA, "_bn_reduced_for", None) is self
 
         Np, Bp = pad_to(N, 8), pad_to(B, 8)
         d_hi = ws.get(f"d_hi{B}", (B, Np), torch.float16, zero=True)
@@ -574,10 +628,11 @@ class BinaryLayer(LinearLayer):
         need_dx = not self.skip_input_grad
         self.batchNormLayer.backward_kernels(delta, Z, B, c["sums"], c["mu"], c["var"], lr, False,
                                              (d_hi, d_lo) if need_dx else None, (dt_hi, dt_lo),
-                                             d_scale)
+                                             d_scale, reduced=reduced)
 
         # ---- dX = delta' . W^T with the latent, pre-update weights (layers.py:266)
         dX = None
+        bstats = below = None
         if need_dx:
             w_amax = ws.get("w_amax", (1,), torch.float32)
             w_scale = ws.get("w_scale", (1,), torch.float32)
@@ -586,9 +641,16 @@ class BinaryLayer(LinearLayer):
             # W has not changed since this step's forward, whose binarize pass left max|W| in w_amax
             K_.split_f16(self._weights.t, w_amax, hi=w_hi, lo=w_lo, scale_out=w_scale)
             dX = empty((B, pad_to(Kd, 4)))
+            # dX is the delta of the layer below: its batch-norm backward needs sum(delta) and
+            # sum(delta*(z-mu)) per column, which this GEMM's epilogue accumulates on the way out
+            below = getattr(self, "input_layer", None)
+            bstats = None
+            if (below is not None and isinstance(below, BinaryLayer) and "z" in below.cache
+                    and below.cache.get("B") == B and K_.fused_stats_ok(Kd)):
+                bstats = below.batchNormLayer.bwd_reduce_target(below.cache["z"], below.cache["mu"])
             K_.gemm(M=B, N=Kd, K=N, A=(d_hi, d_lo), B=(w_hi, w_lo), lda=Np, ldb=Np, D=dX,
                     ldd=dX.stride(0), in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32,
-                    passes=((0, 0), (0, 1), (1, 0)), sa=d_scale, sb=w_scale)
+                    passes=((0, 0), (0, 1), (1, 0)), sa=d_scale, sb=w_scale, stats=bstats)
             dX = dX[:, :Kd]
 
         # ---- dW = X^T . delta'  (layers.py:260) and W -= lr * dW (:268)
@@ -655,4 +717,9 @@ class BinaryLayer(LinearLayer):
             self._pending_update = (self.comm.allreduce_sum_async(dW), dW, lr)
 
         self.cache.clear()
-        return DeviceArray(dX) if dX is not None else None
+        if dX is None:
+            return None
+        out = DeviceArray(dX)
+        if bstats is not None:
+            out._bn_reduced_for = below
+        return out

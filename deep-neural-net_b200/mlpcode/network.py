@@ -55,6 +55,7 @@ class Network(object):
         ]
         for i, layer in enumerate(self._layers):
             layer.layer_index = i
+            layer.input_layer = self._layers[i - 1] if i > 0 else None
         if self._layers:
             self._layers[0].skip_input_grad = True
         self._lossF: lf = None

@@ -121,6 +121,15 @@ enum {
 };
 #define BNN_MAX_RANKS 16
 
+/* Column reductions fused into the GEMM epilogue (tcgen05 path; N must be a multiple of the tile
+ * width — 256 for N > 128, 128 for N > 32, else 32 — the output 16-byte aligned and batch == 1,
+ * otherwise BNN_ERR_UNSUPPORTED and the caller uses the stand-alone kernels):
+ *   BNN_STATS_COLSUM  stats_sums[2,N] += (sum_m D, sum_m D^2)        == bnn_colstats on the result
+ *   BNN_STATS_BN_BWD  stats_sums[2,N] += (sum_m D, sum_m D*(Z-mu)),  stats_max[2,N] = max(.., |D|, |Z-mu|)
+ *                                                                    == bnn_bn_bwd_reduce(delta = D)
+ * The accumulators are NOT cleared by the GEMM. */
+enum { BNN_STATS_NONE = 0, BNN_STATS_COLSUM = 1, BNN_STATS_BN_BWD = 2 };
+
 /* Row ownership and peer mappings for BNN_EPI_SCATTER_F32.  Rank r owns output rows
  * [r*rows_per_owner, (r+1)*rows_per_owner) (rows_per_owner a multiple of 128).  Every rank holds a
  * staging buffer float[world][rows_per_owner][ldd]; stage[o] is the address of rank o's buffer as
@@ -160,6 +169,13 @@ typedef struct bnn_gemm_desc {
     const float* epi_thr; /* BNN_EPI_SIGN_I8: per-column threshold and orientation (device, [N]) */
     const float* epi_sgn;
     const bnn_peer_scatter* scatter; /* BNN_EPI_SCATTER_F32 (host pointer), else NULL */
+    int32_t stats;         /* BNN_STATS_* */
+    int32_t stats_z_dtype; /* BNN_Z_* of stats_z (BNN_STATS_BN_BWD) */
+    double* stats_sums;    /* device [2, N] */
+    uint32_t* stats_max;   /* device [2, N] (BNN_STATS_BN_BWD) */
+    const void* stats_z;   /* device [M, stats_ldz] (BNN_STATS_BN_BWD) */
+    int64_t stats_ldz;
+    const float* stats_mu; /* device [N] (BNN_STATS_BN_BWD) */
 } bnn_gemm_desc;
 
 int bnn_gemm(const bnn_gemm_desc* desc_host, int impl, bnn_stream_t stream);

@@ -54,7 +54,8 @@ def test_pack_sign_rows(T, oracle, R, C):
     assert np.all(got[:, words] == 0xFFFFFFFF)  # pad word beyond ceil(C/32) untouched
 
 
-@pytest.mark.parametrize("K_,N", [(32, 32), (784, 256), (100, 10), (4096, 70), (33, 129)])
+@pytest.mark.parametrize("K_,N", [(32, 32), (784, 256), (100, 10), (4096, 70), (33, 129), (130, 260),
+                                  (1024, 1028), (257, 4)])
 def test_binarize_weights_t(T, oracle, K_, N):
     from mlpcode import kernels as K
     rng = np.random.default_rng(K_ + N)
@@ -69,6 +70,7 @@ def test_binarize_weights_t(T, oracle, K_, N):
     assert np.array_equal(i8.cpu().numpy()[:, :K_], ref.astype(np.int8))
     assert np.array_equal(f16.cpu().numpy()[:, :K_].astype(np.float32), ref)
     assert np.array_equal(bits.cpu().numpy().view(np.uint32), oracle.c_pack_weights_t(W))
+    assert not i8[:, K_:].any() and not f16[:, K_:].any()   # pitch padding past K stays zero
     # round trip through unpack
     back = T.zeros_like(i8)
     K.unpack_bits(bits, K_, out_i8=back)
@@ -237,6 +239,97 @@ def test_gemm_f16_split_matches_fp64(T, impl, M, N, K_):
                sa=ops["a"][2], sb=ops["b"][2], host_scale=0.01, impl=which)
         want = W0.astype(np.float64) - 0.01 * ref
         assert rel_err(Wd.cpu().numpy(), want) < 3e-6
+
+
+@pytest.mark.parametrize("M,N,K_", [(128, 256, 128), (300, 512, 784), (1000, 128, 256), (77, 32, 64),
+                                    (8192, 4096, 512)])
+def test_gemm_fused_colstats_epilogue(T, M, N, K_):
+    """BNN_STATS_COLSUM: the +-1 GEMM's epilogue accumulates (sum z, sum z^2) per column — exact
+    integers, so it must equal the int64 column sums of the result bit for bit (layers.py:81-82)."""
+    from mlpcode import _native as nat, kernels as K
+    assert K.fused_stats_ok(N)
+    rng = np.random.default_rng(M + N + K_)
+    a, b = pm1(rng, (M, K_)), pm1(rng, (N, K_))
+    A, Bm = padded(a, 16), padded(b, 16)
+    ref = (dev(a).float() @ dev(b).float().T).to(T.int64)        # exact: |z| <= K < 2^24
+    for epi, dt in ((nat.EPI_STORE_S16, T.int16), (nat.EPI_STORE_S32, T.int32)):
+        D = T.zeros((M, N), dtype=dt, device="cuda")
+        sums = T.zeros((2, N), dtype=T.float64, device="cuda")
+        K.gemm(M=M, N=N, K=K_, A=(A,), B=(Bm,), lda=A.stride(0), ldb=Bm.stride(0), D=D, ldd=N,
+               in_dtype=nat.DT_I8, epilogue=epi, stats=dict(mode=nat.STATS_COLSUM, sums=sums))
+        assert T.equal(D.to(T.int64), ref)
+        assert T.equal(sums[0].to(T.int64), ref.sum(0))
+        assert T.equal(sums[1].to(T.int64), (ref * ref).sum(0))
+    # and it agrees with the stand-alone kernel it replaces
+    sums2 = T.zeros((2, N), dtype=T.float64, device="cuda")
+    K.colstats(D, M, N, sums2)
+    assert T.equal(sums, sums2)
+
+
+@pytest.mark.parametrize("M,N,K_,zdt", [(128, 256, 64, "s16"), (300, 512, 200, "f32"), (1000, 128, 96, "s16"),
+                                        (4096, 4096, 256, "s16")])
+def test_gemm_fused_bn_bwd_reduce_epilogue(T, M, N, K_, zdt):
+    """BNN_STATS_BN_BWD: the dX GEMM's epilogue accumulates sum(d), sum(d*(z-mu)), max|d|, max|z-mu| of
+    its own output d against the layer below's Z — the reductions of layers.py:107-115 that
+    bnn_bn_bwd_reduce would otherwise re-read d and Z for.  Tolerance 1e-6 (fp32 32-row partials,
+    fp64 across; the stand-alone kernel uses 16-row partials)."""
+    from mlpcode import _native as nat, kernels as K
+    rng = np.random.default_rng(M * 3 + N + K_)
+    a = (rng.standard_normal((M, K_)) * 1e-3).astype(np.float32)
+    b = (rng.standard_normal((N, K_)) / 16).astype(np.float32)
+    Kp = (K_ + 7) // 8 * 8
+    ops = {}
+    for name, x in (("a", a), ("b", b)):
+        xd = dev(x)
+        amax = T.zeros(1, dtype=T.float32, device="cuda")
+        sc = T.zeros(1, dtype=T.float32, device="cuda")
+        hi, lo = (T.zeros((x.shape[0], Kp), dtype=T.float16, device="cuda") for _ in range(2))
+        K.absmax_f32(xd, amax)
+        K.split_f16(xd, amax, hi=hi, lo=lo, scale_out=sc)
+        ops[name] = (hi, lo, sc)
+    if zdt == "s16":
+        Z = dev(rng.integers(-K_, K_ + 1, (M, N)).astype(np.int16))
+    else:
+        Z = dev(rng.standard_normal((M, N)).astype(np.float32) * 20)
+    mu = dev(rng.standard_normal(N).astype(np.float32))
+    D = T.zeros((M, N), dtype=T.float32, device="cuda")
+    red = T.zeros((2, N), dtype=T.float64, device="cuda")
+    red_max = T.zeros((2, N), dtype=T.int32, device="cuda")
+    K.gemm(M=M, N=N, K=K_, A=ops["a"][:2], B=ops["b"][:2], lda=Kp, ldb=Kp, D=D, ldd=N,
+           in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32, passes=((0, 0), (0, 1), (1, 0)),
+           sa=ops["a"][2], sb=ops["b"][2],
+           stats=dict(mode=nat.STATS_BN_BWD, sums=red, max=red_max, Z=Z, mu=mu))
+    # same product without the fused reductions: the stored result must not change
+    D0 = T.zeros_like(D)
+    K.gemm(M=M, N=N, K=K_, A=ops["a"][:2], B=ops["b"][:2], lda=Kp, ldb=Kp, D=D0, ldd=N,
+           in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32, passes=((0, 0), (0, 1), (1, 0)),
+           sa=ops["a"][2], sb=ops["b"][2])
+    assert T.equal(D, D0)
+    d64, xm = D.double(), Z.double() - mu.double()
+    want = T.stack([d64.sum(0), (d64 * (Z.float() - mu).double()).sum(0)])
+    scale = T.stack([d64.abs().sum(0), (d64 * xm).abs().sum(0)])
+    assert float(((red - want).abs() / scale).max()) < 1e-6
+    assert T.equal(red_max[0].view(T.float32), D.abs().amax(0))
+    assert T.equal(red_max[1].view(T.float32), (Z.float() - mu).abs().amax(0))
+    # the stand-alone kernel on the same delta agrees
+    red2 = T.zeros_like(red)
+    red_max2 = T.zeros_like(red_max)
+    K.bn_bwd_reduce(D, Z, M, N, mu, red2, red_max2)
+    assert float(((red - red2).abs() / scale).max()) < 1e-6
+    assert T.equal(red_max, red_max2)
+
+
+def test_gemm_fused_stats_refuses_ragged_widths(T):
+    from mlpcode import _native as nat, kernels as K
+    assert not K.fused_stats_ok(130) and not K.fused_stats_ok(10) and K.fused_stats_ok(4096)
+    a = T.ones((64, 64), dtype=T.int8, device="cuda")
+    D = T.zeros((64, 136), dtype=T.int16, device="cuda")
+    sums = T.zeros((2, 130), dtype=T.float64, device="cuda")
+    b = T.ones((130, 64), dtype=T.int8, device="cuda")
+    with pytest.raises(nat.BnnError) as e:
+        K.gemm(M=64, N=130, K=64, A=(a,), B=(b,), lda=64, ldb=64, D=D, ldd=136, in_dtype=nat.DT_I8,
+               epilogue=nat.EPI_STORE_S16, stats=dict(mode=nat.STATS_COLSUM, sums=sums))
+    assert e.value.code == nat.BNN_ERR_UNSUPPORTED
 
 
 def test_split_gemm_precision_at_full_size(T):
