@@ -210,6 +210,15 @@ dw_reduce_sgd_p2p_kernel(const float* __restrict__ stage, const WTable wt, const
     const int world = WORLD ? WORLD : world_rt;
     const uint32_t epoch = resolve_epoch(epoch_ptr, epoch_imm);
     if (epoch_word && blockIdx.x == 0 && threadIdx.x == 0) *epoch_word = epoch;
+    if (broadcast & 2) {
+        // "my partial rows are pushed" (the dW GEMM is the previous kernel of this stream, so its peer
+        // stores are performed): block 0 tells every rank, which saves a separate signal launch
+        if (blockIdx.x == 0 && threadIdx.x < world) {
+            __threadfence_system();
+            st_release_sys(ft.flags[threadIdx.x] + slot_pushed * kMaxRanks + rank, epoch);
+        }
+        broadcast &= 1;
+    }
     // wait for every rank's partial rows of this epoch (bounded)
     if (threadIdx.x < world)
         spin_until(ft.flags[rank] + slot_pushed * kMaxRanks + threadIdx.x, epoch, rank, threadIdx.x,

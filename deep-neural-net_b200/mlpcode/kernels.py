@@ -188,10 +188,10 @@ def peer_wait(flags_local_ptr, slot, slot_stride, n_slots, rank, world, step_dev
 
 
 def dw_reduce_sgd_p2p(stage_local_ptr, peer_w, peer_flags, slot_pushed, slot_landed, rank, world,
-                      step_dev, K, N, rows_per_owner, lr, broadcast, counter) -> None:
+                      step_dev, K, N, rows_per_owner, lr, broadcast, counter, signal=False) -> None:
     _call("bnn_dw_reduce_sgd_p2p", C.c_void_p(stage_local_ptr), _u64_array(peer_w),
           _u64_array(peer_flags), slot_pushed, slot_landed, rank, world, 0, ptr(step_dev), K, N,
-          rows_per_owner, lr, int(broadcast), ptr(counter), None)
+          rows_per_owner, lr, int(bool(broadcast)) | (2 if signal else 0), ptr(counter), None)
 
 
 def peer_broadcast_rows(peer_w, peer_flags, slot_landed, rank, world, K, N, rows_per_owner,

@@ -261,6 +261,8 @@ class BatchNormLayer(Layer):
                 slot, call = px.begin(self.exchange_site + 1, 2 * n)
                 K_.bn_bwd_reduce(delta, Z, B, n, mu, slot.view(2, n), red_max)
             K_.allreduce_f64_p2p(call, 2 * n, red)
+            if getattr(self.comm, "dw_exchange", None) is not None:
+                self.comm.dw_exchange.start_broadcasts()
         else:
             if not reduced:
                 K_.bn_bwd_reduce(delta, Z, B, n, mu, red, red_max)
@@ -488,7 +490,7 @@ class BinaryLayer(LinearLayer):
         L = dwx.layout[li]
         K_.dw_reduce_sgd_p2p(dwx.stage_ptrs(li)[dwx.rank], dwx.w_ptrs(li), dwx.flag_ptrs(), 2 * li,
                              2 * li + 1, dwx.rank, dwx.world, dwx.comm.step_dev, L["K"], L["N"],
-                             L["rows_per_owner"], lr, broadcast, dwx.counters[li:li + 1])
+                             L["rows_per_owner"], lr, broadcast, dwx.counters[li:li + 1], signal=True)
 
     # ------------------------------------------------------------------ forward
     def forward(self, X, isTrain=True):
@@ -687,20 +689,14 @@ class BinaryLayer(LinearLayer):
                     scatter=dict(world=dwx.world, rank=dwx.rank,
                                  rows_per_owner=dwx.layout[li]["rows_per_owner"],
                                  stage=dwx.stage_ptrs(li)))
-            K_.peer_signal(dwx.flag_ptrs(), 2 * li, dwx.rank, dwx.world, step_dev)
             if dwx.copy_engine_broadcast and not self.skip_input_grad:
-                # owner update now (local rows only); the rows then travel to the peers on the copy
-                # engines, on a side stream, while this stream carries on with the backward pass
-                main = torch.cuda.current_stream()
+                # owner update now (local rows only; the kernel also signals "pushed" to the peers);
+                # the rows then travel to the peers on the copy engines, on a side stream, while this
+                # stream carries on with the backward pass.  The copies are started only after the
+                # next batch-norm exchange (dwx.start_broadcasts): queued right here, 10s of MB of
+                # copy traffic would sit in front of that exchange's flags on the NVLink ports.
                 self._dw_reduce(lr, broadcast=False)
-                dwx.reduced[li].record(main)
-                with torch.cuda.stream(dwx.side):
-                    dwx.side.wait_event(dwx.reduced[li])
-                    L = dwx.layout[li]
-                    K_.peer_broadcast_rows(dwx.w_ptrs(li), dwx.flag_ptrs(), 2 * li + 1, dwx.rank,
-                                           dwx.world, L["K"], L["N"], L["rows_per_owner"], step_dev)
-                    dwx.copied[li].record(dwx.side)
-                dwx.in_flight.append(li)
+                dwx.deferred.append(li)
             else:
                 # first layer (its dW GEMM ends the step and its weights open the next one, so there
                 # is nothing left to overlap copies with) or BNN_DW_BCAST=kernel: the owner-update

@@ -118,6 +118,7 @@ class DwExchange:
         self.side = torch.cuda.Stream()
         self.reduced = [torch.cuda.Event() for _ in range(n_layers)]
         self.copied = [torch.cuda.Event() for _ in range(n_layers)]
+        self.deferred = []    # layers updated locally whose copy-engine broadcast has not started yet
         self.in_flight = []   # layers whose rows are on their way to the peers (this step)
         self.pending = []     # layers whose updated rows have not been awaited yet (this step)
         torch.cuda.synchronize()
@@ -136,9 +137,30 @@ class DwExchange:
     def flag_ptrs(self):
         return list(self.base)
 
+    def start_broadcasts(self) -> None:
+        """Queue the copy-engine all-gather of every layer whose owner update has run: the side stream
+        waits for the current point of the compute stream, then copies this rank's rows (and the
+        "landed" flag) into every peer."""
+        if not self.deferred:
+            return
+        from . import kernels as K_
+        main = torch.cuda.current_stream()
+        for li in self.deferred:
+            L = self.layout[li]
+            self.reduced[li].record(main)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.reduced[li])
+                K_.peer_broadcast_rows(self.w_ptrs(li), self.flag_ptrs(), 2 * li + 1, self.rank,
+                                       self.world, L["K"], L["N"], L["rows_per_owner"],
+                                       self.comm.step_dev)
+                self.copied[li].record(self.side)
+            self.in_flight.append(li)
+        self.deferred.clear()
+
     def finish_step(self) -> None:
         """End of a training step: join the copy-engine stream, then ONE kernel waits until every
         rank's updated rows of every layer exchanged this step have landed in the local W."""
+        self.start_broadcasts()
         main = torch.cuda.current_stream()
         for li in self.in_flight:
             main.wait_event(self.copied[li])

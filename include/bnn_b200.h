@@ -329,7 +329,9 @@ int bnn_peer_wait(const uint32_t* flags_local, int slot, int slot_stride, int n_
 /* stage_local: this rank's staging buffer float[world][rows_per_owner][ld]; W: [K, N] fp32 row-major
  * with pitch ld == N on every rank (peer_w_host[r] = rank r's W as mapped here; may alias W for
  * r == rank).  counter: device uint32, zero-initialised once (self-resetting block counter).
- * broadcast = 0 updates only the local rows and writes `epoch` to *epoch_word (device uint32): the
+ * broadcast bit 1 (value 2): the kernel also performs this rank's bnn_peer_signal(slot_pushed) itself
+ * (valid when it directly follows the dW GEMM on the same stream).
+ * broadcast bit 0 clear: updates only the local rows and writes `epoch` to *epoch_word (device uint32): the
  * caller then runs bnn_peer_broadcast_rows on another stream, which moves the rows with the copy
  * engines while the compute stream carries on with the backward pass. */
 int bnn_dw_reduce_sgd_p2p(const float* stage_local, const uint64_t* peer_w_host,
