@@ -446,101 +446,111 @@ __global__ void bn_sign_thresholds_kernel(const float* __restrict__ mu, const fl
     sgn[n] = s;
 }
 
-// Sign pass on thresholds: Z -> int8 +-1, transposed fp16 +-1, packed bits.  64 x 128 tiles, 8 columns
-// per thread, few registers (the normalisation constants collapse into thr / sgn).
+// Sign pass on thresholds: Z -> int8 +-1, transposed fp16 +-1, packed bits.
+// A thread owns an 8 (rows) x 8 (columns) block and never leaves its registers: the 64 sign bits are
+// one 8x8 bit matrix, whose rows expand to the int8 operand and whose transpose (three masked
+// shift-xor rounds) expands to eight consecutive batch entries of each transposed fp16 row.  Lanes are
+// laid out 4 (column blocks) x 8 (row blocks), so that every access is sector-exact without shared
+// memory: Z loads cover 64 contiguous bytes per row, int8 stores 32, transposed fp16 stores 128.
+// Warp tile 64 x 32, block = 8 warps = 128 rows x 128 columns.
+constexpr int SG_ROWS = 128, SG_COLS = 128;
+
+__device__ __forceinline__ unsigned long long transpose_8x8_bits(unsigned long long x) {
+    unsigned long long t;
+    t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;  x ^= t ^ (t << 7);
+    t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull; x ^= t ^ (t << 14);
+    t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull; x ^= t ^ (t << 28);
+    return x;
+}
+
 template <int ZT>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256)
 bn_sign_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const float* __restrict__ thr,
                const float* __restrict__ sgn, int8_t* __restrict__ act_i8, long long ld_i8,
                __half* __restrict__ act_t16, long long ld_t16, uint32_t* __restrict__ act_bits,
                long long ld_bits) {
-    __shared__ __align__(16) uint32_t sg[AP_ROWS][AP_COLS / 4];
-    const int b0 = blockIdx.y * AP_ROWS, n0 = blockIdx.x * AP_COLS;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int c0 = n0 + tx * 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cb = lane & 3, rb = lane >> 2;
+    const int c0 = blockIdx.x * SG_COLS + (warp & 3) * 32 + cb * 8;
+    const int r0 = blockIdx.y * SG_ROWS + (warp >> 2) * 64 + rb * 8;
     const int valid = max(0, min(8, N - c0));
+    const int rvalid = max(0, min(8, B - r0));
     const bool zvec = z_vec_ok<ZT>(Z, ldz);
-    const bool ivec = act_i8 && ((reinterpret_cast<uintptr_t>(act_i8) & 7u) == 0) && (ld_i8 % 8 == 0);
     float t[8], s[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         t[j] = j < valid ? __ldg(thr + c0 + j) : INFINITY;
         s[j] = j < valid ? __ldg(sgn + c0 + j) : 1.0f;
     }
-    float zall[AP_ROWS / 16][8];
+    uint32_t sb[8];  // sign bits of row i, one bit per column
+    if (zvec && valid == 8 && rvalid == 8) {
+        Raw8 raw[8];  // every row's load is issued before any is consumed
 #pragma unroll
-    for (int i = 0; i < AP_ROWS / 16; ++i) {
-        const int gb = b0 + ty + 16 * i;
-        if (gb < B && valid > 0) load8_z<ZT>(Z, (long long)gb * ldz + c0, valid, zvec, zall[i]);
+        for (int i = 0; i < 8; ++i) raw[i] = load8_raw<ZT>(Z, (long long)(r0 + i) * ldz + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float z[8];
+            cvt8_raw<ZT>(raw[i], z);
+            uint32_t b = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b |= (uint32_t)(__fmul_rn(z[j], s[j]) >= t[j]) << j;
+            sb[i] = b;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t b = 0;
+            if (i < rvalid && valid > 0) {
+                float z[8];
+                load8_z<ZT>(Z, (long long)(r0 + i) * ldz + c0, valid, false, z);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b |= (uint32_t)(j < valid && __fmul_rn(z[j], s[j]) >= t[j]) << j;
+            }
+            sb[i] = b;
+        }
     }
+    if (act_i8) {
+        const bool ivec = ((reinterpret_cast<uintptr_t>(act_i8) & 7u) == 0) && (ld_i8 % 8 == 0) && valid == 8;
 #pragma unroll
-    for (int i = 0; i < AP_ROWS / 16; ++i) {
-        const int r = ty + 16 * i;
-        const int gb = b0 + r;
-        uint32_t sb = 0;
-        if (gb < B && valid > 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) sb |= (uint32_t)(__fmul_rn(zall[i][j], s[j]) >= t[j]) << j;
-            if (act_i8) {
-                int8_t* p = act_i8 + (long long)gb * ld_i8 + c0;
-                if (ivec && valid == 8) {
-                    uint2 w;
-                    w.x = w.y = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        w.x |= (((sb >> j) & 1u) ? 0x01u : 0xFFu) << (8 * j);
-                        w.y |= (((sb >> (j + 4)) & 1u) ? 0x01u : 0xFFu) << (8 * j);
-                    }
-                    *reinterpret_cast<uint2*>(p) = w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < valid) p[j] = ((sb >> j) & 1u) ? (int8_t)1 : (int8_t)-1;
-                }
+        for (int i = 0; i < 8; ++i) {
+            if (i >= rvalid) break;
+            int8_t* p = act_i8 + (long long)(r0 + i) * ld_i8 + c0;
+            if (ivec) {
+                *reinterpret_cast<uint2*>(p) = make_uint2(nibble_to_pm1_bytes(sb[i]), nibble_to_pm1_bytes(sb[i] >> 4));
+            } else {
+                for (int j = 0; j < valid; ++j) p[j] = ((sb[i] >> j) & 1u) ? (int8_t)1 : (int8_t)-1;
             }
         }
-        if (act_bits) {
-            uint32_t w = sb << (8 * (tx & 3));
+    }
+    if (act_bits) {
+        // 4 adjacent lanes own the 32 columns of one word of every row of the block
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t w = sb[i] << (8 * cb);
             w |= __shfl_xor_sync(0xffffffffu, w, 1);
             w |= __shfl_xor_sync(0xffffffffu, w, 2);
-            if ((tx & 3) == 0 && gb < B && c0 < N) act_bits[(long long)gb * ld_bits + (c0 >> 5)] = w;
-        }
-        if (act_t16) {
-            uint32_t w0 = 0, w1 = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                w0 |= ((sb >> j) & 1u) << (8 * j);
-                w1 |= ((sb >> (j + 4)) & 1u) << (8 * j);
-            }
-            const int sw = (r >> 3) & 7;
-            sg[r][(2 * tx) ^ sw] = w0;
-            sg[r][(2 * tx + 1) ^ sw] = w1;
+            if (cb == 0 && i < rvalid && c0 < N) act_bits[(long long)(r0 + i) * ld_bits + (c0 >> 5)] = w;
         }
     }
-    if (!act_t16) return;
-    __syncthreads();
-    const bool tvec = aligned16(act_t16) && (ld_t16 % 8 == 0);
-    const uint8_t* sgb = reinterpret_cast<const uint8_t*>(&sg[0][0]);
+    if (act_t16) {
+        unsigned long long m = 0;
 #pragma unroll
-    for (int k = 0; k < (AP_COLS * AP_ROWS / 8) / 256; ++k) {
-        const int item = threadIdx.x + 256 * k;
-        const int bg = item & 7, n = item >> 3;
-        const int gn = n0 + n, gb = b0 + bg * 8;
-        if (gn >= N || gb >= B) continue;
-        const int word = (n >> 2) ^ bg, byte = n & 3;
-        uint32_t h[4];
+        for (int i = 0; i < 8; ++i) m |= (unsigned long long)(sb[i] & 0xFFu) << (8 * i);
+        m = transpose_8x8_bits(m);  // byte j: column j, bit i: row i
+        const bool tvec = aligned16(act_t16) && (ld_t16 % 8 == 0) && rvalid == 8;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t lo = sgb[(bg * 8 + 2 * j) * AP_COLS + word * 4 + byte] ? 0x3C00u : 0xBC00u;
-            const uint32_t hi = sgb[(bg * 8 + 2 * j + 1) * AP_COLS + word * 4 + byte] ? 0x3C00u : 0xBC00u;
-            h[j] = lo | (hi << 16);
-        }
-        __half* p = act_t16 + (long long)gn * ld_t16 + gb;
-        if (tvec && gb + 8 <= B) {
-            *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
-        } else {
-            for (int j = 0; j < 8 && gb + j < B; ++j)
-                p[j] = __ushort_as_half((unsigned short)(h[j >> 1] >> (16 * (j & 1))));
+        for (int j = 0; j < 8; ++j) {
+            if (j >= valid) break;
+            const uint32_t cbits = (uint32_t)(m >> (8 * j)) & 0xFFu;
+            __half* p = act_t16 + (long long)(c0 + j) * ld_t16 + r0;
+            if (tvec) {
+                *reinterpret_cast<uint4*>(p) =
+                    make_uint4(pair_to_pm1_halves(cbits), pair_to_pm1_halves(cbits >> 2),
+                               pair_to_pm1_halves(cbits >> 4), pair_to_pm1_halves(cbits >> 6));
+            } else {
+                for (int i = 0; i < rvalid; ++i)
+                    p[i] = __ushort_as_half(((cbits >> i) & 1u) ? (unsigned short)0x3C00 : (unsigned short)0xBC00);
+            }
         }
     }
 }
@@ -983,7 +993,7 @@ extern "C" int bnn_bn_sign(const void* Z, int z_dtype, int B, int N, int64_t ldz
     BNN_CHECK_ARG(!act_i8 || ld_i8 >= N, "bnn_bn_sign: ld_i8 < N");
     BNN_CHECK_ARG(!act_t16 || ld_t16 >= B, "bnn_bn_sign: ld_t16 < B");
     BNN_CHECK_ARG(!act_bits || ld_bits >= (N + 31) / 32, "bnn_bn_sign: ld_bits too small");
-    dim3 grid(cdiv(N, AP_COLS), cdiv(B, AP_ROWS));
+    dim3 grid(cdiv(N, SG_COLS), cdiv(B, SG_ROWS));
     BNN_CHECK_ARG(grid.y <= 65535, "bnn_bn_sign: B too large");
     cudaStream_t s = (cudaStream_t)stream;
     return dispatch_z(z_dtype, [&](auto zt) {

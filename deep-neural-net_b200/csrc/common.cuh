@@ -77,4 +77,14 @@ __device__ __forceinline__ void split_f16(float xs, __half& hi, __half& lo) {
     lo = __float2half_rn(xs - __half2float(hi));
 }
 
+// 4 mask bits -> 4 bytes of +-1 (bit ? 0x01 : 0xFF)
+__device__ __forceinline__ uint32_t nibble_to_pm1_bytes(uint32_t nib) {
+    const uint32_t spread = ((nib & 0xFu) * 0x00204081u) & 0x01010101u;
+    return 0xFFFFFFFFu ^ (spread * 0xFEu);
+}
+// 2 mask bits -> 2 halves of +-1.0 (bit ? 0x3C00 : 0xBC00)
+__device__ __forceinline__ uint32_t pair_to_pm1_halves(uint32_t two) {
+    return 0x3C003C00u | ((~two & 1u) << 15) | ((~two & 2u) << 30);
+}
+
 }  // namespace bnn

@@ -45,16 +45,6 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const T* __restrict__ x,
 // ---------------------------------------------------------------------------------------------
 constexpr int BT_K = 128, BT_N = 256;
 
-// 4 mask bits -> 4 bytes of +-1 (bit ? 0x01 : 0xFF)
-__device__ __forceinline__ uint32_t nibble_to_pm1_bytes(uint32_t nib) {
-    const uint32_t spread = ((nib & 0xFu) * 0x00204081u) & 0x01010101u;
-    return 0xFFFFFFFFu ^ (spread * 0xFEu);
-}
-// 2 mask bits -> 2 halves of +-1.0 (bit ? 0x3C00 : 0xBC00)
-__device__ __forceinline__ uint32_t pair_to_pm1_halves(uint32_t two) {
-    return 0x3C003C00u | ((~two & 1u) << 15) | ((~two & 2u) << 30);
-}
-
 __global__ void __launch_bounds__(256)
 binarize_t_kernel(const float* __restrict__ W, int K, int N, int8_t* __restrict__ wt_i8,
                   long long ld_i8, __half* __restrict__ wt_f16, long long ld_f16,

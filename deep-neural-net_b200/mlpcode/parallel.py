@@ -77,6 +77,27 @@ def _symmetric_buffer(comm: "Comm", nbytes: int):
     return buf, base, handle
 
 
+def dw_exchange_layout(shapes, world: int, align: int = 1024):
+    """Byte layout of the DwExchange arena (identical on every rank): returns (flag bytes, per-layer
+    dicts with K, N, rows_per_owner, w_off, stage_off, total bytes).  rows_per_owner is the number of
+    128-row GEMM tiles of W divided evenly over the ranks, rounded up, times 128 — rank r owns rows
+    [r*rows_per_owner, (r+1)*rows_per_owner) (the last owners of a short matrix own fewer, or none)."""
+    def up(n):
+        return -(-n // align) * align
+    flag_bytes = up(2 * len(shapes) * 16 * 4)
+    off = flag_bytes
+    layout = []
+    for (k, n) in shapes:
+        tiles = -(-k // 128)
+        rpo = -(-tiles // world) * 128
+        w_off = off
+        off += up(k * n * 4)
+        s_off = off
+        off += up(world * rpo * n * 4)
+        layout.append(dict(K=int(k), N=int(n), rows_per_owner=rpo, w_off=w_off, stage_off=s_off))
+    return flag_bytes, layout, off
+
+
 class DwExchange:
     """Symmetric arena for the dW all-reduce that libbnn_b200 fuses into its own kernels
     (`dW` all-reduce-sum before `W -= lr*dW`, layers.py:268).
@@ -98,18 +119,7 @@ class DwExchange:
         self.world, self.rank = comm.world, comm.rank
         self.shapes = [(int(k), int(n)) for k, n in shapes]
         n_layers = len(self.shapes)
-        self.flag_bytes = -(-(2 * n_layers * 16 * 4) // self.ALIGN) * self.ALIGN
-        off = self.flag_bytes
-        self.layout = []
-        for (k, n) in self.shapes:
-            tiles = -(-k // 128)
-            rpo = -(-tiles // self.world) * 128
-            w_off = off
-            off += -(-(k * n * 4) // self.ALIGN) * self.ALIGN
-            s_off = off
-            off += -(-(self.world * rpo * n * 4) // self.ALIGN) * self.ALIGN
-            self.layout.append(dict(K=k, N=n, rows_per_owner=rpo, w_off=w_off, stage_off=s_off))
-        self.nbytes = off
+        self.flag_bytes, self.layout, self.nbytes = dw_exchange_layout(self.shapes, self.world, self.ALIGN)
         self.buf, self.base, self.handle = _symmetric_buffer(comm, self.nbytes)
         self.counters = torch.zeros(n_layers, dtype=torch.int32, device=self.buf.device)
         # all-gather half: "ce" = copy engines on a side stream (overlaps the backward pass),

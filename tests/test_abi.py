@@ -119,6 +119,26 @@ def test_shard_range_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_dw_exchange_layout_covers_every_row_once():
+    """Row ownership of the fused dW reduce-scatter: whole 128-row tiles, every row owned by exactly
+    one rank, regions aligned and disjoint."""
+    from mlpcode.parallel import dw_exchange_layout
+    shapes = [(784, 4096), (4096, 4096), (4096, 10), (100, 7), (128, 128)]
+    for world in (2, 3, 4, 8, 16):
+        flag_bytes, layout, total = dw_exchange_layout(shapes, world)
+        assert flag_bytes >= 2 * len(shapes) * 16 * 4 and flag_bytes % 1024 == 0
+        end = flag_bytes
+        for (k, n), L in zip(shapes, layout):
+            rpo = L["rows_per_owner"]
+            assert rpo % 128 == 0 and rpo * world >= k and rpo * world - k < 128 * world
+            owned = [max(0, min(rpo, k - r * rpo)) for r in range(world)]
+            assert sum(owned) == k
+            assert L["w_off"] == end and L["w_off"] % 1024 == 0 and L["stage_off"] % 1024 == 0
+            assert L["stage_off"] >= L["w_off"] + k * n * 4
+            end = L["stage_off"] + -(-(world * rpo * n * 4) // 1024) * 1024
+        assert end == total
+
+
 def test_thresholds_and_flip_counts():
     from mlpcode.callbacks import ImageErrorCallback
     from mlpcode.kernels import bernoulli_threshold
