@@ -24,6 +24,7 @@ Only the configuration the BNN scripts use is implemented on the device: batch-n
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import numpy as np
@@ -106,6 +107,38 @@ class _Workspace:
 
     def clear(self):
         self._bufs.clear()
+
+
+class DwOverlap:
+    """Side stream for the weight-gradient GEMMs of a single-GPU training step.
+
+    dW_l (layers.py:260,268) is needed by nothing until the next step's forward, while the backward
+    pass of the layer below starts with HBM-bound kernels (batch-norm backward, operand splits).  The
+    persistent dW GEMM's last wave leaves most SMs idle (512 tiles on 148 SMs), so it is launched on
+    this side stream and the layer below's memory-bound kernels fill the hole; Network joins the
+    stream at the end of the step.  Works identically under CUDA-graph capture (fork / join edges)."""
+
+    def __init__(self):
+        self.side = torch.cuda.Stream()
+        self.events = []
+
+    @contextlib.contextmanager
+    def branch(self):
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self.side.wait_event(fork)
+        with torch.cuda.stream(self.side):
+            yield
+            done = torch.cuda.Event()
+            done.record(self.side)
+        self.events.append(done)
+
+    def join(self):
+        main = torch.cuda.current_stream()
+        for e in self.events:
+            main.wait_event(e)
+        self.events.clear()
 
 
 class _NoComm:
@@ -310,6 +343,7 @@ class LinearLayer(Layer):
         self.useBias = useBias
         self._pending_update = None   # weight update of a data-parallel step still in flight
         self._dwx = None              # (parallel.DwExchange, layer index): fused dW exchange over NVLink
+        self._dw_overlap = None       # DwOverlap shared by the layers of a Network (single-GPU runs)
         self.weights = None
         self.bias = None
         self.activation = None
@@ -662,20 +696,26 @@ class BinaryLayer(LinearLayer):
             A, passes, sa = (xin.t16,), ((0, 0), (0, 1)), None
         Wt = self._weights.t
         split = 4 if (N <= 32 and Kd >= 1024 and B % 256 == 0 and self.comm.world == 1) else 1
-        if split > 1:
-            # narrow layer (the 10-unit output): a 128 x 32 tile grid has only Kd/128 CTAs, so the
-            # contraction over the batch is cut into `split` slices run as GEMM batches (operand
-            # slices are column ranges: batch stride = slice length), summed by the update kernel
-            Ks = B // split
-            parts = ws.get("dW_parts", (split, Kd, N), torch.float32)
-            K_.gemm(M=Kd, N=N, K=Ks, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=parts, ldd=N,
-                    in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32, passes=passes, sa=sa, sb=d_scale,
-                    batch=split, stride_a=Ks, stride_b=Ks, stride_d=Kd * N)
-            K_.sgd_update(Wt, parts, lr, parts=split)
-        elif self.comm.world == 1:
-            K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=Wt, ldd=N,
-                    in_dtype=nat.DT_F16, epilogue=nat.EPI_SGD_F32, passes=passes, sa=sa, sb=d_scale,
-                    host_scale=lr)
+        # single GPU: the dW GEMM goes to the side stream (see DwOverlap) unless it is the last kernel
+        # of the step (first layer), where there is nothing left to overlap it with
+        ov = self._dw_overlap if (self.comm.world == 1 and not self.skip_input_grad) else None
+        with (ov.branch() if ov is not None else contextlib.nullcontext()):
+            if split > 1:
+                # narrow layer (the 10-unit output): a 128 x 32 tile grid has only Kd/128 CTAs, so the
+                # contraction over the batch is cut into `split` slices run as GEMM batches (operand
+                # slices are column ranges: batch stride = slice length), summed by the update kernel
+                Ks = B // split
+                parts = ws.get("dW_parts", (split, Kd, N), torch.float32)
+                K_.gemm(M=Kd, N=N, K=Ks, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=parts,
+                        ldd=N, in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32, passes=passes, sa=sa,
+                        sb=d_scale, batch=split, stride_a=Ks, stride_b=Ks, stride_d=Kd * N)
+                K_.sgd_update(Wt, parts, lr, parts=split)
+            elif self.comm.world == 1:
+                K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=Wt, ldd=N,
+                        in_dtype=nat.DT_F16, epilogue=nat.EPI_SGD_F32, passes=passes, sa=sa,
+                        sb=d_scale, host_scale=lr)
+        if split > 1 or self.comm.world == 1:
+            pass
         elif self._dwx is not None:
             # reduce-scatter fused into the GEMM epilogue: each 128-row tile of this rank's partial dW
             # is stored over NVLink into the staging buffer of the rank that owns those rows

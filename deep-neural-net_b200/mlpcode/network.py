@@ -15,6 +15,7 @@ in mlpcode.layers.  Differences, all forced by the environment and documented in
 """
 from __future__ import annotations
 
+import os
 from pathlib import Path
 from typing import List, Union
 
@@ -65,6 +66,7 @@ class Network(object):
         self._comm = _NoComm()
         self._graph_on = False
         self._graphs = {}
+        self._dw_overlap = None
 
     # ------------------------------------------------------------------ parameters
     @property
@@ -321,6 +323,11 @@ class Network(object):
     def _train_step_eager(self, X, y, lr: float, global_batch: int = None):
         if self._comm.world > 1:
             self._comm.global_batch = global_batch
+        elif self._dw_overlap is None and os.environ.get("BNN_OVERLAP_DW", "1") != "0":
+            from .layers import DwOverlap
+            self._dw_overlap = DwOverlap()
+            for layer in self._layers:
+                layer._dw_overlap = self._dw_overlap
         self._comm.begin_step()
         output = self.predict(X, isTraining=True)
         loss_mod.GLOBAL_BATCH_ROWS = self._comm.global_rows(X.shape[0])
@@ -334,6 +341,8 @@ class Network(object):
         # rank's rows landed); an NCCL all-reduce still in flight is completed lazily, when that
         # layer's weights are next read
         self._comm.finish_step()
+        if self._dw_overlap is not None:
+            self._dw_overlap.join()  # the side-stream dW GEMMs have updated W before the step ends
         return cost
 
     def train_step(self, X, y, lr: float = None, global_batch: int = None) -> float:
