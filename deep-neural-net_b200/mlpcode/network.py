@@ -280,7 +280,7 @@ class Network(object):
                 v += getattr(layer.batchNormLayer, "version", 0)
         return v
 
-    def _graph_step(self, X, y, lr, global_batch):
+    def _graph_step(self, X, y, lr, global_batch, consumed=None):
         if self._comm.world > 1 and (getattr(self._comm, "dw_exchange", None) is None
                                      or getattr(self._comm, "peer_exchange", None) is None):
             return None  # NCCL collectives in the step: stay eager
@@ -295,6 +295,8 @@ class Network(object):
             return None
         if "graph" not in st:
             st["X"], st["y"] = Xt.clone(), yt.clone()
+            if consumed is not None:
+                consumed.record(torch.cuda.current_stream())
             launches0 = K_.launch_count
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
@@ -305,20 +307,27 @@ class Network(object):
         else:
             st["X"].copy_(Xt, non_blocking=True)
             st["y"].copy_(yt, non_blocking=True)
+            if consumed is not None:  # the caller's batch buffers are free again: the step runs on copies
+                consumed.record(torch.cuda.current_stream())
         st["graph"].replay()
         K_.launch_count += st["launches"]
         return st["cost"]
 
-    def train_step_async(self, X, y, lr: float = None, global_batch: int = None):
+    def train_step_async(self, X, y, lr: float = None, global_batch: int = None, consumed=None):
         """One SGD step on one batch (the body of `__updateBatch`, network.py:372-392) without the
         host read of the loss; returns the device array of per-sample losses.  Data-parallel runs
-        with unequal shards pass the global batch size."""
+        with unequal shards pass the global batch size.  consumed: optional CUDA event recorded on the
+        current stream at the point after which X and y are no longer read (graph replays work on
+        copies, so that is right after the copies; eager steps read them until the end)."""
         lr = self._lr.value if lr is None else lr
         if self._graph_on and K_.gemm_events is None:
-            cost = self._graph_step(X, y, lr, global_batch)
+            cost = self._graph_step(X, y, lr, global_batch, consumed)  # records `consumed` itself
             if cost is not None:
                 return cost
-        return self._train_step_eager(X, y, lr, global_batch)
+        cost = self._train_step_eager(X, y, lr, global_batch)
+        if consumed is not None:
+            consumed.record(torch.cuda.current_stream())
+        return cost
 
     def _train_step_eager(self, X, y, lr: float, global_batch: int = None):
         if self._comm.world > 1:
@@ -399,8 +408,7 @@ class Network(object):
                 more = False
             compute.wait_event(ready[slot])
             Xd, Yd = dev[slot]
-            cost = self.train_step_async(Xd, Yd, lr, global_batch)
-            freed[slot].record(compute)
+            cost = self.train_step_async(Xd, Yd, lr, global_batch, consumed=freed[slot])
             loss_host[slot].copy_(cost._sum, non_blocking=True)
             loss_done[slot].record(compute)
             rows[slot] = Xd.shape[0]

@@ -441,6 +441,13 @@ def test_step_graph_replay_equals_eager_training(oracle):
         assert np.array_equal(runs["eager"][1]["W"][i], runs["graph"][1]["W"][i])
         for k in ("gamma", "beta", "mu", "sigma"):
             assert np.array_equal(runs["eager"][1]["bn"][i][k], runs["graph"][1]["bn"][i][k])
+    # the pipelined host-batch API on top of graph replays (batch buffers released right after the
+    # graph's input copies): same losses from pinned host batches
+    nn = build_net(units, params, lr=0.05)
+    nn.enable_step_graph(True)
+    host = [(X.cpu().pin_memory(), Y.cpu().pin_memory()) for X, Y in batches[:5]]
+    losses = nn.train_stream(host, 0.05)
+    assert losses == pytest.approx(runs["eager"][0][:5], rel=1e-6)
 
 
 def test_fused_epilogue_reductions_match_oracle_training(oracle, monkeypatch):
