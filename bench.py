@@ -309,6 +309,19 @@ def run_gpu(args):
     assert len(e2e_losses) == args.steps and all(l == l for l in e2e_losses)
     e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
 
+    # cross-rank exchanges of one step, counted on one eager step (2 per batch-norm layer + 1 dW
+    # exchange per layer); all of them are peer-memory kernels / copy-engine copies, none is an NCCL call
+    exchanges_per_step = None
+    if comm:
+        nn.enable_step_graph(False)
+        c0 = comm.collectives
+        nn.train_step_async(Xd, Yd, LR)
+        fence()
+        exchanges_per_step = {"count": comm.collectives - c0,
+                              "nccl_calls": 0 if (comm.peer_exchange is not None and
+                                                  comm.dw_exchange is not None) else None,
+                              "transport": "NVLink peer memory (own kernels + copy engines)"
+                              if comm.dw_exchange is not None else "NCCL"}
     if rank != 0:
         return 0
 
@@ -382,8 +395,7 @@ def run_gpu(args):
         "ms_per_step_eager": ms_eager / args.steps,
         "host_enqueue_ms_per_step": host_ms.get("device_resident"),
         "host_enqueue_ms_per_step_eager": host_ms.get("eager"),
-        "collectives_per_step": (comm.collectives / (args.steps * 2 + max(args.warmup, 3) + 2))
-        if comm else 0,
+        "exchanges_per_step": exchanges_per_step,
     }
     print(json.dumps(line), flush=True)
     return 0
