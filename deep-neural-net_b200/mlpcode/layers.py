@@ -715,7 +715,7 @@ class BinaryLayer(LinearLayer):
                         in_dtype=nat.DT_F16, epilogue=nat.EPI_SGD_F32, passes=passes, sa=sa,
                         sb=d_scale, host_scale=lr)
         if split > 1 or self.comm.world == 1:
-            pass
+            pass  # done above (possibly on the side stream)
         elif self._dwx is not None:
             # reduce-scatter fused into the GEMM epilogue: each 128-row tile of this rank's partial dW
             # is stored over NVLink into the staging buffer of the rank that owns those rows
