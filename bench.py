@@ -337,11 +337,13 @@ def run_gpu(args):
     hbm_peak, tensor_peak, peak_kind = measured_peaks()
     split = groups.get("f16", {"ms": 0.0, "n": 0, "flops": 0.0, "exec": 0.0})
     i8 = groups.get("i8", {"ms": 0.0, "n": 0, "flops": 0.0, "exec": 0.0})
+    i8dw = groups.get("i8dw", {"ms": 0.0, "n": 0, "flops": 0.0, "exec": 0.0})
     roofline = None
     if split["n"]:
         ach = split["flops"] / (split["ms"] * 1e-3) / 1e12
         roofline = {
-            "kernel": "gemm_tc_kernel<f16 split> (dW + dX + layer-0 forward)", "bound": "tensor",
+            "kernel": "gemm_tc_kernel<f16 split> (dX of every layer, layer-0 forward and dW, 10-wide dW)",
+            "bound": "tensor",
             "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
             "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
             "traffic_source": "profiles/r01_summary.md section 2: dram__bytes_read+write, average over the "
@@ -370,6 +372,16 @@ def run_gpu(args):
                   "avg_launch_ms": i8["ms"] / i8["n"], "launches": i8["n"],
                   "share_of_step": i8["ms"] / ms_total}
 
+    dw_int8 = None
+    if i8dw["n"]:
+        tops = i8dw["exec"] / (i8dw["ms"] * 1e-3) / 1e12
+        dw_int8 = {"kernel": "gemm_tc_kernel<i8, digit split> (dW = X^T.delta' as 3 exact int8 passes, "
+                             "fused SGD / reduce-scatter epilogue)",
+                   "executed": tops, "unit": "TOP/s", "peak": int8_peak,
+                   "frac": (tops / int8_peak) if int8_peak else None,
+                   "algorithmic_tflops": i8dw["flops"] / (i8dw["ms"] * 1e-3) / 1e12,
+                   "avg_launch_ms": i8dw["ms"] / i8dw["n"], "launches": i8dw["n"],
+                   "share_of_step": i8dw["ms"] / ms_total}
     # the CPU baseline is a rank-0, N=1 measurement (torchrun pins every rank to one OpenMP thread)
     cpu_baseline = None
     if world == 1:
@@ -380,7 +392,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "i8 fwd / f16x2-split f32-acc bwd", "data": "synthetic",
+        "dtype": "i8 fwd + i8x3 fixed-point dW / f16x2-split f32-acc dX", "data": "synthetic",
         "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(Xh.nbytes + Yh.nbytes), "d2h_bytes_per_step": 8,
@@ -390,6 +402,7 @@ def run_gpu(args):
                                       "ms_per_step": ms_serial / args.steps,
                                       "api": "Network.train_step(X_host, y_host) -> float"}},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "binary_gemm": binary,
+        "dw_int8_gemm": dw_int8,
         "cpu_baseline": cpu_baseline,
         "step_launch": "one CUDA graph replay per step" if use_graph else "eager kernel launches",
         "ms_per_step_eager": ms_eager / args.steps,

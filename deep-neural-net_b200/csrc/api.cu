@@ -91,8 +91,10 @@ extern "C" int bnn_gemm(const bnn_gemm_desc* g, int impl, bnn_stream_t stream) {
                       sc->rows_per_owner, g->M);
         for (int r = 0; r < sc->world; ++r)
             BNN_CHECK_ARG(sc->stage[r] != 0, "bnn_gemm: scatter stage[%d] is null", r);
-        BNN_CHECK_ARG(g->batch == 1 && g->in_dtype == BNN_DT_F16 && impl == BNN_GEMM_TCGEN05,
-                      "bnn_gemm: BNN_EPI_SCATTER_F32 is a single fp16-split tcgen05 product");
+        BNN_CHECK_ARG(g->batch == 1 && impl == BNN_GEMM_TCGEN05 &&
+                          (g->in_dtype == BNN_DT_F16 || g->hi_from_pass > 0),
+                      "bnn_gemm: BNN_EPI_SCATTER_F32 is a single tcgen05 product (fp16-split, or "
+                      "digit-split int8)");
     }
     BNN_CHECK_ARG(g->epilogue != BNN_EPI_SIGN_I8 || (g->epi_thr && g->epi_sgn),
                   "bnn_gemm: BNN_EPI_SIGN_I8 needs epi_thr and epi_sgn");
@@ -109,9 +111,10 @@ extern "C" int bnn_gemm(const bnn_gemm_desc* g, int impl, bnn_stream_t stream) {
     BNN_CHECK_ARG(g->A[0] && g->B[0] && (g->D || g->epilogue == BNN_EPI_SCATTER_F32),
                   "bnn_gemm: null operand");
     for (int p = 0; p < g->n_pass; ++p) {
-        BNN_CHECK_ARG(g->pa[p] >= 0 && g->pa[p] <= 1 && g->pb[p] >= 0 && g->pb[p] <= 1,
-                      "bnn_gemm: pass %d refers to a piece outside {0,1}", p);
-        BNN_CHECK_ARG(g->A[g->pa[p]] && g->B[g->pb[p]], "bnn_gemm: pass %d uses a null piece", p);
+        BNN_CHECK_ARG(g->pa[p] >= 0 && g->pa[p] <= 1 && g->pb[p] >= 0 && g->pb[p] <= 2,
+                      "bnn_gemm: pass %d refers to a piece outside A{0,1} / B{0,1,2}", p);
+        BNN_CHECK_ARG(g->A[g->pa[p]] && (g->pb[p] == 2 ? g->B2 : g->B[g->pb[p]]),
+                      "bnn_gemm: pass %d uses a null piece", p);
     }
     BNN_CHECK_ARG(g->stats >= BNN_STATS_NONE && g->stats <= BNN_STATS_BN_BWD, "bnn_gemm: bad stats %d",
                   g->stats);
@@ -125,6 +128,9 @@ extern "C" int bnn_gemm(const bnn_gemm_desc* g, int impl, bnn_stream_t stream) {
                           "bnn_gemm: bad stats_z_dtype %d", g->stats_z_dtype);
         }
     }
+    BNN_CHECK_ARG((g->hi_from_pass == 0 && g->col_scale == nullptr && g->B2 == nullptr) ||
+                      impl == BNN_GEMM_TCGEN05,
+                  "bnn_gemm: B2 / hi_from_pass / col_scale are tcgen05-path features");
     BNN_CHECK_ARG(g->ldd >= g->N, "bnn_gemm: ldd < N");
     BNN_CHECK_ARG(g->batch == 1 || g->stride_d >= (int64_t)g->M * g->ldd,
                   "bnn_gemm: batched output needs stride_d >= M*ldd");

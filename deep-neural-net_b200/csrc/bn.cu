@@ -468,7 +468,8 @@ __global__ void __launch_bounds__(256)
 bn_sign_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const float* __restrict__ thr,
                const float* __restrict__ sgn, int8_t* __restrict__ act_i8, long long ld_i8,
                __half* __restrict__ act_t16, long long ld_t16, uint32_t* __restrict__ act_bits,
-               long long ld_bits) {
+               long long ld_bits, int8_t* __restrict__ act_t8, int8_t* __restrict__ act_t8x64,
+               long long ld_t8) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cb = lane & 3, rb = lane >> 2;
     const int c0 = blockIdx.x * SG_COLS + (warp & 3) * 32 + cb * 8;
@@ -530,6 +531,33 @@ bn_sign_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const fl
             w |= __shfl_xor_sync(0xffffffffu, w, 1);
             w |= __shfl_xor_sync(0xffffffffu, w, 2);
             if (cb == 0 && i < rvalid && c0 < N) act_bits[(long long)(r0 + i) * ld_bits + (c0 >> 5)] = w;
+        }
+    }
+    if (act_t16 || act_t8) {
+        unsigned long long m = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m |= (unsigned long long)(sb[i] & 0xFFu) << (8 * i);
+        m = transpose_8x8_bits(m);  // byte j: column j, bit i: row i
+        if (act_t8) {
+            // transposed int8 copies, +-1 and +-64: the A pieces of the digit-split int8 dW product
+            const bool t8vec = ((reinterpret_cast<uintptr_t>(act_t8) | reinterpret_cast<uintptr_t>(act_t8x64)) & 7u) == 0 &&
+                               (ld_t8 % 8 == 0) && rvalid == 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j >= valid) break;
+                const uint32_t cbits = (uint32_t)(m >> (8 * j)) & 0xFFu;
+                int8_t* p1 = act_t8 + (long long)(c0 + j) * ld_t8 + r0;
+                int8_t* p64 = act_t8x64 + (long long)(c0 + j) * ld_t8 + r0;
+                if (t8vec) {
+                    *reinterpret_cast<uint2*>(p1) = make_uint2(nibble_to_pm1_bytes(cbits), nibble_to_pm1_bytes(cbits >> 4));
+                    *reinterpret_cast<uint2*>(p64) = make_uint2(nibble_to_pm64_bytes(cbits), nibble_to_pm64_bytes(cbits >> 4));
+                } else {
+                    for (int i = 0; i < rvalid; ++i) {
+                        p1[i] = ((cbits >> i) & 1u) ? (int8_t)1 : (int8_t)-1;
+                        p64[i] = ((cbits >> i) & 1u) ? (int8_t)64 : (int8_t)-64;
+                    }
+                }
+            }
         }
     }
     if (act_t16) {
@@ -687,7 +715,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ red,
                                        float lr, float ma, float one_minus_ma,
                                        const double* __restrict__ sums, float* __restrict__ coef,
                                        uint32_t* __restrict__ bound_bits,
-                                       float* __restrict__ dgamma_out, float* __restrict__ dbeta_out) {
+                                       float* __restrict__ dgamma_out, float* __restrict__ dbeta_out,
+                                       float* __restrict__ col_quant) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     float bound = 0.f;
     if (n < N) {
@@ -717,6 +746,20 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ red,
         const float amax_x = __uint_as_float(red_max[N + n]);
         bound = fabsf((float)c0) * amax_d + fabsf((float)c1) * amax_x + fabsf((float)c2);
         bound *= 1.0009765625f;  // absorb fp32 rounding of the bound itself
+        if (col_quant) {
+            // fixed-point scale of this column for the int8 dW product: |delta' * 2^e| <= 2^20, so the
+            // rounded value splits into the digits q1 + 256 * (q2 + 64 * q3) (8 + 6 + 8 signed bits)
+            float q = 1.0f;
+            if (bound > 0.f && isfinite(bound)) {
+                int e;
+                const float m = frexpf(bound, &e);            // bound = m * 2^e, m in [0.5, 1)
+                int sh = 20 - ((m == 0.5f) ? e - 1 : e);       // 20 - ceil(log2(bound))
+                sh = sh > 100 ? 100 : (sh < -100 ? -100 : sh);
+                q = ldexpf(1.0f, sh);
+            }
+            col_quant[n] = q;
+            col_quant[N + n] = 1.0f / q;  // exact: powers of two
+        }
     }
     bound = warp_max(bound);
     if ((threadIdx.x & 31) == 0 && bound > 0.f && isfinite(bound))
@@ -872,6 +915,148 @@ bn_bwd_apply_kernel(const float* __restrict__ delta, long long ldd, const void* 
     store_transposed_pieces(sh, sl, b0, n0, B, N, dt_hi, dt_lo, ld_t);
 }
 
+// ---------------------------------------------------------------------------------------------
+// BN backward, pass 2, fixed-point form: delta' = c0*delta + c1*Z + c2' as
+//   * fp16 hi/lo pieces, row-major (the dX GEMM's A operand), and
+//   * three signed-digit int8 matrices, TRANSPOSED [N, B] (the int8 dW GEMM's B pieces):
+//       q = rn(delta' * 2^e_n) = q1 + 256 * (q2 + 64 * q3),  q1, q3 in [-128, 127], q2 in [-32, 31].
+// Register-only: a thread owns 8 rows x 4 columns, lanes are laid out 8 (column blocks) x 4 (row
+// blocks), so delta loads cover 128 contiguous bytes per row, Z loads and row-major stores 64, and
+// the transposed 8-byte digit stores 32 per column — all sector-exact, no shared memory.
+// Warp tile 32 x 32, block = 8 warps = 128 rows x 64 columns.
+// ---------------------------------------------------------------------------------------------
+constexpr int QA_ROWS = 128, QA_COLS = 64;
+
+template <int ZT>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_q_kernel(const float* __restrict__ delta, long long ldd, const void* __restrict__ Z,
+                      long long ldz, int B, int N, const float* __restrict__ coef,
+                      const float* __restrict__ bound, const float* __restrict__ col_quant,
+                      __half* __restrict__ d_hi, __half* __restrict__ d_lo, long long ld_rm,
+                      int8_t* __restrict__ q1t, int8_t* __restrict__ q3t, int8_t* __restrict__ q2t,
+                      long long ld_q, float* __restrict__ scale_out) {
+    using ZE = typename ZLoad<ZT>::T;
+    const float s = split_scale_from_bound(__ldg(bound));
+    if (scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *scale_out = s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cb = lane & 7, rb = lane >> 3;
+    const int c0 = blockIdx.x * QA_COLS + (warp & 1) * 32 + cb * 4;
+    const int r0 = blockIdx.y * QA_ROWS + (warp >> 1) * 32 + rb * 8;
+    const int valid = max(0, min(4, N - c0));
+    const int rvalid = max(0, min(8, B - r0));
+    if (valid == 0 || rvalid == 0) return;
+    const bool fast = z_vec_ok<ZT>(Z, ldz) && aligned16(delta) && (ldd % 4 == 0) && valid == 4 && rvalid == 8;
+    float k0[4], k1[4], k2[4], qs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool ok = j < valid;
+        k0[j] = ok ? __ldg(coef + c0 + j) : 0.f;
+        k1[j] = ok ? __ldg(coef + N + c0 + j) : 0.f;
+        k2[j] = ok ? __ldg(coef + 2 * N + c0 + j) : 0.f;
+        qs[j] = ok ? __ldg(col_quant + c0 + j) : 1.f;
+    }
+    // digit bytes of column j over the 8 rows: two 32-bit words per digit matrix
+    uint32_t w1[4][2], w2[4][2], w3[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w1[j][0] = w1[j][1] = w2[j][0] = w2[j][1] = w3[j][0] = w3[j][1] = 0u;
+    const bool rvec = d_hi && ((reinterpret_cast<uintptr_t>(d_hi) | reinterpret_cast<uintptr_t>(d_lo)) & 7u) == 0 &&
+                      (ld_rm % 4 == 0) && valid == 4;
+    float4 dv[8];
+    float zv[8][4];
+    if (fast) {  // every load of the block is issued before any is consumed
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dv[i] = __ldg(reinterpret_cast<const float4*>(delta + (long long)(r0 + i) * ldd + c0));
+        if (ZT == BNN_Z_S16) {
+            uint2 zr[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                zr[i] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const ZE*>(Z) + (long long)(r0 + i) * ldz + c0));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                zv[i][0] = int_to_float_exact((int)(short)(zr[i].x & 0xffffu));
+                zv[i][1] = int_to_float_exact((int)zr[i].x >> 16);
+                zv[i][2] = int_to_float_exact((int)(short)(zr[i].y & 0xffffu));
+                zv[i][3] = int_to_float_exact((int)zr[i].y >> 16);
+            }
+        } else {
+            uint4 zr[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                zr[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const ZE*>(Z) + (long long)(r0 + i) * ldz + c0));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t w[4] = {zr[i].x, zr[i].y, zr[i].z, zr[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    zv[i][j] = ZT == BNN_Z_F32 ? __uint_as_float(w[j]) : (float)(int)w[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i >= rvalid) break;
+        const long long r = r0 + i;
+        float dl[4], z[4];
+        if (fast) {
+            dl[0] = dv[i].x; dl[1] = dv[i].y; dl[2] = dv[i].z; dl[3] = dv[i].w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) z[j] = zv[i][j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                dl[j] = j < valid ? __ldg(delta + r * ldd + c0 + j) : 0.f;
+                z[j] = j < valid ? ZLoad<ZT>::get(Z, r * ldz + c0 + j) : 0.f;
+            }
+        }
+        __half h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float nd = fmaf(k0[j], dl[j], fmaf(k1[j], z[j], k2[j]));
+            split_f16(nd * s, h[j], l[j]);
+            const int q = __float2int_rn(nd * qs[j]);       // |q| <= 2^20 (+ rounding)
+            const int d1 = ((q + 128) & 255) - 128;          // balanced low byte
+            const int r8 = (q - d1) >> 8;                    // exact
+            const int d2 = ((r8 + 32) & 63) - 32;            // balanced 6-bit digit
+            const int d3 = (r8 - d2) >> 6;                   // |d3| <= 65
+            w1[j][i >> 2] |= (uint32_t)(d1 & 0xFF) << (8 * (i & 3));
+            w2[j][i >> 2] |= (uint32_t)(d2 & 0xFF) << (8 * (i & 3));
+            w3[j][i >> 2] |= (uint32_t)(d3 & 0xFF) << (8 * (i & 3));
+        }
+        if (d_hi) {
+            __half* ph = d_hi + r * ld_rm + c0;
+            __half* pl = d_lo + r * ld_rm + c0;
+            if (rvec) {
+                *reinterpret_cast<uint2*>(ph) =
+                    make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+                               (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+                *reinterpret_cast<uint2*>(pl) =
+                    make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+                               (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+            } else {
+                for (int j = 0; j < valid; ++j) { ph[j] = h[j]; pl[j] = l[j]; }
+            }
+        }
+    }
+    const bool qvec = ((reinterpret_cast<uintptr_t>(q1t) | reinterpret_cast<uintptr_t>(q2t) |
+                        reinterpret_cast<uintptr_t>(q3t)) & 7u) == 0 && (ld_q % 8 == 0) && rvalid == 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j >= valid) break;
+        const long long off = (long long)(c0 + j) * ld_q + r0;
+        if (qvec) {
+            *reinterpret_cast<uint2*>(q1t + off) = make_uint2(w1[j][0], w1[j][1]);
+            *reinterpret_cast<uint2*>(q2t + off) = make_uint2(w2[j][0], w2[j][1]);
+            *reinterpret_cast<uint2*>(q3t + off) = make_uint2(w3[j][0], w3[j][1]);
+        } else {
+            for (int i = 0; i < rvalid; ++i) {
+                q1t[off + i] = (int8_t)((w1[j][i >> 2] >> (8 * (i & 3))) & 0xFF);
+                q2t[off + i] = (int8_t)((w2[j][i >> 2] >> (8 * (i & 3))) & 0xFF);
+                q3t[off + i] = (int8_t)((w3[j][i >> 2] >> (8 * (i & 3))) & 0xFF);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                   long long n, float lr, int parts, long long part_stride) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -988,7 +1173,10 @@ extern "C" int bnn_bn_sign_thresholds(const float* mu, const float* var, const f
 
 extern "C" int bnn_bn_sign(const void* Z, int z_dtype, int B, int N, int64_t ldz, const float* thr,
                            const float* sgn, int8_t* act_i8, int64_t ld_i8, void* act_t16,
-                           int64_t ld_t16, uint32_t* act_bits, int64_t ld_bits, bnn_stream_t stream) {
+                           int64_t ld_t16, uint32_t* act_bits, int64_t ld_bits, int8_t* act_t8,
+                           int8_t* act_t8x64, int64_t ld_t8, bnn_stream_t stream) {
+    BNN_CHECK_ARG((act_t8 == nullptr) == (act_t8x64 == nullptr) && (!act_t8 || ld_t8 >= B),
+                  "bnn_bn_sign: act_t8 / act_t8x64 come as a pair with ld_t8 >= B");
     BNN_CHECK_ARG(Z && thr && sgn && B > 0 && N > 0 && ldz >= N, "bnn_bn_sign: bad input");
     BNN_CHECK_ARG(!act_i8 || ld_i8 >= N, "bnn_bn_sign: ld_i8 < N");
     BNN_CHECK_ARG(!act_t16 || ld_t16 >= B, "bnn_bn_sign: ld_t16 < B");
@@ -999,7 +1187,7 @@ extern "C" int bnn_bn_sign(const void* Z, int z_dtype, int B, int N, int64_t ldz
     return dispatch_z(z_dtype, [&](auto zt) {
         bn_sign_kernel<decltype(zt)::value><<<grid, 256, 0, s>>>(
             Z, B, N, ldz, thr, sgn, act_i8, ld_i8, static_cast<__half*>(act_t16), ld_t16, act_bits,
-            ld_bits);
+            ld_bits, act_t8, act_t8x64, ld_t8);
         BNN_LAUNCH_CHECK("bn_sign_kernel");
         return (int)BNN_OK;
     });
@@ -1044,7 +1232,7 @@ extern "C" int bnn_bn_bwd_finalize(const double* red, const uint32_t* red_max, i
                                    float* beta, float* mu_run, float* sigma_run, float lr,
                                    double momentum, const double* sums, float* coef,
                                    uint32_t* bound_bits, float* dgamma_out, float* dbeta_out,
-                                   bnn_stream_t stream) {
+                                   float* col_quant, bnn_stream_t stream) {
     BNN_CHECK_ARG(red && red_max && mu && var && gamma && beta && mu_run && sigma_run && coef &&
                       bound_bits && N > 0 && count > 0,
                   "bnn_bn_bwd_finalize: bad input");
@@ -1054,7 +1242,8 @@ extern "C" int bnn_bn_bwd_finalize(const double* red, const uint32_t* red_max, i
     const float ma = (float)momentum, oma = (float)(1.0 - momentum);
     bn_bwd_finalize_kernel<<<cdiv(N, 128), 128, 0, s>>>(red, red_max, N, count, mu, var, eps, gamma,
                                                         beta, mu_run, sigma_run, lr, ma, oma, sums,
-                                                        coef, bound_bits, dgamma_out, dbeta_out);
+                                                        coef, bound_bits, dgamma_out, dbeta_out,
+                                                        col_quant);
     BNN_LAUNCH_CHECK("bn_bwd_finalize_kernel");
     return BNN_OK;
 }
@@ -1080,6 +1269,28 @@ extern "C" int bnn_bn_bwd_apply(const float* delta, int64_t ldd, const void* Z, 
             static_cast<__half*>(d_lo), ld_rm, static_cast<__half*>(dt_hi),
             static_cast<__half*>(dt_lo), ld_t, scale_out);
         BNN_LAUNCH_CHECK("bn_bwd_apply_kernel");
+        return (int)BNN_OK;
+    });
+}
+
+extern "C" int bnn_bn_bwd_apply_q(const float* delta, int64_t ldd, const void* Z, int z_dtype,
+                                  int64_t ldz, int B, int N, const float* coef, const float* bound,
+                                  const float* col_quant, void* d_hi, void* d_lo, int64_t ld_rm,
+                                  int8_t* q1t, int8_t* q3t, int8_t* q2t, int64_t ld_q,
+                                  float* scale_out, bnn_stream_t stream) {
+    BNN_CHECK_ARG(delta && Z && coef && bound && col_quant && q1t && q2t && q3t && B > 0 && N > 0 &&
+                      ldd >= N && ldz >= N && ld_q >= B,
+                  "bnn_bn_bwd_apply_q: bad input");
+    BNN_CHECK_ARG((d_hi == nullptr) == (d_lo == nullptr) && (!d_hi || ld_rm >= N),
+                  "bnn_bn_bwd_apply_q: d_hi / d_lo come as a pair with ld_rm >= N");
+    dim3 grid(cdiv(N, QA_COLS), cdiv(B, QA_ROWS));
+    BNN_CHECK_ARG(grid.y <= 65535, "bnn_bn_bwd_apply_q: B too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    return dispatch_z(z_dtype, [&](auto zt) {
+        bn_bwd_apply_q_kernel<decltype(zt)::value><<<grid, 256, 0, s>>>(
+            delta, ldd, Z, ldz, B, N, coef, bound, col_quant, static_cast<__half*>(d_hi),
+            static_cast<__half*>(d_lo), ld_rm, q1t, q3t, q2t, ld_q, scale_out);
+        BNN_LAUNCH_CHECK("bn_bwd_apply_q_kernel");
         return (int)BNN_OK;
     });
 }

@@ -82,6 +82,11 @@ __device__ __forceinline__ uint32_t nibble_to_pm1_bytes(uint32_t nib) {
     const uint32_t spread = ((nib & 0xFu) * 0x00204081u) & 0x01010101u;
     return 0xFFFFFFFFu ^ (spread * 0xFEu);
 }
+// 4 mask bits -> 4 bytes of +-64 (bit ? 0x40 : 0xC0)
+__device__ __forceinline__ uint32_t nibble_to_pm64_bytes(uint32_t nib) {
+    const uint32_t spread = ((nib & 0xFu) * 0x00204081u) & 0x01010101u;
+    return 0xC0C0C0C0u ^ (spread * 0x80u);
+}
 // 2 mask bits -> 2 halves of +-1.0 (bit ? 0x3C00 : 0xBC00)
 __device__ __forceinline__ uint32_t pair_to_pm1_halves(uint32_t two) {
     return 0x3C003C00u | ((~two & 1u) << 15) | ((~two & 2u) << 30);

@@ -92,6 +92,10 @@ struct TcParams {
     int rows_per_owner;
     int rank;
     int m_rot;  // row-tile rotation: this rank starts with the tiles it owns itself
+    // digit-split int8 product: passes [0, hi_from_pass) accumulate the LOW accumulator, the rest the
+    // HIGH one; the epilogue value is low + 256 * high (float).  0 = off.
+    int hi_from_pass;
+    const float* col_scale;  // optional per-column factor applied with `scale` (fp32 outputs)
     // column reductions fused into the epilogue (BNN_STATS_*)
     double* st_sums;       // [2, N] fp64 accumulators (pre-zeroed by the caller)
     uint32_t* st_max;      // [2, N] float bit patterns (BNN_STATS_BN_BWD)
@@ -303,10 +307,17 @@ __device__ __forceinline__ void staged_rows(const TcParams& p, uint32_t xbuf, fl
                         u = make_uint4(sum[g * GC + j], sum[g * GC + j + 1], sum[g * GC + j + 2],
                                        sum[g * GC + j + 3]);
                     } else {
-                        u.x = __float_as_uint(__fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 0] : __uint_as_float(sum[g * GC + j + 0]), scale));
-                        u.y = __float_as_uint(__fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 1] : __uint_as_float(sum[g * GC + j + 1]), scale));
-                        u.z = __float_as_uint(__fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 2] : __uint_as_float(sum[g * GC + j + 2]), scale));
-                        u.w = __float_as_uint(__fmul_rn(kI8 ? (float)(int)sum[g * GC + j + 3] : __uint_as_float(sum[g * GC + j + 3]), scale));
+                        // digit-split int8 products already hold float bits (low + 256 * high)
+                        const bool fbits = !kI8 || p.hi_from_pass != 0;
+                        float4 cs = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (p.col_scale)  // per-column power of two (exact), then the scalar factor
+                            cs = __ldg(reinterpret_cast<const float4*>(p.col_scale + col_w0 + g * GC + j));
+                        const uint32_t r0 = sum[g * GC + j + 0], r1 = sum[g * GC + j + 1],
+                                       r2 = sum[g * GC + j + 2], r3 = sum[g * GC + j + 3];
+                        u.x = __float_as_uint(__fmul_rn(__fmul_rn(fbits ? __uint_as_float(r0) : (float)(int)r0, cs.x), scale));
+                        u.y = __float_as_uint(__fmul_rn(__fmul_rn(fbits ? __uint_as_float(r1) : (float)(int)r1, cs.y), scale));
+                        u.z = __float_as_uint(__fmul_rn(__fmul_rn(fbits ? __uint_as_float(r2) : (float)(int)r2, cs.z), scale));
+                        u.w = __float_as_uint(__fmul_rn(__fmul_rn(fbits ? __uint_as_float(r3) : (float)(int)r3, cs.w), scale));
                     }
                     ptx::sts_v4(w + (uint32_t)(j * 4), u.x, u.y, u.z, u.w);
                 }
@@ -403,7 +414,7 @@ template <bool kI8, int BLOCK_N, int EPI, int STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
-               const TcParams p) {
+               const __grid_constant__ CUtensorMap mapB2, const TcParams p) {
     using Cfg = TileCfg<BLOCK_N>;
     constexpr int S = Cfg::kStages;
     constexpr int kKElems = kI8 ? kKBytes : kKBytes / 2;
@@ -423,7 +434,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int total_tiles = p.batch * p.m_tiles * p.n_tiles;
     const int k_iters = p.n_pass * p.kblocks;
-    const int n_chunks = (k_iters + p.chunk_iters - 1) / p.chunk_iters;
+    // digit-split products have exactly two "chunks": the low and the high accumulator
+    const int split_iters = p.hi_from_pass * p.kblocks;
+    const int n_chunks = split_iters ? 2 : (k_iters + p.chunk_iters - 1) / p.chunk_iters;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&mapA0);
@@ -467,7 +480,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int bb = p.b_batched ? b : 0;
                 for (int pass = 0; pass < p.n_pass; ++pass) {
                     const CUtensorMap* ma = p.pa[pass] ? &mapA1 : &mapA0;
-                    const CUtensorMap* mb = p.pb[pass] ? &mapB1 : &mapB0;
+                    const CUtensorMap* mb = p.pb[pass] == 2 ? &mapB2 : (p.pb[pass] ? &mapB1 : &mapB0);
                     for (int kb = 0; kb < p.kblocks; ++kb) {
                         ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
                         uint8_t* sa = smem + s * Cfg::kStageBytes;
@@ -493,7 +506,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     ptx::mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
                     ptx::tc_fence_after_sync();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-                    const int it_end = min(it + p.chunk_iters, k_iters);
+                    const int it_end = split_iters ? (c == 0 ? split_iters : k_iters)
+                                                   : min(it + p.chunk_iters, k_iters);
                     for (bool first = true; it < it_end; ++it) {
                         ptx::mbar_wait(&full_bar[s], ph);
                         ptx::tc_fence_after_sync();
@@ -574,7 +588,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < G; ++j)
                             sum[g * G + j] =
-                                kI8 ? sum[g * G + j] + v[j]
+                                kI8 ? (split_iters
+                                           ? __float_as_uint(fmaf((float)(int)v[j], 256.0f,
+                                                                  (float)(int)sum[g * G + j]))
+                                           : sum[g * G + j] + v[j])
                                     : __float_as_uint(__fadd_rn(__uint_as_float(sum[g * G + j]),
                                                                 __uint_as_float(v[j])));
                         if (sum[g * G + G - 1] == 0x7FC12345u) __trap();
@@ -600,7 +617,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int row_w0 = m_blk * kBlockM + q * 32;  // first row of this warp
             const uint32_t xbuf = ptx::smem_u32(xpose) + (uint32_t)((warp - 4) * kXposeRows * kXposeStride * 4);
             // the host only asks for STATS on shapes where every tile is full-width and vector-aligned
-            if (kF32Out && ((p.vec_ok && colbase + CPT <= p.N) || STATS != BNN_STATS_NONE)) {
+            if (kF32Out && ((p.vec_ok && colbase + CPT <= p.N) || STATS != BNN_STATS_NONE)) {  // (digit-split
+                // and column-scaled products are admitted by the host only when every tile is full)
                 // full-width tile: whole 128-byte row segments per store instruction
                 float* dst = reinterpret_cast<float*>(dbase) + (rowoff - (long long)lane * p.ldd) + colbase;
                 staged_rows<kI8, EPI, CPT, STATS, true>(p, xbuf, dst, row_w0, colbase, sum, scale, lane);
@@ -689,12 +707,12 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
                                       Cfg::kSmemBytes));
         attr_set = true;
     }
-    CUtensorMap mA[2], mB[2];
+    CUtensorMap mA[3], mB[3];
     const int nA = (g.A[1] != nullptr) ? 2 : 1;
-    const int nB = (g.B[1] != nullptr) ? 2 : 1;
-    for (int i = 0; i < 2; ++i) {
+    const void* Bp[3] = {g.B[0], g.B[1] ? g.B[1] : g.B[0], g.B2 ? g.B2 : g.B[0]};
+    for (int i = 0; i < 3; ++i) {
         const void* a = g.A[i < nA ? i : 0];
-        const void* b = g.B[i < nB ? i : 0];
+        const void* b = Bp[i];
         int rc = make_operand_map(&mA[i], a, kI8, g.M, g.K, g.lda, g.stride_a ? g.batch : 1,
                                   g.stride_a, kBlockM);
         if (rc) return rc;
@@ -749,6 +767,20 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     }
     const long long tiles = (long long)p.batch * p.m_tiles * p.n_tiles;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    p.hi_from_pass = g.hi_from_pass;
+    p.col_scale = g.col_scale;
+    if (g.hi_from_pass != 0 || g.col_scale != nullptr) {
+        // handled by the staged full-width epilogue only
+        const bool f32out = EPI == BNN_EPI_STORE_F32 || EPI == BNN_EPI_SGD_F32 || EPI == BNN_EPI_SCATTER_F32;
+        if (!(f32out && p.vec_ok && g.N % BLOCK_N == 0 && g.batch == 1 &&
+              (g.hi_from_pass == 0 || (kI8 && g.hi_from_pass > 0 && g.hi_from_pass < g.n_pass)) &&
+              (!g.col_scale || aligned16(g.col_scale)))) {
+            set_error("bnn_gemm: digit-split / column-scaled products need int8 operands (split), an fp32 "
+                      "epilogue, N %% %d == 0, 16-byte aligned output and col_scale, batch == 1 (N=%d)",
+                      BLOCK_N, g.N);
+            return BNN_ERR_UNSUPPORTED;
+        }
+    }
     p.st_sums = g.stats_sums;
     p.st_max = g.stats_max;
     p.st_Z = g.stats_z;
@@ -764,7 +796,7 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
         }
     }
     gemm_tc_kernel<kI8, BLOCK_N, EPI, STATS><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(
-        mA[0], mA[1], mB[0], mB[1], p);
+        mA[0], mA[1], mB[0], mB[1], mB[2], p);
     BNN_LAUNCH_CHECK("gemm_tc_kernel");
     return BNN_OK;
 }
@@ -793,6 +825,7 @@ int pick_epilogue(const bnn_gemm_desc& g, bool i8, cudaStream_t stream) {
             case BNN_EPI_STORE_S32: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S32>(g, stream);
             case BNN_EPI_STORE_F32: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_F32>(g, stream);
             case BNN_EPI_SIGN_I8: return launch_tc<true, BLOCK_N, BNN_EPI_SIGN_I8>(g, stream);
+            case BNN_EPI_SCATTER_F32: return launch_tc<true, BLOCK_N, BNN_EPI_SCATTER_F32>(g, stream);
             default: return launch_tc<true, BLOCK_N, BNN_EPI_SGD_F32>(g, stream);
         }
     }
@@ -813,6 +846,7 @@ int gemm_tc_dispatch(const bnn_gemm_desc& g, cudaStream_t stream) {
         if (g.A[i]) BNN_CHECK_ARG(aligned16(g.A[i]), "bnn_gemm: A[%d] not 16-byte aligned", i);
         if (g.B[i]) BNN_CHECK_ARG(aligned16(g.B[i]), "bnn_gemm: B[%d] not 16-byte aligned", i);
     }
+    if (g.B2) BNN_CHECK_ARG(aligned16(g.B2), "bnn_gemm: B2 not 16-byte aligned");
     BNN_CHECK_ARG((g.lda * es) % 16 == 0 && (g.ldb * es) % 16 == 0,
                   "bnn_gemm: operand pitches must be multiples of 16 bytes (lda=%lld ldb=%lld)",
                   (long long)g.lda, (long long)g.ldb);

@@ -57,6 +57,8 @@ class GemmDesc(C.Structure):
         ("stats", C.c_int32), ("stats_z_dtype", C.c_int32),
         ("stats_sums", C.c_void_p), ("stats_max", C.c_void_p), ("stats_z", C.c_void_p),
         ("stats_ldz", C.c_int64), ("stats_mu", C.c_void_p),
+        ("B2", C.c_void_p), ("hi_from_pass", C.c_int32), ("reserved2", C.c_int32),
+        ("col_scale", C.c_void_p),
     ]
 
 
@@ -80,11 +82,13 @@ PROTOTYPES = {
     "bnn_bn_apply": [_p, _i, _i, _i, _i64, _p, _p, _p, _p, _f, _p, _i64, _p, _i64, _p, _i64, _p,
                      _i64, _p],
     "bnn_bn_sign_thresholds": [_p, _p, _p, _p, _f, _i, _p, _p, _p],
-    "bnn_bn_sign": [_p, _i, _i, _i, _i64, _p, _p, _p, _i64, _p, _i64, _p, _i64, _p],
+    "bnn_bn_sign": [_p, _i, _i, _i, _i64, _p, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p],
     "bnn_softmax_xent": [_p, _i, _i, _i64, _p, _p, _p, _p, _d, _p, _p],
     "bnn_bn_bwd_reduce": [_p, _i64, _p, _i, _i64, _i, _i, _p, _p, _p, _i, _p],
     "bnn_bn_bwd_finalize": [_p, _p, _i, _d, _p, _p, _f, _p, _p, _p, _p, _f, _d, _p, _p, _p, _p, _p,
-                            _p],
+                            _p, _p],
+    "bnn_bn_bwd_apply_q": [_p, _i64, _p, _i, _i64, _i, _i, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _i64,
+                           _p, _p],
     "bnn_bn_bwd_apply": [_p, _i64, _p, _i, _i64, _i, _i, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _p,
                          _i64, _p, _p],
     "bnn_step_tick": [_p, _p],

@@ -83,7 +83,7 @@ def split_f16(x: torch.Tensor, bound: torch.Tensor, hi=None, lo=None, hi_t=None,
 # ------------------------------------------------------------------------------- GEMMs
 def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),), sa=None,
          sb=None, host_scale=1.0, batch=1, stride_a=0, stride_b=0, stride_d=0, impl=None,
-         epi_thr=None, epi_sgn=None, scatter=None, stats=None) -> None:
+         epi_thr=None, epi_sgn=None, scatter=None, stats=None, hi_from_pass=0, col_scale=None) -> None:
     """D = epi(sum_p A[pa] @ B[pb]^T); A/B are sequences of 1..2 operand-piece tensors.
     scatter (EPI_SCATTER_F32): dict(world, rank, rows_per_owner, stage=[address per rank]).
     stats: dict(mode=STATS_COLSUM, sums) or dict(mode=STATS_BN_BWD, sums, max, Z, mu) — column
@@ -96,6 +96,8 @@ def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),
     for i in range(2):
         d.A[i] = ptr(A[i]) if i < len(A) else None
         d.B[i] = ptr(B[i]) if i < len(B) else None
+    d.B2 = ptr(B[2]) if len(B) > 2 else None
+    d.hi_from_pass, d.col_scale = hi_from_pass, ptr(col_scale)
     d.lda, d.ldb, d.stride_a, d.stride_b = lda, ldb, stride_a, stride_b
     d.D, d.ldd, d.stride_d = ptr(D), ldd, stride_d
     d.sa, d.sb = ptr(sa), ptr(sb)
@@ -120,8 +122,22 @@ def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),
     start.record()
     _call("bnn_gemm", C.byref(d), gemm_impl() if impl is None else impl)
     end.record()
-    gemm_events.append((start, end, "i8" if in_dtype == nat.DT_I8 else "f16",
-                        2.0 * M * N * K * batch, len(passes)))
+    kind = "f16" if in_dtype != nat.DT_I8 else ("i8dw" if hi_from_pass else "i8")
+    gemm_events.append((start, end, kind, 2.0 * M * N * K * batch, len(passes)))
+
+
+def full_tiles(N: int, impl=None) -> bool:
+    """tcgen05 path and N a multiple of its tile width (256 for N > 128, 128 for N > 32, else 32)."""
+    if (gemm_impl() if impl is None else impl) != nat.GEMM_TCGEN05:
+        return False
+    tile = 256 if N > 128 else (128 if N > 32 else 32)
+    return N % tile == 0
+
+
+def int8_dw_ok(N: int) -> bool:
+    """dW = X^T . delta' as an exact fixed-point product on the int8 tensor pipe (X = +-1 activations,
+    delta' in three signed digits) instead of two fp16 passes.  BNN_DW_INT8=0 keeps the fp16 form."""
+    return N >= 64 and full_tiles(N) and os.environ.get("BNN_DW_INT8", "1") != "0"
 
 
 def fused_stats_ok(N: int, impl=None) -> bool:
@@ -216,11 +232,13 @@ def bn_sign_thresholds(mu, var, gamma, beta, eps, N, thr, sgn) -> None:
           ptr(sgn))
 
 
-def bn_sign(Z, B, N, thr, sgn, act_i8=None, act_t16=None, act_bits=None) -> None:
+def bn_sign(Z, B, N, thr, sgn, act_i8=None, act_t16=None, act_bits=None, act_t8=None,
+            act_t8x64=None) -> None:
     _call("bnn_bn_sign", ptr(Z), z_dtype_of(Z), B, N, _ld(Z), ptr(thr), ptr(sgn),
           ptr(act_i8), _ld(act_i8) if act_i8 is not None else 0,
           ptr(act_t16), _ld(act_t16) if act_t16 is not None else 0,
-          ptr(act_bits), _ld(act_bits) if act_bits is not None else 0)
+          ptr(act_bits), _ld(act_bits) if act_bits is not None else 0,
+          ptr(act_t8), ptr(act_t8x64), _ld(act_t8) if act_t8 is not None else 0)
 
 
 def softmax_xent(logits, B, Cc, onehot=None, probs=None, loss_rows=None, grad=None, count=None,
@@ -235,10 +253,18 @@ def bn_bwd_reduce(delta, Z, B, N, mu, red, red_max, accumulate=False) -> None:
 
 
 def bn_bwd_finalize(red, red_max, N, count, mu, var, eps, gamma, beta, mu_run, sigma_run, lr,
-                    momentum, sums, coef, bound_bits, dgamma_out=None, dbeta_out=None) -> None:
+                    momentum, sums, coef, bound_bits, dgamma_out=None, dbeta_out=None,
+                    col_quant=None) -> None:
     _call("bnn_bn_bwd_finalize", ptr(red), ptr(red_max), N, float(count), ptr(mu), ptr(var), eps,
           ptr(gamma), ptr(beta), ptr(mu_run), ptr(sigma_run), lr, momentum, ptr(sums), ptr(coef),
-          ptr(bound_bits), ptr(dgamma_out), ptr(dbeta_out))
+          ptr(bound_bits), ptr(dgamma_out), ptr(dbeta_out), ptr(col_quant))
+
+
+def bn_bwd_apply_q(delta, Z, B, N, coef, bound, col_quant, q1t, q3t, q2t, d_hi=None, d_lo=None,
+                   scale_out=None) -> None:
+    _call("bnn_bn_bwd_apply_q", ptr(delta), _ld(delta), ptr(Z), z_dtype_of(Z), _ld(Z), B, N, ptr(coef),
+          ptr(bound), ptr(col_quant), ptr(d_hi), ptr(d_lo), _ld(d_hi) if d_hi is not None else 0,
+          ptr(q1t), ptr(q3t), ptr(q2t), _ld(q1t), ptr(scale_out))
 
 
 def bn_bwd_apply(delta, Z, B, N, mu, coef, bound, out_f32=None, d_hi=None, d_lo=None, dt_hi=None,

@@ -48,8 +48,9 @@ def binary_gemm_variant() -> str:
 class SignActivation(DeviceArray):
     """Output of a sign-activated layer: values in {+1,-1} kept in GEMM-operand form."""
 
-    def __init__(self, i8, n, t16=None, bits=None):
+    def __init__(self, i8, n, t16=None, bits=None, t8=None, t8x64=None):
         self.i8, self.n, self.t16, self.bits = i8, n, t16, bits
+        self.t8, self.t8x64 = t8, t8x64   # transposed int8 +-1 / +-64 (int8 dW operand pieces)
         self._dense = None
 
     @property
@@ -278,9 +279,11 @@ class BatchNormLayer(Layer):
         return dict(mode=nat.STATS_BN_BWD, sums=red, max=red_max, Z=Z, mu=mu)
 
     def backward_kernels(self, delta, Z, B, sums, mu, var, lr, want_f32, d_rm, d_t, scale,
-                         reduced=False):
+                         reduced=False, digits=None):
         """reduced: the reductions were already accumulated into bwd_reduce_target() by the GEMM that
-        produced `delta`."""
+        produced `delta`.  digits: (q1t, q3t, q2t) int8 [N, pad16(B)] — emit delta' transposed as
+        signed fixed-point digits for the int8 dW product instead of the fp16 pieces `d_t`; returns
+        the [2, N] per-column scales (row 1 is the GEMM's col_scale)."""
         n = self.layerUnits
         red = self._ws.get("red", (2, n), torch.float64)
         red_max = self._ws.get("red_max", (2, n), torch.int32)
@@ -300,9 +303,16 @@ class BatchNormLayer(Layer):
             if not reduced:
                 K_.bn_bwd_reduce(delta, Z, B, n, mu, red, red_max)
             self.comm.allreduce_sum(red)
+        colq = self._ws.get("col_quant", (2, n), torch.float32) if digits is not None else None
         K_.bn_bwd_finalize(red, red_max, n, self.comm.global_rows(B), mu, var, self.EPSILON,
                            self.gamma.t, self.beta.t, self.mu.t, self.sigma.t, lr, self.MA_BETA,
-                           sums, coef, bound)
+                           sums, coef, bound, col_quant=colq)
+        if digits is not None:
+            assert not want_f32
+            K_.bn_bwd_apply_q(delta, Z, B, n, coef, bound, colq, digits[0], digits[1], digits[2],
+                              d_hi=d_rm[0] if d_rm else None, d_lo=d_rm[1] if d_rm else None,
+                              scale_out=scale)
+            return colq
         out = empty((B, n)) if want_f32 else None
         K_.bn_bwd_apply(delta, Z, B, n, mu, coef, bound, out_f32=out,
                         d_hi=d_rm[0] if d_rm else None, d_lo=d_rm[1] if d_rm else None,
@@ -613,16 +623,24 @@ class BinaryLayer(LinearLayer):
 
         # ---- BN + activation
         if sign_out:
-            act_t16 = ws.get(f"a_t16_{B}", (N, pad_to(B, 8)), torch.float16, zero=True) if isTrain else None
+            act_t16 = act_t8 = act_t8x64 = None
+            consumer = getattr(self, "output_layer", None)
+            if isTrain and consumer is not None and K_.int8_dw_ok(consumer.layerUnits):
+                # the layer above forms its dW on the int8 tensor pipe: transposed +-1 / +-64 bytes
+                act_t8 = ws.get(f"a_t8_{B}", (N, pad_to(B, 16)), torch.int8, zero=True)
+                act_t8x64 = ws.get(f"a_t8x64_{B}", (N, pad_to(B, 16)), torch.int8, zero=True)
+            elif isTrain:
+                act_t16 = ws.get(f"a_t16_{B}", (N, pad_to(B, 8)), torch.float16, zero=True)
             act_bits = ws.get(f"a_bits{B}", (B, pad_to(N, 32) // 32), torch.int32, zero=True) if popc else None
             if not fuse_sign:
                 # sign(BN(z)) through the per-column thresholds: one compare per element, bit-identical
                 # to evaluating gamma*((z-mu)/sqrt(var+eps))+beta and taking the sign
                 K_.bn_sign_thresholds(mu, var, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
-                K_.bn_sign(Z, B, N, thr, sgn, act_i8=act_i8, act_t16=act_t16, act_bits=act_bits)
+                K_.bn_sign(Z, B, N, thr, sgn, act_i8=act_i8, act_t16=act_t16, act_bits=act_bits,
+                           act_t8=act_t8, act_t8x64=act_t8x64)
             elif act_bits is not None:
                 K_.pack_i8_rows(act_i8, N, act_bits)
-            out = SignActivation(act_i8, N, t16=act_t16, bits=act_bits)
+            out = SignActivation(act_i8, N, t16=act_t16, bits=act_bits, t8=act_t8, t8x64=act_t8x64)
         else:
             logits = empty((B, N))
             K_.bn_apply(Z, B, N, mu, var, bn.gamma.t, bn.beta.t, bn.EPSILON, out_f32=logits)
@@ -658,13 +676,21 @@ class BinaryLayer(LinearLayer):
         Np, Bp = pad_to(N, 8), pad_to(B, 8)
         d_hi = ws.get(f"d_hi{B}", (B, Np), torch.float16, zero=True)
         d_lo = ws.get(f"d_lo{B}", (B, Np), torch.float16, zero=True)
-        dt_hi = ws.get(f"dt_hi{B}", (N, Bp), torch.float16, zero=True)
-        dt_lo = ws.get(f"dt_lo{B}", (N, Bp), torch.float16, zero=True)
         d_scale = ws.get("d_scale", (1,), torch.float32)
         need_dx = not self.skip_input_grad
-        self.batchNormLayer.backward_kernels(delta, Z, B, c["sums"], c["mu"], c["var"], lr, False,
-                                             (d_hi, d_lo) if need_dx else None, (dt_hi, dt_lo),
-                                             d_scale, reduced=reduced)
+        # dW on the int8 tensor pipe (exact fixed-point sums, 2x the fp16 rate) when the input is a
+        # +-1 activation whose producer emitted the transposed int8 pieces; else two fp16 passes
+        use_q = (not c["real_input"]) and getattr(xin, "t8", None) is not None and K_.int8_dw_ok(N)
+        digits = dt_hi = dt_lo = colq = None
+        if use_q:
+            Bq = pad_to(B, 16)
+            digits = tuple(ws.get(f"{nm}{B}", (N, Bq), torch.int8, zero=True) for nm in ("q1t", "q3t", "q2t"))
+        else:
+            dt_hi = ws.get(f"dt_hi{B}", (N, Bp), torch.float16, zero=True)
+            dt_lo = ws.get(f"dt_lo{B}", (N, Bp), torch.float16, zero=True)
+        colq = self.batchNormLayer.backward_kernels(
+            delta, Z, B, c["sums"], c["mu"], c["var"], lr, False, (d_hi, d_lo) if need_dx else None,
+            (dt_hi, dt_lo) if not use_q else None, d_scale, reduced=reduced, digits=digits)
 
         # ---- dX = delta' . W^T with the latent, pre-update weights (layers.py:266)
         dX = None
@@ -690,10 +716,18 @@ class BinaryLayer(LinearLayer):
             dX = dX[:, :Kd]
 
         # ---- dW = X^T . delta'  (layers.py:260) and W -= lr * dW (:268)
-        if c["real_input"]:
-            A, passes, sa = (xin["hi_t"], xin["lo_t"]), ((0, 0), (0, 1), (1, 0)), xin["scale"]
+        if use_q:
+            # dW = 2^-e_n * (X^T.q1 + 256 * ((64 X)^T.q3 + X^T.q2)): low / high int32 accumulators
+            dw = dict(in_dtype=nat.DT_I8, A=(xin.t8, xin.t8x64), B=digits, lda=xin.t8.stride(0),
+                      ldb=digits[0].stride(0), passes=((0, 0), (1, 1), (0, 2)), hi_from_pass=1,
+                      col_scale=colq[1], sa=None, sb=None)
+        elif c["real_input"]:
+            dw = dict(in_dtype=nat.DT_F16, A=(xin["hi_t"], xin["lo_t"]), B=(dt_hi, dt_lo),
+                      lda=xin["hi_t"].stride(0), ldb=Bp, passes=((0, 0), (0, 1), (1, 0)),
+                      sa=xin["scale"], sb=d_scale)
         else:
-            A, passes, sa = (xin.t16,), ((0, 0), (0, 1)), None
+            dw = dict(in_dtype=nat.DT_F16, A=(xin.t16,), B=(dt_hi, dt_lo), lda=xin.t16.stride(0), ldb=Bp,
+                      passes=((0, 0), (0, 1)), sa=None, sb=d_scale)
         Wt = self._weights.t
         split = 4 if (N <= 32 and Kd >= 1024 and B % 256 == 0 and self.comm.world == 1) else 1
         # single GPU: the dW GEMM goes to the side stream (see DwOverlap) unless it is the last kernel
@@ -706,14 +740,11 @@ class BinaryLayer(LinearLayer):
                 # slices are column ranges: batch stride = slice length), summed by the update kernel
                 Ks = B // split
                 parts = ws.get("dW_parts", (split, Kd, N), torch.float32)
-                K_.gemm(M=Kd, N=N, K=Ks, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=parts,
-                        ldd=N, in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32, passes=passes, sa=sa,
-                        sb=d_scale, batch=split, stride_a=Ks, stride_b=Ks, stride_d=Kd * N)
+                K_.gemm(M=Kd, N=N, K=Ks, D=parts, ldd=N, epilogue=nat.EPI_STORE_F32, batch=split,
+                        stride_a=Ks, stride_b=Ks, stride_d=Kd * N, **dw)
                 K_.sgd_update(Wt, parts, lr, parts=split)
             elif self.comm.world == 1:
-                K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=Wt, ldd=N,
-                        in_dtype=nat.DT_F16, epilogue=nat.EPI_SGD_F32, passes=passes, sa=sa,
-                        sb=d_scale, host_scale=lr)
+                K_.gemm(M=Kd, N=N, K=B, D=Wt, ldd=N, epilogue=nat.EPI_SGD_F32, host_scale=lr, **dw)
         if split > 1 or self.comm.world == 1:
             pass  # done above (possibly on the side stream)
         elif self._dwx is not None:
@@ -723,12 +754,10 @@ class BinaryLayer(LinearLayer):
             dwx, li = self._dwx
             step_dev = dwx.comm.step_dev
             dwx.comm.collectives += 1
-            K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=None, ldd=N,
-                    in_dtype=nat.DT_F16, epilogue=nat.EPI_SCATTER_F32, passes=passes, sa=sa,
-                    sb=d_scale,
+            K_.gemm(M=Kd, N=N, K=B, D=None, ldd=N, epilogue=nat.EPI_SCATTER_F32,
                     scatter=dict(world=dwx.world, rank=dwx.rank,
                                  rows_per_owner=dwx.layout[li]["rows_per_owner"],
-                                 stage=dwx.stage_ptrs(li)))
+                                 stage=dwx.stage_ptrs(li)), **dw)
             if dwx.copy_engine_broadcast and not self.skip_input_grad:
                 # owner update now (local rows only; the kernel also signals "pushed" to the peers);
                 # the rows then travel to the peers on the copy engines, on a side stream, while this
@@ -745,9 +774,7 @@ class BinaryLayer(LinearLayer):
             dwx.pending.append(li)  # awaited by comm.finish_step() at the end of the training step
         else:
             dW = ws.get("dW", (Kd, N), torch.float32)
-            K_.gemm(M=Kd, N=N, K=B, A=A, B=(dt_hi, dt_lo), lda=A[0].stride(0), ldb=Bp, D=dW, ldd=N,
-                    in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32, passes=passes, sa=sa,
-                    sb=d_scale)
+            K_.gemm(M=Kd, N=N, K=B, D=dW, ldd=N, epilogue=nat.EPI_STORE_F32, **dw)
             # batch-sharded dW -> global dW over NCCL/NVLink, started now and awaited only when the
             # weights are next needed, so it overlaps the lower layers' backward kernels
             self._pending_update = (self.comm.allreduce_sum_async(dW), dW, lr)

@@ -57,6 +57,7 @@ class Network(object):
         for i, layer in enumerate(self._layers):
             layer.layer_index = i
             layer.input_layer = self._layers[i - 1] if i > 0 else None
+            layer.output_layer = self._layers[i + 1] if i + 1 < len(self._layers) else None
         if self._layers:
             self._layers[0].skip_input_grad = True
         self._lossF: lf = None

@@ -176,6 +176,17 @@ typedef struct bnn_gemm_desc {
     const void* stats_z;   /* device [M, stats_ldz] (BNN_STATS_BN_BWD) */
     int64_t stats_ldz;
     const float* stats_mu; /* device [N] (BNN_STATS_BN_BWD) */
+    /* Exact fixed-point products on the int8 tensor pipe (dW = X^T . delta' with X = +-1 and delta'
+     * cut into signed digits, layers.py:260).  B2 is a third B piece (pb[p] == 2).  With
+     * hi_from_pass = k > 0 (int8 operands only) the passes [0, k) accumulate a LOW int32 accumulator
+     * and the passes [k, n_pass) a HIGH one; the epilogue value is low + 256 * high, formed in fp32.
+     * col_scale: optional device [N] per-column factor (a power of two: the fixed-point scale of that
+     * column) multiplied in before host_scale.  tcgen05 path, fp32 epilogues, N a multiple of the tile
+     * width (see BNN_STATS_*), batch == 1; otherwise BNN_ERR_UNSUPPORTED. */
+    const void* B2;
+    int32_t hi_from_pass;
+    int32_t reserved2;
+    const float* col_scale;
 } bnn_gemm_desc;
 
 int bnn_gemm(const bnn_gemm_desc* desc_host, int impl, bnn_stream_t stream);
@@ -225,10 +236,13 @@ int bnn_bn_apply(const void* Z, int z_dtype, int B, int N, int64_t ldz, const fl
 int bnn_bn_sign_thresholds(const float* mu, const float* var, const float* gamma, const float* beta,
                            float eps, int N, float* thr, float* sgn, bnn_stream_t stream);
 
-/* The sign-only form of bnn_bn_apply on those thresholds (same outputs, no out_f32). */
+/* The sign-only form of bnn_bn_apply on those thresholds (same outputs, no out_f32), plus optionally
+ * the transposed int8 copies act_t8 [N, ld_t8] = +-1 and act_t8x64 = +-64: the A pieces of the
+ * digit-split int8 dW product (bnn_gemm hi_from_pass). */
 int bnn_bn_sign(const void* Z, int z_dtype, int B, int N, int64_t ldz, const float* thr,
                 const float* sgn, int8_t* act_i8, int64_t ld_i8, void* act_t16, int64_t ld_t16,
-                uint32_t* act_bits, int64_t ld_bits, bnn_stream_t stream);
+                uint32_t* act_bits, int64_t ld_bits, int8_t* act_t8, int8_t* act_t8x64, int64_t ld_t8,
+                bnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * A6/A10  output activation, loss and its gradient   (softmax activation.py:44-53;
@@ -266,7 +280,8 @@ int bnn_bn_bwd_finalize(const double* red, const uint32_t* red_max, int N, doubl
                         const float* mu, const float* var, float eps, float* gamma, float* beta,
                         float* mu_run, float* sigma_run, float lr, double momentum,
                         const double* sums, float* coef, uint32_t* bound_bits, float* dgamma_out,
-                        float* dbeta_out, bnn_stream_t stream);
+                        float* dbeta_out, float* col_quant,
+                        bnn_stream_t stream);
 
 /* delta' (see above) written as fp32 (out_f32, may be NULL) and/or as scaled fp16 hi/lo pieces in
  * both operand layouts: d_hi/d_lo [B, ld_rm] (dX operand) and dt_hi/dt_lo [N, ld_t] (dW operand).
@@ -276,6 +291,17 @@ int bnn_bn_bwd_apply(const float* delta, int64_t ldd, const void* Z, int z_dtype
                      const float* bound, float* out_f32, int64_t ld_f32, void* d_hi, void* d_lo,
                      int64_t ld_rm, void* dt_hi, void* dt_lo, int64_t ld_t, float* scale_out,
                      bnn_stream_t stream);
+
+/* Fixed-point form of the same pass for the int8 dW product.  col_quant: device [2, N] written by
+ * bnn_bn_bwd_finalize (row 0: 2^e_n with |delta'_n * 2^e_n| <= 2^20, row 1: 2^-e_n = the GEMM's
+ * col_scale).  Outputs: d_hi / d_lo [B, ld_rm] as above (may be NULL), and the TRANSPOSED signed digits
+ * of q = rn(delta' * 2^e_n) = q1 + 256 * (q2 + 64 * q3):  q1t, q3t, q2t int8 [N, ld_q] with
+ * q1, q3 in [-128, 127] and q2 in [-32, 31] — the three B pieces of
+ *   dW = 2^-e_n * ( X^T.q1 + 256 * ( (64 X)^T.q3 + X^T.q2 ) )          (exact integer sums). */
+int bnn_bn_bwd_apply_q(const float* delta, int64_t ldd, const void* Z, int z_dtype, int64_t ldz,
+                       int B, int N, const float* coef, const float* bound, const float* col_quant,
+                       void* d_hi, void* d_lo, int64_t ld_rm, int8_t* q1t, int8_t* q3t, int8_t* q2t,
+                       int64_t ld_q, float* scale_out, bnn_stream_t stream);
 
 /* p[i] -= lr * sum_s g[s*part_stride + i]     (weights -= lr*dw, layers.py:268): the data-parallel path
  * (dW all-reduced before the update, parts = 1) and split-K dW products of narrow layers (parts > 1). */
