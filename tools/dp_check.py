@@ -43,6 +43,35 @@ def main():
                 if comm.rank == 0:
                     print(name, "step", s, "layer", i, {k: f"{v:.2e}" for k, v in errs.items()})
                 worst = max(worst, max(errs.values()))
+    # ---- widths that take the fused epilogues and the int8 dW product (the fixtures are narrower):
+    # one full-batch step of the oracle vs the same step sharded over the ranks
+    sys.path.insert(0, str(REPO / "oracle"))
+    import bnn_oracle as O
+    units, Bg, lr = [64, 512, 256, 10], 512, 0.05
+    rng = np.random.default_rng(21)
+    params = O.new_params(units, rng)
+    X = rng.random((Bg, units[0]), dtype=np.float32) * 2 - 1
+    Y = np.eye(10, dtype=np.int8)[rng.integers(0, 10, Bg)]
+    ref = O.copy_params(params)
+    ref_cost = O.train_step(ref, X, Y, lr)
+    nn = Network(units, useGpu=True, binarized=True, useBatchNorm=True)
+    nn.compile(lr=lr, hiddenAf=af.sign, outAf=af.softmax, lossF=lf.cross_entropy)
+    nn.load_weights([w.copy() for w in params["W"]])
+    nn.set_data_parallel(comm)
+    lo, hi = parallel.shard_range(Bg, comm.rank, comm.world)
+    nn.train_step(X[lo:hi], Y[lo:hi], lr, global_batch=Bg)
+    gam, bet, mus, sig = nn.batchNormParams
+    n = len(units) - 1
+    for i in range(n):
+        errs = {"W": rel_err(nn.weights[i].get(), ref["W"][i]),
+                "dW": rel_err(nn.weights[i].get().astype(np.float64) - params["W"][i],
+                              ref["W"][i].astype(np.float64) - params["W"][i])}
+        for key, arr in (("gamma", gam), ("mu", mus), ("sigma", sig)) + ((("beta", bet),) if i == n - 1 else ()):
+            errs[key] = rel_err(arr[i].get(), ref["bn"][i][key])
+        if comm.rank == 0:
+            print("fused_widths layer", i, {k: f"{v:.2e}" for k, v in errs.items()})
+        worst = max(worst, max(v for k, v in errs.items() if k != "dW"))
+        assert errs["dW"] < 1e-3, errs   # the update itself (fp32 cancellation in W - W0 limits this)
     t = torch.tensor([worst], device="cuda")
     torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     if comm.rank == 0:
