@@ -34,7 +34,7 @@ UNITS = [784, 4096, 4096, 4096, 10]
 BATCH = 8192
 LR = 0.01
 METRIC, UNIT = "BNN MLP train samples/s", "samples/s"
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 528.7e6  # profiles/r01_gemm_full_raw.csv (see profiles/r01_summary.md section 2)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 436.4e6  # profiles/r01_gemm_full_raw.csv (see profiles/r01_summary.md section 2)
 
 
 def workload_config(n_gpus):
@@ -347,9 +347,9 @@ def run_gpu(args):
             "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
             "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
             "traffic_source": "profiles/r01_summary.md section 2: dram__bytes_read+write, average over the "
-                              "8 launches/step of this kernel in one ncu --set full capture "
-                              "(algorithmic: 402e6 for a 4096-wide dX incl. the Z read of the fused "
-                              "BN reductions, 329e6 for a dW)",
+                              "6 fp16-split launches/step (3 dX, layer-0 forward and dW, 10-wide dW) in one "
+                              "ncu --set full capture (algorithmic: 402e6 for a 4096-wide dX incl. the "
+                              "Z read of the fused BN reductions)",
             "peak_source": f"bf16_tflops_sustained of {peak_kind}",
             "executed_tflops": split["exec"] / (split["ms"] * 1e-3) / 1e12,
             "executed_frac": split["exec"] / (split["ms"] * 1e-3) / 1e12 / tensor_peak,

@@ -289,7 +289,11 @@ class Network(object):
         key = (tuple(Xt.shape), tuple(yt.shape), yt.dtype, float(lr), global_batch, self._param_version())
         st = self._graphs.get(key)
         if st is None:
-            self._graphs = {k: v for k, v in self._graphs.items() if k[-1] == key[-1]}
+            # graphs of other parameter identities are stale; of the rest keep the two most recent
+            # (each captured step pins its own pool of activations, and an lr schedule would
+            # otherwise grow one graph per lr value)
+            keep = [(k, v) for k, v in self._graphs.items() if k[-1] == key[-1]][-2:]
+            self._graphs = dict(keep)
             st = self._graphs[key] = {"warm": 0}
         if st["warm"] < 2:
             st["warm"] += 1
