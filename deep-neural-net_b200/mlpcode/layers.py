@@ -680,7 +680,8 @@ class BinaryLayer(LinearLayer):
         need_dx = not self.skip_input_grad
         # dW on the int8 tensor pipe (exact fixed-point sums, 2x the fp16 rate) when the input is a
         # +-1 activation whose producer emitted the transposed int8 pieces; else two fp16 passes
-        use_q = (not c["real_input"]) and getattr(xin, "t8", None) is not None and K_.int8_dw_ok(N)
+        use_q = ((not c["real_input"]) and getattr(xin, "t8", None) is not None
+                 and (xin.t16 is None or K_.int8_dw_ok(N)))  # follow what the producer emitted
         digits = dt_hi = dt_lo = colq = None
         if use_q:
             Bq = pad_to(B, 16)
