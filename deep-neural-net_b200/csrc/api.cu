@@ -71,6 +71,12 @@ extern "C" int bnn_device_query(int* sm_count_host, int* cc_major_host, int* cc_
     return BNN_OK;
 }
 
+extern "C" int bnn_zero_async(void* ptr, int64_t bytes, bnn_stream_t stream) {
+    BNN_CHECK_ARG(bytes >= 0 && (ptr != nullptr || bytes == 0), "bnn_zero_async: bad input");
+    if (bytes) BNN_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, static_cast<cudaStream_t>(stream)));
+    return BNN_OK;
+}
+
 extern "C" int bnn_gemm(const bnn_gemm_desc* g, int impl, bnn_stream_t stream) {
     BNN_CHECK_ARG(g != nullptr, "bnn_gemm: null descriptor");
     BNN_CHECK_ARG(g->M > 0 && g->N > 0 && g->K > 0 && g->batch >= 1,

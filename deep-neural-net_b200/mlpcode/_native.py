@@ -76,6 +76,7 @@ PROTOTYPES = {
     "bnn_absmax_f32": [_p, _i64, _p, _i, _p],
     "bnn_split_f16": [_p, _i, _i, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p, _p],
     "bnn_gemm": [C.POINTER(GemmDesc), _i, _p],
+    "bnn_zero_async": [_p, _i64, _p],
     "bnn_gemm_popc": [_p, _i64, _p, _i64, _i, _i, _i, _p, _i64, _i, _p],
     "bnn_colstats": [_p, _i, _i, _i, _i64, _p, _i, _p],
     "bnn_bn_stats_finalize": [_p, _i, _d, _p, _p, _p],

@@ -18,7 +18,7 @@ launch_count = 0  # kernels launched through this module (bench.py reports it as
 gemm_events = None  # bench.py sets this to a list to collect (start, end, kind, 2MNK, passes) per GEMM
 
 # launches (kernels + memsets are not counted) issued per C call
-_LAUNCHES = {"bnn_minmax_u8": 2, "bnn_peer_broadcast_rows": 0}
+_LAUNCHES = {"bnn_minmax_u8": 2, "bnn_peer_broadcast_rows": 0, "bnn_zero_async": 0}
 
 
 def _call(name, *args):
@@ -138,6 +138,12 @@ def int8_dw_ok(N: int) -> bool:
     """dW = X^T . delta' as an exact fixed-point product on the int8 tensor pipe (X = +-1 activations,
     delta' in three signed digits) instead of two fp16 passes.  BNN_DW_INT8=0 keeps the fp16 form."""
     return N >= 64 and full_tiles(N) and os.environ.get("BNN_DW_INT8", "1") != "0"
+
+
+def zero(t: torch.Tensor) -> None:
+    """Clear a contiguous device buffer with a memset on the current stream."""
+    assert t.is_contiguous()
+    _call("bnn_zero_async", ptr(t), t.numel() * t.element_size())
 
 
 def fused_stats_ok(N: int, impl=None) -> bool:

@@ -234,7 +234,7 @@ class BatchNormLayer(Layer):
         else:
             acc = self._ws.get("sums", (2, n), torch.float64)
             self._stats_call = None
-        acc.zero_()
+        K_.zero(acc)
         return acc
 
     def batch_stats(self, Z, B, filled=None):
@@ -274,8 +274,8 @@ class BatchNormLayer(Layer):
         else:
             red = self._ws.get("red", (2, n), torch.float64)
             self._red_call = None
-        red.zero_()
-        red_max.zero_()
+        K_.zero(red)
+        K_.zero(red_max)
         return dict(mode=nat.STATS_BN_BWD, sums=red, max=red_max, Z=Z, mu=mu)
 
     def backward_kernels(self, delta, Z, B, sums, mu, var, lr, want_f32, d_rm, d_t, scale,

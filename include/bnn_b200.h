@@ -191,6 +191,10 @@ typedef struct bnn_gemm_desc {
 
 int bnn_gemm(const bnn_gemm_desc* desc_host, int impl, bnn_stream_t stream);
 
+/* cudaMemsetAsync(ptr, 0, bytes) on the stream: clears the accumulators that the fused epilogue
+ * reductions (BNN_STATS_*) add into — a memset node under graph capture instead of a fill kernel. */
+int bnn_zero_async(void* ptr, int64_t bytes, bnn_stream_t stream);
+
 /* Variant A of the binary GEMM: XOR + popc on CUDA cores over packed sign bits.
  * D[m, n] = K - 2*popc(a_bits[m,:] ^ b_bits[n,:]); pad bits must be equal in A and B (the pack
  * kernels write zeros).  out_dtype: 1 = int32 (BNN_EPI_STORE_S32), 2 = int16. */
