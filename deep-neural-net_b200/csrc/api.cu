@@ -107,6 +107,17 @@ extern "C" int bnn_gemm(const bnn_gemm_desc* g, int impl, bnn_stream_t stream) {
     BNN_CHECK_ARG(g->epilogue != BNN_EPI_SIGN_I8 ||
                       (aligned16(g->epi_thr) && aligned16(g->epi_sgn)),
                   "bnn_gemm: epi_thr / epi_sgn must be 16-byte aligned");
+    BNN_CHECK_ARG(g->epi_thr_stride == 0 ||
+                      (g->epilogue == BNN_EPI_SIGN_I8 && g->epi_thr_stride >= g->N &&
+                       g->epi_thr_stride % 4 == 0),
+                  "bnn_gemm: epi_thr_stride %d must be 0 or a multiple of 4 >= N (BNN_EPI_SIGN_I8 only)",
+                  g->epi_thr_stride);
+    BNN_CHECK_ARG((g->a_unsigned == 0 || g->a_unsigned == 1) &&
+                      (g->a_unsigned == 0 || (g->in_dtype == BNN_DT_I8 && g->hi_from_pass == 0)),
+                  "bnn_gemm: a_unsigned is 0 or 1 and goes with plain int8-path products");
+    BNN_CHECK_ARG(g->epilogue != BNN_EPI_STORE_S16 || !g->a_unsigned ||
+                      255 * (int64_t)g->K * g->n_pass < 32768,
+                  "bnn_gemm: K too large for an int16 result of a uint8 operand");
     BNN_CHECK_ARG(g->in_dtype == BNN_DT_I8 ||
                       (g->epilogue != BNN_EPI_STORE_S32 && g->epilogue != BNN_EPI_STORE_S16),
                   "bnn_gemm: integer stores need int8 operands");

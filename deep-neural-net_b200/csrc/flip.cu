@@ -153,21 +153,30 @@ flip_mask_kernel(const uint8_t* __restrict__ mask_kn, int K, int N, int8_t* __re
 // ---------------------------------------------------------------------------------------------
 constexpr int IMG_MAX_F = 4096;
 
+// `words` = rows start on 4-byte boundaries (F % 4 == 0, aligned bases): whole-word loads and stores.
+// xor_out / minmax: the by-products of bnn_flip_images_ex (operand form and utils.normalize's
+// min/max of the corrupted set), taken from the row while it is still in shared memory.
 __global__ void __launch_bounds__(128)
 flip_images_kernel(const uint8_t* __restrict__ in, int R, int F, int k, int mode,
-                   unsigned long long seed, uint32_t trial0, uint8_t* __restrict__ out) {
+                   unsigned long long seed, uint32_t trial0, uint8_t* __restrict__ out, int words,
+                   uint32_t xor_out, uint32_t* __restrict__ minmax) {
     __shared__ uint32_t row[IMG_MAX_F / 4];
     __shared__ uint32_t orig[IMG_MAX_F / 4];
     __shared__ int pref[IMG_MAX_F / 4 + 1];  // exclusive prefix of candidate counts per 32-bit word
     __shared__ int s_ncand;
+    __shared__ uint32_t s_lo[4], s_hi[4];
     const int r = blockIdx.x, t = blockIdx.y;
     const int nwords = (F + 3) >> 2;
     const uint8_t* src = in + (long long)r * F;
     for (int w = threadIdx.x; w < nwords; w += blockDim.x) {
         uint32_t v = 0;
-        for (int b = 0; b < 4; ++b) {
-            const int j = w * 4 + b;
-            if (j < F) v |= (uint32_t)src[j] << (8 * b);
+        if (words) {
+            v = __ldg(reinterpret_cast<const uint32_t*>(src) + w);
+        } else {
+            for (int b = 0; b < 4; ++b) {
+                const int j = w * 4 + b;
+                if (j < F) v |= (uint32_t)src[j] << (8 * b);
+            }
         }
         row[w] = v;
         orig[w] = v;
@@ -235,8 +244,87 @@ flip_images_kernel(const uint8_t* __restrict__ in, int R, int F, int k, int mode
     }
     __syncthreads();
     uint8_t* dst = out + ((long long)t * R + r) * F;
-    for (int j = threadIdx.x; j < F; j += blockDim.x)
-        dst[j] = (uint8_t)(row[j >> 2] >> (8 * (j & 3)));
+    const uint32_t x4 = xor_out * 0x01010101u;
+    if (words) {
+        for (int w = threadIdx.x; w < nwords; w += blockDim.x)
+            reinterpret_cast<uint32_t*>(dst)[w] = row[w] ^ x4;
+    } else {
+        for (int j = threadIdx.x; j < F; j += blockDim.x)
+            dst[j] = (uint8_t)((row[j >> 2] >> (8 * (j & 3))) ^ xor_out);
+    }
+    if (minmax) {
+        uint32_t lo = 255u, hi = 0u;
+        for (int j = threadIdx.x; j < F; j += blockDim.x) {
+            const uint32_t v = (row[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            lo = min(lo, v);
+            hi = max(hi, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            s_lo[threadIdx.x >> 5] = lo;
+            s_hi[threadIdx.x >> 5] = hi;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+                lo = min(lo, s_lo[w]);
+                hi = max(hi, s_hi[w]);
+            }
+            // R blocks share one pair of words per trial: only a block that improves on the value
+            // it can already see issues the atomic
+            uint32_t* mm = minmax + 2 * t;
+            if (lo < *reinterpret_cast<volatile uint32_t*>(mm)) atomicMin(mm, lo);
+            if (hi > *reinterpret_cast<volatile uint32_t*>(mm + 1)) atomicMax(mm + 1, hi);
+        }
+    }
+}
+
+__global__ void minmax_init_kernel(uint32_t* __restrict__ minmax, int n_trials) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_trials) {
+        minmax[2 * t] = 255u;
+        minmax[2 * t + 1] = 0u;
+    }
+}
+
+// One warp per output unit n: S_n = sum_k Wb[k, n] from the packed bits, then the per-trial thresholds
+// (see bnn_u8_input_thresholds in the header for the algebra).
+__global__ void __launch_bounds__(256)
+u8_input_thresholds_kernel(const uint32_t* __restrict__ wt_bits, long long ld_bits, int N, int K,
+                           const float* __restrict__ thr, const float* __restrict__ sgn,
+                           const uint32_t* __restrict__ minmax, int n_trials, float new_min,
+                           float new_max, int bias, float* __restrict__ thr_out, long long ld_thr) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const int nw = (K + 31) >> 5;
+    int ones = 0;
+    for (int w = lane; w < nw; w += 32) ones += __popc(__ldg(wt_bits + (long long)n * ld_bits + w));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ones += __shfl_xor_sync(0xffffffffu, ones, o);
+    const double S = (double)(2 * ones - K);
+    const float tz = __ldg(thr + n);
+    const double s = (double)__ldg(sgn + n);
+    for (int t = lane; t < n_trials; t += 32) {
+        const double mn = (double)minmax[2 * t], mx = (double)minmax[2 * t + 1];
+        float o;
+        if (!(mx > mn)) {
+            o = INFINITY;
+        } else if (isinf(tz) || isnan(tz)) {
+            o = isnan(tz) ? INFINITY : tz;
+        } else {
+            const double rr = ((double)new_max - (double)new_min) / (mx - mn);
+            // s*z >= tz  with  z = rr*(g + (bias - mn)*S) + new_min*S
+            const double tau = ((double)tz - s * (double)new_min * S) / rr - s * ((double)bias - mn) * S;
+            const double c = ceil(tau);
+            o = c > 1.6e7 ? INFINITY : (c < -1.6e7 ? -INFINITY : (float)c);
+        }
+        thr_out[(long long)t * ld_thr + n] = o;
+    }
 }
 
 __global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __restrict__ in, long long n,
@@ -344,16 +432,46 @@ extern "C" int bnn_flip_weights_mask(const uint8_t* mask_kn, int K, int N, int8_
     return BNN_OK;
 }
 
-extern "C" int bnn_flip_images(const uint8_t* in, int R, int F, int k, int mode, uint64_t seed,
-                               uint32_t trial0, int n_trials, uint8_t* out, bnn_stream_t stream) {
+extern "C" int bnn_flip_images_ex(const uint8_t* in, int R, int F, int k, int mode, uint64_t seed,
+                                  uint32_t trial0, int n_trials, uint8_t* out, int xor_out,
+                                  uint32_t* minmax, bnn_stream_t stream) {
     BNN_CHECK_ARG(in && out && R > 0 && F > 0 && n_trials > 0, "bnn_flip_images: bad input");
     BNN_CHECK_ARG(F <= IMG_MAX_F, "bnn_flip_images: F > %d", IMG_MAX_F);
     BNN_CHECK_ARG(mode >= 0 && mode <= 2, "bnn_flip_images: mode must be 0, 1 or 2");
     BNN_CHECK_ARG(k >= 0, "bnn_flip_images: negative k");
     BNN_CHECK_ARG(n_trials <= 65535, "bnn_flip_images: at most 65535 trials per launch");
+    BNN_CHECK_ARG(xor_out >= 0 && xor_out <= 255, "bnn_flip_images_ex: xor_out must be a byte value");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (minmax) {
+        minmax_init_kernel<<<cdiv(n_trials, 128), 128, 0, s>>>(minmax, n_trials);
+        BNN_LAUNCH_CHECK("minmax_init_kernel");
+    }
+    const int words = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 3u) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(out) & 3u) == 0);
     dim3 grid(R, n_trials);
-    flip_images_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(in, R, F, k, mode, seed, trial0, out);
+    flip_images_kernel<<<grid, 128, 0, s>>>(in, R, F, k, mode, seed, trial0, out, words,
+                                            (uint32_t)xor_out, minmax);
     BNN_LAUNCH_CHECK("flip_images_kernel");
+    return BNN_OK;
+}
+
+extern "C" int bnn_flip_images(const uint8_t* in, int R, int F, int k, int mode, uint64_t seed,
+                               uint32_t trial0, int n_trials, uint8_t* out, bnn_stream_t stream) {
+    return bnn_flip_images_ex(in, R, F, k, mode, seed, trial0, n_trials, out, 0, nullptr, stream);
+}
+
+extern "C" int bnn_u8_input_thresholds(const uint32_t* wt_bits, int64_t ld_bits, int N, int K,
+                                       const float* thr, const float* sgn, const uint32_t* minmax,
+                                       int n_trials, float new_min, float new_max, int bias,
+                                       float* thr_out, int64_t ld_thr, bnn_stream_t stream) {
+    BNN_CHECK_ARG(wt_bits && thr && sgn && minmax && thr_out && N > 0 && K > 0 && n_trials > 0,
+                  "bnn_u8_input_thresholds: bad input");
+    BNN_CHECK_ARG(ld_bits >= (K + 31) / 32 && ld_thr >= N, "bnn_u8_input_thresholds: pitch too small");
+    BNN_CHECK_ARG(new_max > new_min, "bnn_u8_input_thresholds: new_max must exceed new_min");
+    BNN_CHECK_ARG(bias == 0 || bias == 128, "bnn_u8_input_thresholds: bias is 0 (uint8 operand) or 128");
+    u8_input_thresholds_kernel<<<cdiv(N, 8), 256, 0, (cudaStream_t)stream>>>(
+        wt_bits, ld_bits, N, K, thr, sgn, minmax, n_trials, new_min, new_max, bias, thr_out, ld_thr);
+    BNN_LAUNCH_CHECK("u8_input_thresholds_kernel");
     return BNN_OK;
 }
 

@@ -38,6 +38,8 @@ struct SimtParams {
     int epilogue;
     const float* thr;
     const float* sgn;
+    int thr_stride;
+    int a_unsigned;
 };
 
 template <bool kI8>
@@ -63,7 +65,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
             for (int i = threadIdx.x; i < TM * TK; i += 256) {
                 const int r = i / TK, c = i % TK;
                 const int gm = m0 + r, gk = k0 + c;
-                As[c][r] = (gm < p.M && gk < p.K) ? E::cvt(A[(long long)gm * p.lda + gk]) : (acc_t)0;
+                acc_t av = (acc_t)0;
+                if (gm < p.M && gk < p.K) {
+                    av = E::cvt(A[(long long)gm * p.lda + gk]);
+                    if (kI8 && p.a_unsigned) av = (acc_t)((int)av & 0xFF);  // the byte read as uint8
+                }
+                As[c][r] = av;
                 const int gn = n0 + r;
                 Bs[c][r] = (gn < p.N && gk < p.K) ? E::cvt(B[(long long)gn * p.ldb + gk]) : (acc_t)0;
             }
@@ -106,7 +113,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
                 case BNN_EPI_SIGN_I8: {
                     const float a = kI8 ? (float)acc[i][j] : __fmul_rn((float)acc[i][j], scale);
                     reinterpret_cast<int8_t*>(p.D)[off] =
-                        (__fmul_rn(a, p.sgn[gn]) >= p.thr[gn]) ? (int8_t)1 : (int8_t)-1;
+                        (__fmul_rn(a, p.sgn[gn]) >= p.thr[(long long)b * p.thr_stride + gn]) ? (int8_t)1
+                                                                                               : (int8_t)-1;
                 } break;
                 case BNN_EPI_SGD_F32: {
                     float* d = reinterpret_cast<float*>(p.D) + off;
@@ -131,6 +139,7 @@ int gemm_simt_dispatch(const bnn_gemm_desc& g, cudaStream_t stream) {
     p.D = g.D; p.ldd = g.ldd; p.stride_d = g.stride_d;
     p.sa = g.sa; p.sb = g.sb; p.host_scale = g.host_scale; p.epilogue = g.epilogue;
     p.thr = g.epi_thr; p.sgn = g.epi_sgn;
+    p.thr_stride = g.epi_thr_stride; p.a_unsigned = g.a_unsigned;
     dim3 grid(cdiv(g.N, TN), cdiv(g.M, TM), g.batch);
     BNN_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "bnn_gemm(simt): grid too large");
     if (g.in_dtype == BNN_DT_I8)

@@ -87,6 +87,8 @@ struct TcParams {
     float host_scale;
     const float* thr;  // BNN_EPI_SIGN_I8
     const float* sgn;
+    int thr_stride;    // elements between the threshold rows of consecutive batches (0 = shared)
+    int a_unsigned;    // kind::i8: the A operand holds uint8 (u8 x s8 product)
     // BNN_EPI_SCATTER_F32: row tiles go to the staging buffer of the rank that owns them
     unsigned long long peer[BNN_MAX_RANKS];
     int rows_per_owner;
@@ -127,7 +129,7 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& b,
 // Store / update one group of G consecutive columns of one output row from registers.
 template <bool kI8, int EPI, int G>
 __device__ __forceinline__ void store_group(const TcParams& p, char* dbase, long long off, int col0,
-                                            const uint32_t (&v)[G], float scale) {
+                                            const uint32_t (&v)[G], float scale, const float* thr) {
     const bool full = (col0 + G <= p.N) && p.vec_ok;
     if (EPI == BNN_EPI_SIGN_I8) {
         // batch-norm + sign as one compare against the per-column threshold (bn.cu)
@@ -137,7 +139,7 @@ __device__ __forceinline__ void store_group(const TcParams& p, char* dbase, long
         for (int j = 0; j < G; j += 4) {
             float t[4], s[4];
             if (col0 + j + 4 <= p.N) {
-                const float4 tv = __ldg(reinterpret_cast<const float4*>(p.thr + col0 + j));
+                const float4 tv = __ldg(reinterpret_cast<const float4*>(thr + col0 + j));
                 const float4 sv = __ldg(reinterpret_cast<const float4*>(p.sgn + col0 + j));
                 t[0] = tv.x; t[1] = tv.y; t[2] = tv.z; t[3] = tv.w;
                 s[0] = sv.x; s[1] = sv.y; s[2] = sv.z; s[3] = sv.w;
@@ -145,7 +147,7 @@ __device__ __forceinline__ void store_group(const TcParams& p, char* dbase, long
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const bool ok = col0 + j + q < p.N;
-                    t[q] = ok ? __ldg(p.thr + col0 + j + q) : INFINITY;
+                    t[q] = ok ? __ldg(thr + col0 + j + q) : INFINITY;
                     s[q] = ok ? __ldg(p.sgn + col0 + j + q) : 1.0f;
                 }
             }
@@ -494,8 +496,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
         } else if (warp == 1 && lane == 0) {
             // ------------------------------------------------------------- MMA issuer
-            constexpr uint32_t idesc = kI8 ? ptx::umma_idesc(2u, 1u, kBlockM, BLOCK_N)
-                                           : ptx::umma_idesc(1u, 0u, kBlockM, BLOCK_N);
+            uint32_t idesc = kI8 ? ptx::umma_idesc(2u, 1u, kBlockM, BLOCK_N)
+                                 : ptx::umma_idesc(1u, 0u, kBlockM, BLOCK_N);
+            // kind::i8 operand formats: 1 = signed, 0 = unsigned 8-bit; A and B are independent fields
+            if (kI8 && p.a_unsigned) idesc &= ~(7u << 7);
             int s = 0;
             uint32_t ph = 0;
             int acc = 0;
@@ -630,7 +634,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         uint32_t v[G];
 #pragma unroll
                         for (int j = 0; j < G; ++j) v[j] = sum[g * G + j];
-                        store_group<kI8, EPI, G>(p, dbase, rowoff + col0, col0, v, scale);
+                        store_group<kI8, EPI, G>(p, dbase, rowoff + col0, col0, v, scale,
+                                                 p.thr + (long long)b * p.thr_stride);
                         asm volatile("" ::: "memory");  // keep the groups' live ranges disjoint
                     }
                 }
@@ -748,6 +753,8 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     p.host_scale = g.host_scale;
     p.thr = g.epi_thr;
     p.sgn = g.epi_sgn;
+    p.thr_stride = g.epi_thr_stride;
+    p.a_unsigned = g.a_unsigned;
     p.rows_per_owner = 0;
     p.rank = 0;
     p.m_rot = 0;

@@ -51,13 +51,13 @@ class GemmDesc(C.Structure):
         ("stride_a", C.c_int64), ("stride_b", C.c_int64),
         ("D", C.c_void_p), ("ldd", C.c_int64), ("stride_d", C.c_int64),
         ("sa", C.c_void_p), ("sb", C.c_void_p),
-        ("host_scale", C.c_float), ("reserved", C.c_int32),
+        ("host_scale", C.c_float), ("a_unsigned", C.c_int32),
         ("epi_thr", C.c_void_p), ("epi_sgn", C.c_void_p),
         ("scatter", C.POINTER(PeerScatter)),
         ("stats", C.c_int32), ("stats_z_dtype", C.c_int32),
         ("stats_sums", C.c_void_p), ("stats_max", C.c_void_p), ("stats_z", C.c_void_p),
         ("stats_ldz", C.c_int64), ("stats_mu", C.c_void_p),
-        ("B2", C.c_void_p), ("hi_from_pass", C.c_int32), ("reserved2", C.c_int32),
+        ("B2", C.c_void_p), ("hi_from_pass", C.c_int32), ("epi_thr_stride", C.c_int32),
         ("col_scale", C.c_void_p),
     ]
 
@@ -106,6 +106,8 @@ PROTOTYPES = {
                                 _i64, _p, _i64, _i64, _p],
     "bnn_flip_weights_mask": [_p, _i, _i, _p, _i64, _p, _i64, _p, _i64, _p],
     "bnn_flip_images": [_p, _i, _i, _i, _i, _u64, _u32, _i, _p, _p],
+    "bnn_flip_images_ex": [_p, _i, _i, _i, _i, _u64, _u32, _i, _p, _i, _p, _p],
+    "bnn_u8_input_thresholds": [_p, _i64, _i, _i, _p, _p, _p, _i, _f, _f, _i, _p, _i64, _p],
     "bnn_normalize_u8": [_p, _i64, _p, _p, _f, _f, _p, _p],
     "bnn_minmax_u8": [_p, _i64, _p, _p, _p],
     "bnn_count_correct": [_p, _i, _i, _i64, _p, _p, _i, _p],

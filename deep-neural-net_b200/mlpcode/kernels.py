@@ -18,7 +18,8 @@ launch_count = 0  # kernels launched through this module (bench.py reports it as
 gemm_events = None  # bench.py sets this to a list to collect (start, end, kind, 2MNK, passes) per GEMM
 
 # launches (kernels + memsets are not counted) issued per C call
-_LAUNCHES = {"bnn_minmax_u8": 2, "bnn_peer_broadcast_rows": 0, "bnn_zero_async": 0}
+_LAUNCHES = {"bnn_minmax_u8": 2, "bnn_peer_broadcast_rows": 0, "bnn_zero_async": 0,
+             "bnn_flip_images_ex": 2}
 
 
 def _call(name, *args):
@@ -83,7 +84,8 @@ def split_f16(x: torch.Tensor, bound: torch.Tensor, hi=None, lo=None, hi_t=None,
 # ------------------------------------------------------------------------------- GEMMs
 def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),), sa=None,
          sb=None, host_scale=1.0, batch=1, stride_a=0, stride_b=0, stride_d=0, impl=None,
-         epi_thr=None, epi_sgn=None, scatter=None, stats=None, hi_from_pass=0, col_scale=None) -> None:
+         epi_thr=None, epi_sgn=None, scatter=None, stats=None, hi_from_pass=0, col_scale=None,
+         a_unsigned=False, epi_thr_stride=0) -> None:
     """D = epi(sum_p A[pa] @ B[pb]^T); A/B are sequences of 1..2 operand-piece tensors.
     scatter (EPI_SCATTER_F32): dict(world, rank, rows_per_owner, stage=[address per rank]).
     stats: dict(mode=STATS_COLSUM, sums) or dict(mode=STATS_BN_BWD, sums, max, Z, mu) — column
@@ -103,6 +105,7 @@ def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),
     d.sa, d.sb = ptr(sa), ptr(sb)
     d.host_scale = host_scale
     d.epi_thr, d.epi_sgn = ptr(epi_thr), ptr(epi_sgn)
+    d.a_unsigned, d.epi_thr_stride = int(a_unsigned), epi_thr_stride
     if stats is not None:
         d.stats, d.stats_sums = stats["mode"], ptr(stats["sums"])
         if stats["mode"] == nat.STATS_BN_BWD:
@@ -344,11 +347,24 @@ def flip_weights_mask(mask_kn_u8, K, N, io_i8=None, io_f16=None, io_bits=None) -
           ld(io_f16), ptr(io_bits), ld(io_bits))
 
 
-def flip_images(inp_u8, k, mode, seed, trial0, n_trials, out_u8) -> None:
+def flip_images(inp_u8, k, mode, seed, trial0, n_trials, out_u8, xor_out=0, minmax=None) -> None:
+    """xor_out / minmax: by-products for the uint8-input layer 0 (bnn_flip_images_ex): the output bytes
+    XOR-ed into int8 operand form, and the per-trial {min, max} ([n_trials, 2] int32) of the corrupted set."""
     R, F = inp_u8.shape
     assert inp_u8.is_contiguous() and out_u8.is_contiguous()
-    _call("bnn_flip_images", ptr(inp_u8), R, F, k, mode, seed & (2**64 - 1), trial0, n_trials,
-          ptr(out_u8))
+    if xor_out == 0 and minmax is None:
+        _call("bnn_flip_images", ptr(inp_u8), R, F, k, mode, seed & (2**64 - 1), trial0, n_trials,
+              ptr(out_u8))
+        return
+    assert minmax is None or (minmax.is_contiguous() and minmax.numel() >= 2 * n_trials)
+    _call("bnn_flip_images_ex", ptr(inp_u8), R, F, k, mode, seed & (2**64 - 1), trial0, n_trials,
+          ptr(out_u8), xor_out, ptr(minmax))
+
+
+def u8_input_thresholds(wt_bits, N, K, thr, sgn, minmax, n_trials, new_min, new_max, bias, thr_out) -> None:
+    """Per-trial integer thresholds of normalize + batch-norm + sign for a uint8-fed layer 0."""
+    _call("bnn_u8_input_thresholds", ptr(wt_bits), _ld(wt_bits), N, K, ptr(thr), ptr(sgn), ptr(minmax),
+          n_trials, new_min, new_max, bias, ptr(thr_out), _ld(thr_out))
 
 
 def minmax_u8(inp_u8, minmax_u32, minmax_f32=None) -> None:

@@ -181,33 +181,141 @@ class WeightFaultSweep:
 
 class ImageFaultSweep:
     """imageBitflipTrainModelSel.py:19-32: corrupt the uint8 test images (exactly round(p*8F) bit flips
-    per image), normalize to [-1, 1] with the corrupted set's own min/max, evaluate; repeat."""
+    per image), normalize to [-1, 1] with the corrupted set's own min/max, evaluate; repeat.
 
-    def __init__(self, nn, images_u8, labels, trials_per_launch: int = 8):
+    Batched form (taken whenever the shapes allow, see `batched`): T trials advance
+    together and the corrupted images never exist as fp32.
+      * one bnn_flip_images_ex launch writes the T corrupted copies [T, R, F] uint8 and, from the rows
+        it already holds in shared memory, each trial's min / max (utils.normalize's xmin / xmax);
+      * normalize (an affine map per trial), layer 0's batch-norm and its sign collapse into per-trial,
+        per-unit integer thresholds on acc = U . Wb (bnn_u8_input_thresholds), so layer 0 is ONE exact
+        u8 x s8 tensor-core GEMM over the raw bytes (batch = T, weights shared) whose epilogue writes
+        the +-1 activations — 1 byte read per pixel instead of the 4 + 4 + 4 written and read by
+        normalize and the fp16 split, and one int8 pass instead of two fp16 passes;
+      * deeper layers see the T trials as one [T*R, N] stack (weights are clean and shared);
+      * one grouped bnn_count_correct yields T correct-counts.
+    Layer 0's sums are exact where the reference's fp32 SGEMM rounds, so a sign can differ from the
+    reference only where |BN output| is within rounding of 0.  BNN_U8_GEMM=s8 feeds the bytes as
+    int8 (u - 128, XOR 0x80 at the flip kernel's store) instead of as an unsigned operand."""
+
+    def __init__(self, nn, images_u8, labels, trials_per_launch: int = 8, batched=None):
         from .callbacks import ImageErrorCallback  # noqa: F401 (documented entry point)
         self.nn = nn
-        self.images = to_tensor(images_u8)
+        self.images = to_tensor(images_u8).contiguous()
         assert self.images.dtype == torch.uint8 and self.images.ndim == 2
         self.labels = to_tensor(labels).reshape(-1).to(torch.int32).contiguous()
         self.T = int(trials_per_launch)
         self.R, self.F = self.images.shape
+        self.layers = nn._layers
+        ok = self.batch_ok(nn, self.R, self.F)
+        self.batched = ok if batched is None else bool(batched)
+        if self.batched and not ok:
+            raise ValueError("ImageFaultSweep(batched=True) needs a compiled binarized batch-norm network "
+                             "of >= 2 layers without weight callbacks, F % 16 == 0 and >= 32 rows")
         self.flipped = empty((self.T, self.R, self.F), torch.uint8)
-        self.xf = empty((self.R, self.F), torch.float32)
-        self.mm_u32 = zeros((2,), torch.int32)
-        self.mm_f32 = zeros((2,), torch.float32)
+        if self.batched:
+            self._setup_batched()
+        else:
+            self.xf = empty((self.R, self.F), torch.float32)
+            self.mm_u32 = zeros((2,), torch.int32)
+            self.mm_f32 = zeros((2,), torch.float32)
 
+    @staticmethod
+    def batch_ok(nn, R: int, F: int) -> bool:
+        layers = nn._layers
+        return bool(nn.isCompiled and nn.isBinarized and nn.useBatchNorm and len(layers) >= 2
+                    and F % 16 == 0 and R >= 32 and F == nn.unitList[0]
+                    and not any(getattr(l, "callbacks", None) for l in layers)
+                    and K_.gemm_impl() == nat.GEMM_TCGEN05)
+
+    # ------------------------------------------------------------------ batched path
+    def _setup_batched(self) -> None:
+        import os
+        T, R = self.T, self.R
+        mode = os.environ.get("BNN_U8_GEMM", "u8").lower()
+        if mode not in ("u8", "s8"):
+            raise ValueError(f"BNN_U8_GEMM={mode!r}: expected 'u8' or 's8'")
+        self.a_unsigned = mode == "u8"
+        self.units = self.nn.unitList
+        self.mm = zeros((T, 2), torch.int32)
+        self.w, self.thr, self.act, self.z = [], [], [], None
+        for i, layer in enumerate(self.layers):
+            Kd, N = layer.weights_shape
+            bn = layer.batchNormLayer
+            last = i == len(self.layers) - 1
+            w = zeros((N, pad_to(Kd, 16)), torch.int8)
+            bits = zeros((N, pad_to(Kd, 32) // 32), torch.int32) if i == 0 else None
+            K_.binarize_weights_t(layer.weights.t, wt_i8=w, wt_bits=bits)
+            self.w.append(w)
+            if i == 0:
+                self.bits0 = bits
+                self.thr0 = zeros((T, pad_to(N, 4)), torch.float32)
+            if last:
+                zdt = torch.int16 if Kd < 32768 else torch.int32
+                self.z = empty((T * R, pad_to(N, 8)), zdt)
+                self.thr.append(None)
+                self.act.append(empty((T * R, N)))
+            else:
+                thr, sgn = zeros((N,), torch.float32), zeros((N,), torch.float32)
+                K_.bn_sign_thresholds(bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
+                self.thr.append((thr, sgn))
+                self.act.append(zeros((T * R, pad_to(N, 16)), torch.int8))
+        self.correct = zeros((T,), torch.int32)
+
+    def _batched_group(self, k: int, mode: int, seed: int, t0: int, n_live: int) -> torch.Tensor:
+        T, R, F = n_live, self.R, self.F
+        flipped = self.flipped[:T]
+        K_.flip_images(self.images, k, mode, seed, t0, T, flipped,
+                       xor_out=0 if self.a_unsigned else 0x80, minmax=self.mm)
+        N0 = self.units[1]
+        thr, sgn = self.thr[0]
+        K_.u8_input_thresholds(self.bits0, N0, F, thr, sgn, self.mm, T, -1.0, 1.0,
+                               0 if self.a_unsigned else 128, self.thr0)
+        a0, w0 = self.act[0], self.w[0]
+        K_.gemm(M=R, N=N0, K=F, A=(flipped.view(torch.int8),), B=(w0,), lda=F, ldb=w0.stride(0), D=a0,
+                ldd=a0.stride(0), in_dtype=nat.DT_I8, epilogue=nat.EPI_SIGN_I8, batch=T, stride_a=R * F,
+                stride_b=0, stride_d=R * a0.stride(0), epi_thr=self.thr0, epi_sgn=sgn,
+                epi_thr_stride=self.thr0.stride(0), a_unsigned=self.a_unsigned)
+        for i in range(1, len(self.layers)):
+            layer = self.layers[i]
+            Kd, N = layer.weights_shape
+            a, w = self.act[i - 1], self.w[i]
+            if i == len(self.layers) - 1:
+                Z, bn = self.z, layer.batchNormLayer
+                epi = nat.EPI_STORE_S16 if Z.dtype == torch.int16 else nat.EPI_STORE_S32
+                K_.gemm(M=T * R, N=N, K=Kd, A=(a,), B=(w,), lda=a.stride(0), ldb=w.stride(0), D=Z,
+                        ldd=Z.stride(0), in_dtype=nat.DT_I8, epilogue=epi)
+                # softmax / identity are monotone per row: the argmax of the BN output decides the class
+                K_.bn_apply(Z, T * R, N, bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON,
+                            out_f32=self.act[i])
+            else:
+                out = self.act[i]
+                thr_i, sgn_i = self.thr[i]
+                K_.gemm(M=T * R, N=N, K=Kd, A=(a,), B=(w,), lda=a.stride(0), ldb=w.stride(0), D=out,
+                        ldd=out.stride(0), in_dtype=nat.DT_I8, epilogue=nat.EPI_SIGN_I8, epi_thr=thr_i,
+                        epi_sgn=sgn_i)
+        self.correct.zero_()
+        K_.count_correct(self.act[-1], R, self.units[-1], self.labels, self.correct, groups=T)
+        return self.correct[:T].clone()
+
+    # ------------------------------------------------------------------ public sweep
     def run(self, p: float, n_trials: int, seed: int, mode: int = 2, comm=None) -> np.ndarray:
         k = int(round(p * self.F * 8))
         lo, hi = shard_range(n_trials, comm.rank, comm.world) if comm else (0, n_trials)
-        accs = []
+        accs, counts = [], []
         for t0 in range(lo, hi, self.T):
             n_live = min(self.T, hi - t0)
+            if self.batched:
+                counts.append(self._batched_group(k, mode, seed, t0, n_live))
+                continue
             K_.flip_images(self.images, k, mode, seed, t0, n_live, self.flipped[:n_live])
             for t in range(n_live):
                 img = self.flipped[t]
                 K_.minmax_u8(img, self.mm_u32, self.mm_f32)
                 K_.normalize_u8(img, self.mm_f32[0:1], self.mm_f32[1:2], -1.0, 1.0, self.xf)
                 accs.append(self.nn.get_accuracy(self.xf, self.labels))
+        if self.batched:
+            accs = (torch.cat(counts).cpu().numpy().astype(np.float64) * 100.0 / self.R) if counts else []
         mine = np.array(accs, np.float64)
         if comm is None or comm.world == 1:
             return mine

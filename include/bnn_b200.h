@@ -165,9 +165,11 @@ typedef struct bnn_gemm_desc {
     const float* sa; /* device scalars (may be NULL = 1): the split scales of A and B */
     const float* sb;
     float host_scale; /* 1 for plain stores, lr for BNN_EPI_SGD_F32 */
-    int32_t reserved;
-    const float* epi_thr; /* BNN_EPI_SIGN_I8: per-column threshold and orientation (device, [N]) */
-    const float* epi_sgn;
+    int32_t a_unsigned; /* BNN_DT_I8 only: 1 = the A pieces hold uint8 (0..255) instead of int8 — the
+                           exact u8 x s8 product of a uint8 image batch with +-1 weights (layer 0 fed
+                           from ImageErrorCallback output, imageBitflipTrainModelSel.py:26-28) */
+    const float* epi_thr; /* BNN_EPI_SIGN_I8: per-column threshold and orientation (device, [N]);  */
+    const float* epi_sgn; /* batch b reads epi_thr + b*epi_thr_stride (epi_sgn is shared)          */
     const bnn_peer_scatter* scatter; /* BNN_EPI_SCATTER_F32 (host pointer), else NULL */
     int32_t stats;         /* BNN_STATS_* */
     int32_t stats_z_dtype; /* BNN_Z_* of stats_z (BNN_STATS_BN_BWD) */
@@ -185,7 +187,8 @@ typedef struct bnn_gemm_desc {
      * width (see BNN_STATS_*), batch == 1; otherwise BNN_ERR_UNSUPPORTED. */
     const void* B2;
     int32_t hi_from_pass;
-    int32_t reserved2;
+    int32_t epi_thr_stride; /* BNN_EPI_SIGN_I8: elements between the threshold rows of consecutive
+                               batches (a multiple of 4); 0 = one row shared by all batches */
     const float* col_scale;
 } bnn_gemm_desc;
 
@@ -423,6 +426,34 @@ int bnn_flip_weights_mask(const uint8_t* mask_kn, int K, int N, int8_t* io_i8, i
  * F <= 4096. */
 int bnn_flip_images(const uint8_t* in, int R, int F, int k, int mode, uint64_t seed, uint32_t trial0,
                     int n_trials, uint8_t* out, bnn_stream_t stream);
+
+/* The same flips with two by-products that let layer 0 consume the corrupted uint8 images directly
+ * (no fp32 copy, no separate min/max pass):
+ *   xor_out  every output byte is XOR-ed with this value (0, or 0x80: the byte then reads as the int8
+ *            u - 128, the operand form of a plain s8 x s8 product);
+ *   minmax   device uint32 [n_trials][2] (may be NULL) <- {min, max} over all R*F corrupted bytes of the
+ *            trial (of the un-XOR-ed values): the xmin / xmax of utils.normalize (utils.py:181-182).
+ *            Initialised by the call. */
+int bnn_flip_images_ex(const uint8_t* in, int R, int F, int k, int mode, uint64_t seed, uint32_t trial0,
+                       int n_trials, uint8_t* out, int xor_out, uint32_t* minmax, bnn_stream_t stream);
+
+/* utils.normalize (utils.py:178-187) + layer-0 batch-norm + sign folded into per-trial integer
+ * thresholds, so that layer 0 runs as an exact integer GEMM on the uint8 images:
+ *   x = (u - mn) * (new_max - new_min) / (mx - mn) + new_min,   z_n = sum_k x_k * Wb[k, n]
+ *       = r * (acc_n - mn * S_n) + new_min * S_n,   r = (new_max - new_min) / (mx - mn),
+ *   acc_n = sum_k u_k * Wb[k, n] (what the int8 tensor pipe computes), S_n = sum_k Wb[k, n]
+ * and sign(BN(z_n)) = +1  <=>  z_n * sgn[n] >= thr[n]  (bnn_bn_sign_thresholds)
+ *                         <=>  g_n * sgn[n] >= thr_out[t, n]
+ * where g_n = acc_n - bias * S_n is the GEMM result (bias = 0 for a_unsigned operands, 128 for
+ * xor_out = 0x80 int8 operands).  thr_out[t, n] is the ceiling of the real threshold (g_n*sgn[n] is an
+ * integer), evaluated in fp64; +-inf thresholds stay +-inf.  A trial with mx == mn (the reference
+ * divides by zero there) gets +inf (every unit -1).
+ *   wt_bits [N, ld_bits]  packed K-major binarized weights (bnn_binarize_weights_t; pad bits 0)
+ *   minmax  [n_trials][2] from bnn_flip_images_ex / bnn_minmax_u8;  thr_out [n_trials, ld_thr]. */
+int bnn_u8_input_thresholds(const uint32_t* wt_bits, int64_t ld_bits, int N, int K, const float* thr,
+                            const float* sgn, const uint32_t* minmax, int n_trials, float new_min,
+                            float new_max, int bias, float* thr_out, int64_t ld_thr,
+                            bnn_stream_t stream);
 
 /* uint8 -> fp32 affine map used by utils.normalize (utils.py:178-187) with caller-supplied
  * min/max (device floats): y = ((x - mn) * (new_max - new_min)) / (mx - mn) + new_min, in the

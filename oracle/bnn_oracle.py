@@ -227,6 +227,33 @@ def normalize(x, new_min=0.0, new_max=1.0):
     return out
 
 
+def u8_layer0_reference(U, W, bnp):
+    """What the reference computes for layer 0 of the image sweep (imageBitflipTrainModelSel.py:26-28):
+    normalize(U, -1, 1) (utils.py:178-187) -> X.dot(sign(W)) (layers.py:286, 220) -> eval batch-norm
+    (layers.py:93-97) -> unitstep (activation.py:106-113).  Returns (activations, BN output)."""
+    x = normalize(U, new_min=-1, new_max=1)
+    zt = bn_forward_eval(x.dot(binarize(W)), bnp["gamma"], bnp["beta"], bnp["mu"], bnp["sigma"])
+    return unitstep(zt), zt
+
+
+def u8_input_thresholds(W, bnp, lo, hi, new_min=-1.0, new_max=1.0, bias=0):
+    """fp64 restatement of the algebra behind bnn_u8_input_thresholds: with acc_n = sum_k u_k*Wb[k,n],
+    S_n = sum_k Wb[k,n] and r = (new_max-new_min)/(hi-lo), the reference's pre-activation is
+    z_n = r*(acc_n - lo*S_n) + new_min*S_n, and sign(BN(z_n)) = +1 <=> (acc_n - bias*S_n)*sgn_n >= tau_n.
+    Returns (ceil(tau), sgn).  The real-valued BN threshold is used (the device kernel takes the
+    bit-exact fp32 one from bnn_bn_sign_thresholds; they differ by rounding only)."""
+    Wb = binarize(W).astype(np.float64)
+    S = Wb.sum(axis=0)
+    g, be = bnp["gamma"].astype(np.float64), bnp["beta"].astype(np.float64)
+    mu, d = bnp["mu"].astype(np.float64), np.sqrt(bnp["sigma"].astype(np.float64) + EPSILON)
+    sgn = np.where(g < 0, -1.0, 1.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tz = sgn * (mu - be * d / g)                   # s*z >= tz  <=>  gamma*(z-mu)/d + beta >= 0
+    r = (new_max - new_min) / (float(hi) - float(lo))
+    tau = (tz - sgn * new_min * S) / r - sgn * (bias - float(lo)) * S
+    return np.ceil(tau), sgn
+
+
 # ----------------------------------------------------------------------------------------------
 # ctypes front-end of bnn_oracle.c
 # ----------------------------------------------------------------------------------------------

@@ -41,7 +41,7 @@ def test_gemm_desc_layout_matches_c(tmp_path):
     """ctypes mirror of bnn_gemm_desc has the C compiler's size and field offsets."""
     from mlpcode._native import GemmDesc
     fields = ["M", "n_pass", "pa", "pb", "A", "B", "lda", "stride_a", "D", "ldd", "sa", "host_scale",
-              "epi_thr", "epi_sgn", "scatter", "stats", "stats_z_dtype", "stats_sums", "stats_max",
+              "a_unsigned", "epi_thr_stride", "epi_thr", "epi_sgn", "scatter", "stats", "stats_z_dtype", "stats_sums", "stats_max",
               "stats_z", "stats_ldz", "stats_mu", "B2", "hi_from_pass", "col_scale"]
     prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "bnn_b200.h"', 'int main(void){',
             'printf("%zu\\n", sizeof(bnn_gemm_desc));']

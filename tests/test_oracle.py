@@ -156,3 +156,28 @@ def test_c_image_flips_follow_reference_semantics(golden, oracle):
         hits += np.unpackbits(oracle.c_flip_image_rows(row, 16, 2, seed=11, trial=t), axis=1)[0]
     assert hits.sum() == 400 * 16
     assert hits.min() > 20 and hits.max() < 85        # mean 50, sd ~6.6
+
+
+@pytest.mark.parametrize("bias", [0, 128])
+@pytest.mark.parametrize("lo_hi", [(0, 255), (3, 250), (17, 18)])
+def test_u8_input_threshold_algebra_reproduces_reference_layer0(oracle, bias, lo_hi):
+    """normalize + X.dot(sign(W)) + eval BN + sign on a uint8 batch (utils.py:178-187, layers.py:220,
+    93-97) == integer compare of acc = U . Wb against per-unit thresholds; the only units allowed to
+    differ are those whose BN output is within fp32 rounding of 0."""
+    rng = np.random.default_rng(bias + lo_hi[0])
+    R, F, N = 96, 112, 40
+    lo, hi = lo_hi
+    U = rng.integers(lo, hi + 1, (R, F), dtype=np.uint8)
+    U[0, 0], U[1, 1] = lo, hi                       # the set's min / max are exactly lo / hi
+    W = rng.standard_normal((F, N)).astype(np.float32)
+    bnp = dict(gamma=(rng.random(N) + 0.5).astype(np.float32), beta=(rng.standard_normal(N) * 0.3).astype(np.float32),
+               mu=(rng.standard_normal(N) * 2).astype(np.float32), sigma=(rng.random(N) * 5 + 0.5).astype(np.float32))
+    bnp["gamma"][::5] *= -1
+    want, zt = oracle.u8_layer0_reference(U, W, bnp)
+    tau, sgn = oracle.u8_input_thresholds(W, bnp, lo, hi, bias=bias)
+    Wb = oracle.binarize(W).astype(np.int64)
+    g = (U.astype(np.int64) - bias) @ Wb              # what the int8 tensor pipe sums (u8, or u-128 as s8)
+    got = np.where(g * sgn >= tau, 1.0, -1.0)
+    diff = got != want
+    assert np.all(np.abs(zt[diff]) < 1e-4), np.abs(zt[diff]).max()
+    assert diff.mean() < 0.01

@@ -1,0 +1,203 @@
+"""GPU parity of the uint8-input layer 0: the image fault sweep of
+imageBitflipTrainModelSel.py:19-32 with ImageErrorCallback output (callbacks.py:125-172) and
+utils.normalize (utils.py:178-187) folded into an exact u8 x s8 tensor-core GEMM.
+
+Bar: bit-exact for the integer product, the flipped bytes and the per-trial min / max; sign decisions
+equal the reference's except where its batch-norm output is within fp32 rounding of 0 (the reference
+forms z with an fp32 SGEMM, the device with exact integer sums)."""
+import numpy as np
+import pytest
+
+from conftest import params_from_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    from mlpcode import _native
+    _native.load()
+    return torch
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def pm1(rng, shape):
+    return np.where(rng.random(shape) < 0.5, -1, 1).astype(np.int8)
+
+
+def padded(a, mult):
+    import torch
+    r, c = a.shape
+    cp = (c + mult - 1) // mult * mult
+    t = torch.zeros((r, cp), dtype=dev(a[:1, :1]).dtype, device="cuda")
+    t[:, :c] = dev(a)
+    return t
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+@pytest.mark.parametrize("M,N,K_", [(128, 256, 128), (130, 40, 200), (300, 300, 784), (64, 16, 32),
+                                    (257, 513, 3072), (1000, 4096, 784)])
+def test_gemm_u8_s8_exact(T, impl, M, N, K_):
+    """a_unsigned: D = U . B^T with U uint8 (0..255, including bytes >= 128) and B = +-1, exact."""
+    from mlpcode import _native as nat, kernels as K
+    rng = np.random.default_rng(M + 3 * N + K_)
+    u = rng.integers(0, 256, (M, K_), dtype=np.uint8)
+    u[0, :] = 255
+    b = pm1(rng, (N, K_))
+    ref = u.astype(np.int32) @ b.astype(np.int32).T
+    A, Bm = padded(u, 16), padded(b, 16)
+    ldd = (N + 3) // 4 * 4
+    D = T.full((M, ldd), 12345, dtype=T.int32, device="cuda")
+    K.gemm(M=M, N=N, K=K_, A=(A,), B=(Bm,), lda=A.stride(0), ldb=Bm.stride(0), D=D, ldd=ldd,
+           in_dtype=nat.DT_I8, epilogue=nat.EPI_STORE_S32, a_unsigned=True,
+           impl=nat.GEMM_TCGEN05 if impl == "tcgen05" else nat.GEMM_SIMT)
+    got = D.cpu().numpy()
+    assert np.array_equal(got[:, :N], ref)
+    assert np.all(got[:, N:] == 12345)
+    # the same bytes read as int8 (a_unsigned off) give the two's-complement product: the flag matters
+    D2 = T.zeros((M, ldd), dtype=T.int32, device="cuda")
+    K.gemm(M=M, N=N, K=K_, A=(A,), B=(Bm,), lda=A.stride(0), ldb=Bm.stride(0), D=D2, ldd=ldd,
+           in_dtype=nat.DT_I8, epilogue=nat.EPI_STORE_S32,
+           impl=nat.GEMM_TCGEN05 if impl == "tcgen05" else nat.GEMM_SIMT)
+    ref2 = u.view(np.int8).astype(np.int32) @ b.astype(np.int32).T
+    assert np.array_equal(D2.cpu().numpy()[:, :N], ref2)
+
+
+def test_gemm_rejects_bad_u8_arguments(T):
+    from mlpcode import _native as nat, kernels as K
+    A = T.zeros((128, 64), dtype=T.float16, device="cuda")
+    D = T.zeros((128, 128), dtype=T.float32, device="cuda")
+    with pytest.raises(nat.BnnError, match="a_unsigned"):
+        K.gemm(M=128, N=128, K=64, A=(A,), B=(A,), lda=64, ldb=64, D=D, ldd=128, in_dtype=nat.DT_F16,
+               epilogue=nat.EPI_STORE_F32, a_unsigned=True)
+    A8 = T.zeros((128, 64), dtype=T.int8, device="cuda")
+    with pytest.raises(nat.BnnError, match="epi_thr_stride"):
+        K.gemm(M=128, N=128, K=64, A=(A8,), B=(A8,), lda=64, ldb=64, D=D, ldd=128, in_dtype=nat.DT_I8,
+               epilogue=nat.EPI_STORE_S32, epi_thr_stride=128)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("xor_out", [0, 0x80])
+def test_flip_images_ex_byproducts(T, oracle, mode, xor_out):
+    """Flipped bytes (XOR-ed into operand form) and per-trial min / max of the corrupted set, for word
+    (F % 4 == 0) and byte (F % 4 != 0) row layouts."""
+    from mlpcode import kernels as K
+    rng = np.random.default_rng(10 * mode + (xor_out > 0))
+    for R, F, kk, lo, hi in ((40, 784, 878, 0, 256), (33, 64, 2, 64, 128), (7, 30, 5, 16, 32), (5, 18, 1, 0, 2)):
+        images = rng.integers(lo, hi, (R, F), dtype=np.uint8)
+        nt = 3
+        out = T.zeros((nt, R, F), dtype=T.uint8, device="cuda")
+        mm = T.full((nt, 2), -7, dtype=T.int32, device="cuda")
+        K.flip_images(dev(images), kk, mode, 0xC0FFEE, 5, nt, out, xor_out=xor_out, minmax=mm)
+        got, gmm = out.cpu().numpy(), mm.cpu().numpy()
+        for t in range(nt):
+            want = oracle.c_flip_image_rows(images, kk, mode, 0xC0FFEE, 5 + t)
+            assert np.array_equal(got[t] ^ np.uint8(xor_out), want), (R, F, t)
+            assert gmm[t].tolist() == [int(want.min()), int(want.max())], (R, F, t)
+
+
+@pytest.mark.parametrize("variant", ["u8", "s8"])
+def test_u8_layer0_sign_decisions_match_reference(T, oracle, variant):
+    """Per-trial thresholds + batched u8 x s8 GEMM with the sign epilogue == the reference's
+    normalize -> dot -> eval BN -> unitstep on each trial's images (different min / max per trial)."""
+    from mlpcode import _native as nat, kernels as K
+    rng = np.random.default_rng(21)
+    nt, R, F, N = 3, 200, 784, 136
+    ranges = [(0, 255), (5, 250), (30, 31)]
+    U = np.stack([rng.integers(lo, hi + 1, (R, F), dtype=np.uint8) for lo, hi in ranges])
+    for t, (lo, hi) in enumerate(ranges):
+        U[t, 0, 0], U[t, 1, 1] = lo, hi
+    W = rng.standard_normal((F, N)).astype(np.float32)
+    bnp = dict(gamma=(rng.random(N) + 0.5).astype(np.float32), beta=(rng.standard_normal(N) * 0.3).astype(np.float32),
+               mu=(rng.standard_normal(N) * 3).astype(np.float32), sigma=(rng.random(N) * 20 + 1).astype(np.float32))
+    bnp["gamma"][::7] *= -1
+    bias = 0 if variant == "u8" else 128
+    wt = T.zeros((N, F), dtype=T.int8, device="cuda")
+    bits = T.zeros((N, (F + 31) // 32), dtype=T.int32, device="cuda")
+    K.binarize_weights_t(dev(W), wt_i8=wt, wt_bits=bits)
+    thr, sgn = (T.zeros(N, dtype=T.float32, device="cuda") for _ in range(2))
+    K.bn_sign_thresholds(dev(bnp["mu"]), dev(bnp["sigma"]), dev(bnp["gamma"]), dev(bnp["beta"]), 1e-4, N, thr, sgn)
+    mm = dev(np.array(ranges, dtype=np.int32))
+    thr_t = T.zeros((nt, N), dtype=T.float32, device="cuda")
+    K.u8_input_thresholds(bits, N, F, thr, sgn, mm, nt, -1.0, 1.0, bias, thr_t)
+    # the kernel's thresholds are the fp64 algebra's, up to the rounding of the fp32 BN threshold
+    for t, (lo, hi) in enumerate(ranges):
+        tau, s = oracle.u8_input_thresholds(W, bnp, lo, hi, bias=bias)
+        assert np.array_equal(sgn.cpu().numpy(), s.astype(np.float32))
+        assert np.max(np.abs(thr_t[t].cpu().numpy() - tau)) <= 1.0, t
+    A = dev(U ^ np.uint8(0x80 if bias else 0))
+    Np = (N + 15) // 16 * 16
+    out = T.full((nt, R, Np), 7, dtype=T.int8, device="cuda")
+    K.gemm(M=R, N=N, K=F, A=(A,), B=(wt,), lda=F, ldb=F, D=out, ldd=Np, in_dtype=nat.DT_I8,
+           epilogue=nat.EPI_SIGN_I8, batch=nt, stride_a=R * F, stride_b=0, stride_d=R * Np, epi_thr=thr_t,
+           epi_sgn=sgn, epi_thr_stride=N, a_unsigned=bias == 0)
+    got = out.cpu().numpy()
+    assert np.all(got[:, :, N:] == 7)
+    for t in range(nt):
+        want, zt = oracle.u8_layer0_reference(U[t], W, bnp)
+        diff = got[t, :, :N] != want.astype(np.int8)
+        assert np.all(np.abs(zt[diff]) < 1e-4), (t, np.abs(zt[diff]).max())
+        assert diff.mean() < 0.01, t
+
+
+def _small_net(golden):
+    from test_layers_gpu import build_net
+    g = golden("train_small")                          # 784-64-32-10
+    units = [int(u) for u in g["units"]]
+    params = params_from_golden(g, "after1_", len(units) - 1)
+    return units, params, build_net(units, params, out="identity")
+
+
+@pytest.mark.parametrize("variant", ["u8", "s8"])
+def test_batched_image_sweep_matches_oracle_and_per_trial_path(golden, oracle, monkeypatch, variant):
+    from mlpcode.sweep import ImageFaultSweep
+    monkeypatch.setenv("BNN_U8_GEMM", variant)
+    units, params, nn = _small_net(golden)
+    rng = np.random.default_rng(8)
+    R = 96
+    imgs = rng.integers(0, 256, (R, units[0]), dtype=np.uint8)
+    labels = rng.integers(0, 10, R).astype(np.uint8)
+    p, seed, n_trials = 0.14, 99, 5
+    k = int(round(p * units[0] * 8))
+    fast = ImageFaultSweep(nn, imgs, labels, trials_per_launch=2)
+    assert fast.batched
+    slow = ImageFaultSweep(nn, imgs, labels, trials_per_launch=2, batched=False)
+    for mode in (2, 0):
+        got = fast.run(p, n_trials, seed, mode=mode)
+        ref = slow.run(p, n_trials, seed, mode=mode)
+        want = np.array([oracle.accuracy(params, oracle.normalize(
+            oracle.c_flip_image_rows(imgs, k, mode, seed, t), -1, 1), labels, out_af="identity")
+            for t in range(n_trials)])
+        assert np.array_equal(ref, want)
+        # exact sums vs the reference's fp32 SGEMM: at most one row may sit on a sign boundary
+        assert np.max(np.abs(got - want)) <= 100.0 / R + 1e-9, (got, want)
+
+
+def test_batched_image_sweep_at_full_size_equals_per_trial_path():
+    """BASELINE-sized property: 10 000 MNIST-shaped images through the 784-4096-4096-4096-10 network —
+    the exact u8 x s8 layer 0 and the fp32-normalize + fp16-split layer 0 classify alike (the two differ
+    only in rows whose layer-0 batch-norm output is within fp32 rounding of 0)."""
+    import bnn_oracle as O
+    from mlpcode.sweep import ImageFaultSweep
+    from test_layers_gpu import build_net
+    units = [784, 4096, 4096, 4096, 10]
+    rng = np.random.default_rng(3)
+    params = O.new_params(units, rng)
+    for b in params["bn"][:-1]:                      # pre-activations of +-1 layers have variance ~ K
+        b["sigma"][:] = 1000.0
+    nn = build_net(units, params, out="identity")
+    R = 10000
+    imgs = rng.integers(0, 256, (R, 784), dtype=np.uint8)
+    imgs[rng.random((R, 784)) < 0.8] = 0             # MNIST-like: mostly background
+    labels = rng.integers(0, 10, R).astype(np.uint8)
+    fast = ImageFaultSweep(nn, imgs, labels, trials_per_launch=4)
+    slow = ImageFaultSweep(nn, imgs, labels, trials_per_launch=4, batched=False)
+    assert fast.batched and not slow.batched
+    got, ref = fast.run(0.14, 4, 77), slow.run(0.14, 4, 77)
+    assert np.max(np.abs(got - ref)) <= 0.05, (got, ref)     # <= 5 of 10 000 rows
+    assert len(set(np.round(got, 6))) > 1                    # the trials really differ
