@@ -3,6 +3,7 @@
 //   A12  ImageErrorCallback.intError    mlpcode/callbacks.py:130-147 (exact-k bit flips per row)
 // plus the exact-k weight flips of BASELINE config 4 and utils.normalize (utils.py:178-187).
 #include "common.cuh"
+#include "fault_math.cuh"
 #include "rng.cuh"
 
 namespace bnn {
@@ -114,6 +115,20 @@ flip_exactk_kernel(int N, int K, unsigned long long total, unsigned long long of
     if (io_bits)
         atomicXor(io_bits + (long long)t * io_bits_stride + (long long)n * ld_bits + (k >> 5),
                   1u << (k & 31));
+}
+
+// IEEE-754 bit flips of real-valued weights (ErrorCallback non-BNN branch, callbacks.py:35-59, 100-123).
+// Thread i owns chosen element P(i): distinct elements, so the read-modify-write needs no atomics.
+// The per-element arithmetic lives in fault_math.cuh (also compiled for the host by the tests).
+__global__ void __launch_bounds__(256)
+flip_f32_bits_kernel(uint32_t* __restrict__ w, unsigned long long n, unsigned long long n_sel, double p,
+                     int mode, unsigned long long seed, uint32_t trial, int ebits) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sel) return;
+    const unsigned long long e = fault::f32_flip_element(i, n, ebits, seed, trial);
+    const uint32_t v = w[e];
+    const uint32_t m = fault::f32_flip_mask(v, e, p, mode, seed, trial);
+    if (m) w[e] = v ^ m;
 }
 
 __global__ void __launch_bounds__(256)
@@ -309,22 +324,10 @@ u8_input_thresholds_kernel(const uint32_t* __restrict__ wt_bits, long long ld_bi
     const double S = (double)(2 * ones - K);
     const float tz = __ldg(thr + n);
     const double s = (double)__ldg(sgn + n);
-    for (int t = lane; t < n_trials; t += 32) {
-        const double mn = (double)minmax[2 * t], mx = (double)minmax[2 * t + 1];
-        float o;
-        if (!(mx > mn)) {
-            o = INFINITY;
-        } else if (isinf(tz) || isnan(tz)) {
-            o = isnan(tz) ? INFINITY : tz;
-        } else {
-            const double rr = ((double)new_max - (double)new_min) / (mx - mn);
-            // s*z >= tz  with  z = rr*(g + (bias - mn)*S) + new_min*S
-            const double tau = ((double)tz - s * (double)new_min * S) / rr - s * ((double)bias - mn) * S;
-            const double c = ceil(tau);
-            o = c > 1.6e7 ? INFINITY : (c < -1.6e7 ? -INFINITY : (float)c);
-        }
-        thr_out[(long long)t * ld_thr + n] = o;
-    }
+    for (int t = lane; t < n_trials; t += 32)
+        thr_out[(long long)t * ld_thr + n] = fault::u8_input_threshold(
+            tz, s, S, (double)minmax[2 * t], (double)minmax[2 * t + 1], (double)new_min, (double)new_max,
+            (double)bias);
 }
 
 __global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __restrict__ in, long long n,
@@ -500,5 +503,20 @@ extern "C" int bnn_minmax_u8(const uint8_t* in, int64_t n, uint32_t* minmax, flo
         u8_to_f32_minmax_kernel<<<1, 1, 0, s>>>(minmax, minmax_f32);
         BNN_LAUNCH_CHECK("u8_to_f32_minmax_kernel");
     }
+    return BNN_OK;
+}
+
+extern "C" int bnn_flip_f32_bits(float* w, int64_t n, int64_t n_sel, double p, int mode, uint64_t seed,
+                                 uint32_t trial, bnn_stream_t stream) {
+    BNN_CHECK_ARG(w && n > 0 && n < (1ll << 32), "bnn_flip_f32_bits: need 0 < n < 2^32 elements");
+    BNN_CHECK_ARG(n_sel >= 0 && n_sel <= n, "bnn_flip_f32_bits: n_sel outside [0, n]");
+    BNN_CHECK_ARG(p >= 0.0 && p <= 1.0, "bnn_flip_f32_bits: p outside [0, 1]");
+    BNN_CHECK_ARG(mode >= 0 && mode <= 2, "bnn_flip_f32_bits: mode must be 0, 1 or 2");
+    if (n_sel == 0) return BNN_OK;
+    const long long blocks = (n_sel + 255) / 256;
+    flip_f32_bits_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<uint32_t*>(w), (unsigned long long)n, (unsigned long long)n_sel, p, mode, seed,
+        trial, rng::feistel_bits((unsigned long long)n));
+    BNN_LAUNCH_CHECK("flip_f32_bits_kernel");
     return BNN_OK;
 }

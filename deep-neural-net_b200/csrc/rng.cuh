@@ -69,6 +69,8 @@ __host__ __device__ inline uint64_t feistel_perm(uint64_t x, uint64_t n, int bit
 // Stream ids keep the Philox counter spaces of the different consumers disjoint.
 constexpr uint32_t kStreamExactK = 0xE7AC0001u;
 constexpr uint32_t kStreamImage = 0x1A6E0001u;
+constexpr uint32_t kStreamF32Elem = 0xF32E0001u;
+constexpr uint32_t kStreamF32Bits = 0xF32B0001u;
 
 __host__ __device__ inline FeistelKey feistel_key(uint64_t seed, uint32_t stream, uint32_t trial,
                                                   uint32_t item) {

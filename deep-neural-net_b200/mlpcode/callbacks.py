@@ -53,8 +53,10 @@ class ErrorCallback(Callback):
     # ---- fast path used by BinaryLayer.forward (eval mode) --------------------------------
     def apply_to_layer(self, layer, wops) -> None:
         if not self.forBnn:
-            raise NotImplementedError("IEEE-754 float32 bit flips (callbacks.py:35-59, 85-123) are the "
-                                      "non-BNN path and are not built here")
+            raise NotImplementedError(
+                "IEEE-754 bit flips (callbacks.py:35-59, 85-123) turn +-1 weights into arbitrary reals; the "
+                "binarized layer's integer forward cannot consume them.  The flips themselves are available "
+                "on dense arrays: ErrorCallback(p, mode, bnn=False)(array)")
         Kd, N = layer.weights_shape
         trial, self.calls = self.calls, self.calls + 1
         i8, f16, bits = wops.get("i8"), wops.get("f16"), wops["bits"]
@@ -76,7 +78,16 @@ class ErrorCallback(Callback):
     def __call__(self, inp, gpu=False):
         assert inp.ndim == 2
         if not self.forBnn:
-            raise NotImplementedError("non-BNN float32 bit flips are out of scope of this build")
+            # IEEE-754 bit flips of a real-valued array (callbacks.py:100-123): round(size*p) elements,
+            # round(candidates*p) bits in each.  The input is left untouched, like the reference's
+            # flatten() copy; with no element selected the input itself is returned (callbacks.py:111-112).
+            w = to_tensor(inp, torch.float32)
+            if round(w.numel() * self.p) == 0:
+                return inp
+            out = w.clone()
+            trial, self.calls = self.calls, self.calls + 1
+            K_.flip_f32_bits(out, float(self.p), self.mode, self.seed, trial)
+            return DeviceArray(out)
         w = to_tensor(inp, torch.float32)
         Kd, N = w.shape
         words = (Kd + 31) // 32

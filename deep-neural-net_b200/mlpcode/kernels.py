@@ -347,6 +347,13 @@ def flip_weights_mask(mask_kn_u8, K, N, io_i8=None, io_f16=None, io_bits=None) -
           ld(io_f16), ptr(io_bits), ld(io_bits))
 
 
+def flip_f32_bits(w_f32, p, mode, seed, trial) -> None:
+    """In place: IEEE-754 bit flips in round(size*p) elements of a contiguous fp32 tensor."""
+    assert w_f32.is_contiguous() and w_f32.dtype == torch.float32
+    n = w_f32.numel()
+    _call("bnn_flip_f32_bits", ptr(w_f32), n, round(n * p), float(p), mode, seed & (2**64 - 1), trial)
+
+
 def flip_images(inp_u8, k, mode, seed, trial0, n_trials, out_u8, xor_out=0, minmax=None) -> None:
     """xor_out / minmax: by-products for the uint8-input layer 0 (bnn_flip_images_ex): the output bytes
     XOR-ed into int8 operand form, and the per-trial {min, max} ([n_trials, 2] int32) of the corrupted set."""

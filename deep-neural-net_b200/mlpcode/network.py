@@ -229,10 +229,16 @@ class Network(object):
             if shuffle:
                 perm = torch.randperm(n, device=trainX.t.device)
                 trainX, trainY = trainX[perm], trainY[perm]
-            batch_costs = [self.train_step(bx, by)
-                           for bx, by in self.get_batches(trainX, trainY, batch_size, n)]
+            # the epoch stays on the device: every batch's mean loss is parked in a device vector and
+            # the host reads them once per epoch (the reference syncs on float(cost.mean()) per batch,
+            # network.py:378); graph replays reuse one loss buffer, hence the copy right after each step
+            n_batches = 1 if batch_size == -1 else (n + batch_size - 1) // batch_size
+            batch_costs = torch.zeros(n_batches, dtype=torch.float32, device=trainX.t.device)
+            for i, (bx, by) in enumerate(self.get_batches(trainX, trainY, batch_size, n)):
+                rows = self.train_step_async(bx, by)
+                batch_costs[i] = rows.mean().t
             self._lr.step()
-            cost = sum(batch_costs) / len(batch_costs)
+            cost = float(batch_costs.double().sum()) / n_batches
             acc = self.get_accuracy(trainX, trainY.argmax(axis=1))
             train_accs.append(acc)
             costs.append(cost)

@@ -416,6 +416,19 @@ int bnn_flip_weights_mask(const uint8_t* mask_kn, int K, int N, int8_t* io_i8, i
                           void* io_f16, int64_t ld_f16, uint32_t* io_bits, int64_t ld_bits,
                           bnn_stream_t stream);
 
+/* IEEE-754 bit flips of real-valued fp32 weights — the non-BNN branch of ErrorCallback
+ * (_flipFunc callbacks.py:35-59, _flip :85-92, __call__ :100-123), in place on w[n]:
+ *   n_sel = round(n * p) distinct elements (the caller rounds like Python: half to even) are chosen —
+ *   element i of the draw is P(i), P a keyed Feistel bijection on [0, n) (key from Philox(seed, trial));
+ *   in each, the candidate bits follow the reference: with the exponent MSB (bit 30) set the other
+ *   exponent bits (29..23) are protected, otherwise bit 30 itself; mode 0 keeps only 0-bits, mode 1
+ *   only 1-bits, mode 2 all; rint(cnt * p) of the cnt candidates are inverted, chosen by a second
+ *   bijection keyed by (seed, trial, element) over the candidates ranked in the reference's bit order
+ *   (np.unpackbits of the little-endian bytes: rank j <-> word bit 8*(j/8) + 7 - j%8).
+ * n < 2^32. */
+int bnn_flip_f32_bits(float* w, int64_t n, int64_t n_sel, double p, int mode, uint64_t seed,
+                      uint32_t trial, bnn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * A12  image fault injection                           (ImageErrorCallback.intError
  *                                                       callbacks.py:130-147, __call__ :149-172)

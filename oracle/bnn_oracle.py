@@ -227,6 +227,44 @@ def normalize(x, new_min=0.0, new_max=1.0):
     return out
 
 
+# ----------------------------------------------------------------------------------------------
+# IEEE-754 bit flips of real-valued weights (the non-BNN branch)       callbacks.py:35-59, 85-123
+# ----------------------------------------------------------------------------------------------
+def float_flip_candidates(bits32, mode):
+    """ErrorCallback._flipFunc, callbacks.py:35-52: bits32 = np.unpackbits of the value's 4 bytes in
+    memory order (little endian: index 24 = sign, 25 = exponent MSB, 26..31 + 16 = the other exponent
+    bits).  With the exponent MSB set, the other exponent bits are protected, otherwise the MSB itself;
+    mode 0 keeps only 0-bits, mode 1 only 1-bits.  Returns the candidate indices in ascending order."""
+    idx = np.arange(0, 32, dtype=np.int8)
+    if bits32[25]:
+        idx[26:32] = -1
+        idx[16] = -1
+    else:
+        idx[25] = -1
+    if mode == 0:
+        idx[bits32[idx]] = -1
+    elif mode == 1:
+        idx[~bits32[idx]] = -1
+    return idx[idx != -1]
+
+
+def flip_float_bits(values, elem_idx, p, mode, choose):
+    """ErrorCallback.__call__ non-BNN branch (callbacks.py:100-123) with explicit draws: `elem_idx` are
+    the chosen elements (round(size*p) of them, callbacks.py:109); for each, `choose(cand, k)` picks
+    k = min(len(cand), round(len(cand)*p)) candidate bit indices (callbacks.py:54-56), which are inverted."""
+    shape = values.shape
+    flat = np.array(values.flatten())
+    picked = flat[elem_idx]
+    unpacked = np.unpackbits(np.frombuffer(picked, dtype=np.uint8)).astype(bool).reshape(-1, 32)
+    for row in unpacked:
+        cand = float_flip_candidates(row, mode)
+        k = min(cand.size, round(cand.size * p))
+        sel = choose(cand, k)
+        row[sel] = ~row[sel]
+    flat[elem_idx] = np.frombuffer(np.packbits(unpacked), dtype=np.float32)
+    return flat.reshape(shape)
+
+
 def u8_layer0_reference(U, W, bnp):
     """What the reference computes for layer 0 of the image sweep (imageBitflipTrainModelSel.py:26-28):
     normalize(U, -1, 1) (utils.py:178-187) -> X.dot(sign(W)) (layers.py:286, 220) -> eval batch-norm
@@ -266,7 +304,7 @@ def build_c(force=False) -> Path:
     src = _HERE / "bnn_oracle.c"
     if force or not C_LIB.exists() or C_LIB.stat().st_mtime < src.stat().st_mtime:
         C_LIB.parent.mkdir(exist_ok=True)
-        subprocess.check_call(["gcc", "-O2", "-std=c11", "-shared", "-fPIC", "-o", str(C_LIB), str(src)])
+        subprocess.check_call(["gcc", "-O2", "-std=c11", "-shared", "-fPIC", "-o", str(C_LIB), str(src), "-lm"])
     return C_LIB
 
 
@@ -348,3 +386,12 @@ def c_flip_image_rows(images, k, mode, seed, trial):
     out = np.zeros_like(images)
     clib().oracle_flip_image_rows(_p(images), R, F, k, mode, C.c_uint64(seed), C.c_uint32(trial), _p(out))
     return out
+
+
+def c_flip_f32_bits(values, p, mode, seed, trial):
+    """In-kernel draw of bnn_flip_f32_bits restated: elements P(0..n_sel-1), bits by per-element Feistel."""
+    v = np.ascontiguousarray(values, dtype=np.float32).copy()
+    n_sel = round(v.size * p)
+    clib().oracle_flip_f32_bits(_p(v), C.c_uint64(v.size), C.c_uint64(n_sel), C.c_double(p),
+                                C.c_int(mode), C.c_uint64(seed), C.c_uint32(trial))
+    return v

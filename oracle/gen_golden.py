@@ -71,8 +71,39 @@ def flat_state(prefix, st):
     return out
 
 
+def gen_float_faults(Cb, O):
+    """IEEE-754 bit flips of real-valued weights (ErrorCallback(bnn=False), callbacks.py:35-59, 85-123):
+    the reference draws from the global NumPy stream; replaying the same stream through the oracle's
+    explicit-draw restatement must give identical bits."""
+    rng = np.random.default_rng(57)
+    W = (rng.standard_normal((12, 9)) * np.exp(rng.standard_normal((12, 9)) * 3)).astype(np.float32)
+    W[0, :4] = [1.0, -1.0, 0.0, 3.0]                 # +-1 (a binarized weight), zero, exponent MSB set
+    W[1, 0], W[1, 1] = np.float32(2.0 ** 64), np.float32(2.0 ** -100)
+    blob = dict(W=W)
+    for mode in (0, 1, 2):
+        for p in (0.1, 0.5):
+            cb = Cb.ErrorCallback(p, mode=mode, bnn=False)
+            np.random.seed(300 + mode)
+            out = cb(W.copy())
+            np.random.seed(300 + mode)
+            elem = np.random.choice(W.size, round(W.size * p), replace=False)
+            mine = O.flip_float_bits(W, elem, p, mode, lambda c, k: np.random.choice(c, k, replace=False))
+            exact(mine.view(np.uint32), np.asarray(out, np.float32).view(np.uint32),
+                  f"ErrorCallback float flips mode {mode} p {p}")
+            tag = f"m{mode}_p{int(p * 10)}"
+            blob[f"out_{tag}"] = np.asarray(out, np.float32)
+            blob[f"elem_{tag}"] = elem.astype(np.int64)
+    np.savez_compressed(GOLDEN / "float_faults.npz", **blob)
+
+
 def main():
     sys.path.insert(0, str(HERE))
+    if "--only-float-faults" in sys.argv:            # leaves the other fixtures byte-identical
+        import bnn_oracle as O
+        _L, _A, _Lo, Cb, _Nw, _U = import_reference()
+        gen_float_faults(Cb, O)
+        print("float_faults.npz written")
+        return
     L, A, Lo, Cb, Nw, U = import_reference()
     import bnn_oracle as O
 
@@ -257,6 +288,8 @@ def main():
     exact(O.normalize(imgs, -1, 1), norm.astype(np.float32), "normalize")
     blob["normalized"] = norm.astype(np.float32)
     np.savez_compressed(GOLDEN / "image_faults.npz", **blob)
+
+    gen_float_faults(Cb, O)
 
     sizes = {p.name: p.stat().st_size for p in sorted(GOLDEN.glob("*.npz"))}
     print("golden fixtures written:", sizes)

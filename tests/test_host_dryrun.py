@@ -1,0 +1,90 @@
+"""Host logic of the fault sweeps, exercised WITHOUT a GPU: device buffers are replaced by CPU tensors
+and every C-ABI call goes to the real libbnn_b200, which validates its arguments (shapes, pitches,
+alignment, enum combinations) and then fails at its first CUDA call with BNN_ERR_CUDA.  A
+BNN_ERR_ARG / BNN_ERR_UNSUPPORTED from any call is a bug in the Python side of the boundary.  Nothing is
+computed here; the numbers are checked by the `-m gpu` tests."""
+import numpy as np
+import pytest
+
+
+@pytest.fixture
+def dry(monkeypatch):
+    import torch
+    if torch.cuda.is_available():   # with a device the calls would really launch — on host pointers
+        pytest.skip("argument-validation dry run is for machines without a GPU")
+    from mlpcode import _native as nat, device, kernels, layers, network, sweep
+    nat.load()
+    cpu = torch.device("cpu")
+
+    def to_tensor(a, dtype=None):
+        t = a.t if isinstance(a, device.DeviceArray) else (
+            a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)))
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.contiguous()
+
+    for mod in (device, kernels, layers, network, sweep):
+        for name, fn in (("require_cuda", lambda: cpu), ("stream_ptr", lambda: 0), ("to_tensor", to_tensor)):
+            if hasattr(mod, name):
+                monkeypatch.setattr(mod, name, fn)
+    calls = []
+
+    def call(name, *args):
+        lib = nat.load()
+        rc = getattr(lib, name)(*args)
+        calls.append((name, rc))
+        if rc not in (nat.BNN_OK, nat.BNN_ERR_CUDA):
+            raise nat.BnnError(name, rc, (lib.bnn_last_error() or b"").decode(errors="replace"))
+
+    monkeypatch.setattr(nat, "call", call)
+    monkeypatch.setenv("BNN_GEMM_IMPL", "tcgen05")
+    return calls
+
+
+def _net(units):
+    import bnn_oracle as O
+    from mlpcode.activation import ActivationFuncs as af
+    from mlpcode.network import Network
+    params = O.new_params(units, np.random.default_rng(0))
+    nn = Network(units, useGpu=True, binarized=True, useBatchNorm=True)
+    nn.compile(lr=0.01, hiddenAf=af.sign, outAf=af.identity)
+    nn.load_weights(params["W"])
+    return nn
+
+
+@pytest.mark.parametrize("variant", ["u8", "s8"])
+def test_batched_image_sweep_emits_wellformed_abi_calls(dry, monkeypatch, variant):
+    from mlpcode.sweep import ImageFaultSweep
+    monkeypatch.setenv("BNN_U8_GEMM", variant)
+    units = [784, 64, 32, 10]
+    nn = _net(units)
+    imgs = np.random.default_rng(1).integers(0, 256, (96, 784), dtype=np.uint8)
+    sw = ImageFaultSweep(nn, imgs, np.zeros(96, np.uint8), trials_per_launch=2)
+    assert sw.batched
+    del dry[:]
+    acc = sw.run(0.14, 3, seed=5)                       # groups of 2 + 1 trials
+    assert acc.shape == (3,)
+    names = [n for n, _ in dry]
+    per_group = ["bnn_flip_images_ex", "bnn_u8_input_thresholds", "bnn_gemm", "bnn_gemm", "bnn_gemm",
+                 "bnn_bn_apply", "bnn_count_correct"]
+    assert names == per_group * 2                       # no normalize, no fp16 split, no per-trial loop
+    # shapes the batched path cannot take fall back to the per-trial device path (never to the CPU)
+    assert not ImageFaultSweep.batch_ok(nn, 96, 780) and not ImageFaultSweep.batch_ok(nn, 16, 784)
+    with pytest.raises(ValueError):
+        ImageFaultSweep(_net([780, 64, 10]), imgs[:, :780], np.zeros(96, np.uint8), batched=True)
+
+
+def test_weight_sweep_emits_wellformed_abi_calls(dry):
+    from mlpcode.sweep import WeightFaultSweep
+    units = [784, 256, 128, 10]
+    nn = _net(units)
+    X = np.random.default_rng(2).random((64, 784), dtype=np.float32) * 2 - 1
+    sw = WeightFaultSweep(nn, X, np.zeros(64, np.uint8), trials_per_launch=4)
+    del dry[:]
+    assert sw.run_bernoulli(0.1, 6, seed=3).shape == (6,)
+    assert sw.run_exactk(lambda t: 1 + t, 6, seed=3).shape == (6,)
+    names = [n for n, _ in dry]
+    assert names.count("bnn_flip_weights_bernoulli") == 2 * 3 + 2 * 3   # per layer and group, both modes
+    assert names.count("bnn_flip_weights_exactk") == 2 * 3
+    assert names.count("bnn_gemm") == 4 * 3
+    assert all(rc in (0, -2) for _, rc in dry)

@@ -181,3 +181,54 @@ def test_u8_input_threshold_algebra_reproduces_reference_layer0(oracle, bias, lo
     diff = got != want
     assert np.all(np.abs(zt[diff]) < 1e-4), np.abs(zt[diff]).max()
     assert diff.mean() < 0.01
+
+
+def test_float_bit_flips_against_reference(golden, oracle):
+    """ErrorCallback(bnn=False) (callbacks.py:35-59, 85-123): the fixture holds the reference's outputs
+    and element draws; the per-element bit draws are re-derived from the output itself."""
+    g = golden("float_faults")
+    W = g["W"]
+    for mode in (0, 1, 2):
+        for p in (0.1, 0.5):
+            tag = f"m{mode}_p{int(p * 10)}"
+            out, elem = g[f"out_{tag}"], g[f"elem_{tag}"]
+            assert elem.size == round(W.size * p) and np.unique(elem).size == elem.size
+            xor = W.view(np.uint32) ^ out.view(np.uint32)
+
+            def choose(cand, k, _state={"i": 0}):
+                e = elem[_state["i"]]
+                _state["i"] += 1
+                x = np.array([xor.flat[e]], dtype=np.uint32)
+                flipped = np.flatnonzero(np.unpackbits(x.view(np.uint8)))
+                assert flipped.size == k and np.all(np.isin(flipped, cand))
+                return flipped
+            mine = oracle.flip_float_bits(W, elem, p, mode, choose)
+            assert np.array_equal(mine.view(np.uint32), out.view(np.uint32))
+            untouched = np.ones(W.size, bool)
+            untouched[elem] = False
+            assert not xor.flat[untouched].any()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_c_float_bit_flips_follow_reference_semantics(golden, oracle, mode):
+    """The device's draw (restated in C): exactly round(size*p) distinct elements; in each, exactly
+    round(cnt*p) candidate bits per _flipFunc (callbacks.py:35-59) are inverted, nothing else."""
+    W = golden("float_faults")["W"]
+    for p in (0.1, 0.5, 1.0):
+        out = oracle.c_flip_f32_bits(W, p, mode, seed=0xF00D, trial=3)
+        xor = (W.view(np.uint32) ^ out.view(np.uint32)).ravel()
+        bits_all = np.unpackbits(W.ravel().view(np.uint8)).astype(bool).reshape(-1, 32)
+        # which elements were selected cannot be seen when round(cnt*p) == 0; count those that must change
+        changed = np.flatnonzero(xor)
+        for e in changed:
+            cand = oracle.float_flip_candidates(bits_all[e], mode)
+            flipped = np.flatnonzero(np.unpackbits(np.array([xor[e]], np.uint32).view(np.uint8)))
+            assert flipped.size == min(cand.size, round(cand.size * p)) and np.all(np.isin(flipped, cand))
+        assert changed.size <= round(W.size * p)
+        if p == 1.0 and mode == 2:
+            assert changed.size == W.size
+        again = oracle.c_flip_f32_bits(W, p, mode, seed=0xF00D, trial=3)
+        assert np.array_equal(again.view(np.uint32), out.view(np.uint32))
+        if p < 1.0:                                   # p = 1 flips every candidate of every element
+            other = oracle.c_flip_f32_bits(W, p, mode, seed=0xF00D, trial=4)
+            assert not np.array_equal(other.view(np.uint32), out.view(np.uint32))

@@ -1,4 +1,5 @@
-"""GPU parity of the uint8-input layer 0: the image fault sweep of
+"""GPU parity of the rows SURVEY 8(f) marks "next": the IEEE-754 weight bit flips of the non-BNN
+ErrorCallback branch (row 4, at the end of this file) and the uint8-input layer 0 (row 1): the image fault sweep of
 imageBitflipTrainModelSel.py:19-32 with ImageErrorCallback output (callbacks.py:125-172) and
 utils.normalize (utils.py:178-187) folded into an exact u8 x s8 tensor-core GEMM.
 
@@ -201,3 +202,36 @@ def test_batched_image_sweep_at_full_size_equals_per_trial_path():
     got, ref = fast.run(0.14, 4, 77), slow.run(0.14, 4, 77)
     assert np.max(np.abs(got - ref)) <= 0.05, (got, ref)     # <= 5 of 10 000 rows
     assert len(set(np.round(got, 6))) > 1                    # the trials really differ
+
+
+# ------------------------------------------------------------------------- IEEE-754 weight bit flips
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_f32_bit_flips_match_oracle(T, oracle, golden, mode):
+    """bnn_flip_f32_bits (ErrorCallback non-BNN branch, callbacks.py:35-59, 100-123) == the C restatement
+    of the same draw, bit for bit; the restatement's semantics are pinned against the reference's own
+    outputs in tests/test_oracle.py."""
+    from mlpcode import kernels as K
+    rng = np.random.default_rng(40 + mode)
+    big = (rng.standard_normal((300, 257)) * np.exp(rng.standard_normal((300, 257)) * 4)).astype(np.float32)
+    pm = np.where(rng.random((784, 64)) < 0.5, -1.0, 1.0).astype(np.float32)
+    for arr in (golden("float_faults")["W"], big, pm):
+        for p in (0.1, 0.5, 1.0):
+            d = dev(arr.copy())
+            K.flip_f32_bits(d, p, mode, 0xABCD1234, 2)
+            want = oracle.c_flip_f32_bits(arr, p, mode, seed=0xABCD1234, trial=2)
+            assert np.array_equal(d.cpu().numpy().view(np.uint32), want.view(np.uint32)), (arr.shape, p)
+
+
+def test_error_callback_float_branch(T, oracle, golden):
+    """ErrorCallback(p, mode, bnn=False)(array): reference call signature on a dense real-valued array."""
+    from mlpcode.callbacks import ErrorCallback
+    W = golden("float_faults")["W"]
+    cb = ErrorCallback(0.5, mode=2, bnn=False, seed=77)
+    out0 = cb(W, gpu=True).get()
+    out1 = cb(W, gpu=True).get()                               # next call = next trial
+    assert np.array_equal(out0.view(np.uint32), oracle.c_flip_f32_bits(W, 0.5, 2, 77, 0).view(np.uint32))
+    assert np.array_equal(out1.view(np.uint32), oracle.c_flip_f32_bits(W, 0.5, 2, 77, 1).view(np.uint32))
+    changed = (out0.view(np.uint32) != W.view(np.uint32)).sum()
+    assert 0 < changed <= round(W.size * 0.5)
+    small = ErrorCallback(0.001, mode=2, bnn=False, seed=1)    # round(108 * 0.001) == 0 elements
+    assert small(W, gpu=True) is W                             # callbacks.py:111-112 returns the input

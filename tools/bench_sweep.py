@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--trials", type=int, default=64)
     ap.add_argument("--cpu-trials", type=int, default=1)
     ap.add_argument("--per-launch", type=int, default=8)
+    ap.add_argument("--image-trials", type=int, default=32)
     args = ap.parse_args()
     comm = parallel.init_from_env("nccl")
     rank = comm.rank if comm else 0
@@ -67,6 +68,36 @@ def main():
         out[name] = {"trials": n_trials, "seconds": dt, "trials_per_s": n_trials / dt,
                      "mean_accuracy": float(np.mean(acc)),
                      "flop_equiv_per_trial": 2.0 * 10000 * sum(a * b for a, b in zip(units[:-1], units[1:]))}
+    # ---- image bit-flip sweep (imageBitflipTrainModelSel.py:19-32) on the same network ----------
+    if args.image_trials > 0:
+        from mlpcode.sweep import ImageFaultSweep
+        imgs = rng.integers(0, 256, (10000, 784), dtype=np.uint8)
+        imgs[rng.random((10000, 784)) < 0.8] = 0                  # MNIST-like: mostly background
+        n_img = args.image_trials * world
+        for name, batched in (("image_p0.14_u8_batched", True), ("image_p0.14_per_trial_fp32", False)):
+            isw = ImageFaultSweep(nn, imgs, labels, trials_per_launch=args.per_launch, batched=batched)
+            isw.run(0.14, n_img, 11, comm=comm)
+            sync()
+            t0 = time.perf_counter()
+            acc = isw.run(0.14, n_img, 11, comm=comm)
+            sync()
+            dt = time.perf_counter() - t0
+            out[name] = {"trials": n_img, "seconds": dt, "trials_per_s": n_img / dt,
+                         "mean_accuracy": float(np.mean(acc)),
+                         # flips: 7.84 MB read + written per trial; layer 0 reads the bytes once more
+                         "image_bytes_per_trial": 3 * 10000 * 784}
+            del isw
+        if rank == 0 and args.cpu_trials > 0:
+            import bnn_oracle as O
+            t0 = time.perf_counter()
+            for t in range(args.cpu_trials):
+                # callbacks.py:125-172 (row loop, choice without replacement) + normalize + get_accuracy
+                r2 = np.random.default_rng(t)
+                bad = np.stack([O.flip_image_row(row, r2.choice(784 * 8, 878, replace=False)) for row in imgs])
+                O.accuracy(params, O.normalize(bad, -1, 1), labels, out_af="identity")
+            dt = (time.perf_counter() - t0) / args.cpu_trials
+            out["cpu_reference_port_image"] = {"seconds_per_trial": dt, "trials_per_s": 1.0 / dt,
+                                               "sample": f"{args.cpu_trials} image trial(s), p = 0.14, 10 000 rows"}
     # ---- config 5: large-batch inference --------------------------------------------------------
     del sweep, nn
     torch.cuda.empty_cache()
