@@ -102,7 +102,7 @@ def test_flip_images_ex_byproducts(T, oracle, mode, xor_out):
             assert gmm[t].tolist() == [int(want.min()), int(want.max())], (R, F, t)
 
 
-@pytest.mark.parametrize("variant", ["u8", "s8"])
+@pytest.mark.parametrize("variant", [pytest.param("u8", id="native"), pytest.param("s8", id="biased")])
 def test_u8_layer0_sign_decisions_match_reference(T, oracle, variant):
     """Per-trial thresholds + batched u8 x s8 GEMM with the sign epilogue == the reference's
     normalize -> dot -> eval BN -> unitstep on each trial's images (different min / max per trial)."""
@@ -154,7 +154,7 @@ def _small_net(golden):
     return units, params, build_net(units, params, out="identity")
 
 
-@pytest.mark.parametrize("variant", ["u8", "s8"])
+@pytest.mark.parametrize("variant", [pytest.param("u8", id="native"), pytest.param("s8", id="biased")])
 def test_batched_image_sweep_matches_oracle_and_per_trial_path(golden, oracle, monkeypatch, variant):
     from mlpcode.sweep import ImageFaultSweep
     monkeypatch.setenv("BNN_U8_GEMM", variant)
@@ -180,28 +180,52 @@ def test_batched_image_sweep_matches_oracle_and_per_trial_path(golden, oracle, m
 
 
 def test_batched_image_sweep_at_full_size_equals_per_trial_path():
-    """BASELINE-sized property: 10 000 MNIST-shaped images through the 784-4096-4096-4096-10 network —
-    the exact u8 x s8 layer 0 and the fp32-normalize + fp16-split layer 0 classify alike (the two differ
-    only in rows whose layer-0 batch-norm output is within fp32 rounding of 0)."""
+    """BASELINE-sized property: 10 000 MNIST-shaped images through the 784-4096-4096-4096-10 network.
+    The exact u8 x s8 layer 0 and the fp32-normalize + fp16-split layer 0 are independent
+    implementations of the same map; their layer-0 activations may differ only where z sits within
+    rounding of its threshold (batch-norm parameters are generic reals here, as after training —
+    untrained mu = beta = 0 would put the threshold ON the lattice of exact sums, where thousands of
+    units per trial tie), and a random 4-layer network amplifies each such unit into a changed
+    prediction, so accuracies agree to a few rows, not exactly."""
+    import torch
     import bnn_oracle as O
+    from mlpcode import kernels as K
     from mlpcode.sweep import ImageFaultSweep
     from test_layers_gpu import build_net
     units = [784, 4096, 4096, 4096, 10]
     rng = np.random.default_rng(3)
     params = O.new_params(units, rng)
-    for b in params["bn"][:-1]:                      # pre-activations of +-1 layers have variance ~ K
-        b["sigma"][:] = 1000.0
+    for i, b in enumerate(params["bn"][:-1]):
+        n = b["mu"].size
+        b["sigma"][:] = 1000.0                       # pre-activations of +-1 layers have variance ~ K
+        b["mu"][:] = (rng.standard_normal(n) * 3).astype(np.float32)
+        b["beta"][:] = (rng.standard_normal(n) * 0.1).astype(np.float32)
+        b["gamma"][:] = (rng.random(n) + 0.5).astype(np.float32) * np.where(rng.random(n) < 0.2, -1, 1)
     nn = build_net(units, params, out="identity")
-    R = 10000
+    R, T = 10000, 4
     imgs = rng.integers(0, 256, (R, 784), dtype=np.uint8)
     imgs[rng.random((R, 784)) < 0.8] = 0             # MNIST-like: mostly background
     labels = rng.integers(0, 10, R).astype(np.uint8)
-    fast = ImageFaultSweep(nn, imgs, labels, trials_per_launch=4)
-    slow = ImageFaultSweep(nn, imgs, labels, trials_per_launch=4, batched=False)
+    fast = ImageFaultSweep(nn, imgs, labels, trials_per_launch=T)
+    slow = ImageFaultSweep(nn, imgs, labels, trials_per_launch=T, batched=False)
     assert fast.batched and not slow.batched
-    got, ref = fast.run(0.14, 4, 77), slow.run(0.14, 4, 77)
-    assert np.max(np.abs(got - ref)) <= 0.05, (got, ref)     # <= 5 of 10 000 rows
+    got, ref = fast.run(0.14, T, 77), slow.run(0.14, T, 77)
     assert len(set(np.round(got, 6))) > 1                    # the trials really differ
+    # both sweeps hold the same corrupted bytes, and the fused min / max equals a separate pass
+    assert torch.equal(fast.flipped, slow.flipped)
+    mm = torch.zeros(2, dtype=torch.int32, device="cuda")
+    for t in range(T):
+        K.minmax_u8(slow.flipped[t], mm)
+        assert fast.mm[t].tolist() == mm.tolist()
+    # layer 0, trial by trial: at most 1e-5 of the R x 4096 sign decisions may sit on a rounding boundary
+    N0, xf, mmf = units[1], torch.empty((R, 784), device="cuda"), torch.zeros(2, device="cuda")
+    for t in range(T):
+        K.minmax_u8(slow.flipped[t], mm, mmf)
+        K.normalize_u8(slow.flipped[t], mmf[0:1], mmf[1:2], -1.0, 1.0, xf)
+        a_ref = nn._layers[0].forward(xf, isTrain=False).i8[:, :N0]
+        a_got = fast.act[0][t * R:(t + 1) * R, :N0]
+        assert int((a_ref != a_got).sum()) <= 1e-5 * R * N0, t
+    assert np.max(np.abs(got - ref)) <= 0.3, (got, ref)      # <= 30 of 10 000 rows
 
 
 # ------------------------------------------------------------------------- IEEE-754 weight bit flips

@@ -36,7 +36,10 @@ def main():
     ap.add_argument("--cpu-trials", type=int, default=1)
     ap.add_argument("--per-launch", type=int, default=8)
     ap.add_argument("--image-trials", type=int, default=32)
+    ap.add_argument("--sections", default="weights,image,inference",
+                    help="comma-separated subset of: weights, image, inference")
     args = ap.parse_args()
+    sections = set(args.sections.split(","))
     comm = parallel.init_from_env("nccl")
     rank = comm.rank if comm else 0
     world = comm.world if comm else 1
@@ -59,6 +62,8 @@ def main():
     n_trials = args.trials * world
     for name, fn in (("bernoulli_p0.1", lambda: sweep.run_bernoulli(0.1, n_trials, 7, comm)),
                      ("exactk_1..1000", lambda: sweep.run_exactk(lambda t: 1 + (t % 1000), n_trials, 7, comm))):
+        if "weights" not in sections:
+            break
         fn()                                                  # warm-up (allocations, first launches)
         sync()
         t0 = time.perf_counter()
@@ -69,7 +74,7 @@ def main():
                      "mean_accuracy": float(np.mean(acc)),
                      "flop_equiv_per_trial": 2.0 * 10000 * sum(a * b for a, b in zip(units[:-1], units[1:]))}
     # ---- image bit-flip sweep (imageBitflipTrainModelSel.py:19-32) on the same network ----------
-    if args.image_trials > 0:
+    if args.image_trials > 0 and "image" in sections:
         from mlpcode.sweep import ImageFaultSweep
         imgs = rng.integers(0, 256, (10000, 784), dtype=np.uint8)
         imgs[rng.random((10000, 784)) < 0.8] = 0                  # MNIST-like: mostly background
@@ -99,25 +104,26 @@ def main():
             out["cpu_reference_port_image"] = {"seconds_per_trial": dt, "trials_per_s": 1.0 / dt,
                                                "sample": f"{args.cpu_trials} image trial(s), p = 0.14, 10 000 rows"}
     # ---- config 5: large-batch inference --------------------------------------------------------
-    del sweep, nn
-    torch.cuda.empty_cache()
-    units5 = [3072, 8192, 8192, 10]
-    nn5, _ = build(units5, seed=2)
-    B5 = 65536
-    X5 = torch.rand((B5, 3072), device="cuda") * 2 - 1
-    for _ in range(2):
-        nn5.predict(X5)
-    sync()
-    t0 = time.perf_counter()
-    reps = 5
-    for _ in range(reps):
-        nn5.predict(X5)
-    sync()
-    dt = time.perf_counter() - t0
-    out["inference_3072-8192-8192-10"] = {"batch_per_gpu": B5, "samples_per_s": world * B5 * reps / dt,
-                                          "ms_per_batch": 1e3 * dt / reps}
+    if "inference" in sections:
+        del sweep, nn
+        torch.cuda.empty_cache()
+        units5 = [3072, 8192, 8192, 10]
+        nn5, _ = build(units5, seed=2)
+        B5 = 65536
+        X5 = torch.rand((B5, 3072), device="cuda") * 2 - 1
+        for _ in range(2):
+            nn5.predict(X5)
+        sync()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            nn5.predict(X5)
+        sync()
+        dt = time.perf_counter() - t0
+        out["inference_3072-8192-8192-10"] = {"batch_per_gpu": B5, "samples_per_s": world * B5 * reps / dt,
+                                              "ms_per_batch": 1e3 * dt / reps}
     # ---- CPU baseline: the oracle port of one reference trial (callbacks.py:79-83 + get_accuracy) --
-    if rank == 0 and args.cpu_trials > 0:
+    if rank == 0 and args.cpu_trials > 0 and "weights" in sections:
         import bnn_oracle as O
         t0 = time.perf_counter()
         for t in range(args.cpu_trials):
