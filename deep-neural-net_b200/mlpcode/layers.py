@@ -536,6 +536,44 @@ class BinaryLayer(LinearLayer):
                              2 * li + 1, dwx.rank, dwx.world, dwx.comm.step_dev, L["K"], L["N"],
                              L["rows_per_owner"], lr, broadcast, dwx.counters[li:li + 1], signal=True)
 
+    # ------------------------------------------------------------------ uint8-fed layer 0 (eval)
+    def _u8_input_ok(self, X) -> bool:
+        """`utils.normalize(uint8 images)` arriving at a sign-activated layer: consumed as bytes."""
+        from .utils import NormalizedU8
+        Kd, _N = self.weights_shape
+        return (isinstance(X, NormalizedU8) and self.activation == af.sign and X.u8.ndim == 2
+                and X.u8.shape[1] == Kd and Kd % 16 == 0 and X.new_max > X.new_min
+                and X.u8.data_ptr() % 16 == 0)
+
+    def _forward_u8(self, X):
+        """Evaluation-mode forward on raw uint8 input (imageBitflipTrainModelSel.py:26-28): normalize
+        (utils.py:178-187), X.dot(sign(W)) (layers.py:220), running-statistic batch-norm (:93-97) and sign
+        as ONE exact u8 x s8 GEMM whose epilogue compares the integer sums with per-unit thresholds
+        (bnn_u8_input_thresholds).  Weight-fault callbacks act on the packed copies as usual."""
+        Kd, N = self.weights_shape
+        ws, bn = self._ws, self.batchNormLayer
+        B = X.u8.shape[0]
+        wops = self._weight_operands(False)
+        for cb in self.callbacks:
+            if hasattr(cb, "apply_to_layer"):
+                cb.apply_to_layer(self, wops)
+            else:
+                self._apply_foreign_callback(cb, wops)
+        thr = ws.get("thr", (N,), torch.float32)
+        sgn = ws.get("sgn", (N,), torch.float32)
+        thr_u8 = ws.get("thr_u8", (1, pad_to(N, 4)), torch.float32)
+        K_.bn_sign_thresholds(bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
+        K_.u8_input_thresholds(wops["bits"], N, Kd, thr, sgn, X.mm_u32, 1, X.new_min, X.new_max, 0, thr_u8)
+        act_i8 = ws.get(f"a_i8_{B}", (B, pad_to(N, 16)), torch.int8, zero=True)
+        K_.gemm(M=B, N=N, K=Kd, A=(X.u8,), B=(wops["i8"],), lda=X.u8.stride(0), ldb=wops["i8"].stride(0),
+                D=act_i8, ldd=act_i8.stride(0), in_dtype=nat.DT_I8, epilogue=nat.EPI_SIGN_I8,
+                epi_thr=thr_u8, epi_sgn=sgn, a_unsigned=True)
+        act_bits = None
+        if binary_gemm_variant() == "popc":
+            act_bits = ws.get(f"a_bits{B}", (B, pad_to(N, 32) // 32), torch.int32, zero=True)
+            K_.pack_i8_rows(act_i8, N, act_bits)
+        return SignActivation(act_i8, N, bits=act_bits)
+
     # ------------------------------------------------------------------ forward
     def forward(self, X, isTrain=True):
         assert self.isBuilt
@@ -544,6 +582,8 @@ class BinaryLayer(LinearLayer):
         bn = self.batchNormLayer
         self.cache.clear()
 
+        if not isTrain and self._u8_input_ok(X):
+            return self._forward_u8(X)
         real_input = not isinstance(X, SignActivation)
         if real_input:
             Xt = to_tensor(X, torch.float32)

@@ -88,3 +88,29 @@ def test_weight_sweep_emits_wellformed_abi_calls(dry):
     assert names.count("bnn_flip_weights_exactk") == 2 * 3
     assert names.count("bnn_gemm") == 4 * 3
     assert all(rc in (0, -2) for _, rc in dry)
+
+
+def test_unchanged_script_flow_stays_on_bytes(dry):
+    """imageBitflipTrainModelSel.py:24-28 verbatim — icb(testX); normalize(newX, -1, 1); get_accuracy —
+    reaches layer 0 as uint8: no normalize kernel, no fp16 split, one u8 x s8 GEMM."""
+    from mlpcode.callbacks import ImageErrorCallback
+    from mlpcode.utils import NormalizedU8, normalize
+    nn = _net([784, 64, 32, 10])
+    testX = np.random.default_rng(1).integers(0, 256, (96, 784), dtype=np.uint8)
+    testY = np.zeros(96, np.uint8)
+    icb = ImageErrorCallback(0.14)
+    del dry[:]
+    newX = icb(testX, gpu=True)
+    newX = normalize(newX, newMin=-1, newMax=1)
+    assert isinstance(newX, NormalizedU8) and newX.shape == (96, 784) and newX.dtype == np.float32
+    nn.get_accuracy(newX, testY)
+    names = [n for n, _ in dry]
+    assert "bnn_normalize_u8" not in names and "bnn_split_f16" not in names
+    assert names.count("bnn_u8_input_thresholds") == 1 and names.count("bnn_gemm") == 3
+    # a batched evaluation slices rows and keeps the parent's min / max
+    part = newX[10:50]
+    assert isinstance(part, NormalizedU8) and part.shape == (40, 784) and part.mm_u32 is newX.mm_u32
+    # generic consumers still get the fp32 values (materialised on demand)
+    del dry[:]
+    assert tuple(newX.t.shape) == (96, 784)
+    assert [n for n, _ in dry] == ["bnn_normalize_u8"]

@@ -228,6 +228,40 @@ def test_batched_image_sweep_at_full_size_equals_per_trial_path():
     assert np.max(np.abs(got - ref)) <= 0.3, (got, ref)      # <= 30 of 10 000 rows
 
 
+def test_unchanged_script_flow_on_bytes_matches_oracle(golden, oracle):
+    """imageBitflipTrainModelSel.py:24-28 verbatim: icb(testX) -> normalize(newX, -1, 1) -> get_accuracy.
+    `normalize` hands layer 0 the bytes (NormalizedU8); results equal the reference semantics, also with
+    weight faults attached and with a batched evaluation."""
+    from mlpcode.callbacks import ErrorCallback, ImageErrorCallback
+    from mlpcode.utils import NormalizedU8, normalize
+    units, params, nn = _small_net(golden)
+    rng = np.random.default_rng(12)
+    R = 96
+    imgs = rng.integers(0, 256, (R, units[0]), dtype=np.uint8)
+    labels = rng.integers(0, 10, R).astype(np.uint8)
+    k = int(round(0.14 * units[0] * 8))
+    icb = ImageErrorCallback(0.14, seed=31)
+    for trial in range(3):
+        newX = icb(imgs, gpu=True)
+        nx = normalize(newX, newMin=-1, newMax=1)
+        assert isinstance(nx, NormalizedU8)
+        acc = nn.get_accuracy(nx, labels)
+        want_x = oracle.normalize(oracle.c_flip_image_rows(imgs, k, 2, 31, trial), -1, 1)
+        want = oracle.accuracy(params, want_x, labels, out_af="identity")
+        assert abs(acc - want) <= 100.0 / R + 1e-9, (trial, acc, want)
+        assert abs(nn.get_accuracy(nx, labels, batch_size=40) - acc) < 1e-9      # row slices keep min / max
+        assert np.array_equal(nx.get(), want_x)              # materialised values = the reference's bits
+    # weight faults on top: the callbacks flip the packed copies the u8 GEMM reads, and S_n follows them
+    nn.addCallbacks(ErrorCallback(0.1, mode=2, bnn=True, seed=1234))
+    got = nn.predict(nx).get()
+    n = len(units) - 1
+    masks = [oracle.c_bernoulli_mask(units[i], units[i + 1], 0.1, 1234, i, i) for i in range(n)]
+    hooks = [(lambda mk: (lambda W: oracle.flip_bnn_mask(W, mk)))(mk) for mk in masks]
+    ref = oracle.predict(params, want_x.copy(), out_af="identity", weight_hooks=hooks)
+    assert np.mean(got.argmax(1) == ref.argmax(1)) >= 1 - 1.5 / R
+    nn.clearCallbacks()
+
+
 # ------------------------------------------------------------------------- IEEE-754 weight bit flips
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_f32_bit_flips_match_oracle(T, oracle, golden, mode):

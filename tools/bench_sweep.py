@@ -27,6 +27,32 @@ def build(units, seed=0):
     return nn, params
 
 
+def call_timeline(fn, period):
+    """CUDA-event time of every C-ABI call issued by fn(), summed by position within a launch group of
+    `period` calls: {"<pos>:<symbol>": ms}."""
+    import torch
+    import mlpcode.kernels as K_
+    rec, orig = [], K_._call
+
+    def timed(name, *a):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        orig(name, *a)
+        e.record()
+        rec.append((name, s, e))
+    K_._call = timed
+    try:
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        K_._call = orig
+    agg = {}
+    for i, (name, s, e) in enumerate(rec):
+        key = f"{i % period}:{name}"
+        agg[key] = agg.get(key, 0.0) + s.elapsed_time(e)
+    return agg
+
+
 def main():
     import torch
     from mlpcode import parallel
@@ -87,6 +113,9 @@ def main():
             acc = isw.run(0.14, n_img, 11, comm=comm)
             sync()
             dt = time.perf_counter() - t0
+            if batched and world == 1:           # a collective-free run only (the sweep gathers at its end)
+                tl = call_timeline(lambda: isw.run(0.14, n_img, 11, comm=comm), 7)
+                out["image_u8_batched_ms_per_trial_by_call"] = {k: v / n_img for k, v in tl.items()}
             out[name] = {"trials": n_img, "seconds": dt, "trials_per_s": n_img / dt,
                          "mean_accuracy": float(np.mean(acc)),
                          # flips: 7.84 MB read + written per trial; layer 0 reads the bytes once more
