@@ -4,6 +4,9 @@
 // plus the exact-k weight flips of BASELINE config 4 and utils.normalize (utils.py:178-187).
 #include "common.cuh"
 #include "fault_math.cuh"
+
+#include <stdlib.h>
+#include <string.h>
 #include "rng.cuh"
 
 namespace bnn {
@@ -174,7 +177,7 @@ constexpr int IMG_MAX_F = 4096;
 __global__ void __launch_bounds__(128)
 flip_images_kernel(const uint8_t* __restrict__ in, int R, int F, int k, int mode,
                    unsigned long long seed, uint32_t trial0, uint8_t* __restrict__ out, int words,
-                   uint32_t xor_out, uint32_t* __restrict__ minmax) {
+                   uint32_t xor_out, uint32_t* __restrict__ minmax, int lockstep) {
     __shared__ uint32_t row[IMG_MAX_F / 4];
     __shared__ uint32_t orig[IMG_MAX_F / 4];
     __shared__ int pref[IMG_MAX_F / 4 + 1];  // exclusive prefix of candidate counts per 32-bit word
@@ -219,9 +222,8 @@ flip_images_kernel(const uint8_t* __restrict__ in, int R, int F, int k, int mode
     if (kk > 0) {
         const rng::FeistelKey key = rng::feistel_key(seed, rng::kStreamImage, trial0 + t, (uint32_t)r);
         const int bits = rng::feistel_bits((unsigned long long)ncand);
-        for (int i = threadIdx.x; i < kk; i += blockDim.x) {
-            const int rank = (int)rng::feistel_perm((unsigned long long)i, (unsigned long long)ncand,
-                                                    bits, key);
+        // flip the candidate of the given rank (candidates ranked in MSB-first bit order)
+        auto commit = [&](int rank) {
             int byte_idx, bit_in_byte;  // bit_in_byte counted MSB first (0 = 0x80)
             if (mode == 2) {
                 byte_idx = rank >> 3;
@@ -255,6 +257,25 @@ flip_images_kernel(const uint8_t* __restrict__ in, int R, int F, int k, int mode
             }
             if (byte_idx >= 0)
                 atomicXor(&row[byte_idx >> 2], (0x80u >> bit_in_byte) << (8 * (byte_idx & 3)));
+        };
+        if (lockstep) {
+            // Thread `tid` owns draws tid, tid + 128, ...  Every lane applies the bijection ONCE per trip;
+            // a lane whose value lands in range commits it and moves to its next draw.  A warp's trip
+            // count is then the longest SUM of walks among its lanes (about 1.4x the mean) instead of
+            // the sum over draws of the longest walk (about 3x): same positions, less divergence.
+            int i = threadIdx.x;
+            unsigned long long x = (unsigned long long)i;
+            while (i < kk) {
+                x = rng::feistel_once(x, bits, key);
+                if (x < (unsigned long long)ncand) {
+                    commit((int)x);
+                    i += blockDim.x;
+                    x = (unsigned long long)i;
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < kk; i += blockDim.x)
+                commit((int)rng::feistel_perm((unsigned long long)i, (unsigned long long)ncand, bits, key));
         }
     }
     __syncthreads();
@@ -452,8 +473,11 @@ extern "C" int bnn_flip_images_ex(const uint8_t* in, int R, int F, int k, int mo
     const int words = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 3u) == 0) &&
                       ((reinterpret_cast<uintptr_t>(out) & 3u) == 0);
     dim3 grid(R, n_trials);
+    // BNN_FLIP_WALK=perdraw keeps round 1's loop (one complete walk per draw); same output
+    const char* walk = getenv("BNN_FLIP_WALK");  // read per call: tests switch it within one process
+    const int lockstep = (walk && strcmp(walk, "perdraw") == 0) ? 0 : 1;
     flip_images_kernel<<<grid, 128, 0, s>>>(in, R, F, k, mode, seed, trial0, out, words,
-                                            (uint32_t)xor_out, minmax);
+                                            (uint32_t)xor_out, minmax, lockstep);
     BNN_LAUNCH_CHECK("flip_images_kernel");
     return BNN_OK;
 }

@@ -36,32 +36,46 @@ __host__ __device__ inline uint32_t fmix32(uint32_t h) {
     return h;
 }
 
-// Smallest even bit count whose range covers [0, n).
-__host__ __device__ inline int feistel_bits(uint64_t n) {
-    int b = 2;
-    while (b < 64 && ((uint64_t)1 << b) < n) b += 2;
-    return b;
-}
-
 struct FeistelKey {
     uint32_t k[6];
 };
 
-// Keyed bijection on [0, n): 6-round balanced Feistel on feistel_bits(n) bits with cycle walking.
+// Smallest bit count (>= 2) whose range covers [0, n): the walk below accepts more than half of the
+// domain.  (Round 1 used the smallest EVEN count; for the 6272 candidate bits of an MNIST row that was
+// 2^14, 38 % acceptance, and a warp pays the longest walk of its 32 lanes.)
+__host__ __device__ inline int feistel_bits(uint64_t n) {
+    int b = 2;
+    while (b < 64 && ((uint64_t)1 << b) < n) ++b;
+    return b;
+}
+
+__host__ __device__ inline uint32_t low_mask(int bits) {
+    return bits >= 32 ? 0xFFFFFFFFu : (((uint32_t)1 << bits) - 1u);
+}
+
+// One application of the keyed bijection F on [0, 2^bits): 6 Feistel rounds on a (high, low) split of
+// ceil(bits/2) and floor(bits/2) bits.  Each round maps (L, R) -> (R, L ^ f(R)) with f cut to the width of
+// L, so the two widths swap every round and are back after the even number of rounds; for even `bits`
+// this is the ordinary balanced network.
+__host__ __device__ inline uint64_t feistel_once(uint64_t x, int bits, const FeistelKey& key) {
+    int wr = bits >> 1, wl = bits - wr;  // widths of R (low part) and L (high part)
+    uint32_t L = (uint32_t)(x >> wr), R = (uint32_t)x & low_mask(wr);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const uint32_t f = fmix32(R ^ key.k[r]) & low_mask(wl);
+        const uint32_t nl = R;
+        R = L ^ f;
+        L = nl;
+        const int t = wl; wl = wr; wr = t;
+    }
+    return ((uint64_t)L << wr) | R;
+}
+
+// Keyed bijection on [0, n): F with cycle walking (apply F until the value falls below n).
 __host__ __device__ inline uint64_t feistel_perm(uint64_t x, uint64_t n, int bits,
                                                  const FeistelKey& key) {
-    const int half = bits >> 1;
-    const uint64_t mask = (half >= 32) ? 0xFFFFFFFFull : (((uint64_t)1 << half) - 1);
     do {
-        uint32_t L = (uint32_t)(x >> half), R = (uint32_t)(x & mask);
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const uint32_t f = fmix32(R ^ key.k[r]) & (uint32_t)mask;
-            const uint32_t nl = R;
-            R = L ^ f;
-            L = nl;
-        }
-        x = ((uint64_t)L << half) | R;
+        x = feistel_once(x, bits, key);
     } while (x >= n);
     return x;
 }

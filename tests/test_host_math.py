@@ -61,11 +61,16 @@ def test_device_rng_source_matches_oracle_restatement(shim, oracle):
     shim.host_philox(ctr, key, out)
     assert list(out) == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]      # Random123 kat_vectors
     assert list(out) == list(oracle.c_philox(list(ctr), list(key)))
-    for total, k in ((1000, 1000), (36806656, 500), (5, 5), (2 ** 33 + 7, 64)):
+    for total, k in ((1000, 1000), (36806656, 500), (5, 5), (2 ** 33 + 7, 64), (6272, 6272), (100000, 777),
+                     (2 ** 31 + 5, 100), (2 ** 32 + 1, 100), (3, 3), (2, 2), (1, 1)):
         pos = (C.c_uint64 * k)()
         shim.host_exactk(C.c_uint64(total), C.c_uint64(0xBEEF), 9, k, pos)
         want = oracle.c_exactk_positions(total, 0xBEEF, 9, k)
         assert np.array_equal(np.array(pos[:], dtype=np.uint64), np.asarray(want, dtype=np.uint64))
+        got = np.array(pos[:], dtype=np.uint64)
+        assert got.max() < total and np.unique(got).size == k          # distinct, in range
+        if k == total:
+            assert np.array_equal(np.sort(got), np.arange(total, dtype=np.uint64))   # a permutation of [0, n)
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])

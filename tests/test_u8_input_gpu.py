@@ -102,6 +102,25 @@ def test_flip_images_ex_byproducts(T, oracle, mode, xor_out):
             assert gmm[t].tolist() == [int(want.min()), int(want.max())], (R, F, t)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_flip_walk_schedules_agree(T, oracle, monkeypatch, mode):
+    """The lock-step walk (default) and round 1's one-walk-per-draw loop are two schedules of the same
+    draws: identical bytes, both equal to the oracle."""
+    from mlpcode import kernels as K
+    rng = np.random.default_rng(70 + mode)
+    images = rng.integers(0, 256, (50, 784), dtype=np.uint8)
+    images[rng.random(images.shape) < 0.8] = 0
+    outs = []
+    for walk in ("lockstep", "perdraw"):
+        monkeypatch.setenv("BNN_FLIP_WALK", walk)
+        out = T.zeros((2, 50, 784), dtype=T.uint8, device="cuda")
+        K.flip_images(dev(images), 878, mode, 0xFEED, 3, 2, out)
+        outs.append(out.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    for t in range(2):
+        assert np.array_equal(outs[0][t], oracle.c_flip_image_rows(images, 878, mode, 0xFEED, 3 + t))
+
+
 @pytest.mark.parametrize("variant", [pytest.param("u8", id="native"), pytest.param("s8", id="biased")])
 def test_u8_layer0_sign_decisions_match_reference(T, oracle, variant):
     """Per-trial thresholds + batched u8 x s8 GEMM with the sign epilogue == the reference's
