@@ -330,25 +330,44 @@ __global__ void minmax_init_kernel(uint32_t* __restrict__ minmax, int n_trials) 
 // One warp per output unit n: S_n = sum_k Wb[k, n] from the packed bits, then the per-trial thresholds
 // (see bnn_u8_input_thresholds in the header for the algebra).
 __global__ void __launch_bounds__(256)
-u8_input_thresholds_kernel(const uint32_t* __restrict__ wt_bits, long long ld_bits, int N, int K,
-                           const float* __restrict__ thr, const float* __restrict__ sgn,
-                           const uint32_t* __restrict__ minmax, int n_trials, float new_min,
-                           float new_max, int bias, float* __restrict__ thr_out, long long ld_thr) {
+u8_input_thresholds_kernel(const uint32_t* __restrict__ wt_bits, long long ld_bits,
+                           long long bits_stride, int N, int K, const float* __restrict__ thr,
+                           const float* __restrict__ sgn, const uint32_t* __restrict__ minmax,
+                           int minmax_stride, int n_trials, float new_min, float new_max, int bias,
+                           float* __restrict__ thr_out, long long ld_thr) {
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
     const int nw = (K + 31) >> 5;
-    int ones = 0;
-    for (int w = lane; w < nw; w += 32) ones += __popc(__ldg(wt_bits + (long long)n * ld_bits + w));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ones += __shfl_xor_sync(0xffffffffu, ones, o);
-    const double S = (double)(2 * ones - K);
     const float tz = __ldg(thr + n);
     const double s = (double)__ldg(sgn + n);
-    for (int t = lane; t < n_trials; t += 32)
-        thr_out[(long long)t * ld_thr + n] = fault::u8_input_threshold(
-            tz, s, S, (double)minmax[2 * t], (double)minmax[2 * t + 1], (double)new_min, (double)new_max,
-            (double)bias);
+    if (bits_stride == 0) {
+        // one weight matrix, one min / max per trial (image faults): S_n once, lanes take trials
+        int ones = 0;
+        for (int w = lane; w < nw; w += 32) ones += __popc(__ldg(wt_bits + (long long)n * ld_bits + w));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ones += __shfl_xor_sync(0xffffffffu, ones, o);
+        const double S = (double)(2 * ones - K);
+        for (int t = lane; t < n_trials; t += 32)
+            thr_out[(long long)t * ld_thr + n] = fault::u8_input_threshold(
+                tz, s, S, (double)minmax[(long long)t * minmax_stride],
+                (double)minmax[(long long)t * minmax_stride + 1], (double)new_min, (double)new_max,
+                (double)bias);
+    } else {
+        // one weight matrix per trial (weight faults): S_n of every trial's own (flipped) column
+        for (int t = 0; t < n_trials; ++t) {
+            const uint32_t* row = wt_bits + (long long)t * bits_stride + (long long)n * ld_bits;
+            int ones = 0;
+            for (int w = lane; w < nw; w += 32) ones += __popc(__ldg(row + w));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ones += __shfl_xor_sync(0xffffffffu, ones, o);
+            if (lane == 0)
+                thr_out[(long long)t * ld_thr + n] = fault::u8_input_threshold(
+                    tz, s, (double)(2 * ones - K), (double)minmax[(long long)t * minmax_stride],
+                    (double)minmax[(long long)t * minmax_stride + 1], (double)new_min, (double)new_max,
+                    (double)bias);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __restrict__ in, long long n,
@@ -487,17 +506,23 @@ extern "C" int bnn_flip_images(const uint8_t* in, int R, int F, int k, int mode,
     return bnn_flip_images_ex(in, R, F, k, mode, seed, trial0, n_trials, out, 0, nullptr, stream);
 }
 
-extern "C" int bnn_u8_input_thresholds(const uint32_t* wt_bits, int64_t ld_bits, int N, int K,
-                                       const float* thr, const float* sgn, const uint32_t* minmax,
-                                       int n_trials, float new_min, float new_max, int bias,
-                                       float* thr_out, int64_t ld_thr, bnn_stream_t stream) {
+extern "C" int bnn_u8_input_thresholds(const uint32_t* wt_bits, int64_t ld_bits, int64_t bits_stride,
+                                       int N, int K, const float* thr, const float* sgn,
+                                       const uint32_t* minmax, int minmax_stride, int n_trials,
+                                       float new_min, float new_max, int bias, float* thr_out,
+                                       int64_t ld_thr, bnn_stream_t stream) {
     BNN_CHECK_ARG(wt_bits && thr && sgn && minmax && thr_out && N > 0 && K > 0 && n_trials > 0,
                   "bnn_u8_input_thresholds: bad input");
     BNN_CHECK_ARG(ld_bits >= (K + 31) / 32 && ld_thr >= N, "bnn_u8_input_thresholds: pitch too small");
     BNN_CHECK_ARG(new_max > new_min, "bnn_u8_input_thresholds: new_max must exceed new_min");
     BNN_CHECK_ARG(bias == 0 || bias == 128, "bnn_u8_input_thresholds: bias is 0 (uint8 operand) or 128");
+    BNN_CHECK_ARG(bits_stride == 0 || bits_stride >= (int64_t)N * ld_bits,
+                  "bnn_u8_input_thresholds: bits_stride is 0 (shared weights) or >= N*ld_bits");
+    BNN_CHECK_ARG(minmax_stride == 0 || minmax_stride >= 2,
+                  "bnn_u8_input_thresholds: minmax_stride is 0 (shared images) or >= 2");
     u8_input_thresholds_kernel<<<cdiv(N, 8), 256, 0, (cudaStream_t)stream>>>(
-        wt_bits, ld_bits, N, K, thr, sgn, minmax, n_trials, new_min, new_max, bias, thr_out, ld_thr);
+        wt_bits, ld_bits, bits_stride, N, K, thr, sgn, minmax, minmax_stride, n_trials, new_min, new_max,
+        bias, thr_out, ld_thr);
     BNN_LAUNCH_CHECK("u8_input_thresholds_kernel");
     return BNN_OK;
 }

@@ -705,12 +705,15 @@ int make_operand_map(CUtensorMap* map, const void* base, bool i8, long long rows
 template <bool kI8, int BLOCK_N, int EPI, int STATS = BNN_STATS_NONE>
 int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     using Cfg = TileCfg<BLOCK_N>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in shared-memory size is a per-device attribute of the function
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    BNN_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         BNN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kI8, BLOCK_N, EPI, STATS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::kSmemBytes));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     CUtensorMap mA[3], mB[3];
     const int nA = (g.A[1] != nullptr) ? 2 : 1;

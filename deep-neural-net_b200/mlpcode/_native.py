@@ -108,7 +108,7 @@ PROTOTYPES = {
     "bnn_flip_f32_bits": [_p, _i64, _i64, _d, _i, _u64, _u32, _p],
     "bnn_flip_images": [_p, _i, _i, _i, _i, _u64, _u32, _i, _p, _p],
     "bnn_flip_images_ex": [_p, _i, _i, _i, _i, _u64, _u32, _i, _p, _i, _p, _p],
-    "bnn_u8_input_thresholds": [_p, _i64, _i, _i, _p, _p, _p, _i, _f, _f, _i, _p, _i64, _p],
+    "bnn_u8_input_thresholds": [_p, _i64, _i64, _i, _i, _p, _p, _p, _i, _i, _f, _f, _i, _p, _i64, _p],
     "bnn_normalize_u8": [_p, _i64, _p, _p, _f, _f, _p, _p],
     "bnn_minmax_u8": [_p, _i64, _p, _p, _p],
     "bnn_count_correct": [_p, _i, _i, _i64, _p, _p, _i, _p],

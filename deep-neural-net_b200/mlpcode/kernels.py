@@ -368,10 +368,14 @@ def flip_images(inp_u8, k, mode, seed, trial0, n_trials, out_u8, xor_out=0, minm
           ptr(out_u8), xor_out, ptr(minmax))
 
 
-def u8_input_thresholds(wt_bits, N, K, thr, sgn, minmax, n_trials, new_min, new_max, bias, thr_out) -> None:
-    """Per-trial integer thresholds of normalize + batch-norm + sign for a uint8-fed layer 0."""
-    _call("bnn_u8_input_thresholds", ptr(wt_bits), _ld(wt_bits), N, K, ptr(thr), ptr(sgn), ptr(minmax),
-          n_trials, new_min, new_max, bias, ptr(thr_out), _ld(thr_out))
+def u8_input_thresholds(wt_bits, N, K, thr, sgn, minmax, n_trials, new_min, new_max, bias, thr_out,
+                        per_trial_weights=False, shared_minmax=False) -> None:
+    """Per-trial integer thresholds of normalize + batch-norm + sign for a uint8-fed layer 0.
+    wt_bits: [N, words] (image faults) or, with per_trial_weights, [n_trials, N, words] (weight faults);
+    minmax: [n_trials, 2], or with shared_minmax one {min, max} pair for every trial."""
+    bits_stride = wt_bits.stride(0) if per_trial_weights else 0
+    _call("bnn_u8_input_thresholds", ptr(wt_bits), _ld(wt_bits), bits_stride, N, K, ptr(thr), ptr(sgn),
+          ptr(minmax), 0 if shared_minmax else 2, n_trials, new_min, new_max, bias, ptr(thr_out), _ld(thr_out))
 
 
 def minmax_u8(inp_u8, minmax_u32, minmax_f32=None) -> None:

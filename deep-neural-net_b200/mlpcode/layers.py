@@ -563,7 +563,8 @@ class BinaryLayer(LinearLayer):
         sgn = ws.get("sgn", (N,), torch.float32)
         thr_u8 = ws.get("thr_u8", (1, pad_to(N, 4)), torch.float32)
         K_.bn_sign_thresholds(bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
-        K_.u8_input_thresholds(wops["bits"], N, Kd, thr, sgn, X.mm_u32, 1, X.new_min, X.new_max, 0, thr_u8)
+        K_.u8_input_thresholds(wops["bits"], N, Kd, thr, sgn, X.mm_u32, 1, X.new_min, X.new_max, 0, thr_u8,
+                               shared_minmax=True)
         act_i8 = ws.get(f"a_i8_{B}", (B, pad_to(N, 16)), torch.int8, zero=True)
         K_.gemm(M=B, N=N, K=Kd, A=(X.u8,), B=(wops["i8"],), lda=X.u8.stride(0), ldb=wops["i8"].stride(0),
                 D=act_i8, ldd=act_i8.stride(0), in_dtype=nat.DT_I8, epilogue=nat.EPI_SIGN_I8,

@@ -34,11 +34,19 @@ from .parallel import shard_range
 
 class WeightFaultSweep:
     def __init__(self, nn, X, labels, trials_per_launch: int = 8):
+        from .utils import NormalizedU8
         assert nn.isCompiled and nn.isBinarized and nn.useBatchNorm
         self.nn = nn
         self.T = int(trials_per_launch)
         self.layers = nn._layers
-        X = to_tensor(X, torch.float32)
+        # `normalize(uint8 images)` (weightsErrorInjectionv2.py:15) stays bytes: layer 0 becomes an exact
+        # u8 x s8 GEMM against the T corrupted int8 weight copies, with the affine map and each trial's own
+        # column sums folded into per-trial thresholds (see ImageFaultSweep / bnn_u8_input_thresholds)
+        self.u8 = None
+        if (isinstance(X, NormalizedU8) and X.u8.ndim == 2 and X.u8.shape[1] % 16 == 0 and len(self.layers) >= 2
+                and X.new_max > X.new_min and K_.gemm_impl() == nat.GEMM_TCGEN05):
+            self.u8 = X
+        X = X.u8 if self.u8 is not None else to_tensor(X, torch.float32)
         self.R, self.F = X.shape
         assert self.R >= 32, "grouped accuracy counting needs at least 32 evaluation rows"
         self.labels = to_tensor(labels).reshape(-1).to(torch.int32).contiguous()
@@ -48,13 +56,14 @@ class WeightFaultSweep:
         self.offsets = np.cumsum([0] + [k * n for k, n in zip(self.units[:-1], self.units[1:])])[:-1]
 
         # ---- once per sweep: split input, clean packed weights -------------------------------
-        Fp = pad_to(self.F, 8)
-        self.x_amax = zeros((1,), torch.float32)
-        self.x_scale = zeros((1,), torch.float32)
-        self.x_hi = zeros((self.R, Fp), torch.float16)
-        self.x_lo = zeros((self.R, Fp), torch.float16)
-        K_.absmax_f32(X, self.x_amax)
-        K_.split_f16(X, self.x_amax, hi=self.x_hi, lo=self.x_lo, scale_out=self.x_scale)
+        if self.u8 is None:
+            Fp = pad_to(self.F, 8)
+            self.x_amax = zeros((1,), torch.float32)
+            self.x_scale = zeros((1,), torch.float32)
+            self.x_hi = zeros((self.R, Fp), torch.float16)
+            self.x_lo = zeros((self.R, Fp), torch.float16)
+            K_.absmax_f32(X, self.x_amax)
+            K_.split_f16(X, self.x_amax, hi=self.x_hi, lo=self.x_lo, scale_out=self.x_scale)
         self.clean_bits, self.w, self.z, self.act, self.thr = [], [], [], [], []
         T, R = self.T, self.R
         for i, layer in enumerate(self.layers):
@@ -64,10 +73,13 @@ class WeightFaultSweep:
             bits = zeros((N, pad_to(Kd, 32) // 32), torch.int32)
             K_.binarize_weights_t(layer.weights.t, wt_bits=bits)
             self.clean_bits.append(bits)
-            if i == 0:
+            if i == 0 and self.u8 is None:
                 self.w.append(zeros((T, N, pad_to(Kd, 8)), torch.float16))
             else:
                 self.w.append(zeros((T, N, pad_to(Kd, 16)), torch.int8))
+            if i == 0 and self.u8 is not None:
+                self.bits0 = zeros((T,) + tuple(bits.shape), torch.int32)   # the trials' flipped bit copies
+                self.thr0 = zeros((T, pad_to(N, 4)), torch.float32)
             if last:   # the output layer keeps its pre-activation: Z -> batch-norm -> scores
                 zdt = torch.float32 if i == 0 else (torch.int16 if Kd < 32768 else torch.int32)
                 self.z.append(empty((T * R, pad_to(N, 8)), zdt))
@@ -96,7 +108,15 @@ class WeightFaultSweep:
             else:
                 D, ldd, epi = out, out.stride(0), nat.EPI_SIGN_I8
                 thr, sgn = self.thr[i]
-            if i == 0:
+            if i == 0 and self.u8 is not None:
+                u8 = self.u8
+                K_.u8_input_thresholds(self.bits0, N, Kd, thr, sgn, u8.mm_u32, T, u8.new_min, u8.new_max, 0,
+                                       self.thr0, per_trial_weights=True, shared_minmax=True)
+                K_.gemm(M=R, N=N, K=Kd, A=(u8.u8,), B=(w,), lda=u8.u8.stride(0), ldb=w.stride(1), D=D, ldd=ldd,
+                        in_dtype=nat.DT_I8, epilogue=epi, batch=T, stride_a=0, stride_b=w.stride(0),
+                        stride_d=R * ldd, epi_thr=self.thr0, epi_sgn=sgn, epi_thr_stride=self.thr0.stride(0),
+                        a_unsigned=True)
+            elif i == 0:
                 K_.gemm(M=R, N=N, K=Kd, A=(self.x_hi, self.x_lo), B=(w,), lda=self.x_hi.stride(0),
                         ldb=w.stride(1), D=D, ldd=ldd, in_dtype=nat.DT_F16, epilogue=epi,
                         passes=((0, 0), (1, 0)), sa=self.x_scale, batch=T, stride_a=0,
@@ -118,22 +138,26 @@ class WeightFaultSweep:
         for i, layer in enumerate(self.layers):
             Kd, N = layer.weights_shape
             w = self.w[i][:n_live]
+            f16 = i == 0 and self.u8 is None
             K_.flip_weights_bernoulli(N=N, K=Kd, p=p, seed=seed, stream_id=i, trial0=trial0,
                                       n_trials=n_live, wt_bits=self.clean_bits[i],
-                                      out_f16=w if i == 0 else None, out_i8=None if i == 0 else w)
+                                      out_f16=w if f16 else None, out_i8=None if f16 else w,
+                                      out_bits=self.bits0[:n_live] if i == 0 and self.u8 is not None else None)
 
     def _flip_exactk(self, ks: torch.Tensor, k_max: int, seed: int, trial0: int) -> None:
         n_live = ks.numel()
         for i, layer in enumerate(self.layers):
             Kd, N = layer.weights_shape
             w = self.w[i][:n_live]
+            f16 = i == 0 and self.u8 is None
+            bits = self.bits0[:n_live] if i == 0 and self.u8 is not None else None
             # replicate the clean weights (p = 0), then scatter this layer's share of the flips
             K_.flip_weights_bernoulli(N=N, K=Kd, p=0.0, seed=0, stream_id=0, trial0=0, n_trials=n_live,
-                                      wt_bits=self.clean_bits[i], out_f16=w if i == 0 else None,
-                                      out_i8=None if i == 0 else w)
+                                      wt_bits=self.clean_bits[i], out_f16=w if f16 else None,
+                                      out_i8=None if f16 else w, out_bits=bits)
             K_.flip_weights_exactk(N=N, K=Kd, total=self.total_weights, offset=int(self.offsets[i]),
                                    seed=seed, trial0=trial0, k_per_trial=ks, k_max=k_max,
-                                   io_f16=w if i == 0 else None, io_i8=None if i == 0 else w)
+                                   io_f16=w if f16 else None, io_i8=None if f16 else w, io_bits=bits)
 
     # ------------------------------------------------------------------ public sweeps
     def trial_range(self, n_trials: int, comm=None):

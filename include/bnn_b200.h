@@ -461,12 +461,17 @@ int bnn_flip_images_ex(const uint8_t* in, int R, int F, int k, int mode, uint64_
  * xor_out = 0x80 int8 operands).  thr_out[t, n] is the ceiling of the real threshold (g_n*sgn[n] is an
  * integer), evaluated in fp64; +-inf thresholds stay +-inf.  A trial with mx == mn (the reference
  * divides by zero there) gets +inf (every unit -1).
- *   wt_bits [N, ld_bits]  packed K-major binarized weights (bnn_binarize_weights_t; pad bits 0)
- *   minmax  [n_trials][2] from bnn_flip_images_ex / bnn_minmax_u8;  thr_out [n_trials, ld_thr]. */
-int bnn_u8_input_thresholds(const uint32_t* wt_bits, int64_t ld_bits, int N, int K, const float* thr,
-                            const float* sgn, const uint32_t* minmax, int n_trials, float new_min,
-                            float new_max, int bias, float* thr_out, int64_t ld_thr,
-                            bnn_stream_t stream);
+ *   wt_bits [N, ld_bits]  packed K-major binarized weights (bnn_binarize_weights_t; pad bits 0);
+ *                         trial t reads wt_bits + t*bits_stride (0 = one matrix shared by all trials:
+ *                         image faults; N*ld_bits or more = the per-trial copies bnn_flip_weights_*
+ *                         writes: weight faults, whose S_n differs per trial)
+ *   minmax  trial t reads {min, max} at minmax + t*minmax_stride (2 = per trial, from
+ *                         bnn_flip_images_ex; 0 = one image set shared by all trials, bnn_minmax_u8)
+ *   thr_out [n_trials, ld_thr]. */
+int bnn_u8_input_thresholds(const uint32_t* wt_bits, int64_t ld_bits, int64_t bits_stride, int N, int K,
+                            const float* thr, const float* sgn, const uint32_t* minmax,
+                            int minmax_stride, int n_trials, float new_min, float new_max, int bias,
+                            float* thr_out, int64_t ld_thr, bnn_stream_t stream);
 
 /* uint8 -> fp32 affine map used by utils.normalize (utils.py:178-187) with caller-supplied
  * min/max (device floats): y = ((x - mn) * (new_max - new_min)) / (mx - mn) + new_min, in the

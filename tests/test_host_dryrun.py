@@ -114,3 +114,23 @@ def test_unchanged_script_flow_stays_on_bytes(dry):
     del dry[:]
     assert tuple(newX.t.shape) == (96, 784)
     assert [n for n, _ in dry] == ["bnn_normalize_u8"]
+
+
+def test_weight_sweep_on_uint8_images_emits_wellformed_abi_calls(dry):
+    """weightsErrorInjectionv2.py:15 normalizes the uint8 test set; the sweep keeps it as bytes."""
+    from mlpcode.sweep import WeightFaultSweep
+    from mlpcode.utils import normalize
+    nn = _net([784, 256, 128, 10])
+    imgs = np.random.default_rng(4).integers(0, 256, (64, 784), dtype=np.uint8)
+    sw = WeightFaultSweep(nn, normalize(imgs, newMin=-1., newMax=1.), np.zeros(64, np.uint8), trials_per_launch=4)
+    assert sw.u8 is not None
+    del dry[:]
+    assert sw.run_bernoulli(0.1, 6, seed=3).shape == (6,)
+    assert sw.run_exactk(lambda t: 1 + t, 6, seed=3).shape == (6,)
+    names = [n for n, _ in dry]
+    assert "bnn_split_f16" not in names and "bnn_normalize_u8" not in names
+    assert names.count("bnn_u8_input_thresholds") == 4          # once per launch group
+    assert names.count("bnn_gemm") == 4 * 3
+    # a real-valued evaluation set keeps the fp16-split layer 0
+    X = np.random.default_rng(2).random((64, 784), dtype=np.float32) * 2 - 1
+    assert WeightFaultSweep(nn, X, np.zeros(64, np.uint8)).u8 is None

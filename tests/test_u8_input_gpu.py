@@ -281,6 +281,56 @@ def test_unchanged_script_flow_on_bytes_matches_oracle(golden, oracle):
     nn.clearCallbacks()
 
 
+def test_weight_fault_sweep_on_uint8_images_matches_oracle(golden, oracle):
+    """WeightFaultSweep fed `normalize(uint8 images)` (weightsErrorInjectionv2.py:15-25): layer 0 runs on
+    the bytes against each trial's corrupted weights, thresholds carry each trial's own column sums.
+    Accuracies equal the reference semantics for Bernoulli and exact-k faults."""
+    from mlpcode.sweep import WeightFaultSweep
+    from mlpcode.utils import normalize
+    units, params, nn = _small_net(golden)                    # 784-64-32-10, identity output
+    n = len(units) - 1
+    rng = np.random.default_rng(15)
+    R = 96
+    imgs = rng.integers(0, 256, (R, units[0]), dtype=np.uint8)
+    imgs[rng.random(imgs.shape) < 0.5] = 0
+    labels = rng.integers(0, 10, R).astype(np.uint8)
+    X = oracle.normalize(imgs, -1, 1)
+    sweep = WeightFaultSweep(nn, normalize(imgs, newMin=-1., newMax=1.), labels, trials_per_launch=2)
+    assert sweep.u8 is not None
+    tol = 100.0 / R + 1e-9                                    # one row may sit on a rounding boundary
+    assert abs(sweep.clean_accuracy() - oracle.accuracy(params, X.copy(), labels, out_af="identity")) <= tol
+    p, seed, n_trials = 0.15, 20251, 5
+    got = sweep.run_bernoulli(p, n_trials, seed)
+    want = []
+    for t in range(n_trials):
+        masks = [oracle.c_bernoulli_mask(units[i], units[i + 1], p, seed, i, t) for i in range(n)]
+        hooks = [(lambda m: (lambda W: oracle.flip_bnn_mask(W, m)))(m) for m in masks]
+        want.append(oracle.accuracy(params, X.copy(), labels, out_af="identity", weight_hooks=hooks))
+    assert np.max(np.abs(got - np.array(want))) <= tol, (got, want)
+    assert len(set(got)) > 1
+    # the same sweep on the materialised fp32 images (fp16-split layer 0) agrees
+    ref = WeightFaultSweep(nn, X, labels, trials_per_launch=2)
+    assert ref.u8 is None
+    assert np.max(np.abs(ref.run_bernoulli(p, n_trials, seed) - got)) <= tol
+    # exact-k over the whole network
+    ks = [0, 1, 500, 20000]
+    total = sum(units[i] * units[i + 1] for i in range(n))
+    got = sweep.run_exactk(lambda t: ks[t], len(ks), 77)
+    offs = np.cumsum([0] + [units[i] * units[i + 1] for i in range(n)])
+    want = []
+    for t, k in enumerate(ks):
+        pos = oracle.c_exactk_positions(total, 77, t, k).astype(np.int64)
+        hooks = []
+        for i in range(n):
+            Kd, N = units[i], units[i + 1]
+            mine = pos[(pos >= offs[i]) & (pos < offs[i + 1])] - offs[i]
+            mask = np.zeros((Kd, N), bool)
+            mask[mine % Kd, mine // Kd] = True                # e = n*K + k  ->  W[k, n]
+            hooks.append((lambda m: (lambda W: oracle.flip_bnn_mask(W, m)))(mask))
+        want.append(oracle.accuracy(params, X.copy(), labels, out_af="identity", weight_hooks=hooks))
+    assert np.max(np.abs(got - np.array(want))) <= tol, (got, want)
+
+
 # ------------------------------------------------------------------------- IEEE-754 weight bit flips
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_f32_bit_flips_match_oracle(T, oracle, golden, mode):

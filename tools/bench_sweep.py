@@ -83,6 +83,8 @@ def main():
     rng = np.random.default_rng(1)
     X = rng.random((10000, 784), dtype=np.float32) * 2 - 1
     labels = rng.integers(0, 10, 10000).astype(np.uint8)
+    imgs = rng.integers(0, 256, (10000, 784), dtype=np.uint8)
+    imgs[rng.random((10000, 784)) < 0.8] = 0                      # MNIST-like: mostly background
     sweep = WeightFaultSweep(nn, X, labels, trials_per_launch=args.per_launch)
     out["clean_accuracy"] = sweep.clean_accuracy()
     n_trials = args.trials * world
@@ -99,11 +101,23 @@ def main():
         out[name] = {"trials": n_trials, "seconds": dt, "trials_per_s": n_trials / dt,
                      "mean_accuracy": float(np.mean(acc)),
                      "flop_equiv_per_trial": 2.0 * 10000 * sum(a * b for a, b in zip(units[:-1], units[1:]))}
+    if "weights" in sections:
+        # the same sweep fed `normalize(uint8 test set)` as weightsErrorInjectionv2.py:15 does: layer 0 on bytes
+        from mlpcode.utils import normalize
+        sweep8 = WeightFaultSweep(nn, normalize(imgs, newMin=-1., newMax=1.), labels,
+                                  trials_per_launch=args.per_launch)
+        sweep8.run_bernoulli(0.1, n_trials, 7, comm)
+        sync()
+        t0 = time.perf_counter()
+        acc = sweep8.run_bernoulli(0.1, n_trials, 7, comm)
+        sync()
+        dt = time.perf_counter() - t0
+        out["bernoulli_p0.1_uint8_images"] = {"trials": n_trials, "seconds": dt, "trials_per_s": n_trials / dt,
+                                              "mean_accuracy": float(np.mean(acc)), "layer0": "u8 x s8" if sweep8.u8 is not None else "fp16 split"}
+        del sweep8
     # ---- image bit-flip sweep (imageBitflipTrainModelSel.py:19-32) on the same network ----------
     if args.image_trials > 0 and "image" in sections:
         from mlpcode.sweep import ImageFaultSweep
-        imgs = rng.integers(0, 256, (10000, 784), dtype=np.uint8)
-        imgs[rng.random((10000, 784)) < 0.8] = 0                  # MNIST-like: mostly background
         n_img = args.image_trials * world
         for name, batched in (("image_p0.14_u8_batched", True), ("image_p0.14_per_trial_fp32", False)):
             isw = ImageFaultSweep(nn, imgs, labels, trials_per_launch=args.per_launch, batched=batched)
