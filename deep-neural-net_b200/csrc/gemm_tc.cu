@@ -32,6 +32,7 @@
 
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace bnn {
 
@@ -412,7 +413,12 @@ __device__ __forceinline__ void staged_rows(const TcParams& p, uint32_t xbuf, fl
     }
 }
 
-template <bool kI8, int BLOCK_N, int EPI, int STATS>
+// kCta2: the CTA-pair form (cta_group::2, opt-in with BNN_GEMM_CTA2=1, see launch_tc_pair).  Two CTAs of a
+// cluster share one 256 x BLOCK_N tile: each loads its own 128 rows of A and HALF of the B tile, the leader
+// issues UMMAs of M = 256 that read both halves, each CTA's TMEM receives its own 128 rows and is drained
+// by that CTA's epilogue warps exactly as in the single-CTA form.  The B tile then crosses L2 -> shared
+// memory once per pair instead of once per CTA.  p.m_tiles counts PAIRS of row tiles in this form.
+template <bool kI8, int BLOCK_N, int EPI, int STATS, bool kCta2 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
@@ -435,6 +441,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_tiles = p.batch * p.m_tiles * p.n_tiles;
+    const uint32_t cta_rank = kCta2 ? ptx::cluster_ctarank() : 0u;
+// a CTA's (pair: a CTA pair's) walk over the output tiles; the single-CTA form keeps its original expressions
+#define BNN_TILE_LOOP                                                                       \
+    for (int tile = kCta2 ? (blockIdx.x >> 1) : blockIdx.x; tile < total_tiles;             \
+         tile += kCta2 ? (gridDim.x >> 1) : gridDim.x)
     const int k_iters = p.n_pass * p.kblocks;
     // digit-split products have exactly two "chunks": the low and the high accumulator
     const int split_iters = p.hi_from_pass * p.kblocks;
@@ -450,19 +461,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&full_bar[s], kCta2 ? 2 : 1);  // pair: the leader's arrive.expect_tx + the peer
             ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < kAccStages; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
-            ptx::mbar_init(&tempty_bar[a], kEpiWarps);
+            ptx::mbar_init(&tempty_bar[a], kCta2 ? 2 * kEpiWarps : kEpiWarps);  // pair: both CTAs' warps
         }
         ptx::fence_mbar_init();
         ptx::fence_proxy_async();
     }
-    if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    if (warp == 2) ptx::tmem_alloc_t<kCta2, Cfg::kTmemCols>(tmem_ptr);
     ptx::tc_fence_before_sync();
     __syncthreads();
+    ptx::cluster_sync_if<kCta2>();  // pair: the peer's barriers are initialised before anyone signals them
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -475,9 +487,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             // ------------------------------------------------------------- TMA producer
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            BNN_TILE_LOOP {
                 int b, m_blk, n_blk;
                 tile_coords(p, tile, b, m_blk, n_blk);
+                if constexpr (kCta2) m_blk = 2 * m_blk + (int)cta_rank;
                 const int ba = p.a_batched ? b : 0;
                 const int bb = p.b_batched ? b : 0;
                 for (int pass = 0; pass < p.n_pass; ++pass) {
@@ -487,24 +500,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
                         uint8_t* sa = smem + s * Cfg::kStageBytes;
                         uint8_t* sb = sa + Cfg::kABytes;
-                        ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-                        ptx::tma_load_3d(sa, ma, &full_bar[s], kb * kKElems, m_blk * kBlockM, ba);
-                        ptx::tma_load_3d(sb, mb, &full_bar[s], kb * kKElems, n_blk * BLOCK_N, bb);
+                        // pair: both CTAs' bytes are counted on the LEADER's barrier, each CTA loads its own
+                        // 128 rows of A and its half of the B tile, the peer then arrives on that barrier
+                        if (!kCta2 || cta_rank == 0)
+                            ptx::mbar_arrive_expect_tx(&full_bar[s],
+                                                       kCta2 ? 2u * (Cfg::kABytes + Cfg::kBBytes / 2)
+                                                             : Cfg::kStageBytes);
+                        ptx::tma_load_3d_t<kCta2>(sa, ma, &full_bar[s], kb * kKElems, m_blk * kBlockM, ba);
+                        ptx::tma_load_3d_t<kCta2>(sb, mb, &full_bar[s], kb * kKElems,
+                                                  kCta2 ? n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2)
+                                                        : n_blk * BLOCK_N, bb);
+                        if (kCta2 && cta_rank != 0) ptx::mbar_arrive_remote(&full_bar[s], 0u);
                         if (++s == S) { s = 0; ph ^= 1u; }
                     }
                 }
             }
-        } else if (warp == 1 && lane == 0) {
-            // ------------------------------------------------------------- MMA issuer
-            uint32_t idesc = kI8 ? ptx::umma_idesc(2u, 1u, kBlockM, BLOCK_N)
-                                 : ptx::umma_idesc(1u, 0u, kBlockM, BLOCK_N);
+        } else if (warp == 1 && lane == 0 && (!kCta2 || cta_rank == 0)) {
+            // ------------------------------------------------------------- MMA issuer (pair: the leader)
+            uint32_t idesc = kI8 ? ptx::umma_idesc(2u, 1u, kCta2 ? 2 * kBlockM : kBlockM, BLOCK_N)
+                                 : ptx::umma_idesc(1u, 0u, kCta2 ? 2 * kBlockM : kBlockM, BLOCK_N);
             // kind::i8 operand formats: 1 = signed, 0 = unsigned 8-bit; A and B are independent fields
             if (kI8 && p.a_unsigned) idesc &= ~(7u << 7);
             int s = 0;
             uint32_t ph = 0;
             int acc = 0;
             uint32_t acc_ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            BNN_TILE_LOOP {
                 int it = 0;
                 for (int c = 0; c < n_chunks; ++c) {
                     ptx::mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
@@ -523,15 +544,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             const uint64_t adv = (uint64_t)((j * kUmmaKBytes) >> 4);
                             const uint32_t accum = (!first || j > 0) ? 1u : 0u;
                             if (kI8)
-                                ptx::mma_i8(d_tmem, da + adv, db + adv, idesc, accum);
+                                ptx::mma_i8_t<kCta2>(d_tmem, da + adv, db + adv, idesc, accum);
                             else
-                                ptx::mma_f16(d_tmem, da + adv, db + adv, idesc, accum);
+                                ptx::mma_f16_t<kCta2>(d_tmem, da + adv, db + adv, idesc, accum);
                         }
                         first = false;
-                        ptx::mma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs retire
-                        if (++s == S) { s = 0; ph ^= 1u; }
+                        ptx::mma_commit_t<kCta2>(&empty_bar[s]);  // frees the smem stage once the MMAs retire
+                        if (++s == S) { s = 0; ph ^= 1u; }        // (pair: in both CTAs)
                     }
-                    ptx::mma_commit(&tfull_bar[acc]);  // chunk complete -> epilogue
+                    ptx::mma_commit_t<kCta2>(&tfull_bar[acc]);  // chunk complete -> epilogue (pair: both CTAs')
                     if (++acc == kAccStages) { acc = 0; acc_ph ^= 1u; }
                 }
             }
@@ -548,10 +569,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const float scale = p.host_scale * inv;  // lr * 2^-e : exact
         int acc = 0;
         uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        BNN_TILE_LOOP {
             uint32_t sum[CPT];  // running sum of the chunks (fp32 bit patterns, or int32)
             int b, m_blk, n_blk;
             tile_coords(p, tile, b, m_blk, n_blk);
+            if constexpr (kCta2) m_blk = 2 * m_blk + (int)cta_rank;
             const int row = m_blk * kBlockM + q * 32 + lane;
             const int colbase = n_blk * BLOCK_N + h * CPT;
             for (int c = 0; c < n_chunks; ++c) {
@@ -603,7 +625,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 }
                 ptx::tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) ptx::mbar_arrive_leader<kCta2>(&tempty_bar[acc]);
                 if (++acc == kAccStages) { acc = 0; acc_ph ^= 1u; }
             }
             constexpr bool kF32Out = EPI == BNN_EPI_STORE_F32 || EPI == BNN_EPI_SGD_F32 ||
@@ -650,10 +672,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
     ptx::tc_fence_before_sync();
     __syncthreads();
+    ptx::cluster_sync_if<kCta2>();  // pair: neither CTA leaves while the other may still reach into it
     if (warp == 2) {
         ptx::tc_fence_after_sync();
-        ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+        ptx::tmem_dealloc_t<kCta2, Cfg::kTmemCols>(tmem_base);
     }
+#undef BNN_TILE_LOOP
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -702,9 +726,122 @@ int make_operand_map(CUtensorMap* map, const void* base, bool i8, long long rows
     return BNN_OK;
 }
 
+// BNN_GEMM_CTA2=1 (read per call) routes 256-wide products with more than one row tile to the CTA-pair form.
+// EXPERIMENTAL in round 1: written and compiled without access to a GPU; the default path is untouched.
+bool pair_form_requested() {
+    const char* e = getenv("BNN_GEMM_CTA2");
+    return e != nullptr && atoi(e) != 0;
+}
+
+// The CTA-pair launch (gemm_tc_kernel<..., kCta2 = true>): clusters of two CTAs, 256 x 256 tiles per pair.
+// Differences from launch_tc: the B maps fetch half tiles (128 rows per CTA), m_tiles counts PAIRS of row
+// tiles (an odd last tile leaves the peer CTA with rows past M: TMA zero-fills them and the epilogue's row
+// guards drop them), the grid is an even number of CTAs launched with a cluster dimension of 2.
+template <bool kI8, int EPI, int STATS>
+int launch_tc_pair(const bnn_gemm_desc& g, cudaStream_t stream) {
+    constexpr int BLOCK_N = 256;
+    using Cfg = TileCfg<BLOCK_N>;
+    auto kernel = gemm_tc_kernel<kI8, BLOCK_N, EPI, STATS, true>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    BNN_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        BNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    CUtensorMap mA[3], mB[3];
+    const int nA = (g.A[1] != nullptr) ? 2 : 1;
+    const void* Bp[3] = {g.B[0], g.B[1] ? g.B[1] : g.B[0], g.B2 ? g.B2 : g.B[0]};
+    for (int i = 0; i < 3; ++i) {
+        int rc = make_operand_map(&mA[i], g.A[i < nA ? i : 0], kI8, g.M, g.K, g.lda,
+                                  g.stride_a ? g.batch : 1, g.stride_a, kBlockM);
+        if (rc) return rc;
+        rc = make_operand_map(&mB[i], Bp[i], kI8, g.N, g.K, g.ldb, g.stride_b ? g.batch : 1, g.stride_b,
+                              BLOCK_N / 2);
+        if (rc) return rc;
+    }
+    TcParams p;
+    p.M = g.M;
+    p.N = g.N;
+    p.batch = g.batch;
+    p.kblocks = cdiv(g.K, kI8 ? kKBytes : kKBytes / 2);
+    p.n_pass = g.n_pass;
+    p.chunk_iters = kI8 ? (p.kblocks * g.n_pass) : gemm_chunk_iters();
+    for (int i = 0; i < BNN_GEMM_MAX_PASS; ++i) {
+        p.pa[i] = g.pa[i];
+        p.pb[i] = g.pb[i];
+    }
+    p.m_tiles = cdiv(cdiv(g.M, kBlockM), 2);  // pairs of row tiles
+    p.n_tiles = cdiv(g.N, BLOCK_N);
+    p.epilogue = g.epilogue;
+    const int esz = (g.epilogue == BNN_EPI_STORE_S16) ? 2 : (g.epilogue == BNN_EPI_SIGN_I8 ? 1 : 4);
+    p.vec_ok = aligned16(g.D) && ((g.ldd * esz) % 16 == 0) && ((g.stride_d * esz) % 16 == 0);
+    p.a_batched = g.stride_a != 0;
+    p.b_batched = g.stride_b != 0;
+    p.D = g.D;
+    p.ldd = g.ldd;
+    p.stride_d = g.stride_d;
+    p.sa = g.sa;
+    p.sb = g.sb;
+    p.host_scale = g.host_scale;
+    p.thr = g.epi_thr;
+    p.sgn = g.epi_sgn;
+    p.thr_stride = g.epi_thr_stride;
+    p.a_unsigned = g.a_unsigned;
+    p.rows_per_owner = 0;
+    p.rank = 0;
+    p.m_rot = 0;
+    for (int r = 0; r < BNN_MAX_RANKS; ++r) p.peer[r] = 0;
+    p.hi_from_pass = g.hi_from_pass;
+    p.col_scale = g.col_scale;
+    const bool f32out = EPI == BNN_EPI_STORE_F32 || EPI == BNN_EPI_SGD_F32;
+    if (g.hi_from_pass != 0 || g.col_scale != nullptr) {
+        if (!(f32out && p.vec_ok && g.N % BLOCK_N == 0 && g.batch == 1 &&
+              (g.hi_from_pass == 0 || (kI8 && g.hi_from_pass > 0 && g.hi_from_pass < g.n_pass)) &&
+              (!g.col_scale || aligned16(g.col_scale)))) {
+            set_error("bnn_gemm: digit-split / column-scaled products need int8 operands (split), an fp32 "
+                      "epilogue, N %% %d == 0, 16-byte aligned output and col_scale, batch == 1 (N=%d)",
+                      BLOCK_N, g.N);
+            return BNN_ERR_UNSUPPORTED;
+        }
+    }
+    p.st_sums = g.stats_sums;
+    p.st_max = g.stats_max;
+    p.st_Z = g.stats_z;
+    p.st_ldz = g.stats_ldz;
+    p.st_zdtype = g.stats_z_dtype;
+    p.st_mu = g.stats_mu;
+    if (STATS != BNN_STATS_NONE && !(p.vec_ok && g.N % BLOCK_N == 0 && g.batch == 1)) {
+        set_error("bnn_gemm: fused column statistics need N %% %d == 0, a 16-byte aligned output "
+                  "and batch == 1 (N=%d)", BLOCK_N, g.N);
+        return BNN_ERR_UNSUPPORTED;
+    }
+    const long long pairs = (long long)p.batch * p.m_tiles * p.n_tiles;
+    const long long max_clusters = sm_count() / 2;
+    const unsigned grid = 2u * (unsigned)(pairs < max_clusters ? pairs : max_clusters);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BNN_CUDA(cudaLaunchKernelEx(&cfg, kernel, mA[0], mA[1], mB[0], mB[1], mB[2], p));
+    BNN_LAUNCH_CHECK("gemm_tc_kernel<pair>");
+    return BNN_OK;
+}
+
 template <bool kI8, int BLOCK_N, int EPI, int STATS = BNN_STATS_NONE>
 int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     using Cfg = TileCfg<BLOCK_N>;
+    if constexpr (BLOCK_N == 256 && EPI != BNN_EPI_SCATTER_F32) {
+        if (g.M > kBlockM && pair_form_requested()) return launch_tc_pair<kI8, EPI, STATS>(g, stream);
+    }
     // the opt-in shared-memory size is a per-device attribute of the function
     static bool attr_set[64] = {false};
     int dev = 0;

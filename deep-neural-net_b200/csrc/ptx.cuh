@@ -216,6 +216,129 @@ __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of a cluster on the SMs of one TPC execute one UMMA of M = 256: each holds its own 128 rows
+// of A and HALF of the B tile in shared memory and its own 128 accumulator rows in TMEM; the leader
+// (cluster rank 0) issues the instruction for both.  Barriers that the leader waits on live in the
+// leader's shared memory and are reached from the peer through the shared::cluster window.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(rank)
+        : "memory");
+}
+// TMA load issued by either CTA of a pair into ITS OWN shared memory; the transaction bytes are
+// counted on the LEADER's barrier (peer bit of the shared::cluster address cleared, as CUTLASS'
+// SM100_TMA_2SM_LOAD does).
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result) {  // the same warp of BOTH CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(smem_result)), "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_i8_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                           uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrive on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far are done.
+__device__ __forceinline__ void mma_commit_2sm(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+        : "memory");
+}
+
+// Compile-time selection between the single-CTA and the pair form, so that a kernel templated on the
+// form keeps ONE statement per operation.
+template <bool kPair>
+__device__ __forceinline__ void mma_f16_t(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if constexpr (kPair) mma_f16_2sm(d, a, b, idesc, acc);
+    else mma_f16(d, a, b, idesc, acc);
+}
+template <bool kPair>
+__device__ __forceinline__ void mma_i8_t(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if constexpr (kPair) mma_i8_2sm(d, a, b, idesc, acc);
+    else mma_i8(d, a, b, idesc, acc);
+}
+template <bool kPair>
+__device__ __forceinline__ void mma_commit_t(uint64_t* bar) {
+    if constexpr (kPair) mma_commit_2sm(bar);
+    else mma_commit(bar);
+}
+template <bool kPair, uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_t(uint32_t* smem_result) {
+    if constexpr (kPair) tmem_alloc_2sm<kCols>(smem_result);
+    else tmem_alloc<kCols>(smem_result);
+}
+template <bool kPair, uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_t(uint32_t taddr) {
+    if constexpr (kPair) tmem_dealloc_2sm<kCols>(taddr);
+    else tmem_dealloc<kCols>(taddr);
+}
+// arrive on a barrier the LEADER waits on (single-CTA form: the CTA's own barrier)
+template <bool kPair>
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    if constexpr (kPair) mbar_arrive_remote(bar, 0u);
+    else mbar_arrive(bar);
+}
+template <bool kPair>
+__device__ __forceinline__ void tma_load_3d_t(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                              int c1, int c2) {
+    if constexpr (kPair) tma_load_3d_2sm(smem_dst, map, bar, c0, c1, c2);
+    else tma_load_3d(smem_dst, map, bar, c0, c1, c2);
+}
+template <bool kPair>
+__device__ __forceinline__ void cluster_sync_if() {
+    if constexpr (kPair) cluster_sync();
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (rows of 128 B, 8-row
 // groups 1024 B apart).  Bit layout: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4,
