@@ -22,6 +22,8 @@ final gather of accuracies.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -30,11 +32,11 @@ from . import kernels as K_
 from .activation import ActivationFuncs as af
 from .device import empty, pad_to, to_tensor, zeros
 from .parallel import shard_range
+from .utils import NormalizedU8
 
 
 class WeightFaultSweep:
     def __init__(self, nn, X, labels, trials_per_launch: int = 8):
-        from .utils import NormalizedU8
         assert nn.isCompiled and nn.isBinarized and nn.useBatchNorm
         self.nn = nn
         self.T = int(trials_per_launch)
@@ -223,7 +225,6 @@ class ImageFaultSweep:
     int8 (u - 128, XOR 0x80 at the flip kernel's store) instead of as an unsigned operand."""
 
     def __init__(self, nn, images_u8, labels, trials_per_launch: int = 8, batched=None):
-        from .callbacks import ImageErrorCallback  # noqa: F401 (documented entry point)
         self.nn = nn
         self.images = to_tensor(images_u8).contiguous()
         assert self.images.dtype == torch.uint8 and self.images.ndim == 2
@@ -254,7 +255,6 @@ class ImageFaultSweep:
 
     # ------------------------------------------------------------------ batched path
     def _setup_batched(self) -> None:
-        import os
         T, R = self.T, self.R
         mode = os.environ.get("BNN_U8_GEMM", "u8").lower()
         if mode not in ("u8", "s8"):
