@@ -23,6 +23,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """The shared library is a build artefact (git-ignored): build it once if a fresh checkout lacks it."""
+    lib = PKG_ROOT / "lib" / "libbnn_b200.so"
+    if not lib.exists():
+        import subprocess
+        subprocess.check_call(["make", "-C", str(PKG_ROOT / "csrc"), "-j", "8"])
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch
