@@ -110,3 +110,33 @@ def test_device_u8_threshold_source_matches_oracle_algebra(shim, oracle, bias):
     assert shim.host_u8_threshold(inf, 1.0, 10.0, 0, 255, -1.0, 1.0, 0.0) == inf
     assert shim.host_u8_threshold(-inf, 1.0, 10.0, 0, 255, -1.0, 1.0, 0.0) == -inf
     assert shim.host_u8_threshold(float("nan"), 1.0, 10.0, 0, 255, -1.0, 1.0, 0.0) == inf
+
+
+def test_device_u8_threshold_is_the_exact_decision_boundary(shim):
+    """For random (range, column sum, BN threshold, orientation, operand bias): the integer compare
+    s*g >= thr decides exactly like s*z >= tz evaluated in rational arithmetic, for every integer g around
+    the boundary — the ceiling is on the right side and the fp64 evaluation does not lose the boundary."""
+    from fractions import Fraction
+    rng = np.random.default_rng(99)
+    checked = 0
+    for _ in range(400):
+        lo = int(rng.integers(0, 200))
+        hi = int(rng.integers(lo + 1, 256))
+        K = int(rng.choice([16, 784, 3072, 4096]))
+        S = int(rng.integers(-K // 4, K // 4 + 1))
+        s = float(rng.choice([-1.0, 1.0]))
+        bias = int(rng.choice([0, 128]))
+        new_min, new_max = (-1.0, 1.0) if rng.random() < 0.7 else (0.0, 1.0)
+        tz = float(np.float32(rng.standard_normal() * 20))
+        thr = shim.host_u8_threshold(tz, s, float(S), float(lo), float(hi), new_min, new_max, float(bias))
+        if not np.isfinite(thr):
+            continue
+        r = Fraction(new_max - new_min) / (hi - lo)
+        for g in range(int(thr) - 3, int(thr) + 4):
+            for sg in (g, -g):
+                z = r * (sg + (bias - lo) * S) + Fraction(new_min) * S
+                want = Fraction(s) * z >= Fraction(tz)
+                got = s * sg >= thr
+                assert want == got, (lo, hi, K, S, s, bias, tz, thr, sg)
+                checked += 1
+    assert checked > 3000
