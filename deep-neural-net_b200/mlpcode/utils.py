@@ -144,7 +144,7 @@ def _read_idx(path: Path, labels: bool) -> np.ndarray:
         magic = struct.unpack(">I", header[:4])[0]
         if magic != (2049 if labels else 2051):
             raise ValueError(f"Magic number mismatch in {path.name}: {magic}")
-        return np.frombuffer(f.read(), dtype=np.uint8)
+        return np.frombuffer(f.read(), dtype=np.uint8).copy()   # writable: it becomes a tensor
 
 
 def _xy(X: np.ndarray, y: np.ndarray, encoded: bool, test: bool):

@@ -134,3 +134,41 @@ def test_weight_sweep_on_uint8_images_emits_wellformed_abi_calls(dry):
     # a real-valued evaluation set keeps the fp16-split layer 0
     X = np.random.default_rng(2).random((64, 784), dtype=np.float32) * 2 - 1
     assert WeightFaultSweep(nn, X, np.zeros(64, np.uint8)).u8 is None
+
+
+def test_dataset_readers_parse_idx_and_npy(dry, tmp_path, monkeypatch):
+    """mlpcode.utils.loadDataset (utils.py:191-661): IDX files for mnist / fashion-mnist, NPY for mnist-c;
+    images stay uint8, training labels one-hot int8, test labels uint8."""
+    import struct
+    from mlpcode import utils
+    rng = np.random.default_rng(0)
+    d = tmp_path / "mnist"
+    d.mkdir()
+    for prefix, n in (("train", 50), ("t10k", 20)):
+        imgs = rng.integers(0, 256, (n, 28, 28), dtype=np.uint8)
+        labs = rng.integers(0, 10, n, dtype=np.uint8)
+        (d / f"{prefix}-images-idx3-ubyte").write_bytes(struct.pack(">IIII", 2051, n, 28, 28) + imgs.tobytes())
+        (d / f"{prefix}-labels-idx1-ubyte").write_bytes(struct.pack(">II", 2049, n) + labs.tobytes())
+        if prefix == "t10k":
+            want_test = (imgs.reshape(n, 784), labs)
+    monkeypatch.setattr(utils, "DATADIR", tmp_path)
+    trainX, trainY, testX, testY = utils.loadDataset(utils.DATASETS.mnist, useGpu=True)
+    assert trainX.shape == (50, 784) and trainX.dtype == np.uint8
+    assert trainY.shape == (50, 10) and trainY.dtype == np.int8 and int(trainY.t.sum()) == 50
+    assert np.array_equal(testX.get(), want_test[0]) and np.array_equal(testY.get(), want_test[1])
+    nx = utils.normalize(testX, newMin=-1, newMax=1)
+    assert isinstance(nx, utils.NormalizedU8) and nx.mm_u32.shape == (2,)
+    (d / "t10k-labels-idx1-ubyte").write_bytes(struct.pack(">II", 1234, 20) + bytes(20))
+    with pytest.raises(ValueError, match="Magic number"):
+        utils.loadDataset(utils.DATASETS.mnist, useGpu=True)
+    with pytest.raises(FileNotFoundError):
+        utils.loadDataset(utils.DATASETS.fashion, useGpu=True)
+    c = tmp_path / "mnist-c" / "fog"
+    c.mkdir(parents=True)
+    for name, arr in (("train_images", rng.integers(0, 256, (30, 28, 28, 1), dtype=np.uint8)),
+                      ("train_labels", rng.integers(0, 10, 30)), ("test_images", rng.integers(0, 256, (10, 28, 28, 1), dtype=np.uint8)),
+                      ("test_labels", rng.integers(0, 10, 10))):
+        np.save(c / f"{name}.npy", arr)
+    tX, tY, eX, eY = utils.loadDataset(utils.DATASETS.mnistc_fog, useGpu=True, encoded=False)
+    assert tX.shape == (30, 784) and tY.shape == (30,) and eX.shape == (10, 784) and eY.dtype == np.uint8
+    assert str(utils.DATASETS.mnistc_fog) == "mnist_c-fog" and len(list(utils.DATASETS)) == 34
