@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256)
 bn_sign_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const float* __restrict__ thr,
                const float* __restrict__ sgn, int8_t* __restrict__ act_i8, long long ld_i8,
                __half* __restrict__ act_t16, long long ld_t16, uint32_t* __restrict__ act_bits,
-               long long ld_bits, int8_t* __restrict__ act_t8, int8_t* __restrict__ act_t8x64,
+               long long ld_bits, int8_t* __restrict__ act_t8, int8_t* __restrict__ act_t8x127,
                long long ld_t8) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cb = lane & 3, rb = lane >> 2;
@@ -539,22 +539,22 @@ bn_sign_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const fl
         for (int i = 0; i < 8; ++i) m |= (unsigned long long)(sb[i] & 0xFFu) << (8 * i);
         m = transpose_8x8_bits(m);  // byte j: column j, bit i: row i
         if (act_t8) {
-            // transposed int8 copies, +-1 and +-64: the A pieces of the digit-split int8 dW product
-            const bool t8vec = ((reinterpret_cast<uintptr_t>(act_t8) | reinterpret_cast<uintptr_t>(act_t8x64)) & 7u) == 0 &&
+            // transposed int8 copies, +-1 and +-127: the A pieces of the digit-split int8 dW product
+            const bool t8vec = ((reinterpret_cast<uintptr_t>(act_t8) | reinterpret_cast<uintptr_t>(act_t8x127)) & 7u) == 0 &&
                                (ld_t8 % 8 == 0) && rvalid == 8;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 if (j >= valid) break;
                 const uint32_t cbits = (uint32_t)(m >> (8 * j)) & 0xFFu;
                 int8_t* p1 = act_t8 + (long long)(c0 + j) * ld_t8 + r0;
-                int8_t* p64 = act_t8x64 + (long long)(c0 + j) * ld_t8 + r0;
+                int8_t* p127 = act_t8x127 + (long long)(c0 + j) * ld_t8 + r0;
                 if (t8vec) {
                     *reinterpret_cast<uint2*>(p1) = make_uint2(nibble_to_pm1_bytes(cbits), nibble_to_pm1_bytes(cbits >> 4));
-                    *reinterpret_cast<uint2*>(p64) = make_uint2(nibble_to_pm64_bytes(cbits), nibble_to_pm64_bytes(cbits >> 4));
+                    *reinterpret_cast<uint2*>(p127) = make_uint2(nibble_to_pm127_bytes(cbits), nibble_to_pm127_bytes(cbits >> 4));
                 } else {
                     for (int i = 0; i < rvalid; ++i) {
                         p1[i] = ((cbits >> i) & 1u) ? (int8_t)1 : (int8_t)-1;
-                        p64[i] = ((cbits >> i) & 1u) ? (int8_t)64 : (int8_t)-64;
+                        p127[i] = ((cbits >> i) & 1u) ? (int8_t)kDwMidRadix : (int8_t)-kDwMidRadix;
                     }
                 }
             }
@@ -747,18 +747,16 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ red,
         bound = fabsf((float)c0) * amax_d + fabsf((float)c1) * amax_x + fabsf((float)c2);
         bound *= 1.0009765625f;  // absorb fp32 rounding of the bound itself
         if (col_quant) {
-            // fixed-point scale of this column for the int8 dW product: |delta' * 2^e| <= 2^20, so the
-            // rounded value splits into the digits q1 + 256 * (q2 + 64 * q3) (8 + 6 + 8 signed bits)
+            // fixed-point scale of this column for the int8 dW product: |delta' * s| <= kDwQuantMax, so the
+            // rounded value splits into the digits q1 + 256 * (q2 + 127 * q3) (common.cuh).  The scale uses
+            // the whole range (not a power of two): 1 / s is rounded once, a relative 6e-8 per column.
             float q = 1.0f;
             if (bound > 0.f && isfinite(bound)) {
-                int e;
-                const float m = frexpf(bound, &e);            // bound = m * 2^e, m in [0.5, 1)
-                int sh = 20 - ((m == 0.5f) ? e - 1 : e);       // 20 - ceil(log2(bound))
-                sh = sh > 100 ? 100 : (sh < -100 ? -100 : sh);
-                q = ldexpf(1.0f, sh);
+                q = __fdiv_rn(kDwQuantMax, bound);
+                if (!(q < 1e30f)) q = 1e30f;                   // denormal-sized gradients
             }
             col_quant[n] = q;
-            col_quant[N + n] = 1.0f / q;  // exact: powers of two
+            col_quant[N + n] = __fdiv_rn(1.0f, q);
         }
     }
     bound = warp_max(bound);
@@ -919,7 +917,7 @@ bn_bwd_apply_kernel(const float* __restrict__ delta, long long ldd, const void* 
 // BN backward, pass 2, fixed-point form: delta' = c0*delta + c1*Z + c2' as
 //   * fp16 hi/lo pieces, row-major (the dX GEMM's A operand), and
 //   * three signed-digit int8 matrices, TRANSPOSED [N, B] (the int8 dW GEMM's B pieces):
-//       q = rn(delta' * 2^e_n) = q1 + 256 * (q2 + 64 * q3),  q1, q3 in [-128, 127], q2 in [-32, 31].
+//       q = rn(delta' * s_n) = q1 + 256 * (q2 + 127 * q3),  q1, q3 in [-128, 127], q2 in [-63, 63].
 // Register-only: a thread owns 8 rows x 4 columns, lanes are laid out 8 (column blocks) x 4 (row
 // blocks), so delta loads cover 128 contiguous bytes per row, Z loads and row-major stores 64, and
 // the transposed 8-byte digit stores 32 per column — all sector-exact, no shared memory.
@@ -1013,11 +1011,13 @@ bn_bwd_apply_q_kernel(const float* __restrict__ delta, long long ldd, const void
         for (int j = 0; j < 4; ++j) {
             const float nd = fmaf(k0[j], dl[j], fmaf(k1[j], z[j], k2[j]));
             split_f16(nd * s, h[j], l[j]);
-            const int q = __float2int_rn(nd * qs[j]);       // |q| <= 2^20 (+ rounding)
+            const int q = __float2int_rn(nd * qs[j]);       // |q| <= kDwQuantMax (+ rounding)
             const int d1 = ((q + 128) & 255) - 128;          // balanced low byte
-            const int r8 = (q - d1) >> 8;                    // exact
-            const int d2 = ((r8 + 32) & 63) - 32;            // balanced 6-bit digit
-            const int d3 = (r8 - d2) >> 6;                   // |d3| <= 65
+            const int r8 = (q - d1) >> 8;                    // exact, |r8| <= 16017
+            // balanced radix-127 split: r8 = d2 + 127 * d3 with |d2| <= 63 (r8 / 127 is never within
+            // 0.003 of a half-integer, so the fp32 rounding below picks the exact nearest multiple)
+            const int d3 = __float2int_rn((float)r8 * (1.0f / kDwMidRadix));   // |d3| <= 127
+            const int d2 = r8 - kDwMidRadix * d3;
             w1[j][i >> 2] |= (uint32_t)(d1 & 0xFF) << (8 * (i & 3));
             w2[j][i >> 2] |= (uint32_t)(d2 & 0xFF) << (8 * (i & 3));
             w3[j][i >> 2] |= (uint32_t)(d3 & 0xFF) << (8 * (i & 3));
@@ -1174,9 +1174,9 @@ extern "C" int bnn_bn_sign_thresholds(const float* mu, const float* var, const f
 extern "C" int bnn_bn_sign(const void* Z, int z_dtype, int B, int N, int64_t ldz, const float* thr,
                            const float* sgn, int8_t* act_i8, int64_t ld_i8, void* act_t16,
                            int64_t ld_t16, uint32_t* act_bits, int64_t ld_bits, int8_t* act_t8,
-                           int8_t* act_t8x64, int64_t ld_t8, bnn_stream_t stream) {
-    BNN_CHECK_ARG((act_t8 == nullptr) == (act_t8x64 == nullptr) && (!act_t8 || ld_t8 >= B),
-                  "bnn_bn_sign: act_t8 / act_t8x64 come as a pair with ld_t8 >= B");
+                           int8_t* act_t8x127, int64_t ld_t8, bnn_stream_t stream) {
+    BNN_CHECK_ARG((act_t8 == nullptr) == (act_t8x127 == nullptr) && (!act_t8 || ld_t8 >= B),
+                  "bnn_bn_sign: act_t8 / act_t8x127 come as a pair with ld_t8 >= B");
     BNN_CHECK_ARG(Z && thr && sgn && B > 0 && N > 0 && ldz >= N, "bnn_bn_sign: bad input");
     BNN_CHECK_ARG(!act_i8 || ld_i8 >= N, "bnn_bn_sign: ld_i8 < N");
     BNN_CHECK_ARG(!act_t16 || ld_t16 >= B, "bnn_bn_sign: ld_t16 < B");
@@ -1187,7 +1187,7 @@ extern "C" int bnn_bn_sign(const void* Z, int z_dtype, int B, int N, int64_t ldz
     return dispatch_z(z_dtype, [&](auto zt) {
         bn_sign_kernel<decltype(zt)::value><<<grid, 256, 0, s>>>(
             Z, B, N, ldz, thr, sgn, act_i8, ld_i8, static_cast<__half*>(act_t16), ld_t16, act_bits,
-            ld_bits, act_t8, act_t8x64, ld_t8);
+            ld_bits, act_t8, act_t8x127, ld_t8);
         BNN_LAUNCH_CHECK("bn_sign_kernel");
         return (int)BNN_OK;
     });

@@ -82,11 +82,19 @@ __device__ __forceinline__ uint32_t nibble_to_pm1_bytes(uint32_t nib) {
     const uint32_t spread = ((nib & 0xFu) * 0x00204081u) & 0x01010101u;
     return 0xFFFFFFFFu ^ (spread * 0xFEu);
 }
-// 4 mask bits -> 4 bytes of +-64 (bit ? 0x40 : 0xC0)
-__device__ __forceinline__ uint32_t nibble_to_pm64_bytes(uint32_t nib) {
+// 4 mask bits -> 4 bytes of +-127 (bit ? 0x7F : 0x81)
+__device__ __forceinline__ uint32_t nibble_to_pm127_bytes(uint32_t nib) {
     const uint32_t spread = ((nib & 0xFu) * 0x00204081u) & 0x01010101u;
-    return 0xC0C0C0C0u ^ (spread * 0x80u);
+    return 0x81818181u ^ (spread * 0xFEu);
 }
+
+// Fixed-point form of delta' for the int8 dW product (bn.cu, gemm_tc.cu hi_from_pass):
+//   q = rn(delta' * s_n) = q1 + 256 * (q2 + 127 * q3),  q1, q3 in [-128, 127], q2 in [-63, 63]
+// (the middle radix is 127 because the A piece that carries it, 127 * X with X = +-1, must fit int8).
+// Representable: |q| <= 256 * (63 + 127 * 127) - 128 = 4 145 024; s_n = kDwQuantMax / bound_n keeps
+// |q| <= kDwQuantMax (+ rounding) for |delta'| <= bound_n: 22.97 bits of the column's bound.
+constexpr float kDwQuantMax = 4100000.0f;
+constexpr int kDwMidRadix = 127;
 // 2 mask bits -> 2 halves of +-1.0 (bit ? 0x3C00 : 0xBC00)
 __device__ __forceinline__ uint32_t pair_to_pm1_halves(uint32_t two) {
     return 0x3C003C00u | ((~two & 1u) << 15) | ((~two & 2u) << 30);

@@ -54,11 +54,13 @@ constexpr int kAccStages = 2;
 constexpr int kXposeRows = 16;    // half a warp's rows per phase
 constexpr int kXposeStride = 36;  // floats per staged row (32 + 4: conflict-free 128-bit access)
 
-template <int BLOCK_N>
+// kCta2: the CTA-pair form keeps only HALF of the B tile in each CTA, so a stage is 32 KB instead of 48 KB and
+// six of them fit where the single-CTA form holds four.
+template <int BLOCK_N, bool kCta2 = false>
 struct TileCfg {
-    static constexpr int kStages = (BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 6 : 8);
+    static constexpr int kStages = kCta2 ? 6 : ((BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 6 : 8));
     static constexpr int kABytes = kBlockM * kKBytes;
-    static constexpr int kBBytes = BLOCK_N * kKBytes;
+    static constexpr int kBBytes = (kCta2 ? BLOCK_N / 2 : BLOCK_N) * kKBytes;   // per CTA
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = (kAccStages * BLOCK_N) < 32 ? 32 : (kAccStages * BLOCK_N);
     static constexpr int kBarBytes = (2 * kStages + 2 * kAccStages) * 8 + 16;
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                const __grid_constant__ CUtensorMap mapB2, const TcParams p) {
-    using Cfg = TileCfg<BLOCK_N>;
+    using Cfg = TileCfg<BLOCK_N, kCta2>;
     constexpr int S = Cfg::kStages;
     constexpr int kKElems = kI8 ? kKBytes : kKBytes / 2;
 
@@ -504,8 +506,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         // 128 rows of A and its half of the B tile, the peer then arrives on that barrier
                         if (!kCta2 || cta_rank == 0)
                             ptx::mbar_arrive_expect_tx(&full_bar[s],
-                                                       kCta2 ? 2u * (Cfg::kABytes + Cfg::kBBytes / 2)
-                                                             : Cfg::kStageBytes);
+                                                       kCta2 ? 2u * Cfg::kStageBytes : Cfg::kStageBytes);
                         ptx::tma_load_3d_t<kCta2>(sa, ma, &full_bar[s], kb * kKElems, m_blk * kBlockM, ba);
                         ptx::tma_load_3d_t<kCta2>(sb, mb, &full_bar[s], kb * kKElems,
                                                   kCta2 ? n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2)
@@ -740,7 +741,7 @@ bool pair_form_requested() {
 template <bool kI8, int EPI, int STATS>
 int launch_tc_pair(const bnn_gemm_desc& g, cudaStream_t stream) {
     constexpr int BLOCK_N = 256;
-    using Cfg = TileCfg<BLOCK_N>;
+    using Cfg = TileCfg<BLOCK_N, true>;
     auto kernel = gemm_tc_kernel<kI8, BLOCK_N, EPI, STATS, true>;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -817,10 +818,8 @@ int launch_tc_pair(const bnn_gemm_desc& g, cudaStream_t stream) {
         return BNN_ERR_UNSUPPORTED;
     }
     const long long pairs = (long long)p.batch * p.m_tiles * p.n_tiles;
-    const long long max_clusters = sm_count() / 2;
-    const unsigned grid = 2u * (unsigned)(pairs < max_clusters ? pairs : max_clusters);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.gridDim = dim3((unsigned)sm_count() & ~1u, 1, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
@@ -831,6 +830,23 @@ int launch_tc_pair(const bnn_gemm_desc& g, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // The tile walk is static (cluster c takes tiles c, c + clusters, ...): a cluster that cannot be
+    // co-resident would start only after another has finished ALL its tiles and double the run time
+    // (measured: 74 clusters requested on 148 SMs ran 1.9x slower than the single-CTA form).  So the grid is
+    // what the device can hold at once — GPCs do not all expose an even number of usable SMs to clusters.
+    static int max_clusters_dev[64] = {0};
+    int max_clusters = (dev >= 0 && dev < 64) ? max_clusters_dev[dev] : 0;
+    if (max_clusters <= 0) {
+        BNN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
+        if (max_clusters <= 0) {
+            set_error("bnn_gemm: the device cannot hold a single CTA pair of this kernel");
+            return BNN_ERR_UNSUPPORTED;
+        }
+        if (dev >= 0 && dev < 64) max_clusters_dev[dev] = max_clusters;
+    }
+    if (getenv("BNN_GEMM_CTA2_DEBUG")) fprintf(stderr, "bnn_gemm pair: %d co-resident clusters\n", max_clusters);
+    const unsigned grid = 2u * (unsigned)(pairs < max_clusters ? pairs : max_clusters);
+    cfg.gridDim = dim3(grid, 1, 1);
     BNN_CUDA(cudaLaunchKernelEx(&cfg, kernel, mA[0], mA[1], mB[0], mB[1], mB[2], p));
     BNN_LAUNCH_CHECK("gemm_tc_kernel<pair>");
     return BNN_OK;

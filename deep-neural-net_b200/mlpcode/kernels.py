@@ -137,10 +137,13 @@ def full_tiles(N: int, impl=None) -> bool:
     return N % tile == 0
 
 
-def int8_dw_ok(N: int) -> bool:
+def int8_dw_ok(N: int, B: int = 0) -> bool:
     """dW = X^T . delta' as an exact fixed-point product on the int8 tensor pipe (X = +-1 activations,
-    delta' in three signed digits) instead of two fp16 passes.  BNN_DW_INT8=0 keeps the fp16 form."""
-    return N >= 64 and full_tiles(N) and os.environ.get("BNN_DW_INT8", "1") != "0"
+    delta' in three signed digits) instead of two fp16 passes.  B: rows contracted over — the HIGH int32
+    accumulator holds sums of B terms of magnitude <= 16319, so B <= 131072.  BNN_DW_INT8=0 keeps the
+    fp16 form."""
+    return (N >= 64 and B <= 131072 and full_tiles(N)
+            and os.environ.get("BNN_DW_INT8", "1") != "0")
 
 
 def zero(t: torch.Tensor) -> None:
@@ -242,12 +245,12 @@ def bn_sign_thresholds(mu, var, gamma, beta, eps, N, thr, sgn) -> None:
 
 
 def bn_sign(Z, B, N, thr, sgn, act_i8=None, act_t16=None, act_bits=None, act_t8=None,
-            act_t8x64=None) -> None:
+            act_t8x127=None) -> None:
     _call("bnn_bn_sign", ptr(Z), z_dtype_of(Z), B, N, _ld(Z), ptr(thr), ptr(sgn),
           ptr(act_i8), _ld(act_i8) if act_i8 is not None else 0,
           ptr(act_t16), _ld(act_t16) if act_t16 is not None else 0,
           ptr(act_bits), _ld(act_bits) if act_bits is not None else 0,
-          ptr(act_t8), ptr(act_t8x64), _ld(act_t8) if act_t8 is not None else 0)
+          ptr(act_t8), ptr(act_t8x127), _ld(act_t8) if act_t8 is not None else 0)
 
 
 def softmax_xent(logits, B, Cc, onehot=None, probs=None, loss_rows=None, grad=None, count=None,

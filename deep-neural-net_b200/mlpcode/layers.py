@@ -48,9 +48,9 @@ def binary_gemm_variant() -> str:
 class SignActivation(DeviceArray):
     """Output of a sign-activated layer: values in {+1,-1} kept in GEMM-operand form."""
 
-    def __init__(self, i8, n, t16=None, bits=None, t8=None, t8x64=None):
+    def __init__(self, i8, n, t16=None, bits=None, t8=None, t8x127=None):
         self.i8, self.n, self.t16, self.bits = i8, n, t16, bits
-        self.t8, self.t8x64 = t8, t8x64   # transposed int8 +-1 / +-64 (int8 dW operand pieces)
+        self.t8, self.t8x127 = t8, t8x127   # transposed int8 +-1 / +-127 (int8 dW operand pieces)
         self._dense = None
 
     @property
@@ -361,6 +361,9 @@ class LinearLayer(Layer):
         self.callbacks = []
         self.comm = _NoComm()
         self.skip_input_grad = False  # set on the first layer: its dX is discarded (network.py:389-390)
+        # diagnostics: a [K, N] fp32 device tensor placed here receives dW (layers.py:260) of the next
+        # backwards() call, formed from the very operands and passes of the update GEMM
+        self.capture_dw = None
         self._ws = _Workspace()
         if batchNorm:
             self.batchNormLayer = BatchNormLayer(layerUnits, gpu=gpu)
@@ -664,12 +667,12 @@ class BinaryLayer(LinearLayer):
 
         # ---- BN + activation
         if sign_out:
-            act_t16 = act_t8 = act_t8x64 = None
+            act_t16 = act_t8 = act_t8x127 = None
             consumer = getattr(self, "output_layer", None)
-            if isTrain and consumer is not None and K_.int8_dw_ok(consumer.layerUnits):
-                # the layer above forms its dW on the int8 tensor pipe: transposed +-1 / +-64 bytes
+            if isTrain and consumer is not None and K_.int8_dw_ok(consumer.layerUnits, B):
+                # the layer above forms its dW on the int8 tensor pipe: transposed +-1 / +-127 bytes
                 act_t8 = ws.get(f"a_t8_{B}", (N, pad_to(B, 16)), torch.int8, zero=True)
-                act_t8x64 = ws.get(f"a_t8x64_{B}", (N, pad_to(B, 16)), torch.int8, zero=True)
+                act_t8x127 = ws.get(f"a_t8x127_{B}", (N, pad_to(B, 16)), torch.int8, zero=True)
             elif isTrain:
                 act_t16 = ws.get(f"a_t16_{B}", (N, pad_to(B, 8)), torch.float16, zero=True)
             act_bits = ws.get(f"a_bits{B}", (B, pad_to(N, 32) // 32), torch.int32, zero=True) if popc else None
@@ -678,10 +681,10 @@ class BinaryLayer(LinearLayer):
                 # to evaluating gamma*((z-mu)/sqrt(var+eps))+beta and taking the sign
                 K_.bn_sign_thresholds(mu, var, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
                 K_.bn_sign(Z, B, N, thr, sgn, act_i8=act_i8, act_t16=act_t16, act_bits=act_bits,
-                           act_t8=act_t8, act_t8x64=act_t8x64)
+                           act_t8=act_t8, act_t8x127=act_t8x127)
             elif act_bits is not None:
                 K_.pack_i8_rows(act_i8, N, act_bits)
-            out = SignActivation(act_i8, N, t16=act_t16, bits=act_bits, t8=act_t8, t8x64=act_t8x64)
+            out = SignActivation(act_i8, N, t16=act_t16, bits=act_bits, t8=act_t8, t8x127=act_t8x127)
         else:
             logits = empty((B, N))
             K_.bn_apply(Z, B, N, mu, var, bn.gamma.t, bn.beta.t, bn.EPSILON, out_f32=logits)
@@ -722,7 +725,7 @@ class BinaryLayer(LinearLayer):
         # dW on the int8 tensor pipe (exact fixed-point sums, 2x the fp16 rate) when the input is a
         # +-1 activation whose producer emitted the transposed int8 pieces; else two fp16 passes
         use_q = ((not c["real_input"]) and getattr(xin, "t8", None) is not None
-                 and (xin.t16 is None or K_.int8_dw_ok(N)))  # follow what the producer emitted
+                 and (xin.t16 is None or K_.int8_dw_ok(N, B)))  # follow what the producer emitted
         digits = dt_hi = dt_lo = colq = None
         if use_q:
             Bq = pad_to(B, 16)
@@ -759,8 +762,8 @@ class BinaryLayer(LinearLayer):
 
         # ---- dW = X^T . delta'  (layers.py:260) and W -= lr * dW (:268)
         if use_q:
-            # dW = 2^-e_n * (X^T.q1 + 256 * ((64 X)^T.q3 + X^T.q2)): low / high int32 accumulators
-            dw = dict(in_dtype=nat.DT_I8, A=(xin.t8, xin.t8x64), B=digits, lda=xin.t8.stride(0),
+            # dW = 1/s_n * (X^T.q1 + 256 * ((127 X)^T.q3 + X^T.q2)): low / high int32 accumulators
+            dw = dict(in_dtype=nat.DT_I8, A=(xin.t8, xin.t8x127), B=digits, lda=xin.t8.stride(0),
                       ldb=digits[0].stride(0), passes=((0, 0), (1, 1), (0, 2)), hi_from_pass=1,
                       col_scale=colq[1], sa=None, sb=None)
         elif c["real_input"]:
@@ -771,6 +774,10 @@ class BinaryLayer(LinearLayer):
             dw = dict(in_dtype=nat.DT_F16, A=(xin.t16,), B=(dt_hi, dt_lo), lda=xin.t16.stride(0), ldb=Bp,
                       passes=((0, 0), (0, 1)), sa=None, sb=d_scale)
         Wt = self._weights.t
+        if self.capture_dw is not None:
+            cap = self.capture_dw
+            assert tuple(cap.shape) == (Kd, N) and cap.dtype == torch.float32 and cap.is_contiguous()
+            K_.gemm(M=Kd, N=N, K=B, D=cap, ldd=N, epilogue=nat.EPI_STORE_F32, **dw)
         split = 4 if (N <= 32 and Kd >= 1024 and B % 256 == 0 and self.comm.world == 1) else 1
         # single GPU: the dW GEMM goes to the side stream (see DwOverlap) unless it is the last kernel
         # of the step (first layer), where there is nothing left to overlap it with

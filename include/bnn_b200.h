@@ -182,8 +182,8 @@ typedef struct bnn_gemm_desc {
      * cut into signed digits, layers.py:260).  B2 is a third B piece (pb[p] == 2).  With
      * hi_from_pass = k > 0 (int8 operands only) the passes [0, k) accumulate a LOW int32 accumulator
      * and the passes [k, n_pass) a HIGH one; the epilogue value is low + 256 * high, formed in fp32.
-     * col_scale: optional device [N] per-column factor (a power of two: the fixed-point scale of that
-     * column) multiplied in before host_scale.  tcgen05 path, fp32 epilogues, N a multiple of the tile
+     * col_scale: optional device [N] per-column factor (1 / the fixed-point scale of that column)
+     * multiplied in before host_scale.  tcgen05 path, fp32 epilogues, N a multiple of the tile
      * width (see BNN_STATS_*), batch == 1; otherwise BNN_ERR_UNSUPPORTED. */
     const void* B2;
     int32_t hi_from_pass;
@@ -244,11 +244,11 @@ int bnn_bn_sign_thresholds(const float* mu, const float* var, const float* gamma
                            float eps, int N, float* thr, float* sgn, bnn_stream_t stream);
 
 /* The sign-only form of bnn_bn_apply on those thresholds (same outputs, no out_f32), plus optionally
- * the transposed int8 copies act_t8 [N, ld_t8] = +-1 and act_t8x64 = +-64: the A pieces of the
+ * the transposed int8 copies act_t8 [N, ld_t8] = +-1 and act_t8x127 = +-127: the A pieces of the
  * digit-split int8 dW product (bnn_gemm hi_from_pass). */
 int bnn_bn_sign(const void* Z, int z_dtype, int B, int N, int64_t ldz, const float* thr,
                 const float* sgn, int8_t* act_i8, int64_t ld_i8, void* act_t16, int64_t ld_t16,
-                uint32_t* act_bits, int64_t ld_bits, int8_t* act_t8, int8_t* act_t8x64, int64_t ld_t8,
+                uint32_t* act_bits, int64_t ld_bits, int8_t* act_t8, int8_t* act_t8x127, int64_t ld_t8,
                 bnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -300,11 +300,14 @@ int bnn_bn_bwd_apply(const float* delta, int64_t ldd, const void* Z, int z_dtype
                      bnn_stream_t stream);
 
 /* Fixed-point form of the same pass for the int8 dW product.  col_quant: device [2, N] written by
- * bnn_bn_bwd_finalize (row 0: 2^e_n with |delta'_n * 2^e_n| <= 2^20, row 1: 2^-e_n = the GEMM's
- * col_scale).  Outputs: d_hi / d_lo [B, ld_rm] as above (may be NULL), and the TRANSPOSED signed digits
- * of q = rn(delta' * 2^e_n) = q1 + 256 * (q2 + 64 * q3):  q1t, q3t, q2t int8 [N, ld_q] with
- * q1, q3 in [-128, 127] and q2 in [-32, 31] — the three B pieces of
- *   dW = 2^-e_n * ( X^T.q1 + 256 * ( (64 X)^T.q3 + X^T.q2 ) )          (exact integer sums). */
+ * bnn_bn_bwd_finalize (row 0: s_n = 4.1e6 / bound_n, so that |delta'_n * s_n| <= 4.1e6 — 22.97 bits of
+ * the column's bound; row 1: 1 / s_n = the GEMM's col_scale).  Outputs: d_hi / d_lo [B, ld_rm] as above
+ * (may be NULL), and the TRANSPOSED signed digits of
+ *   q = rn(delta' * s_n) = q1 + 256 * (q2 + 127 * q3):  q1t, q3t, q2t int8 [N, ld_q] with
+ * q1, q3 in [-128, 127] and q2 in [-63, 63] — the three B pieces of
+ *   dW = (1 / s_n) * ( X^T.q1 + 256 * ( (127 X)^T.q3 + X^T.q2 ) )       (exact integer sums;
+ * |high sum| <= B * 16319 < 2^31 for B <= 131 072 rows).  Norm-wise error of a dW column:
+ * 7e-8 * bound_n / rms(delta'_n)  (uniform rounding of q, summed in quadrature over the batch). */
 int bnn_bn_bwd_apply_q(const float* delta, int64_t ldd, const void* Z, int z_dtype, int64_t ldz,
                        int B, int N, const float* coef, const float* bound, const float* col_quant,
                        void* d_hi, void* d_lo, int64_t ld_rm, int8_t* q1t, int8_t* q3t, int8_t* q2t,
