@@ -34,7 +34,7 @@ UNITS = [784, 4096, 4096, 4096, 10]
 BATCH = 8192
 LR = 0.01
 METRIC, UNIT = "BNN MLP train samples/s", "samples/s"
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 436.4e6  # profiles/r01_gemm_full_raw.csv (see profiles/r01_summary.md section 2)
+ROOFLINE_PROFILE = REPO / "profiles" / "r02_roofline_kernel.json"  # written by tools/ncu_table.py --roofline
 
 
 def workload_config(n_gpus):
@@ -194,11 +194,23 @@ class ClockSampler:
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def measured_peaks():
+    """(HBM GB/s, bf16 TFLOP/s burst, bf16 TFLOP/s sustained, source) from the driver-written file."""
     p = REPO / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
-    return 6650.0, 1590.0, "fallback"
+        burst = d.get("bf16_tflops", 1590.0)
+        return d.get("hbm_gbs", 6650.0), burst, d.get("bf16_tflops_sustained", burst), "MEASURED_PEAKS.json"
+    return 6650.0, 1590.0, 1590.0, "B200_PROFILING.md fallback"
+
+
+def profiled_traffic():
+    """dram__bytes_read + dram__bytes_write per launch of the roofline kernel, from the committed ncu --set full
+    capture of this round (never measured in this run: ncu cannot run inside a benchmark)."""
+    try:
+        d = json.loads(ROOFLINE_PROFILE.read_text())
+        return d["dram_bytes_per_launch"], f"profiles/{ROOFLINE_PROFILE.name}: {d['source']}"
+    except Exception:
+        return None, "no committed ncu capture of this kernel"
 
 
 def measure_int8_peak(torch):
@@ -321,14 +333,31 @@ def run_gpu(args):
     exchanges_per_step = None
     if comm:
         nn.enable_step_graph(False)
-        c0 = comm.collectives
+        c0, n0 = comm.collectives, comm.nccl_calls
         nn.train_step_async(Xd, Yd, LR)
         fence()
         exchanges_per_step = {"count": comm.collectives - c0,
-                              "nccl_calls": 0 if (comm.peer_exchange is not None and
-                                                  comm.dw_exchange is not None) else None,
+                              "nccl_calls": comm.nccl_calls - n0,
+                              "nccl_calls_how": "counted: every torch.distributed collective of the step goes "
+                                                "through mlpcode.parallel.Comm, which counts the ones it hands to NCCL",
                               "transport": "NVLink peer memory (own kernels + copy engines)"
                               if comm.dw_exchange is not None else "NCCL"}
+    # ---- the other BASELINE workloads (configs 0, 3, 4 and the image sweep), outside the headline's timed
+    # region, every rank taking its share of the trials / rows; rank 0 adds the CPU legs at N = 1
+    del Xd, Yd, nn
+    torch.cuda.empty_cache()
+    int8_peak = measure_int8_peak(torch) if rank == 0 else None
+    extras = {}
+    if not args.no_extras:
+        sys.path.insert(0, str(REPO / "tools"))
+        import bench_sweep as BS
+        cpu = world == 1 and not args.no_cpu
+        if rank == 0:
+            extras["config1"] = BS.config1_section(steps=50, cpu_steps=20 if cpu else 0)
+        extras["weight_sweep"] = BS.weight_sweep_section(comm, n_trials=args.sweep_trials, cpu_trials=1 if cpu else 0,
+                                                         int8_peak_tops=int8_peak)
+        extras["image_sweep"] = BS.image_sweep_section(comm, n_trials=args.image_trials, cpu_trials=1 if cpu else 0)
+        extras["inference"] = BS.inference_section(comm, cpu_rows=2048 if cpu else 0, int8_peak_tops=int8_peak)
     if rank != 0:
         return 0
 
@@ -341,7 +370,14 @@ def run_gpu(args):
         g["n"] += 1
         g["flops"] += flops
         g["exec"] += flops * passes
-    hbm_peak, tensor_peak, peak_kind = measured_peaks()
+    hbm_peak, peak_burst, peak_sustained, peak_kind = measured_peaks()
+    # which regime did the timed region run in?  The sustained figure belongs to a kernel timed inside a long,
+    # power-limited run; a region of a few tens of milliseconds at full SM clocks is the burst regime.
+    region_s = ms_total * 1e-3
+    sm_frac = (clocks["sm_mhz"] / clocks["sm_max_mhz"]) if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") else None
+    sustained = region_s >= 2.0 or (sm_frac is not None and sm_frac < 0.9)
+    tensor_peak = peak_sustained if sustained else peak_burst
+    traffic, traffic_source = profiled_traffic()
     split = groups.get("f16", {"ms": 0.0, "n": 0, "flops": 0.0, "exec": 0.0})
     i8 = groups.get("i8", {"ms": 0.0, "n": 0, "flops": 0.0, "exec": 0.0})
     i8dw = groups.get("i8dw", {"ms": 0.0, "n": 0, "flops": 0.0, "exec": 0.0})
@@ -352,14 +388,14 @@ def run_gpu(args):
             "kernel": "gemm_tc_kernel<f16 split> (dX of every layer, layer-0 forward and dW, 10-wide dW)",
             "bound": "tensor",
             "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
-            "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
-            "traffic_source": "profiles/r01_summary.md section 2: dram__bytes_read+write, average over the "
-                              "6 fp16-split launches/step (3 dX, layer-0 forward and dW, 10-wide dW) in one "
-                              "ncu --set full capture (algorithmic: 402e6 for a 4096-wide dX incl. the "
-                              "Z read of the fused BN reductions)",
-            "peak_source": f"bf16_tflops_sustained of {peak_kind}",
+            "traffic": traffic, "traffic_source": traffic_source,
+            "peak_source": f"bf16_tflops{'_sustained' if sustained else ' (burst)'} of {peak_kind}: timed region "
+                           f"{region_s * 1e3:.0f} ms at {sm_frac if sm_frac is None else round(sm_frac, 3)} of the "
+                           "maximum SM clock (nvidia-smi median under load)",
+            "frac_vs_burst": ach / peak_burst, "frac_vs_sustained": ach / peak_sustained,
             "executed_tflops": split["exec"] / (split["ms"] * 1e-3) / 1e12,
             "executed_frac": split["exec"] / (split["ms"] * 1e-3) / 1e12 / tensor_peak,
+            "executed_frac_vs_burst": split["exec"] / (split["ms"] * 1e-3) / 1e12 / peak_burst,
             "avg_launch_ms": split["ms"] / split["n"], "launches": split["n"],
             "share_of_step": split["ms"] / ms_total,
             "timed_in": f"eager pass of the same {args.steps} steps ({ms_eager / args.steps:.3f} ms/step, "
@@ -369,7 +405,6 @@ def run_gpu(args):
             "note": "achieved counts the ALGORITHMIC 2MNK of the fp32 product; the kernel executes "
                     "2-3 fp16 passes per product (executed_*), so frac <= 1/2..1/3 by construction",
         }
-    int8_peak = measure_int8_peak(torch)
     binary = None
     if i8["n"]:
         tops = i8["flops"] / (i8["ms"] * 1e-3) / 1e12
@@ -391,7 +426,7 @@ def run_gpu(args):
                    "share_of_step": i8dw["ms"] / ms_total}
     # the CPU baseline is a rank-0, N=1 measurement (torchrun pins every rank to one OpenMP thread)
     cpu_baseline = None
-    if world == 1:
+    if world == 1 and not args.no_cpu:
         cpu_val, _, _, _, cpu_sample = cpu_train_samples_per_s(steps=3, warmup=1, budget_s=40.0)
         cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": host_threads(), "kind": "port",
                         "sample": cpu_sample}
@@ -417,6 +452,7 @@ def run_gpu(args):
         "host_enqueue_ms_per_step_eager": host_ms.get("eager"),
         "exchanges_per_step": exchanges_per_step,
     }
+    line.update(extras)
     print(json.dumps(line), flush=True)
     return 0
 
@@ -427,6 +463,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="headline workload only (skip configs 0, 3, 4)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-baseline legs")
+    ap.add_argument("--sweep-trials", type=int, default=10000, help="fault trials of the weight sweep (config 3)")
+    ap.add_argument("--image-trials", type=int, default=800, help="trials of the image bit-flip sweep")
     ap.add_argument("--profile", action="store_true",
                     help="profiling runs (ncu): skip the e2e, int8-peak and CPU-baseline legs")
     args = ap.parse_args()

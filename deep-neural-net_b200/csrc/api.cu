@@ -1,6 +1,7 @@
 // Library-level entry points of the C ABI: error text, version, device query, GEMM dispatch.
 #include "common.cuh"
 
+#include <atomic>
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
@@ -24,26 +25,26 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int sm_count() {
-    static int cached[64] = {0};
+    // per-device cache; racing first calls from several host threads store the same value (relaxed atomics)
+    static std::atomic<int> cached[64];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-    if (cached[dev] == 0) {
-        int n = 0;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
             n = 148;
-        cached[dev] = n;
+        cached[dev].store(n, std::memory_order_relaxed);
     }
-    return cached[dev];
+    return n;
 }
 
 // K steps (of 128 bytes) per fp32 accumulation chunk of the tcgen05 GEMM; see gemm_tc.cu.
 int gemm_chunk_iters() {
-    static int v = 0;
-    if (v == 0) {
+    static const int v = [] {  // read once per process (thread-safe function-local static)
         const char* e = getenv("BNN_GEMM_CHUNK");
-        int n = e ? atoi(e) : 16;
-        v = n < 1 ? 1 : (n > 4096 ? 4096 : n);
-    }
+        const int n = e ? atoi(e) : 16;
+        return n < 1 ? 1 : (n > 4096 ? 4096 : n);
+    }();
     return v;
 }
 

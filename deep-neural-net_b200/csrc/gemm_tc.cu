@@ -9,12 +9,12 @@
 //   * real-valued products: fp16 hi/lo split operands, kind::f16, fp32 accumulators; the passes of
 //     the split (hi*hi, hi*lo, lo*hi) are extra trips round the K loop into the SAME accumulator.
 //
-// CTA = 20 warps:  w0 lane0  TMA producer       (cp.async.bulk.tensor -> 128B-swizzled smem ring)
+// CTA = 12 warps:  w0 lane0  TMA producer       (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //                  w1 lane0  MMA issuer         (tcgen05.mma, tcgen05.commit -> mbarriers)
-//                  w2        TMEM allocator
-//                  w4..w19   epilogue           (tcgen05.ld -> registers -> global): warp w owns TMEM
-//                                                lane quarter w%4 and column quarter (w-4)/4 of the tile.
-// setmaxnreg moves registers from the role warp group to the four epilogue warp groups.
+//                  w2        TMEM allocator     (w3 idle)
+//                  w4..w11   epilogue           (tcgen05.ld -> registers -> global): warp w owns TMEM
+//                                                lane quarter w%4 and column HALF (w-4)/4 of the tile.
+// setmaxnreg moves registers from the role warp group (56 each) to the two epilogue warp groups (224 each).
 // Tile 128 x BLOCK_N, K step = 128 bytes (one swizzle atom row), 4 UMMAs (32 bytes of K) per step.
 //
 // Chunked accumulation.  Measured on B200: the TMEM fp32 accumulator TRUNCATES on every MMA, a bias of
@@ -31,6 +31,7 @@
 #include "ptx.cuh"
 
 #include <cuda.h>
+#include <atomic>
 #include <mutex>
 #include <stdlib.h>
 
@@ -80,6 +81,7 @@ struct TcParams {
     int pa[BNN_GEMM_MAX_PASS];
     int pb[BNN_GEMM_MAX_PASS];
     int m_tiles, n_tiles;
+    int group_m, group_n;  // tile walk (tile_coords)
     int epilogue;
     int vec_ok;  // D base/pitch allow 16-byte vector access
     int a_batched, b_batched;
@@ -110,19 +112,29 @@ struct TcParams {
     const float* st_mu;
 };
 
+// Tile walk.  The output is cut into SUPER-COLUMNS of p.group_n column tiles; inside one, groups of p.group_m row
+// tiles sweep its column tiles with the row index running fastest.  CTAs that run concurrently (consecutive tile
+// numbers) therefore share a small set of A and B tiles, and — what decides the DRAM traffic — the B tiles of a
+// super-column (group_n x BLOCK_N rows x K x pieces) stay L2-resident while all of A streams past them once:
+// DRAM reads = |A| x (number of super-columns) + |B|, instead of |A| + |B| x (row groups) when the whole of B
+// does not fit in L2 (profiles/r02_summary.md: 4096-wide dX read 0.83-0.95 GB against 0.34 GB algorithmic).
 __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& b, int& m_blk,
                                             int& n_blk) {
     const int per_batch = p.m_tiles * p.n_tiles;
     b = tile / per_batch;
     int r = tile - b * per_batch;
-    // groups of 8 M-blocks sweep all N-blocks: a wave of CTAs shares a small set of A and B tiles
-    const int group = 8 * p.n_tiles;
+    const int sc_tiles = p.m_tiles * p.group_n;       // tiles of a full super-column
+    const int sc = r / sc_tiles;
+    const int first_n = sc * p.group_n;
+    const int ncols = min(p.n_tiles - first_n, p.group_n);
+    r -= sc * sc_tiles;
+    const int group = p.group_m * ncols;
     const int g = r / group;
-    const int first_m = g * 8;
-    const int gsz = min(p.m_tiles - first_m, 8);
+    const int first_m = g * p.group_m;
+    const int gsz = min(p.m_tiles - first_m, p.group_m);
     const int rr = r - g * group;
     m_blk = first_m + rr % gsz;
-    n_blk = rr / gsz;
+    n_blk = first_n + rr / gsz;
     if (p.m_rot) {  // ranks of a data-parallel group walk the row tiles from different starting points
         m_blk += p.m_rot;
         if (m_blk >= p.m_tiles) m_blk -= p.m_tiles;
@@ -559,11 +571,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
         }
     } else {
-        // ----------------------------------------------------------------- epilogue (16 warps)
+        // ----------------------------------------------------------------- epilogue (8 warps)
         ptx::setmaxnreg_inc<224>();
         constexpr int CPT = Cfg::kColsPerThread, G = Cfg::kGroup, NG = Cfg::kGroups;
         const int q = warp & 3;          // TMEM lane quarter this warp may access
-        const int h = (warp - 4) >> 2;   // column quarter of the tile
+        const int h = (warp - 4) >> 2;   // column half of the tile
         float inv = 1.0f;
         if (p.sa) inv /= __ldg(p.sa);
         if (p.sb) inv /= __ldg(p.sb);
@@ -727,11 +739,37 @@ int make_operand_map(CUtensorMap* map, const void* base, bool i8, long long rows
     return BNN_OK;
 }
 
-// BNN_GEMM_CTA2=1 (read per call) routes 256-wide products with more than one row tile to the CTA-pair form.
-// EXPERIMENTAL in round 1: written and compiled without access to a GPU; the default path is untouched.
+// Tile-walk parameters (tile_coords): super-columns whose B tiles (all pieces the passes read) take at most
+// ~40 MB — a third of the 126 MB L2, which holds A's stream and the output beside them — balanced over the width.
+// BNN_GEMM_GN / BNN_GEMM_GM (read once) override for experiments.
+void pick_tile_walk(const bnn_gemm_desc& g, int es, int block_n, int m_tiles, int n_tiles, int& group_m,
+                    int& group_n) {
+    static const int env_gn = [] { const char* e = getenv("BNN_GEMM_GN"); return e ? atoi(e) : 0; }();
+    static const int env_gm = [] { const char* e = getenv("BNN_GEMM_GM"); return e ? atoi(e) : 0; }();
+    bool used[3] = {false, false, false};
+    for (int i = 0; i < g.n_pass && i < BNN_GEMM_MAX_PASS; ++i) used[g.pb[i] < 3 ? g.pb[i] : 0] = true;
+    const int pieces = (int)used[0] + (int)used[1] + (int)used[2];
+    const double tile_bytes = (double)block_n * (double)g.K * es * (pieces > 0 ? pieces : 1);
+    int gn = (int)(40.0e6 / tile_bytes);
+    gn = gn < 1 ? 1 : (gn > n_tiles ? n_tiles : gn);
+    const int cols = cdiv(n_tiles, gn);
+    gn = cdiv(n_tiles, cols);                       // balanced super-columns
+    if (g.batch > 1 || g.stride_b != 0) gn = n_tiles;  // batched products: every batch has its own B
+    group_n = env_gn > 0 ? (env_gn > n_tiles ? n_tiles : env_gn) : gn;
+    group_m = env_gm > 0 ? env_gm : 8;
+    if (group_m > m_tiles) group_m = m_tiles;
+    if (group_m < 1) group_m = 1;
+}
+
+// BNN_GEMM_CTA2=1 (read once per process, like BNN_GEMM_CHUNK) routes 256-wide products with more than one row
+// tile to the CTA-pair form.  Round 2, on a B200: the opt-in tests pass (tests/test_gemm_pair_gpu.py), and the
+// training step runs 1.7x SLOWER with it (profiles/r02_summary.md), so it stays opt-in.
 bool pair_form_requested() {
-    const char* e = getenv("BNN_GEMM_CTA2");
-    return e != nullptr && atoi(e) != 0;
+    static const bool on = [] {
+        const char* e = getenv("BNN_GEMM_CTA2");
+        return e != nullptr && atoi(e) != 0;
+    }();
+    return on;
 }
 
 // The CTA-pair launch (gemm_tc_kernel<..., kCta2 = true>): clusters of two CTAs, 256 x 256 tiles per pair.
@@ -743,7 +781,7 @@ int launch_tc_pair(const bnn_gemm_desc& g, cudaStream_t stream) {
     constexpr int BLOCK_N = 256;
     using Cfg = TileCfg<BLOCK_N, true>;
     auto kernel = gemm_tc_kernel<kI8, BLOCK_N, EPI, STATS, true>;
-    static bool attr_set[64] = {false};
+    static std::atomic<bool> attr_set[64];  // racing first calls set the same attribute twice: harmless
     int dev = 0;
     BNN_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -774,6 +812,7 @@ int launch_tc_pair(const bnn_gemm_desc& g, cudaStream_t stream) {
     }
     p.m_tiles = cdiv(cdiv(g.M, kBlockM), 2);  // pairs of row tiles
     p.n_tiles = cdiv(g.N, BLOCK_N);
+    pick_tile_walk(g, kI8 ? 1 : 2, BLOCK_N, p.m_tiles, p.n_tiles, p.group_m, p.group_n);
     p.epilogue = g.epilogue;
     const int esz = (g.epilogue == BNN_EPI_STORE_S16) ? 2 : (g.epilogue == BNN_EPI_SIGN_I8 ? 1 : 4);
     p.vec_ok = aligned16(g.D) && ((g.ldd * esz) % 16 == 0) && ((g.stride_d * esz) % 16 == 0);
@@ -834,8 +873,8 @@ int launch_tc_pair(const bnn_gemm_desc& g, cudaStream_t stream) {
     // co-resident would start only after another has finished ALL its tiles and double the run time
     // (measured: 74 clusters requested on 148 SMs ran 1.9x slower than the single-CTA form).  So the grid is
     // what the device can hold at once — GPCs do not all expose an even number of usable SMs to clusters.
-    static int max_clusters_dev[64] = {0};
-    int max_clusters = (dev >= 0 && dev < 64) ? max_clusters_dev[dev] : 0;
+    static std::atomic<int> max_clusters_dev[64];
+    int max_clusters = (dev >= 0 && dev < 64) ? max_clusters_dev[dev].load() : 0;
     if (max_clusters <= 0) {
         BNN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
         if (max_clusters <= 0) {
@@ -859,7 +898,7 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
         if (g.M > kBlockM && pair_form_requested()) return launch_tc_pair<kI8, EPI, STATS>(g, stream);
     }
     // the opt-in shared-memory size is a per-device attribute of the function
-    static bool attr_set[64] = {false};
+    static std::atomic<bool> attr_set[64];  // racing first calls set the same attribute twice: harmless
     int dev = 0;
     BNN_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -896,6 +935,7 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     }
     p.m_tiles = cdiv(g.M, kBlockM);
     p.n_tiles = cdiv(g.N, BLOCK_N);
+    pick_tile_walk(g, kI8 ? 1 : 2, BLOCK_N, p.m_tiles, p.n_tiles, p.group_m, p.group_n);
     p.epilogue = g.epilogue;
     const int esz = (g.epilogue == BNN_EPI_STORE_S16) ? 2 : (g.epilogue == BNN_EPI_SIGN_I8 ? 1 : 4);
     p.vec_ok = aligned16(g.D) && ((g.ldd * esz) % 16 == 0) && ((g.stride_d * esz) % 16 == 0);

@@ -194,6 +194,7 @@ class Comm:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.collectives = 0
+        self.nccl_calls = 0   # torch.distributed collectives issued through this object (bench.py reports them)
         self.global_batch = None  # rows of the current step over all ranks (None: local * world)
         self.peer_exchange = None  # PeerExchange once enable_peer_exchange() succeeded
         self.dw_exchange = None    # DwExchange once enable_dw_exchange() succeeded
@@ -267,6 +268,7 @@ class Comm:
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
             self.collectives += 1
+            self.nccl_calls += 1
         return t
 
     def allreduce_sum_async(self, t: torch.Tensor):
@@ -275,16 +277,19 @@ class Comm:
         if self.world == 1:
             return None
         self.collectives += 1
+        self.nccl_calls += 1
         return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def allgather(self, t: torch.Tensor) -> torch.Tensor:
         out = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(out, t, group=self.group)
+        self.nccl_calls += 1
         return torch.stack(out)
 
     def barrier(self):
         if self.world > 1:
             dist.barrier(group=self.group)
+            self.nccl_calls += 1
 
 
 def init_from_env(backend: str = None) -> Comm | None:

@@ -18,6 +18,7 @@
 #   prof-gemm     ncu --set full of the GEMM launches of one training step -> gpurun_out/prof_gemm_raw.csv
 #   prof-hbm      ncu --set full of the HBM-bound kernels of one step      -> gpurun_out/prof_hbm_raw.csv
 #   prof-sweep    ncu --set full of the fault-sweep kernels                 -> gpurun_out/prof_sweep_raw.csv
+#   walk          tile-walk A/B (BNN_GEMM_GN / BNN_GEMM_GM) on the headline step
 #   sweep         tools/bench_sweep.py (configs 4 / 5)
 #   sanitizer     compute-sanitizer memcheck / racecheck / synccheck on small-shape kernel tests
 #   dp N          tools/dp_check.py + bench.py on N GPUs (needs gpurun --gpus N)
@@ -100,7 +101,15 @@ while [ $# -gt 0 ]; do
       run prof_sweep 900 ncu --set full --clock-control none --import-source on \
           -k regex:'flip_|thresholds' -c 24 -f -o /tmp/prof_sweep $SW && raw_csv prof_sweep
       ;;
-    sweep)  run sweep 900 python tools/bench_sweep.py --trials 64 ;;
+    walk)
+      # tile-walk A/B on the headline step: BNN_GEMM_GN = column tiles per super-column (16 = one super-column,
+      # the round-1 walk), BNN_GEMM_GM = row tiles per group
+      for cfg in "0 0" "16 8" "8 8" "4 8" "8 16" "8 4" "4 16"; do
+        set -- $cfg "$@"; gn=$1; gm=$2; shift 2
+        BNN_GEMM_GN=$gn BNN_GEMM_GM=$gm run "walk_gn${gn}_gm${gm}" 240 python bench.py --steps 20 --warmup 5 --no-extras --no-cpu
+      done
+      ;;
+    sweep)  run sweep 900 python tools/bench_sweep.py --sections config1,weights,image,inference ;;
     sanitizer)
       ST="$PT tests/test_kernels_gpu.py -k 'not full_size and not 8192 and not 4096 and not simt'"
       for tool in memcheck racecheck synccheck; do

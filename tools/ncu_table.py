@@ -63,3 +63,15 @@ if __name__ == "__main__":
         print(rec["kernel"][:57].ljust(58) + "".join(str(rec.get(k, "")).rjust(12) for k in keys))
     if "--json" in sys.argv:
         json.dump(t, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
+    if "--roofline" in sys.argv:
+        # --roofline <kernel-name substring> <out.json>: dram bytes per launch of the kernel bench.py's roofline
+        # object describes, averaged over its launches in this capture (bench.py reads the file)
+        i = sys.argv.index("--roofline")
+        pat, dst = sys.argv[i + 1], sys.argv[i + 2]
+        rows = [r for r in t if pat in r["kernel"]]
+        per = [(r["dram_rd_MB"] + r["dram_wr_MB"]) * 1e6 for r in rows]
+        json.dump({"kernel": pat, "launches": len(rows), "dram_bytes_per_launch": sum(per) / len(per),
+                   "dram_bytes_each": per, "us_each": [r["us"] for r in rows],
+                   "source": f"ncu --set full --clock-control none, {sys.argv[1].split('/')[-1]}, "
+                             f"dram__bytes_read.sum + dram__bytes_write.sum averaged over {len(rows)} launches "
+                             "of one eager training step"}, open(dst, "w"), indent=1)
