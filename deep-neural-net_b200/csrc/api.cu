@@ -39,13 +39,10 @@ int sm_count() {
 }
 
 // K steps (of 128 bytes) per fp32 accumulation chunk of the tcgen05 GEMM; see gemm_tc.cu.
-int gemm_chunk_iters() {
-    static const int v = [] {  // read once per process (thread-safe function-local static)
-        const char* e = getenv("BNN_GEMM_CHUNK");
-        const int n = e ? atoi(e) : 16;
-        return n < 1 ? 1 : (n > 4096 ? 4096 : n);
-    }();
-    return v;
+int gemm_chunk_iters() {  // read on every call (no cached state to race on; the tests vary it in one process)
+    const char* e = getenv("BNN_GEMM_CHUNK");
+    const int n = e ? atoi(e) : 16;
+    return n < 1 ? 1 : (n > 4096 ? 4096 : n);
 }
 
 int gemm_tc_dispatch(const bnn_gemm_desc& g, cudaStream_t stream);
@@ -82,10 +79,13 @@ extern "C" int bnn_gemm(const bnn_gemm_desc* g, int impl, bnn_stream_t stream) {
     BNN_CHECK_ARG(g != nullptr, "bnn_gemm: null descriptor");
     BNN_CHECK_ARG(g->M > 0 && g->N > 0 && g->K > 0 && g->batch >= 1,
                   "bnn_gemm: empty shape M=%d N=%d K=%d batch=%d", g->M, g->N, g->K, g->batch);
-    BNN_CHECK_ARG(g->in_dtype == BNN_DT_I8 || g->in_dtype == BNN_DT_F16, "bnn_gemm: bad in_dtype %d",
-                  g->in_dtype);
-    BNN_CHECK_ARG(g->epilogue >= BNN_EPI_STORE_F32 && g->epilogue <= BNN_EPI_SCATTER_F32,
+    BNN_CHECK_ARG(g->in_dtype == BNN_DT_I8 || g->in_dtype == BNN_DT_F16 || g->in_dtype == BNN_DT_F4,
+                  "bnn_gemm: bad in_dtype %d", g->in_dtype);
+    BNN_CHECK_ARG(g->epilogue >= BNN_EPI_STORE_F32 && g->epilogue <= BNN_EPI_SIGN_F4,
                   "bnn_gemm: bad epilogue %d", g->epilogue);
+    const bool sign_epi = g->epilogue == BNN_EPI_SIGN_I8 || g->epilogue == BNN_EPI_SIGN_F4;
+    BNN_CHECK_ARG((g->in_dtype != BNN_DT_F4 && g->epilogue != BNN_EPI_SIGN_F4) || impl == BNN_GEMM_TCGEN05,
+                  "bnn_gemm: E2M1 operands and the nibble epilogue are tcgen05-path features");
     if (g->epilogue == BNN_EPI_SCATTER_F32) {
         const bnn_peer_scatter* sc = g->scatter;
         BNN_CHECK_ARG(sc != nullptr, "bnn_gemm: BNN_EPI_SCATTER_F32 needs desc.scatter");
@@ -103,15 +103,13 @@ extern "C" int bnn_gemm(const bnn_gemm_desc* g, int impl, bnn_stream_t stream) {
                       "bnn_gemm: BNN_EPI_SCATTER_F32 is a single tcgen05 product (fp16-split, or "
                       "digit-split int8)");
     }
-    BNN_CHECK_ARG(g->epilogue != BNN_EPI_SIGN_I8 || (g->epi_thr && g->epi_sgn),
-                  "bnn_gemm: BNN_EPI_SIGN_I8 needs epi_thr and epi_sgn");
-    BNN_CHECK_ARG(g->epilogue != BNN_EPI_SIGN_I8 ||
-                      (aligned16(g->epi_thr) && aligned16(g->epi_sgn)),
+    BNN_CHECK_ARG(!sign_epi || (g->epi_thr && g->epi_sgn),
+                  "bnn_gemm: BNN_EPI_SIGN_I8 / SIGN_F4 need epi_thr and epi_sgn");
+    BNN_CHECK_ARG(!sign_epi || (aligned16(g->epi_thr) && aligned16(g->epi_sgn)),
                   "bnn_gemm: epi_thr / epi_sgn must be 16-byte aligned");
     BNN_CHECK_ARG(g->epi_thr_stride == 0 ||
-                      (g->epilogue == BNN_EPI_SIGN_I8 && g->epi_thr_stride >= g->N &&
-                       g->epi_thr_stride % 4 == 0),
-                  "bnn_gemm: epi_thr_stride %d must be 0 or a multiple of 4 >= N (BNN_EPI_SIGN_I8 only)",
+                      (sign_epi && g->epi_thr_stride >= g->N && g->epi_thr_stride % 4 == 0),
+                  "bnn_gemm: epi_thr_stride %d must be 0 or a multiple of 4 >= N (sign epilogues only)",
                   g->epi_thr_stride);
     BNN_CHECK_ARG((g->a_unsigned == 0 || g->a_unsigned == 1) &&
                       (g->a_unsigned == 0 || (g->in_dtype == BNN_DT_I8 && g->hi_from_pass == 0)),
@@ -119,9 +117,9 @@ extern "C" int bnn_gemm(const bnn_gemm_desc* g, int impl, bnn_stream_t stream) {
     BNN_CHECK_ARG(g->epilogue != BNN_EPI_STORE_S16 || !g->a_unsigned ||
                       255 * (int64_t)g->K * g->n_pass < 32768,
                   "bnn_gemm: K too large for an int16 result of a uint8 operand");
-    BNN_CHECK_ARG(g->in_dtype == BNN_DT_I8 ||
+    BNN_CHECK_ARG(g->in_dtype != BNN_DT_F16 ||
                       (g->epilogue != BNN_EPI_STORE_S32 && g->epilogue != BNN_EPI_STORE_S16),
-                  "bnn_gemm: integer stores need int8 operands");
+                  "bnn_gemm: integer stores need int8 or E2M1 operands");
     BNN_CHECK_ARG(g->epilogue != BNN_EPI_STORE_S16 || g->K * (int64_t)g->n_pass < 32768,
                   "bnn_gemm: K too large for an int16 result");
     BNN_CHECK_ARG(g->n_pass >= 1 && g->n_pass <= BNN_GEMM_MAX_PASS, "bnn_gemm: n_pass %d out of range",

@@ -57,13 +57,20 @@ constexpr int kXposeStride = 36;  // floats per staged row (32 + 4: conflict-fre
 
 // kCta2: the CTA-pair form keeps only HALF of the B tile in each CTA, so a stage is 32 KB instead of 48 KB and
 // six of them fit where the single-CTA form holds four.
-template <int BLOCK_N, bool kCta2 = false>
+// kF4: block-scaled FP4 operands (kind::mxf4).  32 TMEM columns after the two accumulator stages hold the
+// constant unit scale factors, so the widest tile is 224 columns (2 x 224 + 32 <= 512).
+template <int BLOCK_N, bool kCta2 = false, bool kF4 = false>
 struct TileCfg {
-    static constexpr int kStages = kCta2 ? 6 : ((BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 6 : 8));
     static constexpr int kABytes = kBlockM * kKBytes;
     static constexpr int kBBytes = (kCta2 ? BLOCK_N / 2 : BLOCK_N) * kKBytes;   // per CTA
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kTmemCols = (kAccStages * BLOCK_N) < 32 ? 32 : (kAccStages * BLOCK_N);
+    static constexpr int kStages = kCta2 ? 6 : ((BLOCK_N >= 200) ? 4 : ((BLOCK_N >= 128) ? 6 : 8));
+    static constexpr int kSfCol = kAccStages * BLOCK_N;     // first scale-factor column (kF4)
+    static constexpr int kSfCols = 32;
+    static constexpr int kColsNeeded = kAccStages * BLOCK_N + (kF4 ? kSfCols : 0);
+    static constexpr int kTmemCols = kColsNeeded <= 32 ? 32 : (kColsNeeded <= 64 ? 64 : (kColsNeeded <= 128 ? 128 :
+                                     (kColsNeeded <= 256 ? 256 : 512)));
+    static_assert(kColsNeeded <= 512, "accumulator stages + scale factors exceed TMEM");
     static constexpr int kBarBytes = (2 * kStages + 2 * kAccStages) * 8 + 16;
     static constexpr int kXposeBytes = kEpiWarps * kXposeRows * kXposeStride * 4;  // fp32 store staging
     static constexpr int kSmemBytes =
@@ -71,6 +78,7 @@ struct TileCfg {
     static constexpr int kColsPerThread = BLOCK_N / 2;                 // per epilogue thread
     static constexpr int kGroup = kColsPerThread < 16 ? kColsPerThread : 16;  // columns per tcgen05.ld
     static constexpr int kGroups = kColsPerThread / kGroup;
+    static_assert(kColsPerThread % kGroup == 0, "tile width must split into whole tcgen05.ld groups");
 };
 
 struct TcParams {
@@ -142,37 +150,55 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& b,
 }
 
 // Store / update one group of G consecutive columns of one output row from registers.
+// sign epilogues: thr_smem is the shared-memory address of this warp's staged thresholds for the thread's column
+// range (thr at +0, orientation at +kSignStageBytes/2; columns past N hold +inf / 1), cl the group's offset in it.
+constexpr uint32_t kSignStageBytes = 1024;   // 2 x 128 floats: fits the warp's transpose buffer (2304 bytes)
 template <bool kI8, int EPI, int G>
 __device__ __forceinline__ void store_group(const TcParams& p, char* dbase, long long off, int col0,
-                                            const uint32_t (&v)[G], float scale, const float* thr) {
+                                            const uint32_t (&v)[G], float scale, uint32_t thr_smem, int cl) {
     const bool full = (col0 + G <= p.N) && p.vec_ok;
-    if (EPI == BNN_EPI_SIGN_I8) {
-        // batch-norm + sign as one compare against the per-column threshold (bn.cu)
+    if (EPI == BNN_EPI_SIGN_I8 || EPI == BNN_EPI_SIGN_F4) {
+        // batch-norm + sign as one compare against the per-column threshold (bn.cu).  The thresholds come from
+        // shared memory (staged once per tile with coalesced loads): fetched per group straight from global
+        // memory, 56 dependent L2 round trips per tile made this epilogue 3x longer than an FP4 main loop.
         int8_t* d = reinterpret_cast<int8_t*>(dbase) + off;
         uint32_t bits = 0;
 #pragma unroll
         for (int j = 0; j < G; j += 4) {
-            float t[4], s[4];
-            if (col0 + j + 4 <= p.N) {
-                const float4 tv = __ldg(reinterpret_cast<const float4*>(thr + col0 + j));
-                const float4 sv = __ldg(reinterpret_cast<const float4*>(p.sgn + col0 + j));
-                t[0] = tv.x; t[1] = tv.y; t[2] = tv.z; t[3] = tv.w;
-                s[0] = sv.x; s[1] = sv.y; s[2] = sv.z; s[3] = sv.w;
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const bool ok = col0 + j + q < p.N;
-                    t[q] = ok ? __ldg(thr + col0 + j + q) : INFINITY;
-                    s[q] = ok ? __ldg(p.sgn + col0 + j + q) : 1.0f;
-                }
-            }
+            const uint4 tu = ptx::lds_v4(thr_smem + (uint32_t)((cl + j) * 4));
+            const uint4 su = ptx::lds_v4(thr_smem + kSignStageBytes / 2 + (uint32_t)((cl + j) * 4));
+            const float t[4] = {__uint_as_float(tu.x), __uint_as_float(tu.y), __uint_as_float(tu.z), __uint_as_float(tu.w)};
+            const float s[4] = {__uint_as_float(su.x), __uint_as_float(su.y), __uint_as_float(su.z), __uint_as_float(su.w)};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float a = kI8 ? (float)(int)v[j + q] : __fmul_rn(__uint_as_float(v[j + q]), scale);
                 bits |= (uint32_t)(__fmul_rn(a, s[q]) >= t[q]) << (j + q);
             }
         }
-        if (full) {
+        if (EPI == BNN_EPI_SIGN_F4) {
+            // E2M1 nibbles, two columns per byte (low nibble = even column): +1 = 0x2, -1 = 0xA, columns past
+            // N = 0x0 (+0.0: the consumer's K padding).  Whole 8-column words; the host guarantees the pitch
+            // covers them (ldd % 32 == 0) and 16-byte alignment of D.
+            uint8_t* d4 = reinterpret_cast<uint8_t*>(dbase) + (off >> 1);
+            const int nvalid = p.N - col0;   // columns of this group inside the matrix
+            uint32_t w[G / 8];
+#pragma unroll
+            for (int j = 0; j < G; j += 8) {
+                const uint32_t b8 = (bits >> j) & 0xFFu;
+                uint32_t word = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) word |= ((b8 >> b) & 1u) << (4 * b);   // decision bit -> bit 0 of nibble b
+                // +1 -> 0x2, -1 -> 0xA: 0xA everywhere, clear bit 3 where the decision bit is set
+                word = 0xAAAAAAAAu ^ (word << 3);
+                const int live = nvalid - j;                                        // nibbles past N -> 0
+                if (live < 8) word &= live <= 0 ? 0u : (0xFFFFFFFFu >> (32 - 4 * live));
+                w[j / 8] = word;
+            }
+            if (G == 16) *reinterpret_cast<uint2*>(d4) = make_uint2(w[0], w[G / 8 - 1]);
+            else
+#pragma unroll
+                for (int j = 0; j < G / 8; ++j) *reinterpret_cast<uint32_t*>(d4 + 4 * j) = w[j];
+        } else if (full) {
 #pragma unroll
             for (int j = 0; j < G; j += 16) {
                 uint32_t w[4];
@@ -432,14 +458,17 @@ __device__ __forceinline__ void staged_rows(const TcParams& p, uint32_t xbuf, fl
 // issues UMMAs of M = 256 that read both halves, each CTA's TMEM receives its own 128 rows and is drained
 // by that CTA's epilogue warps exactly as in the single-CTA form.  The B tile then crosses L2 -> shared
 // memory once per pair instead of once per CTA.  p.m_tiles counts PAIRS of row tiles in this form.
-template <bool kI8, int BLOCK_N, int EPI, int STATS, bool kCta2 = false>
+// kF4 (with kI8 = true: the epilogues see exact integers): E2M1 operands on kind::mxf4.block_scale with unit scale
+// factors — the +-1 x +-1 products of the evaluation paths at twice the kind::i8 rate and half the operand bytes.
+template <bool kI8, int BLOCK_N, int EPI, int STATS, bool kCta2 = false, bool kF4 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                const __grid_constant__ CUtensorMap mapB2, const TcParams p) {
-    using Cfg = TileCfg<BLOCK_N, kCta2>;
+    using Cfg = TileCfg<BLOCK_N, kCta2, kF4>;
     constexpr int S = Cfg::kStages;
-    constexpr int kKElems = kI8 ? kKBytes : kKBytes / 2;
+    constexpr int kKElems = kI8 ? kKBytes : kKBytes / 2;   // of the tensor map's element type (bytes for i8 / f4)
+    static_assert(!kF4 || (kI8 && !kCta2 && STATS == BNN_STATS_NONE), "FP4 form: integer epilogues, single CTA");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -491,6 +520,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     ptx::cluster_sync_if<kCta2>();  // pair: the peer's barriers are initialised before anyone signals them
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
+    if constexpr (kF4) {
+        // unit scale factors (UE8M0 0x7F = 2^0) in every byte of the 32 columns behind the accumulators, all
+        // 128 lanes: warps 4-7 own the four lane quarters
+        if (warp >= 4 && warp < 8) {
+            for (int c = 0; c < Cfg::kSfCols; ++c)
+                ptx::tmem_st_32x32b_x1(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(Cfg::kSfCol + c),
+                                       0x7F7F7F7Fu);
+            ptx::tmem_st_wait();
+        }
+        ptx::tc_fence_before_sync();
+        __syncthreads();
+        ptx::tc_fence_after_sync();
+    }
 
     if (warp < 4) {
         // give the registers this warp group does not need to the epilogue warp groups.  The budget
@@ -530,10 +572,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
         } else if (warp == 1 && lane == 0 && (!kCta2 || cta_rank == 0)) {
             // ------------------------------------------------------------- MMA issuer (pair: the leader)
-            uint32_t idesc = kI8 ? ptx::umma_idesc(2u, 1u, kCta2 ? 2 * kBlockM : kBlockM, BLOCK_N)
-                                 : ptx::umma_idesc(1u, 0u, kCta2 ? 2 * kBlockM : kBlockM, BLOCK_N);
+            uint32_t idesc = kF4 ? ptx::umma_idesc_mxf4(kBlockM, BLOCK_N)
+                           : (kI8 ? ptx::umma_idesc(2u, 1u, kCta2 ? 2 * kBlockM : kBlockM, BLOCK_N)
+                                  : ptx::umma_idesc(1u, 0u, kCta2 ? 2 * kBlockM : kBlockM, BLOCK_N));
+            const uint32_t sf_tmem = tmem_base + (uint32_t)Cfg::kSfCol;
             // kind::i8 operand formats: 1 = signed, 0 = unsigned 8-bit; A and B are independent fields
-            if (kI8 && p.a_unsigned) idesc &= ~(7u << 7);
+            if (kI8 && !kF4 && p.a_unsigned) idesc &= ~(7u << 7);
             int s = 0;
             uint32_t ph = 0;
             int acc = 0;
@@ -556,7 +600,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         for (int j = 0; j < kKBytes / kUmmaKBytes; ++j) {
                             const uint64_t adv = (uint64_t)((j * kUmmaKBytes) >> 4);
                             const uint32_t accum = (!first || j > 0) ? 1u : 0u;
-                            if (kI8)
+                            if (kF4)
+                                ptx::mma_mxf4(d_tmem, da + adv, db + adv, idesc, accum, sf_tmem, sf_tmem);
+                            else if (kI8)
                                 ptx::mma_i8_t<kCta2>(d_tmem, da + adv, db + adv, idesc, accum);
                             else
                                 ptx::mma_f16_t<kCta2>(d_tmem, da + adv, db + adv, idesc, accum);
@@ -589,6 +635,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if constexpr (kCta2) m_blk = 2 * m_blk + (int)cta_rank;
             const int row = m_blk * kBlockM + q * 32 + lane;
             const int colbase = n_blk * BLOCK_N + h * CPT;
+            const int row_w0 = m_blk * kBlockM + q * 32;  // first row of this warp
+            const uint32_t xbuf = ptx::smem_u32(xpose) + (uint32_t)((warp - 4) * kXposeRows * kXposeStride * 4);
+            if constexpr (EPI == BNN_EPI_SIGN_I8 || EPI == BNN_EPI_SIGN_F4) {
+                // stage this warp's thresholds (thr, orientation) of the tile's column range while the MMAs run:
+                // lane l fetches columns 4l .. 4l+3 (coalesced), columns past N get +inf / 1
+                static_assert(2 * CPT * 4 <= (int)kSignStageBytes && kSignStageBytes <= kXposeRows * kXposeStride * 4,
+                              "threshold staging must fit the warp's transpose buffer");
+                const float* tb = p.thr + (long long)b * p.thr_stride;
+                __syncwarp();   // the previous tile's reads of the buffer are done
+                if (4 * lane < CPT) {
+                    const int c0 = colbase + 4 * lane;
+                    float4 tv, sv;
+                    if (c0 + 4 <= p.N) {   // bases are 16-byte aligned (checked by bnn_gemm), strides multiples of 4
+                        tv = __ldg(reinterpret_cast<const float4*>(tb + c0));
+                        sv = __ldg(reinterpret_cast<const float4*>(p.sgn + c0));
+                    } else {
+                        tv.x = c0 + 0 < p.N ? __ldg(tb + c0 + 0) : INFINITY;  sv.x = c0 + 0 < p.N ? __ldg(p.sgn + c0 + 0) : 1.f;
+                        tv.y = c0 + 1 < p.N ? __ldg(tb + c0 + 1) : INFINITY;  sv.y = c0 + 1 < p.N ? __ldg(p.sgn + c0 + 1) : 1.f;
+                        tv.z = c0 + 2 < p.N ? __ldg(tb + c0 + 2) : INFINITY;  sv.z = c0 + 2 < p.N ? __ldg(p.sgn + c0 + 2) : 1.f;
+                        tv.w = c0 + 3 < p.N ? __ldg(tb + c0 + 3) : INFINITY;  sv.w = c0 + 3 < p.N ? __ldg(p.sgn + c0 + 3) : 1.f;
+                    }
+                    ptx::sts_v4(xbuf + (uint32_t)(16 * lane), __float_as_uint(tv.x), __float_as_uint(tv.y),
+                                __float_as_uint(tv.z), __float_as_uint(tv.w));
+                    ptx::sts_v4(xbuf + kSignStageBytes / 2 + (uint32_t)(16 * lane), __float_as_uint(sv.x),
+                                __float_as_uint(sv.y), __float_as_uint(sv.z), __float_as_uint(sv.w));
+                }
+                __syncwarp();
+            }
             for (int c = 0; c < n_chunks; ++c) {
                 if (STATS == BNN_STATS_BN_BWD && c == n_chunks - 1 && row < p.M) {
                     // pull this row's slice of Z into L2 one chunk ahead of the statistics phase,
@@ -609,8 +683,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     for (int g = 0; g < NG; ++g) {
                         uint32_t v[G];
                         ptx::tmem_ld_cols<G>(t_row + (uint32_t)(g * G), v);
+                        if constexpr (kF4) ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < G; ++j) sum[g * G + j] = v[j];
+                        for (int j = 0; j < G; ++j)   // FP4: fp32 accumulators holding exact integers (|sum| <= K < 2^24)
+                            sum[g * G + j] = kF4 ? (uint32_t)__float2int_rn(__uint_as_float(v[j])) : v[j];
                     }
                     ptx::tmem_ld_wait();
                 } else {
@@ -653,8 +729,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 rowoff = ((long long)p.rank * p.rows_per_owner +
                           (row - owner * p.rows_per_owner)) * p.ldd;
             }
-            const int row_w0 = m_blk * kBlockM + q * 32;  // first row of this warp
-            const uint32_t xbuf = ptx::smem_u32(xpose) + (uint32_t)((warp - 4) * kXposeRows * kXposeStride * 4);
             // the host only asks for STATS on shapes where every tile is full-width and vector-aligned
             if (kF32Out && ((p.vec_ok && colbase + CPT <= p.N) || STATS != BNN_STATS_NONE)) {  // (digit-split
                 // and column-scaled products are admitted by the host only when every tile is full)
@@ -669,8 +743,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         uint32_t v[G];
 #pragma unroll
                         for (int j = 0; j < G; ++j) v[j] = sum[g * G + j];
-                        store_group<kI8, EPI, G>(p, dbase, rowoff + col0, col0, v, scale,
-                                                 p.thr + (long long)b * p.thr_stride);
+                        store_group<kI8, EPI, G>(p, dbase, rowoff + col0, col0, v, scale, xbuf, g * G);
                         asm volatile("" ::: "memory");  // keep the groups' live ranges disjoint
                     }
                 }
@@ -761,15 +834,13 @@ void pick_tile_walk(const bnn_gemm_desc& g, int es, int block_n, int m_tiles, in
     if (group_m < 1) group_m = 1;
 }
 
-// BNN_GEMM_CTA2=1 (read once per process, like BNN_GEMM_CHUNK) routes 256-wide products with more than one row
-// tile to the CTA-pair form.  Round 2, on a B200: the opt-in tests pass (tests/test_gemm_pair_gpu.py), and the
-// training step runs 1.7x SLOWER with it (profiles/r02_summary.md), so it stays opt-in.
+// BNN_GEMM_CTA2=1 (read on every call, like BNN_GEMM_CHUNK: the tests flip both inside one process) routes
+// 256-wide products with more than one row tile to the CTA-pair form.  Round 2, on a B200: the opt-in tests pass
+// (tests/test_gemm_pair_gpu.py) and the training step runs 1.7x SLOWER with it (profiles/r02_summary.md), so it
+// stays opt-in.
 bool pair_form_requested() {
-    static const bool on = [] {
-        const char* e = getenv("BNN_GEMM_CTA2");
-        return e != nullptr && atoi(e) != 0;
-    }();
-    return on;
+    const char* e = getenv("BNN_GEMM_CTA2");
+    return e != nullptr && atoi(e) != 0;
 }
 
 // The CTA-pair launch (gemm_tc_kernel<..., kCta2 = true>): clusters of two CTAs, 256 x 256 tiles per pair.
@@ -891,10 +962,12 @@ int launch_tc_pair(const bnn_gemm_desc& g, cudaStream_t stream) {
     return BNN_OK;
 }
 
-template <bool kI8, int BLOCK_N, int EPI, int STATS = BNN_STATS_NONE>
+template <bool kI8, int BLOCK_N, int EPI, int STATS = BNN_STATS_NONE, bool kF4 = false>
 int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
-    using Cfg = TileCfg<BLOCK_N>;
-    if constexpr (BLOCK_N == 256 && EPI != BNN_EPI_SCATTER_F32) {
+    using Cfg = TileCfg<BLOCK_N, false, kF4>;
+    auto kernel = gemm_tc_kernel<kI8, BLOCK_N, EPI, STATS, false, kF4>;
+    const int pack = kF4 ? 2 : 1;   // operand elements per byte of the tensor map's element type
+    if constexpr (BLOCK_N == 256 && EPI != BNN_EPI_SCATTER_F32 && !kF4) {
         if (g.M > kBlockM && pair_form_requested()) return launch_tc_pair<kI8, EPI, STATS>(g, stream);
     }
     // the opt-in shared-memory size is a per-device attribute of the function
@@ -902,9 +975,7 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     int dev = 0;
     BNN_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        BNN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kI8, BLOCK_N, EPI, STATS>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg::kSmemBytes));
+        BNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     CUtensorMap mA[3], mB[3];
@@ -913,18 +984,18 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     for (int i = 0; i < 3; ++i) {
         const void* a = g.A[i < nA ? i : 0];
         const void* b = Bp[i];
-        int rc = make_operand_map(&mA[i], a, kI8, g.M, g.K, g.lda, g.stride_a ? g.batch : 1,
-                                  g.stride_a, kBlockM);
+        int rc = make_operand_map(&mA[i], a, kI8, g.M, g.K / pack, g.lda / pack, g.stride_a ? g.batch : 1,
+                                  g.stride_a / pack, kBlockM);
         if (rc) return rc;
-        rc = make_operand_map(&mB[i], b, kI8, g.N, g.K, g.ldb, g.stride_b ? g.batch : 1,
-                              g.stride_b, BLOCK_N);
+        rc = make_operand_map(&mB[i], b, kI8, g.N, g.K / pack, g.ldb / pack, g.stride_b ? g.batch : 1,
+                              g.stride_b / pack, BLOCK_N);
         if (rc) return rc;
     }
     TcParams p;
     p.M = g.M;
     p.N = g.N;
     p.batch = g.batch;
-    const int kelems = kI8 ? kKBytes : kKBytes / 2;
+    const int kelems = kF4 ? 2 * kKBytes : (kI8 ? kKBytes : kKBytes / 2);
     p.kblocks = cdiv(g.K, kelems);
     p.n_pass = g.n_pass;
     // integer accumulation is exact: one chunk; fp32 accumulation is re-rounded every chunk
@@ -935,10 +1006,19 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     }
     p.m_tiles = cdiv(g.M, kBlockM);
     p.n_tiles = cdiv(g.N, BLOCK_N);
-    pick_tile_walk(g, kI8 ? 1 : 2, BLOCK_N, p.m_tiles, p.n_tiles, p.group_m, p.group_n);
+    pick_tile_walk(g, kI8 ? 1 : 2, BLOCK_N / pack, p.m_tiles, p.n_tiles, p.group_m, p.group_n);
     p.epilogue = g.epilogue;
     const int esz = (g.epilogue == BNN_EPI_STORE_S16) ? 2 : (g.epilogue == BNN_EPI_SIGN_I8 ? 1 : 4);
     p.vec_ok = aligned16(g.D) && ((g.ldd * esz) % 16 == 0) && ((g.stride_d * esz) % 16 == 0);
+    if (EPI == BNN_EPI_SIGN_F4) {
+        // nibble output: whole 32-bit words of 8 columns are stored, so the pitch must cover the last word
+        if (!(aligned16(g.D) && g.ldd % 32 == 0 && g.stride_d % 32 == 0 && g.ldd >= ((g.N + 7) / 8) * 8)) {
+            set_error("bnn_gemm: BNN_EPI_SIGN_F4 needs a 16-byte aligned D and ldd, stride_d multiples of 32 "
+                      "elements (ldd=%lld)", (long long)g.ldd);
+            return BNN_ERR_ARG;
+        }
+        p.vec_ok = 1;
+    }
     p.a_batched = g.stride_a != 0;
     p.b_batched = g.stride_b != 0;
     p.D = g.D;
@@ -998,8 +1078,7 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
             return BNN_ERR_UNSUPPORTED;
         }
     }
-    gemm_tc_kernel<kI8, BLOCK_N, EPI, STATS><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(
-        mA[0], mA[1], mB[0], mB[1], mB[2], p);
+    kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA[0], mA[1], mB[0], mB[1], mB[2], p);
     BNN_LAUNCH_CHECK("gemm_tc_kernel");
     return BNN_OK;
 }
@@ -1028,6 +1107,7 @@ int pick_epilogue(const bnn_gemm_desc& g, bool i8, cudaStream_t stream) {
             case BNN_EPI_STORE_S32: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S32>(g, stream);
             case BNN_EPI_STORE_F32: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_F32>(g, stream);
             case BNN_EPI_SIGN_I8: return launch_tc<true, BLOCK_N, BNN_EPI_SIGN_I8>(g, stream);
+            case BNN_EPI_SIGN_F4: return launch_tc<true, BLOCK_N, BNN_EPI_SIGN_F4>(g, stream);
             case BNN_EPI_SCATTER_F32: return launch_tc<true, BLOCK_N, BNN_EPI_SCATTER_F32>(g, stream);
             default: return launch_tc<true, BLOCK_N, BNN_EPI_SGD_F32>(g, stream);
         }
@@ -1035,14 +1115,40 @@ int pick_epilogue(const bnn_gemm_desc& g, bool i8, cudaStream_t stream) {
     switch (g.epilogue) {
         case BNN_EPI_SGD_F32: return launch_tc<false, BLOCK_N, BNN_EPI_SGD_F32>(g, stream);
         case BNN_EPI_SIGN_I8: return launch_tc<false, BLOCK_N, BNN_EPI_SIGN_I8>(g, stream);
+        case BNN_EPI_SIGN_F4: return launch_tc<false, BLOCK_N, BNN_EPI_SIGN_F4>(g, stream);
         case BNN_EPI_SCATTER_F32: return launch_tc<false, BLOCK_N, BNN_EPI_SCATTER_F32>(g, stream);
         default: return launch_tc<false, BLOCK_N, BNN_EPI_STORE_F32>(g, stream);
+    }
+}
+
+// E2M1 operands (BNN_DT_F4): integer epilogues only, tiles of 32 / 128 / 224 columns.
+template <int BLOCK_N>
+int pick_epilogue_f4(const bnn_gemm_desc& g, cudaStream_t stream) {
+    switch (g.epilogue) {
+        case BNN_EPI_STORE_S16: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S16, BNN_STATS_NONE, true>(g, stream);
+        case BNN_EPI_STORE_S32: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S32, BNN_STATS_NONE, true>(g, stream);
+        case BNN_EPI_SIGN_I8: return launch_tc<true, BLOCK_N, BNN_EPI_SIGN_I8, BNN_STATS_NONE, true>(g, stream);
+        case BNN_EPI_SIGN_F4: return launch_tc<true, BLOCK_N, BNN_EPI_SIGN_F4, BNN_STATS_NONE, true>(g, stream);
+        default:
+            set_error("bnn_gemm: BNN_DT_F4 products have the integer epilogues STORE_S16 / STORE_S32 / SIGN_I8 / SIGN_F4");
+            return BNN_ERR_UNSUPPORTED;
     }
 }
 
 }  // namespace
 
 int gemm_tc_dispatch(const bnn_gemm_desc& g, cudaStream_t stream) {
+    if (g.in_dtype == BNN_DT_F4) {
+        BNN_CHECK_ARG(g.A[0] && g.B[0] && aligned16(g.A[0]) && aligned16(g.B[0]), "bnn_gemm: F4 operands not 16-byte aligned");
+        BNN_CHECK_ARG(g.n_pass == 1 && g.stats == BNN_STATS_NONE && g.hi_from_pass == 0 && !g.col_scale && !g.a_unsigned,
+                      "bnn_gemm: BNN_DT_F4 is a single-pass +-1 product without fused statistics");
+        BNN_CHECK_ARG(g.K % 32 == 0 && g.lda % 32 == 0 && g.ldb % 32 == 0 && g.stride_a % 32 == 0 &&
+                          g.stride_b % 32 == 0 && g.lda >= g.K && g.ldb >= g.K,
+                      "bnn_gemm: F4 operands need K, pitches and batch strides in multiples of 32 elements (16 bytes)");
+        BNN_CHECK_ARG(g.K < (1 << 24), "bnn_gemm: F4 sums are exact in fp32 only for K < 2^24");
+        return g.N <= 32 ? pick_epilogue_f4<32>(g, stream)
+                         : (g.N <= 128 ? pick_epilogue_f4<128>(g, stream) : pick_epilogue_f4<224>(g, stream));
+    }
     const bool i8 = g.in_dtype == BNN_DT_I8;
     const int es = i8 ? 1 : 2;
     for (int i = 0; i < 2; ++i) {

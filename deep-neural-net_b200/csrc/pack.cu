@@ -143,6 +143,39 @@ unpack_bits_kernel(const uint32_t* __restrict__ bits, int R, int C, long long ld
     }
 }
 
+// Packed sign bits -> E2M1 nibbles (BNN_DT_F4 operand): one thread turns one 32-bit word into 16 bytes
+// (bit j -> nibble j: 1 -> 0x2 = +1.0, 0 -> 0xA = -1.0; columns past C -> 0x0 = +0.0, they pad K).
+// Reads 4 bytes, writes one 16-byte vector per thread, both coalesced.
+__global__ void __launch_bounds__(256)
+bits_to_f4_kernel(const uint32_t* __restrict__ bits, long long R, int C, long long ldw,
+                  uint8_t* __restrict__ out, long long ld_bytes) {
+    const int words = (C + 31) >> 5;
+    const long long total = R * words;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / words;
+        const int w = (int)(i - r * words);
+        const uint32_t b = __ldg(bits + r * ldw + w);
+        const int valid = min(32, C - 32 * w);
+        const uint32_t live = valid >= 32 ? 0xFFFFFFFFu : ((1u << valid) - 1u);
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t bb = (b >> (8 * q)) & 0xFFu, lv = (live >> (8 * q)) & 0xFFu;
+            // spread 8 bits to the bit-3 position of 8 nibbles: sign bit of E2M1 (set = negative)
+            uint32_t sp = 0, lm = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                sp |= ((bb >> j) & 1u) << (4 * j);
+                lm |= ((lv >> j) & 1u) << (4 * j);
+            }
+            // live nibble: 0x2 | (bit ? 0 : 0x8); dead nibble: 0
+            o[q] = (lm * 0xAu) ^ (sp << 3);
+        }
+        *reinterpret_cast<uint4*>(out + r * ld_bytes + 16 * w) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // max |x| via integer atomicMax on the float bit pattern (non-negative floats order like uints).
 // ---------------------------------------------------------------------------------------------
@@ -320,6 +353,21 @@ extern "C" int bnn_unpack_bits(const uint32_t* bits, int R, int C, int64_t ldw, 
     unpack_bits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         bits, R, C, ldw, out_i8, ld_i8, static_cast<__half*>(out_f16), ld_f16);
     BNN_LAUNCH_CHECK("unpack_bits_kernel");
+    return BNN_OK;
+}
+
+extern "C" int bnn_bits_to_f4(const uint32_t* bits, int64_t R, int C, int64_t ldw, void* out_f4,
+                              int64_t ld_f4, bnn_stream_t stream) {
+    BNN_CHECK_ARG(bits && out_f4 && R > 0 && C > 0 && ldw >= (C + 31) / 32, "bnn_bits_to_f4: bad input");
+    BNN_CHECK_ARG(aligned16(out_f4) && ld_f4 % 32 == 0 && ld_f4 >= ((C + 31) / 32) * 32,
+                  "bnn_bits_to_f4: out_f4 must be 16-byte aligned with a pitch of whole 32-element words (ld_f4=%lld)",
+                  (long long)ld_f4);
+    const long long total = R * ((C + 31) / 32);
+    const long long blocks = (total + 255) / 256;
+    const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+    bits_to_f4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bits, R, C, ldw, static_cast<uint8_t*>(out_f4),
+                                                              ld_f4 / 2);
+    BNN_LAUNCH_CHECK("bits_to_f4_kernel");
     return BNN_OK;
 }
 

@@ -150,6 +150,28 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Block-scaled FP4: A and B hold E2M1 values, two per byte; every 32 of them along K are multiplied by a UE8M0
+// scale factor read from TMEM (sf_a / sf_b: TMEM addresses).  K = 64 elements (32 bytes) per instruction, fp32
+// accumulators, twice the rate of kind::i8.  The +-1 GEMMs keep EVERY scale byte at 0x7F (2^0), so the
+// scale-factor layout does not matter and both operands point at the same block of constant columns.
+__device__ __forceinline__ void mma_mxf4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate, uint32_t sf_a, uint32_t sf_b) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(sf_a), "r"(sf_b)
+        : "memory");
+}
+// 32 lanes x 1 column store: thread i of the warp writes lane (base + i).
+__device__ __forceinline__ void tmem_st_32x32b_x1(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 // Arrive on `bar` once every previously issued tcgen05.mma of this thread has completed
 // (implicitly performs tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -357,6 +379,12 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t d_fmt, uint32_t ab_fmt, uint32_t M,
                                                   uint32_t N) {
     return (d_fmt << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// Block-scaled descriptor (CUTLASS InstrDescriptorBlockScaled): [4,6) B scale-factor id, [7,10) A format,
+// [10,13) B format (E2M1 = 1), [17,23) N>>3, [23] scale format (1 = UE8M0), [24,29) M>>4, [29,31) A scale-factor
+// id, [31] K size (0 = K64 dense).
+__host__ __device__ constexpr uint32_t umma_idesc_mxf4(uint32_t M, uint32_t N) {
+    return (1u << 7) | (1u << 10) | ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24);
 }
 
 }  // namespace ptx

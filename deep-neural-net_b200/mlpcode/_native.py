@@ -14,8 +14,8 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("BNN_B200_LIB", _PKG.parent / "lib" / "libbnn_b200.so"))
 
 BNN_OK, BNN_ERR_ARG, BNN_ERR_CUDA, BNN_ERR_UNSUPPORTED = 0, -1, -2, -3
-DT_I8, DT_F16 = 0, 1
-EPI_STORE_F32, EPI_STORE_S32, EPI_STORE_S16, EPI_SGD_F32, EPI_SIGN_I8, EPI_SCATTER_F32 = 0, 1, 2, 3, 4, 5
+DT_I8, DT_F16, DT_F4 = 0, 1, 2
+EPI_STORE_F32, EPI_STORE_S32, EPI_STORE_S16, EPI_SGD_F32, EPI_SIGN_I8, EPI_SCATTER_F32, EPI_SIGN_F4 = 0, 1, 2, 3, 4, 5, 6
 MAX_RANKS = 16
 STATS_NONE, STATS_COLSUM, STATS_BN_BWD = 0, 1, 2
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
@@ -73,6 +73,7 @@ PROTOTYPES = {
     "bnn_pack_i8_rows": [_p, _i, _i, _i64, _p, _i64, _p],
     "bnn_binarize_weights_t": [_p, _i, _i, _p, _i64, _p, _i64, _p, _i64, _p, _p],
     "bnn_unpack_bits": [_p, _i, _i, _i64, _p, _i64, _p, _i64, _p],
+    "bnn_bits_to_f4": [_p, _i64, _i, _i64, _p, _i64, _p],
     "bnn_absmax_f32": [_p, _i64, _p, _i, _p],
     "bnn_split_f16": [_p, _i, _i, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p, _p],
     "bnn_gemm": [C.POINTER(GemmDesc), _i, _p],

@@ -68,6 +68,21 @@ def unpack_bits(bits: torch.Tensor, C_: int, out_i8=None, out_f16=None) -> None:
           ptr(out_f16), _ld(out_f16) if out_f16 is not None else 0)
 
 
+def bits_to_f4(bits: torch.Tensor, C_: int, out_f4: torch.Tensor) -> None:
+    """Packed sign words [..., R, W] -> E2M1 nibbles [..., R, ld/2 bytes] (uint8 storage; leading dims contiguous)."""
+    assert bits.is_contiguous() and out_f4.is_contiguous() and out_f4.dtype in (torch.uint8, torch.int8)
+    rows = bits.numel() // bits.shape[-1]
+    assert out_f4.numel() // out_f4.shape[-1] == rows
+    _call("bnn_bits_to_f4", ptr(bits), rows, C_, bits.shape[-1], ptr(out_f4), 2 * out_f4.shape[-1])
+
+
+def f4_ok(Kd: int, N: int) -> bool:
+    """A +-1 x +-1 evaluation product [*, Kd] x [N, Kd] goes to the FP4 tensor pipe: tcgen05 path, K in whole
+    16-byte words, more than one 32-column tile (the 10-wide output layer stays on kind::i8).  BNN_FP4=0: int8."""
+    return (Kd % 32 == 0 and N > 32 and gemm_impl() == nat.GEMM_TCGEN05
+            and os.environ.get("BNN_FP4", "1") != "0")
+
+
 def absmax_f32(x: torch.Tensor, out_bits: torch.Tensor, zero_first=True) -> None:
     assert x.is_contiguous()
     _call("bnn_absmax_f32", ptr(x), x.numel(), ptr(out_bits), int(zero_first))
@@ -125,7 +140,7 @@ def gemm(*, M, N, K, A, B, lda, ldb, D, ldd, in_dtype, epilogue, passes=((0, 0),
     start.record()
     _call("bnn_gemm", C.byref(d), gemm_impl() if impl is None else impl)
     end.record()
-    kind = "f16" if in_dtype != nat.DT_I8 else ("i8dw" if hi_from_pass else "i8")
+    kind = {nat.DT_F16: "f16", nat.DT_F4: "f4"}.get(in_dtype, "i8dw" if hi_from_pass else "i8")
     gemm_events.append((start, end, kind, 2.0 * M * N * K * batch, len(passes)))
 
 

@@ -48,15 +48,22 @@ def binary_gemm_variant() -> str:
 class SignActivation(DeviceArray):
     """Output of a sign-activated layer: values in {+1,-1} kept in GEMM-operand form."""
 
-    def __init__(self, i8, n, t16=None, bits=None, t8=None, t8x127=None):
+    def __init__(self, i8, n, t16=None, bits=None, t8=None, t8x127=None, f4=None):
         self.i8, self.n, self.t16, self.bits = i8, n, t16, bits
         self.t8, self.t8x127 = t8, t8x127   # transposed int8 +-1 / +-127 (int8 dW operand pieces)
+        self.f4 = f4                        # E2M1 nibbles [B, pad32(n) / 2] (FP4 forward operand, eval mode)
+        self.rows = (i8 if i8 is not None else f4).shape[0]
         self._dense = None
 
     @property
     def t(self):  # fp32 [B, n] view for generic consumers (not used on the hot path)
         if self._dense is None:
-            self._dense = self.i8[:, : self.n].to(torch.float32)
+            if self.i8 is not None:
+                self._dense = self.i8[:, : self.n].to(torch.float32)
+            else:   # nibbles 0x2 / 0xA -> +1 / -1
+                b = self.f4
+                nib = torch.stack((b & 0xF, b >> 4), dim=-1).reshape(b.shape[0], -1)[:, : self.n]
+                self._dense = torch.where(nib == 0x2, 1.0, -1.0).to(torch.float32)
         return self._dense
 
     @t.setter
@@ -65,7 +72,7 @@ class SignActivation(DeviceArray):
 
     @property
     def shape(self):
-        return (self.i8.shape[0], self.n)
+        return (self.rows, self.n)
 
     @property
     def ndim(self):
@@ -73,14 +80,14 @@ class SignActivation(DeviceArray):
 
     @property
     def size(self):
-        return self.i8.shape[0] * self.n
+        return self.rows * self.n
 
     @property
     def dtype(self):
         return np.dtype(np.float32)
 
     def __len__(self):
-        return self.i8.shape[0]
+        return self.rows
 
 
 class SoftmaxOutput(DeviceArray):
@@ -568,6 +575,12 @@ class BinaryLayer(LinearLayer):
         K_.bn_sign_thresholds(bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
         K_.u8_input_thresholds(wops["bits"], N, Kd, thr, sgn, X.mm_u32, 1, X.new_min, X.new_max, 0, thr_u8,
                                shared_minmax=True)
+        if self._consumer_takes_f4():
+            act_f4 = ws.get(f"a_f4_{B}", (B, pad_to(N, 32) // 2), torch.uint8, zero=True)
+            K_.gemm(M=B, N=N, K=Kd, A=(X.u8,), B=(wops["i8"],), lda=X.u8.stride(0), ldb=wops["i8"].stride(0),
+                    D=act_f4, ldd=2 * act_f4.stride(0), in_dtype=nat.DT_I8, epilogue=nat.EPI_SIGN_F4,
+                    epi_thr=thr_u8, epi_sgn=sgn, a_unsigned=True)
+            return SignActivation(None, N, f4=act_f4)
         act_i8 = ws.get(f"a_i8_{B}", (B, pad_to(N, 16)), torch.int8, zero=True)
         K_.gemm(M=B, N=N, K=Kd, A=(X.u8,), B=(wops["i8"],), lda=X.u8.stride(0), ldb=wops["i8"].stride(0),
                 D=act_i8, ldd=act_i8.stride(0), in_dtype=nat.DT_I8, epilogue=nat.EPI_SIGN_I8,
@@ -577,6 +590,13 @@ class BinaryLayer(LinearLayer):
             act_bits = ws.get(f"a_bits{B}", (B, pad_to(N, 32) // 32), torch.int32, zero=True)
             K_.pack_i8_rows(act_i8, N, act_bits)
         return SignActivation(act_i8, N, bits=act_bits)
+
+    def _consumer_takes_f4(self) -> bool:
+        """Eval mode: the layer above multiplies this layer's +-1 output on the FP4 tensor pipe (kernels.f4_ok), so
+        the sign epilogue writes E2M1 nibbles instead of int8 — half the bytes written here and read there."""
+        consumer = getattr(self, "output_layer", None)
+        return (isinstance(consumer, BinaryLayer) and binary_gemm_variant() != "popc"
+                and K_.f4_ok(self.layerUnits, consumer.layerUnits))
 
     # ------------------------------------------------------------------ forward
     def forward(self, X, isTrain=True):
@@ -595,7 +615,9 @@ class BinaryLayer(LinearLayer):
             B = Xt.shape[0]
         else:
             assert X.n == Kd
-            B = X.i8.shape[0]
+            B = X.rows
+        f4_in = (not real_input) and X.f4 is not None and X.i8 is None   # producer emitted nibbles (eval mode)
+        assert not (f4_in and isTrain)
 
         # operand preparation of a real-valued input does not depend on W: queue it before the weight
         # read, which in data-parallel runs first waits for the peers' updated rows to land
@@ -608,6 +630,9 @@ class BinaryLayer(LinearLayer):
                     cb.apply_to_layer(self, wops)
                 else:
                     self._apply_foreign_callback(cb, wops)
+        if f4_in:   # after the hooks: the packed words are what they mutate (callbacks.py:79-83)
+            wops["f4"] = ws.get("wt_f4", (N, pad_to(Kd, 32) // 2), torch.uint8, zero=True)
+            K_.bits_to_f4(wops["bits"], Kd, wops["f4"])
 
         sign_out = self.activation == af.sign
         popc = binary_gemm_variant() == "popc"
@@ -616,8 +641,11 @@ class BinaryLayer(LinearLayer):
         fuse_sign = sign_out and not isTrain and not (popc and not real_input)
         thr = ws.get("thr", (N,), torch.float32)
         sgn = ws.get("sgn", (N,), torch.float32)
-        act_i8 = None
-        if sign_out:
+        act_i8 = act_f4 = None
+        emit_f4 = fuse_sign and self._consumer_takes_f4()
+        if emit_f4:
+            act_f4 = ws.get(f"a_f4_{B}", (B, pad_to(N, 32) // 2), torch.uint8, zero=True)
+        elif sign_out:
             act_i8 = ws.get(f"a_i8_{B}", (B, pad_to(N, 16)), torch.int8, zero=True)
         if fuse_sign:
             K_.bn_sign_thresholds(bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
@@ -632,7 +660,9 @@ class BinaryLayer(LinearLayer):
         # ---- z = X . sign(W)
         Z = None
         if real_input:
-            if fuse_sign:
+            if emit_f4:
+                D, ldd, epi = act_f4, 2 * act_f4.stride(0), nat.EPI_SIGN_F4
+            elif fuse_sign:
                 D, ldd, epi = act_i8, act_i8.stride(0), nat.EPI_SIGN_I8
             else:
                 Z = ws.get(f"z_f32_{B}", (B, pad_to(N, 4)), torch.float32)
@@ -643,10 +673,22 @@ class BinaryLayer(LinearLayer):
                     epi_thr=thr, epi_sgn=sgn, stats=stats)
         else:
             s16 = Kd < 32768
-            if fuse_sign:
-                K_.gemm(M=B, N=N, K=Kd, A=(X.i8,), B=(wops["i8"],), lda=X.i8.stride(0),
-                        ldb=wops["i8"].stride(0), D=act_i8, ldd=act_i8.stride(0), in_dtype=nat.DT_I8,
-                        epilogue=nat.EPI_SIGN_I8, epi_thr=thr, epi_sgn=sgn)
+            if f4_in:   # E2M1 operands: K and pitches in elements (two per byte)
+                pm1 = dict(A=(X.f4,), B=(wops["f4"],), lda=2 * X.f4.stride(0), ldb=2 * wops["f4"].stride(0),
+                           in_dtype=nat.DT_F4, K=pad_to(Kd, 32))
+            else:
+                pm1 = dict(A=(X.i8,), B=(wops["i8"],), lda=X.i8.stride(0), ldb=wops["i8"].stride(0),
+                           in_dtype=nat.DT_I8, K=Kd)
+            if emit_f4:
+                K_.gemm(M=B, N=N, D=act_f4, ldd=2 * act_f4.stride(0), epilogue=nat.EPI_SIGN_F4, epi_thr=thr,
+                        epi_sgn=sgn, **pm1)
+            elif fuse_sign:
+                K_.gemm(M=B, N=N, D=act_i8, ldd=act_i8.stride(0), epilogue=nat.EPI_SIGN_I8, epi_thr=thr,
+                        epi_sgn=sgn, **pm1)
+            elif f4_in:
+                Z = ws.get(f"z_int_{B}", (B, pad_to(N, 8)), torch.int16 if s16 else torch.int32)
+                K_.gemm(M=B, N=N, D=Z, ldd=Z.stride(0), epilogue=nat.EPI_STORE_S16 if s16 else nat.EPI_STORE_S32,
+                        **pm1)
             else:
                 Z = ws.get(f"z_int_{B}", (B, pad_to(N, 8)), torch.int16 if s16 else torch.int32)
                 if popc:
@@ -684,7 +726,7 @@ class BinaryLayer(LinearLayer):
                            act_t8=act_t8, act_t8x127=act_t8x127)
             elif act_bits is not None:
                 K_.pack_i8_rows(act_i8, N, act_bits)
-            out = SignActivation(act_i8, N, t16=act_t16, bits=act_bits, t8=act_t8, t8x127=act_t8x127)
+            out = SignActivation(act_i8, N, t16=act_t16, bits=act_bits, t8=act_t8, t8x127=act_t8x127, f4=act_f4)
         else:
             logits = empty((B, N))
             K_.bn_apply(Z, B, N, mu, var, bn.gamma.t, bn.beta.t, bn.EPSILON, out_f32=logits)

@@ -67,6 +67,11 @@ class WeightFaultSweep:
             K_.absmax_f32(X, self.x_amax)
             K_.split_f16(X, self.x_amax, hi=self.x_hi, lo=self.x_lo, scale_out=self.x_scale)
         self.clean_bits, self.w, self.z, self.act, self.thr = [], [], [], [], []
+        # +-1 x +-1 layers wide enough for it run on the FP4 tensor pipe (kernels.f4_ok): the flip kernels XOR their
+        # masks into the PACKED words of the T trials (1 bit per weight) and bnn_bits_to_f4 expands those to E2M1
+        # nibbles — 4.6 + 18.4 MB written per trial of the 4096-wide network instead of 36.8 MB of int8 copies
+        self.f4 = [i > 0 and K_.f4_ok(*layer.weights_shape) for i, layer in enumerate(self.layers)]
+        self.wbits = []
         T, R = self.T, self.R
         for i, layer in enumerate(self.layers):
             Kd, N = layer.weights_shape
@@ -75,7 +80,10 @@ class WeightFaultSweep:
             bits = zeros((N, pad_to(Kd, 32) // 32), torch.int32)
             K_.binarize_weights_t(layer.weights.t, wt_bits=bits)
             self.clean_bits.append(bits)
-            if i == 0 and self.u8 is None:
+            self.wbits.append(zeros((T,) + tuple(bits.shape), torch.int32) if self.f4[i] else None)
+            if self.f4[i]:
+                self.w.append(zeros((T, N, pad_to(Kd, 32) // 2), torch.uint8))
+            elif i == 0 and self.u8 is None:
                 self.w.append(zeros((T, N, pad_to(Kd, 8)), torch.float16))
             else:
                 self.w.append(zeros((T, N, pad_to(Kd, 16)), torch.int8))
@@ -91,7 +99,12 @@ class WeightFaultSweep:
                 thr, sgn = zeros((N,), torch.float32), zeros((N,), torch.float32)
                 K_.bn_sign_thresholds(bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
                 self.thr.append((thr, sgn))
-            self.act.append(empty((T * R, N)) if last else zeros((T * R, pad_to(N, 16)), torch.int8))
+            if last:
+                self.act.append(empty((T * R, N)))
+            elif self.f4[i + 1]:   # the layer above reads nibbles
+                self.act.append(zeros((T * R, pad_to(N, 32) // 2), torch.uint8))
+            else:
+                self.act.append(zeros((T * R, pad_to(N, 16)), torch.int8))
         self.correct = zeros((T,), torch.int32)
 
     # ------------------------------------------------------------------ one launch group
@@ -109,6 +122,8 @@ class WeightFaultSweep:
                        (nat.EPI_STORE_S16 if Z.dtype == torch.int16 else nat.EPI_STORE_S32))
             else:
                 D, ldd, epi = out, out.stride(0), nat.EPI_SIGN_I8
+                if self.f4[i + 1]:
+                    ldd, epi = 2 * out.stride(0), nat.EPI_SIGN_F4
                 thr, sgn = self.thr[i]
             if i == 0 and self.u8 is not None:
                 u8 = self.u8
@@ -123,6 +138,11 @@ class WeightFaultSweep:
                         ldb=w.stride(1), D=D, ldd=ldd, in_dtype=nat.DT_F16, epilogue=epi,
                         passes=((0, 0), (1, 0)), sa=self.x_scale, batch=T, stride_a=0,
                         stride_b=w.stride(0), stride_d=R * ldd, epi_thr=thr, epi_sgn=sgn)
+            elif self.f4[i]:
+                a = self.act[i - 1]   # nibbles: K, pitches and strides in elements (two per byte)
+                K_.gemm(M=R, N=N, K=pad_to(Kd, 32), A=(a,), B=(w,), lda=2 * a.stride(0), ldb=2 * w.stride(1), D=D,
+                        ldd=ldd, in_dtype=nat.DT_F4, epilogue=epi, batch=T, stride_a=2 * R * a.stride(0),
+                        stride_b=2 * w.stride(0), stride_d=R * ldd, epi_thr=thr, epi_sgn=sgn)
             else:
                 a = self.act[i - 1]
                 K_.gemm(M=R, N=N, K=Kd, A=(a,), B=(w,), lda=a.stride(0), ldb=w.stride(1), D=D, ldd=ldd,
@@ -140,6 +160,12 @@ class WeightFaultSweep:
         for i, layer in enumerate(self.layers):
             Kd, N = layer.weights_shape
             w = self.w[i][:n_live]
+            if self.f4[i]:   # mask XORed into the packed words, then expanded to nibbles
+                wb = self.wbits[i][:n_live]
+                K_.flip_weights_bernoulli(N=N, K=Kd, p=p, seed=seed, stream_id=i, trial0=trial0, n_trials=n_live,
+                                          wt_bits=self.clean_bits[i], out_bits=wb)
+                K_.bits_to_f4(wb, Kd, w)
+                continue
             f16 = i == 0 and self.u8 is None
             K_.flip_weights_bernoulli(N=N, K=Kd, p=p, seed=seed, stream_id=i, trial0=trial0,
                                       n_trials=n_live, wt_bits=self.clean_bits[i],
@@ -151,6 +177,13 @@ class WeightFaultSweep:
         for i, layer in enumerate(self.layers):
             Kd, N = layer.weights_shape
             w = self.w[i][:n_live]
+            if self.f4[i]:
+                wb = self.wbits[i][:n_live]
+                wb.copy_(self.clean_bits[i].unsqueeze(0).expand_as(wb))
+                K_.flip_weights_exactk(N=N, K=Kd, total=self.total_weights, offset=int(self.offsets[i]),
+                                       seed=seed, trial0=trial0, k_per_trial=ks, k_max=k_max, io_bits=wb)
+                K_.bits_to_f4(wb, Kd, w)
+                continue
             f16 = i == 0 and self.u8 is None
             bits = self.bits0[:n_live] if i == 0 and self.u8 is not None else None
             # replicate the clean weights (p = 0), then scatter this layer's share of the flips
@@ -263,13 +296,17 @@ class ImageFaultSweep:
         self.units = self.nn.unitList
         self.mm = zeros((T, 2), torch.int32)
         self.w, self.thr, self.act, self.z = [], [], [], None
+        self.f4 = [i > 0 and K_.f4_ok(*layer.weights_shape) for i, layer in enumerate(self.layers)]
         for i, layer in enumerate(self.layers):
             Kd, N = layer.weights_shape
             bn = layer.batchNormLayer
             last = i == len(self.layers) - 1
-            w = zeros((N, pad_to(Kd, 16)), torch.int8)
-            bits = zeros((N, pad_to(Kd, 32) // 32), torch.int32) if i == 0 else None
+            w = None if self.f4[i] else zeros((N, pad_to(Kd, 16)), torch.int8)
+            bits = zeros((N, pad_to(Kd, 32) // 32), torch.int32) if (i == 0 or self.f4[i]) else None
             K_.binarize_weights_t(layer.weights.t, wt_i8=w, wt_bits=bits)
+            if self.f4[i]:   # clean weights as E2M1 nibbles (FP4 tensor pipe)
+                w = zeros((N, pad_to(Kd, 32) // 2), torch.uint8)
+                K_.bits_to_f4(bits, Kd, w)
             self.w.append(w)
             if i == 0:
                 self.bits0 = bits
@@ -283,7 +320,8 @@ class ImageFaultSweep:
                 thr, sgn = zeros((N,), torch.float32), zeros((N,), torch.float32)
                 K_.bn_sign_thresholds(bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
                 self.thr.append((thr, sgn))
-                self.act.append(zeros((T * R, pad_to(N, 16)), torch.int8))
+                self.act.append(zeros((T * R, pad_to(N, 32) // 2), torch.uint8) if self.f4[i + 1]
+                                else zeros((T * R, pad_to(N, 16)), torch.int8))
         self.correct = zeros((T,), torch.int32)
 
     def _batched_group(self, k: int, mode: int, seed: int, t0: int, n_live: int) -> torch.Tensor:
@@ -296,28 +334,32 @@ class ImageFaultSweep:
         K_.u8_input_thresholds(self.bits0, N0, F, thr, sgn, self.mm, T, -1.0, 1.0,
                                0 if self.a_unsigned else 128, self.thr0)
         a0, w0 = self.act[0], self.w[0]
+        ld0, epi0 = (2 * a0.stride(0), nat.EPI_SIGN_F4) if self.f4[1] else (a0.stride(0), nat.EPI_SIGN_I8)
         K_.gemm(M=R, N=N0, K=F, A=(flipped.view(torch.int8),), B=(w0,), lda=F, ldb=w0.stride(0), D=a0,
-                ldd=a0.stride(0), in_dtype=nat.DT_I8, epilogue=nat.EPI_SIGN_I8, batch=T, stride_a=R * F,
-                stride_b=0, stride_d=R * a0.stride(0), epi_thr=self.thr0, epi_sgn=sgn,
+                ldd=ld0, in_dtype=nat.DT_I8, epilogue=epi0, batch=T, stride_a=R * F,
+                stride_b=0, stride_d=R * ld0, epi_thr=self.thr0, epi_sgn=sgn,
                 epi_thr_stride=self.thr0.stride(0), a_unsigned=self.a_unsigned)
         for i in range(1, len(self.layers)):
             layer = self.layers[i]
             Kd, N = layer.weights_shape
             a, w = self.act[i - 1], self.w[i]
+            if self.f4[i]:
+                ops = dict(K=pad_to(Kd, 32), A=(a,), B=(w,), lda=2 * a.stride(0), ldb=2 * w.stride(0),
+                           in_dtype=nat.DT_F4)
+            else:
+                ops = dict(K=Kd, A=(a,), B=(w,), lda=a.stride(0), ldb=w.stride(0), in_dtype=nat.DT_I8)
             if i == len(self.layers) - 1:
                 Z, bn = self.z, layer.batchNormLayer
                 epi = nat.EPI_STORE_S16 if Z.dtype == torch.int16 else nat.EPI_STORE_S32
-                K_.gemm(M=T * R, N=N, K=Kd, A=(a,), B=(w,), lda=a.stride(0), ldb=w.stride(0), D=Z,
-                        ldd=Z.stride(0), in_dtype=nat.DT_I8, epilogue=epi)
+                K_.gemm(M=T * R, N=N, D=Z, ldd=Z.stride(0), epilogue=epi, **ops)
                 # softmax / identity are monotone per row: the argmax of the BN output decides the class
                 K_.bn_apply(Z, T * R, N, bn.mu.t, bn.sigma.t, bn.gamma.t, bn.beta.t, bn.EPSILON,
                             out_f32=self.act[i])
             else:
                 out = self.act[i]
                 thr_i, sgn_i = self.thr[i]
-                K_.gemm(M=T * R, N=N, K=Kd, A=(a,), B=(w,), lda=a.stride(0), ldb=w.stride(0), D=out,
-                        ldd=out.stride(0), in_dtype=nat.DT_I8, epilogue=nat.EPI_SIGN_I8, epi_thr=thr_i,
-                        epi_sgn=sgn_i)
+                ldo, epo = (2 * out.stride(0), nat.EPI_SIGN_F4) if self.f4[i + 1] else (out.stride(0), nat.EPI_SIGN_I8)
+                K_.gemm(M=T * R, N=N, D=out, ldd=ldo, epilogue=epo, epi_thr=thr_i, epi_sgn=sgn_i, **ops)
         self.correct.zero_()
         K_.count_correct(self.act[-1], R, self.units[-1], self.labels, self.correct, groups=T)
         return self.correct[:T].clone()

@@ -78,6 +78,14 @@ int bnn_binarize_weights_t(const float* W, int K, int N, int8_t* wt_i8, int64_t 
 int bnn_unpack_bits(const uint32_t* bits, int R, int C, int64_t ldw, int8_t* out_i8, int64_t ld_i8,
                     void* out_f16, int64_t ld_f16, bnn_stream_t stream);
 
+/* Expand packed sign bits [R, ldw] to E2M1 nibbles [R, ld_f4 / 2 bytes] — the BNN_DT_F4 operand form of a +-1
+ * matrix: bit j of word w -> nibble (32w + j): 1 -> 0x2 (+1.0), 0 -> 0xA (-1.0); nibbles in [C, 32*ceil(C/32))
+ * -> 0x0 (+0.0, the K padding of the product).  ld_f4 counts ELEMENTS (a multiple of 32).  This is how the
+ * fault sweeps reach the FP4 tensor pipe: the flip kernels XOR their masks into the packed words
+ * (callbacks.py:79-83 on 1 bit per weight) and this pass expands the result. */
+int bnn_bits_to_f4(const uint32_t* bits, int64_t R, int C, int64_t ldw, void* out_f4, int64_t ld_f4,
+                   bnn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * fp32 -> 2 x fp16 split operands for the real-valued GEMMs (layer-0 forward, dW, dX).
  * x*s = hi + lo (+ O(2^-22)), s = 2^(14 - ceil(log2(bound))) a power of two, so three fp16
@@ -105,7 +113,15 @@ int bnn_split_f16(const float* x, int R, int C, int64_t ldx, const float* bound,
  * D[b][M, N] = epilogue( sum_p  A[pa[p]][b][M, K] * B[pb[p]][b][N, K]^T )
  * Both operands K-major (row-major with the contraction index contiguous).
  * ------------------------------------------------------------------------------------------- */
-enum { BNN_DT_I8 = 0, BNN_DT_F16 = 1 };
+enum {
+    BNN_DT_I8 = 0,
+    BNN_DT_F16 = 1,
+    BNN_DT_F4 = 2 /* E2M1 nibbles, two per byte, low nibble = even k (+1 = 0x2, -1 = 0xA, 0 = 0x0): the +-1 x +-1
+                     products of the evaluation paths on tcgen05 kind::mxf4.block_scale with unit scale factors —
+                     exact (fp32 accumulators hold integers, K < 2^24), twice the kind::i8 rate, half the operand
+                     bytes.  K, lda, ldb, stride_a, stride_b count ELEMENTS and are multiples of 32; one pass,
+                     integer epilogues (STORE_S32 / STORE_S16 / SIGN_I8 / SIGN_F4), no fused statistics. */
+};
 enum {
     BNN_EPI_STORE_F32 = 0, /* D fp32  = acc * host_scale / (sa*sb)                       */
     BNN_EPI_STORE_S32 = 1, /* D int32 = acc                      (I8 only)               */
@@ -114,6 +130,9 @@ enum {
     BNN_EPI_SIGN_I8 = 4,   /* D int8 = +1 if acc*host_scale/(sa*sb) * epi_sgn[n] >= epi_thr[n] else -1:
                               batch-norm + sign fused into the GEMM (thresholds from
                               bnn_bn_sign_thresholds); Z never reaches HBM (eval mode)           */
+    BNN_EPI_SIGN_F4 = 6,   /* like SIGN_I8, stored as E2M1 nibbles (the A operand of a BNN_DT_F4 product): D uint8
+                              [M, ldd / 2] with ldd, stride_d in ELEMENTS, multiples of 32; columns in [N, 16*ceil(N/16))
+                              are written as 0 (they are the consumer's K padding)                     */
     BNN_EPI_SCATTER_F32 = 5 /* like STORE_F32, but every 128-row tile is stored over NVLink into the
                               staging buffer of the rank that owns those rows (desc.scatter): the
                               reduce-scatter half of the data-parallel dW all-reduce, fused into the

@@ -84,10 +84,44 @@ def test_weight_sweep_emits_wellformed_abi_calls(dry):
     assert sw.run_bernoulli(0.1, 6, seed=3).shape == (6,)
     assert sw.run_exactk(lambda t: 1 + t, 6, seed=3).shape == (6,)
     names = [n for n, _ in dry]
-    assert names.count("bnn_flip_weights_bernoulli") == 2 * 3 + 2 * 3   # per layer and group, both modes
+    # 256 -> 128 is wide enough for the FP4 pipe: its flips act on packed words, expanded by bnn_bits_to_f4
+    assert sw.f4 == [False, True, False]
+    # per layer and launch group (2 groups); exact-k replicates the clean int8 / fp16 copies with a p = 0 call
+    assert names.count("bnn_flip_weights_bernoulli") == 2 * 3 + 2 * 2
     assert names.count("bnn_flip_weights_exactk") == 2 * 3
+    assert names.count("bnn_bits_to_f4") == 2 * 1 + 2 * 1
     assert names.count("bnn_gemm") == 4 * 3
     assert all(rc in (0, -2) for _, rc in dry)
+
+
+def test_weight_sweep_without_fp4_keeps_int8_copies(dry, monkeypatch):
+    from mlpcode.sweep import WeightFaultSweep
+    monkeypatch.setenv("BNN_FP4", "0")
+    nn = _net([784, 256, 128, 10])
+    X = np.random.default_rng(2).random((64, 784), dtype=np.float32) * 2 - 1
+    sw = WeightFaultSweep(nn, X, np.zeros(64, np.uint8), trials_per_launch=4)
+    del dry[:]
+    assert sw.run_bernoulli(0.1, 6, seed=3).shape == (6,)
+    assert sw.run_exactk(lambda t: 1 + t, 6, seed=3).shape == (6,)
+    names = [n for n, _ in dry]
+    assert sw.f4 == [False, False, False] and "bnn_bits_to_f4" not in names
+    assert names.count("bnn_flip_weights_bernoulli") == 2 * 3 + 2 * 3
+    assert names.count("bnn_gemm") == 4 * 3
+
+
+def test_predict_routes_wide_hidden_layers_through_fp4(dry, monkeypatch):
+    """Eval-mode forward: a layer whose consumer takes nibbles ends in BNN_EPI_SIGN_F4, the consumer expands its
+    packed weights with bnn_bits_to_f4; every call passes the library's argument validation."""
+    nn = _net([784, 256, 128, 10])
+    X = np.random.default_rng(3).random((40, 784), dtype=np.float32) * 2 - 1
+    del dry[:]
+    nn.predict(X)
+    names = [n for n, _ in dry]
+    assert names.count("bnn_bits_to_f4") == 1 and names.count("bnn_gemm") == 3
+    monkeypatch.setenv("BNN_FP4", "0")
+    del dry[:]
+    nn.predict(X)
+    assert "bnn_bits_to_f4" not in [n for n, _ in dry]
 
 
 def test_unchanged_script_flow_stays_on_bytes(dry):

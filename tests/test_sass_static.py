@@ -1,7 +1,8 @@
 """Static evidence from the compiled object (cuobjdump -sass, no GPU): which tensor-core / TMA / cluster
 instructions each GEMM kernel instantiation contains.  The single-CTA kernels (the product path) must hold
-tcgen05 MMAs and TMA loads and NO CTA-pair instruction; the experimental pair-form instantiations (DESIGN
-3.5) must hold the 2-CTA forms of all of them."""
+tcgen05 MMAs and TMA loads and NO CTA-pair instruction; the opt-in pair-form instantiations must hold
+the 2-CTA forms of all of them; the FP4 instantiations hold the block-scaled MMA (UTCOMMA) and nothing else.
+The last two template arguments of gemm_tc_kernel are <kCta2, kF4>."""
 import re
 import shutil
 import subprocess
@@ -33,7 +34,7 @@ def kernels():
 
 
 def test_single_cta_kernels_use_tcgen05_and_tma_only(kernels):
-    single = {k: v for k, v in kernels.items() if "ELb1EEEv" not in k}
+    single = {k: v for k, v in kernels.items() if k.endswith("ELb0ELb0EEEv14CUtensorMap_stS2_S2_S2_S2_NS0_8TcParamsE")}
     assert len(single) >= 40
     for name, ops in single.items():
         assert any(o.startswith(("UTCIMMA", "UTCHMMA")) for o in ops), name        # tcgen05.mma kind::i8 / kind::f16
@@ -42,10 +43,19 @@ def test_single_cta_kernels_use_tcgen05_and_tma_only(kernels):
 
 
 def test_pair_kernels_use_the_two_cta_forms(kernels):
-    pair = {k: v for k, v in kernels.items() if "ELb1EEEv" in k}
+    pair = {k: v for k, v in kernels.items() if "ELb1ELb0EEEv" in k}
     assert len(pair) >= 8
     for name, ops in pair.items():
         assert any(o in ("UTCIMMA.2CTA", "UTCHMMA.2CTA") for o in ops), (name, ops)
         assert "UTMALDG.3D.2CTA" in ops and "UTCBAR.2CTA.MULTICAST" in ops, (name, ops)
         assert "UCGABAR_ARV" in ops and "UCGABAR_WAIT" in ops, (name, ops)
         assert not any(o in ("UTCIMMA", "UTCHMMA", "UTMALDG.3D", "UTCBAR") for o in ops), (name, ops)
+
+
+def test_fp4_kernels_use_the_block_scaled_mma(kernels):
+    f4 = {k: v for k, v in kernels.items() if "ELb0ELb1EEEv" in k}
+    assert len(f4) == 12                                   # 3 tile widths x 4 integer epilogues
+    for name, ops in f4.items():
+        assert any(o.startswith("UTCOMMA") for o in ops), (name, ops)             # tcgen05.mma kind::mxf4.block_scale
+        assert "UTMALDG.3D" in ops, name
+        assert not any(o.startswith(("UTCIMMA", "UTCHMMA")) or "2CTA" in o for o in ops), (name, ops)
