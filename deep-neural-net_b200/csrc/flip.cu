@@ -51,6 +51,21 @@ flip_bernoulli_kernel(const int8_t* __restrict__ wt_i8, long long ld_i8,
         uint32_t mask = 0;
         const unsigned long long e0 = (unsigned long long)n * (unsigned long long)K + kbase;
         U4 rnd = {0, 0, 0, 0};
+        if (threshold && cnt == 32 && (e0 & 3ull) == 0) {
+            // whole word on a counter boundary (K % 4 == 0): 8 Philox calls, four 32-bit compares each — the same
+            // draws as the element loop below, without its per-element branch and 64-bit compares
+            const bool all = threshold >= (1ull << 32);
+            const uint32_t thr32 = all ? 0xFFFFFFFFu : (uint32_t)threshold;
+            const unsigned long long q0 = e0 >> 2;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const unsigned long long q = q0 + g;
+                const U4 r = rng::philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), stream_id, trial0 + t, k0, k1);
+                mask |= ((uint32_t)(r.x < thr32) | ((uint32_t)(r.y < thr32) << 1) | ((uint32_t)(r.z < thr32) << 2) |
+                         ((uint32_t)(r.w < thr32) << 3)) << (4 * g);
+            }
+            if (all) mask = 0xFFFFFFFFu;
+        } else
         for (int j = 0; j < (threshold ? cnt : 0); ++j) {  // threshold 0: plain replication
             const unsigned long long e = e0 + j;
             if (j == 0 || (e & 3ull) == 0) {

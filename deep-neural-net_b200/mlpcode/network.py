@@ -22,6 +22,7 @@ from typing import List, Union
 import numpy as np
 import torch
 
+from . import checkpoint
 from . import kernels as K_
 from . import loss as loss_mod
 from .activation import ACTIVATION_FUNCTIONS
@@ -147,40 +148,36 @@ class Network(object):
     # ------------------------------------------------------------------ checkpoints (.npz bridge)
     @staticmethod
     def fromModel(filePth, useGpu=False, binarized=False):
-        """Load a checkpoint with the key layout of the reference's HDF5 files
-        (network.py:157-228: units, useBias, useBatchNorm, weights/weights_i, gammas/gammas_i, ...),
-        stored as `.npz` because h5py is unavailable."""
+        """Load a checkpoint with the key layout of the reference's HDF5 files (network.py:157-228: units,
+        useBias, useBatchNorm, weights/weights_i, gammas/gammas_i, ...), stored as `.npz` because h5py is
+        unavailable — see mlpcode.checkpoint.  A packed-only file (sign words, no latent weights) loads as
+        latent weights of +-1."""
         filePth = Path(filePth)
         assert filePth.exists()
-        with np.load(filePth) as fp:
-            units = [int(u) for u in fp["units"]]
-            useBias = bool(fp["useBias"])
-            useBN = bool(fp["useBatchNorm"])
-            if useBN and useBias:
-                useBias = False
-            nn = Network(units, useGpu=useGpu, useBias=useBias, binarized=binarized,
-                         useBatchNorm=useBN)
-            n = len(units) - 1
-            nn.load_weights([fp[f"weights/weights_{i}"].astype(np.float32) for i in range(n)])
-            if useBN:
-                nn.loadBatchNormParameters(
-                    *[[fp[f"{g}/{g}_{i}"].astype(np.float32) for i in range(n)]
-                      for g in ("gammas", "betas", "mus", "sigmas")])
+        ck = checkpoint.read_checkpoint(filePth)
+        useBias = ck["useBias"]
+        if ck["useBatchNorm"] and useBias:
+            print("Setting useBias to false cause of batchnorm")
+            useBias = False
+        nn = Network(ck["units"], useGpu=useGpu, useBias=useBias, binarized=binarized,
+                     useBatchNorm=ck["useBatchNorm"])
+        nn.load_weights(ck["weights"], ck["biases"] if useBias else None)
+        if ck["useBatchNorm"]:
+            nn.loadBatchNormParameters(*[ck[g] for g in checkpoint.BN_GROUPS])
         return nn
 
-    def save_weights(self, modelName: str, binarized=False, directory=None):
+    def save_weights(self, modelName: str, binarized=False, directory=None, latent=True):
+        """network.py:428-472 with `.npz` for `.hdf5` (same members; no timestamp in the name so that scripts can
+        find their file).  binarized=True — in the reference only a file-name suffix — also stores the packed
+        sign words `packed_weights/packed_weights_i`; latent=False then drops the float32 weights (a 1-bit-per-
+        weight deployment file that fromModel reads back as +-1)."""
         directory = Path(directory) if directory is not None else MODELDIR
-        directory.mkdir(parents=True, exist_ok=True)
         path = directory / f"{modelName}{'_binarized' if binarized else ''}.npz"
-        blob = {"units": np.array(self.unitList, dtype=np.uint32), "useBias": np.array(self.useBias),
-                "useBatchNorm": np.array(self.useBatchNorm)}
-        for i, w in enumerate(self.weights):
-            blob[f"weights/weights_{i}"] = asnumpy(w)
-        if self.useBatchNorm:
-            for name, group in zip(("gammas", "betas", "mus", "sigmas"), self.batchNormParams):
-                for i, v in enumerate(group):
-                    blob[f"{name}/{name}_{i}"] = asnumpy(v)
-        np.savez(path, **blob)
+        bn = [[asnumpy(v) for v in group] for group in self.batchNormParams] if self.useBatchNorm else None
+        biases = [asnumpy(b) for b in self.biases] if self.useBias else None
+        checkpoint.write_checkpoint(path, self.unitList, self.useBias, self.useBatchNorm,
+                                    [asnumpy(w) for w in self.weights], biases, bn,
+                                    packed=bool(binarized), latent=latent)
         print(f"Saving model to {path}")
         return path
 

@@ -71,6 +71,50 @@ def flat_state(prefix, st):
     return out
 
 
+def gen_checkpoint(A, Lo, Nw, O):
+    """tests/golden/checkpoint_ref.npz is WRITTEN BY THE REFERENCE: its unmodified Network.save_weights
+    (network.py:428-472) runs against the npz-backed h5py stand-in (oracle/refshim/h5py.py) after two training
+    steps on a small network.  The reference's fromModel (:157-228) then has to read back both that file and the
+    one this package's writer (mlpcode/checkpoint.py, loaded by path: both packages are called `mlpcode`)
+    produces from the same state — predictions identical in both cases.  tests/test_checkpoint.py holds this
+    package's reader and writer against the reference-written file."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("b200_checkpoint",
+                                                  REPO / "deep-neural-net_b200" / "mlpcode" / "checkpoint.py")
+    ck = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ck)
+    af = A.ActivationFuncs
+    rng = np.random.default_rng(63)
+    units = [40, 24, 12, 10]
+    params = O.new_params(units, rng)
+    X = rng.random((32, 40), dtype=np.float32) * 2 - 1
+    Y = np.eye(10, dtype=np.int8)[rng.integers(0, 10, 32)]
+    nn = make_net(Nw, A, Lo, units, params, af.softmax)
+    for _ in range(2):
+        nn._Network__updateBatch((X.copy(), Y.copy()), 0.01)
+    probs = nn.predict(X.copy(), isTraining=False)
+    before = set(Nw.MODELDIR.glob("*.hdf5"))
+    nn.save_weights("golden_ckpt")
+    written, = set(Nw.MODELDIR.glob("*.hdf5")) - before
+    # the reference reads its own file ...
+    back = Nw.Network.fromModel(written, useGpu=False, binarized=True)
+    back.compile(hiddenAf=af.sign, outAf=af.softmax)
+    exact(back.predict(X.copy(), isTraining=False), probs, "reference fromModel(reference save_weights)")
+    # ... and this package's writer produces a file the reference reads to the same effect
+    st = net_state(nn)
+    bn = [[b[k] for b in st["bn"]] for k in ("gamma", "beta", "mu", "sigma")]
+    ours = ck.write_checkpoint(Nw.MODELDIR / "ours.hdf5", units, False, True, st["W"], None, bn, packed=True)
+    back2 = Nw.Network.fromModel(ours, useGpu=False, binarized=True)
+    back2.compile(hiddenAf=af.sign, outAf=af.softmax)
+    exact(back2.predict(X.copy(), isTraining=False), probs, "reference fromModel(this package's writer)")
+    # packed-only file: latent weights of +-1 give the same eval-mode result (sign(W) is all that is read)
+    only = ck.read_checkpoint(ck.write_checkpoint(Nw.MODELDIR / "packed.npz", units, False, True, st["W"], None, bn,
+                                                  packed=True, latent=False))
+    assert only["packed_only"] and all(np.array_equal(w, O.binarize(v)) for w, v in zip(only["weights"], st["W"]))
+    shutil.copyfile(written, GOLDEN / "checkpoint_ref.npz")
+    np.savez_compressed(GOLDEN / "checkpoint_ref_io.npz", X=X, probs=probs, **flat_state("", st))
+
+
 def gen_float_faults(Cb, O):
     """IEEE-754 bit flips of real-valued weights (ErrorCallback(bnn=False), callbacks.py:35-59, 85-123):
     the reference draws from the global NumPy stream; replaying the same stream through the oracle's
@@ -97,6 +141,17 @@ def gen_float_faults(Cb, O):
 
 
 def main():
+    if sys.argv[1:] == ["checkpoint"]:      # only this fixture (the others stay byte-identical)
+        L, A, Lo, Cb, Nw, U = import_reference()
+        sys.path.insert(0, str(HERE))
+        import bnn_oracle as O
+        gen_checkpoint(A, Lo, Nw, O)
+        print("checkpoint fixtures written")
+        return
+    _main_all()
+
+
+def _main_all():
     sys.path.insert(0, str(HERE))
     if "--only-float-faults" in sys.argv:            # leaves the other fixtures byte-identical
         import bnn_oracle as O
@@ -290,6 +345,7 @@ def main():
     np.savez_compressed(GOLDEN / "image_faults.npz", **blob)
 
     gen_float_faults(Cb, O)
+    gen_checkpoint(A, Lo, Nw, O)
 
     sizes = {p.name: p.stat().st_size for p in sorted(GOLDEN.glob("*.npz"))}
     print("golden fixtures written:", sizes)

@@ -102,8 +102,9 @@ def call_timeline(fn, period):
     finally:
         K_._call = orig
     agg = {}
+    period = period or len(rec)
     for i, (name, s, e) in enumerate(rec):
-        key = f"{i % period}:{name}"
+        key = f"{i % period:02d}:{name}"
         agg[key] = agg.get(key, 0.0) + s.elapsed_time(e)
     return agg
 
@@ -154,7 +155,7 @@ def config1_section(steps=50, cpu_steps=20):
 
 
 # ------------------------------------------------------------------------------------------------ config 4
-def weight_sweep_section(comm, n_trials=10000, per_launch=8, cpu_trials=1, int8_peak_tops=None):
+def weight_sweep_section(comm, n_trials=10000, per_launch=8, cpu_trials=1, int8_peak_tops=None, timeline=False):
     """BASELINE configs[3]: 10 000 fault trials on the 784-4096^3-10 BNN, 10 000 evaluation rows fed as
     normalize(uint8 images) (weightsErrorInjectionv2.py:15), trials sharded over the ranks.
       bernoulli  every weight of every layer flips with p = 0.1 (callbacks.py:79-83 semantics)
@@ -186,6 +187,11 @@ def weight_sweep_section(comm, n_trials=10000, per_launch=8, cpu_trials=1, int8_
         out[name] = {"trials_per_s": tps, "seconds": ms * 1e-3, "mean_accuracy": float(np.mean(acc)),
                      "top_per_s": tops, "gpu_launches": K_.launch_count - l0,
                      "frac_of_int8_peak": (tops / (world * int8_peak_tops)) if int8_peak_tops else None}
+    out["pipes"] = ["kind::i8 (u8 x s8)" if sweep.u8 is not None else "kind::f16"] + \
+                   ["kind::mxf4 (E2M1)" if f else "kind::i8" for f in sweep.f4[1:]]
+    if timeline and world == 1:   # one launch group, every C-ABI call between its own pair of CUDA events
+        tl = call_timeline(lambda: sweep.run_bernoulli(0.1, per_launch, 7), None)
+        out["bernoulli_ms_per_trial_by_call"] = {k: v / per_launch for k, v in tl.items()}
     del sweep
     torch.cuda.empty_cache()
     if rank == 0 and cpu_trials > 0:
@@ -229,8 +235,8 @@ def image_sweep_section(comm, n_trials=800, per_launch=8, cpu_trials=1, timeline
            "top_per_s": tps * 2.0 * ROWS4 * _sum_kn(UNITS4) / 1e12,
            "flip_bytes_per_trial": 2 * ROWS4 * 784}
     if timeline and world == 1:
-        tl = call_timeline(lambda: isw.run(0.14, 4 * per_launch, 11), 7)
-        out["ms_per_trial_by_call"] = {k: v / (4 * per_launch) for k, v in tl.items()}
+        tl = call_timeline(lambda: isw.run(0.14, per_launch, 11), None)
+        out["ms_per_trial_by_call"] = {k: v / per_launch for k, v in tl.items()}
     del isw
     torch.cuda.empty_cache()
     if rank == 0 and cpu_trials > 0:
@@ -322,7 +328,7 @@ def main():
     if "config1" in sections and rank == 0:
         out["config1"] = config1_section(cpu_steps=20 if args.cpu_trials else 0)
     if "weights" in sections:
-        out["weight_sweep"] = weight_sweep_section(comm, args.trials, args.per_launch, args.cpu_trials)
+        out["weight_sweep"] = weight_sweep_section(comm, args.trials, args.per_launch, args.cpu_trials, timeline=True)
     if "image" in sections:
         out["image_sweep"] = image_sweep_section(comm, args.image_trials, args.per_launch, args.cpu_trials,
                                                  timeline=True)
