@@ -143,6 +143,35 @@ unpack_bits_kernel(const uint32_t* __restrict__ bits, int R, int C, long long ld
     }
 }
 
+// Row gather: dst[i, :] = src[idx[i], :] on raw bytes (any element type).  The mini-batch assembly of an epoch
+// (trainX[p, :][k:k+bs], network.py:312-315, 480) without materialising the shuffled data set: idx is the slice of
+// the composed permutation, dst the training step's static batch buffer.  One warp per row; 16-byte vectors when
+// pointers, pitches and the row length allow, bytes otherwise.  Rows whose index is outside [0, n_src) are
+// zero-filled and counted in *bad (the caller checks it once per epoch).
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const uint8_t* __restrict__ src, long long src_pitch, long long n_src,
+                   const long long* __restrict__ idx, int n_rows, long long row_bytes,
+                   uint8_t* __restrict__ dst, long long dst_pitch, int vec, int* __restrict__ bad) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
+        const long long s = __ldg(idx + r);
+        const bool ok = s >= 0 && s < n_src;
+        if (!ok && lane == 0 && bad) atomicAdd(bad, 1);
+        const uint8_t* sp = src + (ok ? s : 0) * src_pitch;
+        uint8_t* dp = dst + (long long)r * dst_pitch;
+        if (vec) {
+            const long long n16 = row_bytes >> 4;
+            for (long long j = lane; j < n16; j += 32) {
+                const uint4 v = ok ? __ldg(reinterpret_cast<const uint4*>(sp) + j) : make_uint4(0, 0, 0, 0);
+                reinterpret_cast<uint4*>(dp)[j] = v;
+            }
+        } else {
+            for (long long j = lane; j < row_bytes; j += 32) dp[j] = ok ? __ldg(sp + j) : (uint8_t)0;
+        }
+    }
+}
+
 // Packed sign bits -> E2M1 nibbles (BNN_DT_F4 operand): one thread turns one 32-bit word into 16 bytes
 // (bit j -> nibble j: 1 -> 0x2 = +1.0, 0 -> 0xA = -1.0; columns past C -> 0x0 = +0.0, they pad K).
 // Reads 4 bytes, writes one 16-byte vector per thread, both coalesced.
@@ -353,6 +382,24 @@ extern "C" int bnn_unpack_bits(const uint32_t* bits, int R, int C, int64_t ldw, 
     unpack_bits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         bits, R, C, ldw, out_i8, ld_i8, static_cast<__half*>(out_f16), ld_f16);
     BNN_LAUNCH_CHECK("unpack_bits_kernel");
+    return BNN_OK;
+}
+
+extern "C" int bnn_gather_rows(const void* src, int64_t src_pitch_bytes, int64_t n_src_rows, const int64_t* idx,
+                               int n_rows, int64_t row_bytes, void* dst, int64_t dst_pitch_bytes, int32_t* bad_count,
+                               bnn_stream_t stream) {
+    BNN_CHECK_ARG(src && idx && dst && n_rows > 0 && row_bytes > 0 && n_src_rows > 0, "bnn_gather_rows: bad input");
+    BNN_CHECK_ARG(src_pitch_bytes >= row_bytes && dst_pitch_bytes >= row_bytes,
+                  "bnn_gather_rows: pitch smaller than the row (%lld, %lld < %lld)", (long long)src_pitch_bytes,
+                  (long long)dst_pitch_bytes, (long long)row_bytes);
+    const int vec = aligned16(src) && aligned16(dst) && src_pitch_bytes % 16 == 0 && dst_pitch_bytes % 16 == 0 &&
+                    row_bytes % 16 == 0;
+    const int blocks = (n_rows + 7) / 8;   // 8 warps per block, one row per warp
+    const int grid = blocks < 148 * 8 ? blocks : 148 * 8;
+    gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint8_t*>(src), src_pitch_bytes, n_src_rows, reinterpret_cast<const long long*>(idx),
+        n_rows, row_bytes, static_cast<uint8_t*>(dst), dst_pitch_bytes, vec, bad_count);
+    BNN_LAUNCH_CHECK("gather_rows_kernel");
     return BNN_OK;
 }
 

@@ -74,6 +74,7 @@ PROTOTYPES = {
     "bnn_binarize_weights_t": [_p, _i, _i, _p, _i64, _p, _i64, _p, _i64, _p, _p],
     "bnn_unpack_bits": [_p, _i, _i, _i64, _p, _i64, _p, _i64, _p],
     "bnn_bits_to_f4": [_p, _i64, _i, _i64, _p, _i64, _p],
+    "bnn_gather_rows": [_p, _i64, _i64, _p, _i, _i64, _p, _i64, _p, _p],
     "bnn_absmax_f32": [_p, _i64, _p, _i, _p],
     "bnn_split_f16": [_p, _i, _i, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p, _p],
     "bnn_gemm": [C.POINTER(GemmDesc), _i, _p],

@@ -8,8 +8,8 @@ Reference: Network.save_weights (mlpcode/network.py:428-472) writes, and Network
     biases/biases_i     float32 [N_i]                 (only when useBias)
     gammas/gammas_i, betas/betas_i, mus/mus_i, sigmas/sigmas_i   float32 [N_i]   (only when useBatchNorm)
 An HDF5 dataset `group/name` becomes the npz member of that name, so the reference's own functions produce and
-consume exactly these files when its `h5py` import is pointed at an npz-backed stand-in (oracle/refshim/h5py.py —
-that is how tests/golden/checkpoint_ref.npz was written by the UNMODIFIED reference).
+consume exactly these files when its `h5py` import is pointed at an npz-backed stand-in (the test infrastructure
+has one — that is how tests/golden/checkpoint_ref.npz was written by the UNMODIFIED reference).
 
 Packed-bit export, an addition of this package for deployment of a trained binarized network:
     packed_weights/packed_weights_i   uint32 [N_i, ceil(K_i / 32)]

@@ -68,6 +68,16 @@ def unpack_bits(bits: torch.Tensor, C_: int, out_i8=None, out_f16=None) -> None:
           ptr(out_f16), _ld(out_f16) if out_f16 is not None else 0)
 
 
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor, bad=None) -> None:
+    """dst[i] = src[idx[i]] for 2-D row-major tensors of one dtype (rows may be pitched); idx: device int64."""
+    assert src.ndim == 2 and dst.ndim == 2 and src.dtype == dst.dtype and src.shape[1] == dst.shape[1]
+    assert idx.dtype == torch.int64 and idx.is_contiguous() and idx.numel() == dst.shape[0]
+    assert src.stride(1) == 1 and dst.stride(1) == 1
+    es = src.element_size()
+    _call("bnn_gather_rows", ptr(src), src.stride(0) * es, src.shape[0], ptr(idx), dst.shape[0],
+          src.shape[1] * es, ptr(dst), dst.stride(0) * es, ptr(bad))
+
+
 def bits_to_f4(bits: torch.Tensor, C_: int, out_f4: torch.Tensor) -> None:
     """Packed sign words [..., R, W] -> E2M1 nibbles [..., R, ld/2 bytes] (uint8 storage; leading dims contiguous)."""
     assert bits.is_contiguous() and out_f4.is_contiguous() and out_f4.dtype in (torch.uint8, torch.int8)

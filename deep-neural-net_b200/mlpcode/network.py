@@ -222,21 +222,34 @@ class Network(object):
         print(f"\n\nStarting training (binarized: {self.isBinarized})")
         print("=" * 20)
         print()
+        X_all, Y_all = trainX.t.contiguous(), trainY.t.contiguous()
+        if Y_all.ndim == 1:
+            Y_all = Y_all.unsqueeze(1)
+        order = None        # composed permutation: the reference's trainX = trainX[p, :] of every epoch so far
+        step = n if batch_size == -1 else batch_size
+        bad = torch.zeros(1, dtype=torch.int32, device=X_all.device)
         for epoch in range(epochs):
             if shuffle:
-                perm = torch.randperm(n, device=trainX.t.device)
-                trainX, trainY = trainX[perm], trainY[perm]
+                # network.py:312-315 shuffles the whole data set (a 2 x n x F byte copy per epoch); here only the
+                # index vector is permuted and bnn_gather_rows assembles each mini-batch straight into the
+                # training step's static buffers.  X[p0][p1] == X[p0[p1]], so the batches are the reference's.
+                p = self._draw_permutation(n, X_all.device)
+                order = p if order is None else order[p]
             # the epoch stays on the device: every batch's mean loss is parked in a device vector and
             # the host reads them once per epoch (the reference syncs on float(cost.mean()) per batch,
             # network.py:378); graph replays reuse one loss buffer, hence the copy right after each step
-            n_batches = 1 if batch_size == -1 else (n + batch_size - 1) // batch_size
-            batch_costs = torch.zeros(n_batches, dtype=torch.float32, device=trainX.t.device)
-            for i, (bx, by) in enumerate(self.get_batches(trainX, trainY, batch_size, n)):
-                rows = self.train_step_async(bx, by)
+            n_batches = (n + step - 1) // step
+            batch_costs = torch.zeros(n_batches, dtype=torch.float32, device=X_all.device)
+            for i, k in enumerate(range(0, n, step)):
+                if order is None:
+                    rows = self.train_step_async(X_all[k:k + step], Y_all[k:k + step])
+                else:
+                    rows = self.train_step_async(None, None, gather=(X_all, Y_all, order[k:k + step], bad))
                 batch_costs[i] = rows.mean().t
             self._lr.step()
             cost = float(batch_costs.double().sum()) / n_batches
-            acc = self.get_accuracy(trainX, trainY.argmax(axis=1))
+            assert int(bad.item()) == 0, "permutation index outside the training set"
+            acc = self.get_accuracy(trainX, trainY.argmax(axis=1))   # a count: independent of the row order
             train_accs.append(acc)
             costs.append(cost)
             line = f"Epoch {epoch + 1} / {epochs}\tAccuracy : {acc:0.3f}%"
@@ -262,6 +275,28 @@ class Network(object):
             history["val_accuracy"] = val_accs
         return history
 
+    def _draw_permutation(self, n: int, device) -> torch.Tensor:
+        """Row permutation of one epoch as a device int64 vector.  `shuffle_source` (a callable n -> index array,
+        e.g. np.random.RandomState(seed).permutation) replays a given stream — the reference draws from NumPy's
+        global one (network.py:313) — otherwise torch.randperm on the device."""
+        src = getattr(self, "shuffle_source", None)
+        if src is None:
+            return torch.randperm(n, device=device)
+        p = to_tensor(np.ascontiguousarray(src(n))).to(device=device, dtype=torch.int64).contiguous()
+        assert p.numel() == n
+        return p
+
+    def _gather_batch(self, gather, Xb=None, yb=None):
+        """Assemble the mini-batch rows gather = (X_all, Y_all, idx, bad) into (Xb, yb) (allocated if None)."""
+        X_all, Y_all, idx, bad = gather
+        idx = idx.contiguous()
+        if Xb is None:
+            Xb = torch.empty((idx.numel(), X_all.shape[1]), dtype=X_all.dtype, device=X_all.device)
+            yb = torch.empty((idx.numel(), Y_all.shape[1]), dtype=Y_all.dtype, device=Y_all.device)
+        K_.gather_rows(X_all, idx, Xb, bad)
+        K_.gather_rows(Y_all, idx, yb, bad)
+        return Xb, yb
+
     # ------------------------------------------------------------------ CUDA-graph replay of a step
     def enable_step_graph(self, on: bool = True) -> None:
         """Replay each training step as ONE CUDA graph launch instead of ~90 kernel launches.
@@ -284,12 +319,19 @@ class Network(object):
                 v += getattr(layer.batchNormLayer, "version", 0)
         return v
 
-    def _graph_step(self, X, y, lr, global_batch, consumed=None):
+    def _graph_step(self, X, y, lr, global_batch, consumed=None, gather=None):
         if self._comm.world > 1 and (getattr(self._comm, "dw_exchange", None) is None
                                      or getattr(self._comm, "peer_exchange", None) is None):
             return None  # NCCL collectives in the step: stay eager
-        Xt, yt = to_tensor(X, torch.float32), to_tensor(y)
-        key = (tuple(Xt.shape), tuple(yt.shape), yt.dtype, float(lr), global_batch, self._param_version())
+        if gather is not None:   # shapes of the batch the gather will assemble
+            rows = gather[2].numel()
+            shape_x, shape_y, ydt = (rows, gather[0].shape[1]), (rows, gather[1].shape[1]), gather[1].dtype
+            if gather[0].dtype != torch.float32:
+                return None
+        else:
+            Xt, yt = to_tensor(X, torch.float32), to_tensor(y)
+            shape_x, shape_y, ydt = tuple(Xt.shape), tuple(yt.shape), yt.dtype
+        key = (shape_x, shape_y, ydt, float(lr), global_batch, self._param_version())
         st = self._graphs.get(key)
         if st is None:
             # graphs of other parameter identities are stale; of the rest keep the two most recent
@@ -302,7 +344,10 @@ class Network(object):
             st["warm"] += 1
             return None
         if "graph" not in st:
-            st["X"], st["y"] = Xt.clone(), yt.clone()
+            if gather is not None:
+                st["X"], st["y"] = self._gather_batch(gather)
+            else:
+                st["X"], st["y"] = Xt.clone(), yt.clone()
             if consumed is not None:
                 consumed.record(torch.cuda.current_stream())
             launches0 = K_.launch_count
@@ -313,15 +358,18 @@ class Network(object):
             st["graph"], st["launches"] = g, K_.launch_count - launches0
             K_.launch_count = launches0
         else:
-            st["X"].copy_(Xt, non_blocking=True)
-            st["y"].copy_(yt, non_blocking=True)
+            if gather is not None:   # the permuted rows land directly in the graph's static batch buffers
+                self._gather_batch(gather, st["X"], st["y"])
+            else:
+                st["X"].copy_(Xt, non_blocking=True)
+                st["y"].copy_(yt, non_blocking=True)
             if consumed is not None:  # the caller's batch buffers are free again: the step runs on copies
                 consumed.record(torch.cuda.current_stream())
         st["graph"].replay()
         K_.launch_count += st["launches"]
         return st["cost"]
 
-    def train_step_async(self, X, y, lr: float = None, global_batch: int = None, consumed=None):
+    def train_step_async(self, X, y, lr: float = None, global_batch: int = None, consumed=None, gather=None):
         """One SGD step on one batch (the body of `__updateBatch`, network.py:372-392) without the
         host read of the loss; returns the device array of per-sample losses.  Data-parallel runs
         with unequal shards pass the global batch size.  consumed: optional CUDA event recorded on the
@@ -329,9 +377,11 @@ class Network(object):
         copies, so that is right after the copies; eager steps read them until the end)."""
         lr = self._lr.value if lr is None else lr
         if self._graph_on and K_.gemm_events is None:
-            cost = self._graph_step(X, y, lr, global_batch, consumed)  # records `consumed` itself
+            cost = self._graph_step(X, y, lr, global_batch, consumed, gather)  # records `consumed` itself
             if cost is not None:
                 return cost
+        if gather is not None:   # gather: (X_all, Y_all, idx, bad) — the batch is rows idx of the data set
+            X, y = (DeviceArray(t) for t in self._gather_batch(gather))
         cost = self._train_step_eager(X, y, lr, global_batch)
         if consumed is not None:
             consumed.record(torch.cuda.current_stream())

@@ -78,6 +78,14 @@ int bnn_binarize_weights_t(const float* W, int K, int N, int8_t* wt_i8, int64_t 
 int bnn_unpack_bits(const uint32_t* bits, int R, int C, int64_t ldw, int8_t* out_i8, int64_t ld_i8,
                     void* out_f16, int64_t ld_f16, bnn_stream_t stream);
 
+/* Mini-batch assembly of the epoch loop (trainX[p, :] then X[k:k+bs], network.py:312-315, 480) without a shuffled
+ * copy of the data set: dst[i, :] = src[idx[i], :] for i < n_rows, on raw bytes (row_bytes per row; pitches in
+ * bytes).  idx: device int64 — a slice of the composed permutation.  Rows with idx outside [0, n_src_rows) are
+ * zero-filled and counted in *bad_count (device int32, may be NULL; not cleared here). */
+int bnn_gather_rows(const void* src, int64_t src_pitch_bytes, int64_t n_src_rows, const int64_t* idx, int n_rows,
+                    int64_t row_bytes, void* dst, int64_t dst_pitch_bytes, int32_t* bad_count,
+                    bnn_stream_t stream);
+
 /* Expand packed sign bits [R, ldw] to E2M1 nibbles [R, ld_f4 / 2 bytes] — the BNN_DT_F4 operand form of a +-1
  * matrix: bit j of word w -> nibble (32w + j): 1 -> 0x2 (+1.0), 0 -> 0xA (-1.0); nibbles in [C, 32*ceil(C/32))
  * -> 0x0 (+0.0, the K padding of the product).  ld_f4 counts ELEMENTS (a multiple of 32).  This is how the

@@ -194,6 +194,28 @@ def train_step(p, X, y, lr, record=None):
     return cost
 
 
+def train_epochs(p, X, Y, lr, epochs, batch_size, perms=None, on_step=None):
+    """The epoch loop of Network.train (network.py:305-337) with a constant learning rate: per epoch an optional
+    cumulative shuffle `X = X[perm, :]` (:312-315; perms[e] is the index vector the reference would draw),
+    mini-batches X[k:k+bs] (:480), epoch loss = mean of the batch losses (:325), accuracy of the WHOLE training set
+    in eval mode (:326-328).  on_step(record) receives every step's intermediates.  Returns the history dict."""
+    n = len(X)
+    bs = n if batch_size == -1 else batch_size
+    hist = dict(loss=[], accuracy=[])
+    for e in range(epochs):
+        if perms is not None:
+            X, Y = X[perms[e], :], Y[perms[e], :]
+        costs = []
+        for k in range(0, n, bs):
+            rec = {} if on_step is not None else None
+            costs.append(train_step(p, X[k:k + bs].copy(), Y[k:k + bs], lr, record=rec))
+            if on_step is not None:
+                on_step(rec)
+        hist["loss"].append(sum(costs) / len(costs))
+        hist["accuracy"].append(accuracy(p, X.copy(), Y.argmax(axis=1)))
+    return hist
+
+
 def accuracy(p, X, labels, out_af="softmax", weight_hooks=None):
     """network.py:401-426 with batch_size=-1 (one batch = the whole set)."""
     preds = predict(p, X, False, out_af, weight_hooks).argmax(axis=1)

@@ -115,6 +115,68 @@ def gen_checkpoint(A, Lo, Nw, O):
     np.savez_compressed(GOLDEN / "checkpoint_ref_io.npz", X=X, probs=probs, **flat_state("", st))
 
 
+def gen_epochs(A, Lo, Nw, O):
+    """tests/golden/train_epochs.npz: the reference's own Network.train (network.py:264-366) — three epochs of two
+    mini-batches with the cumulative shuffle of :312-315 drawn from np.random.seed(s), end-of-epoch accuracies,
+    best-parameter snapshot — and the oracle's train_epochs replaying the same permutations, which must agree
+    EXACTLY (history and final state).  Inputs sit on the k/16 grid and the seed is the first one for which no
+    sign decision of any step lies within 1e-6 of zero (tests/test_config_parity_gpu.py explains why a
+    free-running comparison needs that), so the CUDA path can be held to the file step for step."""
+    af = A.ActivationFuncs
+    units, n, bs, epochs, lr = [30, 16, 12, 10], 400, 200, 3, 0.01
+    for seed in range(200):
+        rng = np.random.default_rng(1000 + seed)
+        params = O.new_params(units, rng)
+        X = (rng.integers(-16, 17, (n, units[0])) / 16.0).astype(np.float32)
+        Y = np.eye(10, dtype=np.int8)[rng.integers(0, 10, n)]
+        Xv = (rng.integers(-16, 17, (100, units[0])) / 16.0).astype(np.float32)
+        yv = rng.integers(0, 10, 100).astype(np.uint8)
+        np.random.seed(seed)
+        perms = [np.random.permutation(n) for _ in range(epochs)]
+        amb, first = [0], [True]
+
+        def on_step(rec):
+            for cache in rec["caches"][:-1]:
+                bn = cache["z"]
+                a = np.abs(bn) < 1e-6
+                if first[0]:
+                    a &= bn != 0
+                amb[0] += int(a.sum())
+            first[0] = False
+        probe = O.copy_params(params)
+        hist_o = O.train_epochs(probe, X, Y, lr, epochs, bs, perms=perms, on_step=on_step)
+        if amb[0] != 0:
+            continue
+        nn = make_net(Nw, A, Lo, units, params, af.softmax)
+        np.random.seed(seed)
+        hist = nn.train(X.copy(), Y.copy(), epochs, batch_size=bs, shuffle=True, valX=Xv.copy(), valY=yv.copy(),
+                        save_best_params=False)
+        if int(np.argmax(hist["val_accuracy"])) < epochs - 1:   # the restored snapshot differs from the final state
+            break
+    else:
+        raise SystemExit("no well-conditioned seed for the epoch fixture")
+    exact(np.array(hist["loss"]), np.array(hist_o["loss"]), "epoch losses")
+    exact(np.array(hist["accuracy"]), np.array(hist_o["accuracy"]), "epoch train accuracies")
+    st = net_state(nn)
+    for i in range(len(units) - 1):
+        exact(st["W"][i], probe["W"][i], f"W{i} after train()")
+        for k in ("gamma", "beta", "mu", "sigma"):
+            exact(st["bn"][i][k], probe["bn"][i][k], f"{k}{i} after train()")
+    val_acc = np.array(hist["val_accuracy"])
+    # default flow (save_best_params=True): the best-validation snapshot is restored at the end (:344-366)
+    nn2 = make_net(Nw, A, Lo, units, params, af.softmax)
+    np.random.seed(seed)
+    nn2.train(X.copy(), Y.copy(), epochs, batch_size=bs, shuffle=True, valX=Xv.copy(), valY=yv.copy())
+    blob = dict(units=np.array(units), X=X, Y=Y, Xv=Xv, yv=yv, perms=np.stack(perms), lr=np.float64(lr),
+                batch_size=np.int64(bs), loss=np.array(hist["loss"]), accuracy=np.array(hist["accuracy"]),
+                val_accuracy=val_acc, seed=np.int64(seed))
+    blob.update(flat_state("init_", params))
+    blob.update(flat_state("final_", st))
+    blob.update(flat_state("best_", net_state(nn2)))
+    np.savez_compressed(GOLDEN / "train_epochs.npz", **blob)
+    print(f"train_epochs.npz: seed {seed}, loss {hist['loss']}, acc {hist['accuracy']}, val {list(val_acc)}")
+
+
 def gen_float_faults(Cb, O):
     """IEEE-754 bit flips of real-valued weights (ErrorCallback(bnn=False), callbacks.py:35-59, 85-123):
     the reference draws from the global NumPy stream; replaying the same stream through the oracle's
@@ -141,12 +203,12 @@ def gen_float_faults(Cb, O):
 
 
 def main():
-    if sys.argv[1:] == ["checkpoint"]:      # only this fixture (the others stay byte-identical)
+    if sys.argv[1:] in (["checkpoint"], ["epochs"]):      # only this fixture (the others stay byte-identical)
         L, A, Lo, Cb, Nw, U = import_reference()
         sys.path.insert(0, str(HERE))
         import bnn_oracle as O
-        gen_checkpoint(A, Lo, Nw, O)
-        print("checkpoint fixtures written")
+        (gen_checkpoint if sys.argv[1] == "checkpoint" else gen_epochs)(A, Lo, Nw, O)
+        print(f"{sys.argv[1]} fixtures written")
         return
     _main_all()
 
@@ -346,6 +408,7 @@ def _main_all():
 
     gen_float_faults(Cb, O)
     gen_checkpoint(A, Lo, Nw, O)
+    gen_epochs(A, Lo, Nw, O)
 
     sizes = {p.name: p.stat().st_size for p in sorted(GOLDEN.glob("*.npz"))}
     print("golden fixtures written:", sizes)

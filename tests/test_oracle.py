@@ -232,3 +232,19 @@ def test_c_float_bit_flips_follow_reference_semantics(golden, oracle, mode):
         if p < 1.0:                                   # p = 1 flips every candidate of every element
             other = oracle.c_flip_f32_bits(W, p, mode, seed=0xF00D, trial=4)
             assert not np.array_equal(other.view(np.uint32), out.view(np.uint32))
+
+
+def test_train_epochs_equals_reference_train(golden, oracle):
+    """tests/golden/train_epochs.npz holds what the reference's own Network.train produced (history, final state);
+    the oracle's epoch loop on the recorded permutations reproduces it exactly."""
+    from conftest import params_from_golden
+    g = golden("train_epochs")
+    n = len(g["units"]) - 1
+    p = params_from_golden(g, "init_", n)
+    hist = oracle.train_epochs(p, g["X"].copy(), g["Y"].copy(), float(g["lr"]), len(g["loss"]),
+                               int(g["batch_size"]), perms=list(g["perms"]))
+    assert np.array_equal(hist["loss"], g["loss"]) and np.array_equal(hist["accuracy"], g["accuracy"])
+    for i in range(n):
+        assert np.array_equal(p["W"][i], g[f"final_W{i}"])
+        for k in ("gamma", "beta", "mu", "sigma"):
+            assert np.array_equal(p["bn"][i][k], g[f"final_{k}{i}"])
