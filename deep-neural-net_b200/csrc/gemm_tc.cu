@@ -90,6 +90,7 @@ struct TcParams {
     int pb[BNN_GEMM_MAX_PASS];
     int m_tiles, n_tiles;
     int group_m, group_n;  // tile walk (tile_coords)
+    int debug;             // BNN_GEMM_DEBUG (timing experiments only): 1 = no TMA loads, 2 = no global stores
     int epilogue;
     int vec_ok;  // D base/pitch allow 16-byte vector access
     int a_batched, b_batched;
@@ -153,9 +154,14 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& b,
 // sign epilogues: thr_smem is the shared-memory address of this warp's staged thresholds for the thread's column
 // range (thr at +0, orientation at +kSignStageBytes/2; columns past N hold +inf / 1), cl the group's offset in it.
 constexpr uint32_t kSignStageBytes = 1024;   // 2 x 128 floats: fits the warp's transpose buffer (2304 bytes)
-template <bool kI8, int EPI, int G>
+// kIntCmp (kind::i8 sign epilogues): the staged thresholds are INTEGERS — ceil(thr) and the orientation as +-1 —
+// and the decision is acc * s >= ceil(thr) on the int32 accumulator, identical to the float form for every
+// integer acc and free of the int -> float conversions (quarter-rate pipe) that the float form needs.
+// kFloatAcc (kind::mxf4 sign epilogues): v holds the fp32 accumulator bits (exact integers), compared as floats.
+template <bool kI8, bool kF4, int EPI, int G>
 __device__ __forceinline__ void store_group(const TcParams& p, char* dbase, long long off, int col0,
                                             const uint32_t (&v)[G], float scale, uint32_t thr_smem, int cl) {
+    constexpr bool kIntCmp = kI8 && !kF4;
     const bool full = (col0 + G <= p.N) && p.vec_ok;
     if (EPI == BNN_EPI_SIGN_I8 || EPI == BNN_EPI_SIGN_F4) {
         // batch-norm + sign as one compare against the per-column threshold (bn.cu).  The thresholds come from
@@ -167,12 +173,15 @@ __device__ __forceinline__ void store_group(const TcParams& p, char* dbase, long
         for (int j = 0; j < G; j += 4) {
             const uint4 tu = ptx::lds_v4(thr_smem + (uint32_t)((cl + j) * 4));
             const uint4 su = ptx::lds_v4(thr_smem + kSignStageBytes / 2 + (uint32_t)((cl + j) * 4));
-            const float t[4] = {__uint_as_float(tu.x), __uint_as_float(tu.y), __uint_as_float(tu.z), __uint_as_float(tu.w)};
-            const float s[4] = {__uint_as_float(su.x), __uint_as_float(su.y), __uint_as_float(su.z), __uint_as_float(su.w)};
+            const uint32_t tw[4] = {tu.x, tu.y, tu.z, tu.w}, sw[4] = {su.x, su.y, su.z, su.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float a = kI8 ? (float)(int)v[j + q] : __fmul_rn(__uint_as_float(v[j + q]), scale);
-                bits |= (uint32_t)(__fmul_rn(a, s[q]) >= t[q]) << (j + q);
+                if (kIntCmp) {
+                    bits |= (uint32_t)((int)v[j + q] * (int)sw[q] >= (int)tw[q]) << (j + q);
+                } else {
+                    const float a = kF4 ? __uint_as_float(v[j + q]) : __fmul_rn(__uint_as_float(v[j + q]), scale);
+                    bits |= (uint32_t)(__fmul_rn(a, __uint_as_float(sw[q])) >= __uint_as_float(tw[q])) << (j + q);
+                }
             }
         }
         if (EPI == BNN_EPI_SIGN_F4) {
@@ -558,6 +567,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         uint8_t* sb = sa + Cfg::kABytes;
                         // pair: both CTAs' bytes are counted on the LEADER's barrier, each CTA loads its own
                         // 128 rows of A and its half of the B tile, the peer then arrives on that barrier
+                        if (p.debug & 1) {   // timing experiment: the MMAs run on whatever the stage holds
+                            if (!kCta2 || cta_rank == 0) ptx::mbar_arrive(&full_bar[s]);
+                            else ptx::mbar_arrive_remote(&full_bar[s], 0u);
+                            if (++s == S) { s = 0; ph ^= 1u; }
+                            continue;
+                        }
                         if (!kCta2 || cta_rank == 0)
                             ptx::mbar_arrive_expect_tx(&full_bar[s],
                                                        kCta2 ? 2u * Cfg::kStageBytes : Cfg::kStageBytes);
@@ -656,10 +671,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         tv.z = c0 + 2 < p.N ? __ldg(tb + c0 + 2) : INFINITY;  sv.z = c0 + 2 < p.N ? __ldg(p.sgn + c0 + 2) : 1.f;
                         tv.w = c0 + 3 < p.N ? __ldg(tb + c0 + 3) : INFINITY;  sv.w = c0 + 3 < p.N ? __ldg(p.sgn + c0 + 3) : 1.f;
                     }
-                    ptx::sts_v4(xbuf + (uint32_t)(16 * lane), __float_as_uint(tv.x), __float_as_uint(tv.y),
-                                __float_as_uint(tv.z), __float_as_uint(tv.w));
-                    ptx::sts_v4(xbuf + kSignStageBytes / 2 + (uint32_t)(16 * lane), __float_as_uint(sv.x),
-                                __float_as_uint(sv.y), __float_as_uint(sv.z), __float_as_uint(sv.w));
+                    if constexpr (kI8 && !kF4) {
+                        // integer form: acc * s >= t  <=>  acc * (+-1) >= ceil(t) for integer acc (|acc| < 2^31 - 1);
+                        // cvt.rpi saturates (+inf -> INT_MAX: never, -inf -> INT_MIN: always), NaN -> never
+                        auto up = [](float t) { return t != t ? 0x7FFFFFFF : __float2int_ru(t); };
+                        auto or1 = [](float x) { return x < 0.f ? -1 : 1; };
+                        ptx::sts_v4(xbuf + (uint32_t)(16 * lane), (uint32_t)up(tv.x), (uint32_t)up(tv.y),
+                                    (uint32_t)up(tv.z), (uint32_t)up(tv.w));
+                        ptx::sts_v4(xbuf + kSignStageBytes / 2 + (uint32_t)(16 * lane), (uint32_t)or1(sv.x),
+                                    (uint32_t)or1(sv.y), (uint32_t)or1(sv.z), (uint32_t)or1(sv.w));
+                    } else {
+                        ptx::sts_v4(xbuf + (uint32_t)(16 * lane), __float_as_uint(tv.x), __float_as_uint(tv.y),
+                                    __float_as_uint(tv.z), __float_as_uint(tv.w));
+                        ptx::sts_v4(xbuf + kSignStageBytes / 2 + (uint32_t)(16 * lane), __float_as_uint(sv.x),
+                                    __float_as_uint(sv.y), __float_as_uint(sv.z), __float_as_uint(sv.w));
+                    }
                 }
                 __syncwarp();
             }
@@ -683,10 +709,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     for (int g = 0; g < NG; ++g) {
                         uint32_t v[G];
                         ptx::tmem_ld_cols<G>(t_row + (uint32_t)(g * G), v);
-                        if constexpr (kF4) ptx::tmem_ld_wait();
+                        // FP4: fp32 accumulators holding exact integers (|sum| <= K < 2^24).  The integer stores
+                        // convert here; the sign epilogues compare the floats as they are.
+                        constexpr bool kCvt = kF4 && EPI != BNN_EPI_SIGN_I8 && EPI != BNN_EPI_SIGN_F4;
+                        if constexpr (kCvt) ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < G; ++j)   // FP4: fp32 accumulators holding exact integers (|sum| <= K < 2^24)
-                            sum[g * G + j] = kF4 ? (uint32_t)__float2int_rn(__uint_as_float(v[j])) : v[j];
+                        for (int j = 0; j < G; ++j)
+                            sum[g * G + j] = kCvt ? (uint32_t)__float2int_rn(__uint_as_float(v[j])) : v[j];
                     }
                     ptx::tmem_ld_wait();
                 } else {
@@ -719,6 +748,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             constexpr bool kF32Out = EPI == BNN_EPI_STORE_F32 || EPI == BNN_EPI_SGD_F32 ||
                                      EPI == BNN_EPI_SCATTER_F32;
+            if (p.debug & 2) continue;   // timing experiment: accumulators drained, nothing stored
             char* dbase = reinterpret_cast<char*>(p.D);
             long long rowoff = (long long)b * p.stride_d + (long long)row * p.ldd;
             if (EPI == BNN_EPI_SCATTER_F32) {
@@ -743,7 +773,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         uint32_t v[G];
 #pragma unroll
                         for (int j = 0; j < G; ++j) v[j] = sum[g * G + j];
-                        store_group<kI8, EPI, G>(p, dbase, rowoff + col0, col0, v, scale, xbuf, g * G);
+                        store_group<kI8, kF4, EPI, G>(p, dbase, rowoff + col0, col0, v, scale, xbuf, g * G);
                         asm volatile("" ::: "memory");  // keep the groups' live ranges disjoint
                     }
                 }
@@ -810,6 +840,14 @@ int make_operand_map(CUtensorMap* map, const void* base, bool i8, long long rows
         return BNN_ERR_CUDA;
     }
     return BNN_OK;
+}
+
+// BNN_GEMM_DEBUG (read per call): bit mask of timing experiments that break the RESULT on purpose — 1: the producer
+// signals its barriers without issuing the TMA loads (tensor-pipe rate without operand traffic), 2: the epilogue
+// drains the accumulators without storing.  Used by tools/bench_gemm_forms.py; never set in product runs.
+int gemm_debug_flags() {
+    const char* e = getenv("BNN_GEMM_DEBUG");
+    return e ? atoi(e) : 0;
 }
 
 // Tile-walk parameters (tile_coords): super-columns whose B tiles (all pieces the passes read) take at most
@@ -884,6 +922,7 @@ int launch_tc_pair(const bnn_gemm_desc& g, cudaStream_t stream) {
     p.m_tiles = cdiv(cdiv(g.M, kBlockM), 2);  // pairs of row tiles
     p.n_tiles = cdiv(g.N, BLOCK_N);
     pick_tile_walk(g, kI8 ? 1 : 2, BLOCK_N, p.m_tiles, p.n_tiles, p.group_m, p.group_n);
+    p.debug = gemm_debug_flags();
     p.epilogue = g.epilogue;
     const int esz = (g.epilogue == BNN_EPI_STORE_S16) ? 2 : (g.epilogue == BNN_EPI_SIGN_I8 ? 1 : 4);
     p.vec_ok = aligned16(g.D) && ((g.ldd * esz) % 16 == 0) && ((g.stride_d * esz) % 16 == 0);
@@ -1007,6 +1046,7 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     p.m_tiles = cdiv(g.M, kBlockM);
     p.n_tiles = cdiv(g.N, BLOCK_N);
     pick_tile_walk(g, kI8 ? 1 : 2, BLOCK_N / pack, p.m_tiles, p.n_tiles, p.group_m, p.group_n);
+    p.debug = gemm_debug_flags();
     p.epilogue = g.epilogue;
     const int esz = (g.epilogue == BNN_EPI_STORE_S16) ? 2 : (g.epilogue == BNN_EPI_SIGN_I8 ? 1 : 4);
     p.vec_ok = aligned16(g.D) && ((g.ldd * esz) % 16 == 0) && ((g.stride_d * esz) % 16 == 0);

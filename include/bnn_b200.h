@@ -135,7 +135,9 @@ enum {
     BNN_EPI_STORE_S32 = 1, /* D int32 = acc                      (I8 only)               */
     BNN_EPI_STORE_S16 = 2, /* D int16 = acc                      (I8 only, |acc| < 2^15) */
     BNN_EPI_SGD_F32 = 3,   /* D fp32 -= acc * host_scale / (sa*sb)   (fused SGD update)  */
-    BNN_EPI_SIGN_I8 = 4,   /* D int8 = +1 if acc*host_scale/(sa*sb) * epi_sgn[n] >= epi_thr[n] else -1:
+    BNN_EPI_SIGN_I8 = 4,   /* D int8 = +1 if acc*host_scale/(sa*sb) * epi_sgn[n] >= epi_thr[n] else -1 (epi_sgn holds
+                              +-1; integer-accumulating kinds use its sign and decide acc * (+-1) >= ceil(epi_thr),
+                              the same decision for every integer acc):
                               batch-norm + sign fused into the GEMM (thresholds from
                               bnn_bn_sign_thresholds); Z never reaches HBM (eval mode)           */
     BNN_EPI_SIGN_F4 = 6,   /* like SIGN_I8, stored as E2M1 nibbles (the A operand of a BNN_DT_F4 product): D uint8
