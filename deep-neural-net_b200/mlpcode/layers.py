@@ -843,25 +843,31 @@ class BinaryLayer(LinearLayer):
             # is stored over NVLink into the staging buffer of the rank that owns those rows
             self._home_weights()
             dwx, li = self._dwx
-            step_dev = dwx.comm.step_dev
             dwx.comm.collectives += 1
-            K_.gemm(M=Kd, N=N, K=B, D=None, ldd=N, epilogue=nat.EPI_SCATTER_F32,
-                    scatter=dict(world=dwx.world, rank=dwx.rank,
-                                 rows_per_owner=dwx.layout[li]["rows_per_owner"],
-                                 stage=dwx.stage_ptrs(li)), **dw)
-            if dwx.copy_engine_broadcast and not self.skip_input_grad:
-                # owner update now (local rows only; the kernel also signals "pushed" to the peers);
-                # the rows then travel to the peers on the copy engines, on a side stream, while this
-                # stream carries on with the backward pass.  The copies are started only after the
-                # next batch-norm exchange (dwx.start_broadcasts): queued right here, 10s of MB of
-                # copy traffic would sit in front of that exchange's flags on the NVLink ports.
-                self._dw_reduce(lr, broadcast=False)
-                dwx.deferred.append(li)
-            else:
-                # first layer (its dW GEMM ends the step and its weights open the next one, so there
-                # is nothing left to overlap copies with) or BNN_DW_BCAST=kernel: the owner-update
-                # kernel stores the row blocks into the peers itself
-                self._dw_reduce(lr, broadcast=True)
+            # Like the single-GPU step, the whole weight-gradient chain — dW GEMM, the owner's sum + update (which
+            # first waits for the peers' partial rows) — runs on the side stream: nothing on this stream needs
+            # W_l before the next step, and the 40 us owner update of a 4096 x 4096 layer plus the wait for the
+            # slowest peer's GEMM no longer sit between this layer's dX and the next batch-norm exchange.
+            ovd = self._dw_overlap if not self.skip_input_grad else None
+            with (ovd.branch() if ovd is not None else contextlib.nullcontext()):
+                K_.gemm(M=Kd, N=N, K=B, D=None, ldd=N, epilogue=nat.EPI_SCATTER_F32,
+                        scatter=dict(world=dwx.world, rank=dwx.rank,
+                                     rows_per_owner=dwx.layout[li]["rows_per_owner"],
+                                     stage=dwx.stage_ptrs(li)), **dw)
+                if dwx.copy_engine_broadcast and not self.skip_input_grad:
+                    # owner update now (local rows only; the kernel also signals "pushed" to the peers);
+                    # the rows then travel to the peers on the copy engines, on their own stream, while this
+                    # stream carries on with the backward pass.  The copies are started only after the
+                    # next batch-norm exchange (dwx.start_broadcasts): queued right here, 10s of MB of
+                    # copy traffic would sit in front of that exchange's flags on the NVLink ports.
+                    self._dw_reduce(lr, broadcast=False)
+                    dwx.reduced[li].record(torch.cuda.current_stream())
+                    dwx.deferred.append(li)
+                else:
+                    # first layer (its dW GEMM ends the step and its weights open the next one, so there
+                    # is nothing left to overlap copies with) or BNN_DW_BCAST=kernel: the owner-update
+                    # kernel stores the row blocks into the peers itself
+                    self._dw_reduce(lr, broadcast=True)
             dwx.pending.append(li)  # awaited by comm.finish_step() at the end of the training step
         else:
             dW = ws.get("dW", (Kd, N), torch.float32)

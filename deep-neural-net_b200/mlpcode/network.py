@@ -390,7 +390,10 @@ class Network(object):
     def _train_step_eager(self, X, y, lr: float, global_batch: int = None):
         if self._comm.world > 1:
             self._comm.global_batch = global_batch
-        elif self._dw_overlap is None and os.environ.get("BNN_OVERLAP_DW", "1") != "0":
+        # side stream for the weight-gradient chain: single GPU, and data-parallel runs whose dW exchange is
+        # the peer-memory one (an NCCL all-reduce has its own stream and handle)
+        if (self._dw_overlap is None and os.environ.get("BNN_OVERLAP_DW", "1") != "0"
+                and (self._comm.world == 1 or getattr(self._comm, "dw_exchange", None) is not None)):
             from .layers import DwOverlap
             self._dw_overlap = DwOverlap()
             for layer in self._layers:

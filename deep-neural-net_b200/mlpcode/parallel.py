@@ -148,16 +148,14 @@ class DwExchange:
         return list(self.base)
 
     def start_broadcasts(self) -> None:
-        """Queue the copy-engine all-gather of every layer whose owner update has run: the side stream
-        waits for the current point of the compute stream, then copies this rank's rows (and the
-        "landed" flag) into every peer."""
+        """Queue the copy-engine all-gather of every layer whose owner update has been queued: the copy stream
+        waits for that update (event `reduced[li]`, recorded by the layer on whichever stream ran it), then
+        copies this rank's rows (and the "landed" flag) into every peer."""
         if not self.deferred:
             return
         from . import kernels as K_
-        main = torch.cuda.current_stream()
         for li in self.deferred:
             L = self.layout[li]
-            self.reduced[li].record(main)
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.reduced[li])
                 K_.peer_broadcast_rows(self.w_ptrs(li), self.flag_ptrs(), 2 * li + 1, self.rank,
