@@ -335,9 +335,10 @@ def run_gpu(args):
         nn.enable_step_graph(False)
         c0, n0 = comm.collectives, comm.nccl_calls
         nn.train_step_async(Xd, Yd, LR)
+        n_coll, n_nccl = comm.collectives - c0, comm.nccl_calls - n0   # before the fence's own barrier
         fence()
-        exchanges_per_step = {"count": comm.collectives - c0,
-                              "nccl_calls": comm.nccl_calls - n0,
+        exchanges_per_step = {"count": n_coll,
+                              "nccl_calls": n_nccl,
                               "nccl_calls_how": "counted: every torch.distributed collective of the step goes "
                                                 "through mlpcode.parallel.Comm, which counts the ones it hands to NCCL",
                               "transport": "NVLink peer memory (own kernels + copy engines)"

@@ -95,6 +95,18 @@ __device__ __forceinline__ uint32_t nibble_to_pm127_bytes(uint32_t nib) {
 // |q| <= kDwQuantMax (+ rounding) for |delta'| <= bound_n: 22.97 bits of the column's bound.
 constexpr float kDwQuantMax = 4100000.0f;
 constexpr int kDwMidRadix = 127;
+// 8 bits -> bit 0 of 8 nibbles (bit j -> bit 4j): three shift-or-mask steps
+__host__ __device__ __forceinline__ uint32_t spread_bits_to_nibbles(uint32_t b8) {
+    uint32_t x = b8 & 0xFFu;
+    x = (x | (x << 12)) & 0x000F000Fu;
+    x = (x | (x << 6)) & 0x03030303u;
+    x = (x | (x << 3)) & 0x11111111u;
+    return x;
+}
+// 8 sign bits (1 = +1) -> 8 E2M1 nibbles: +1.0 = 0x2, -1.0 = 0xA
+__host__ __device__ __forceinline__ uint32_t bits_to_e2m1x8(uint32_t b8) {
+    return 0xAAAAAAAAu ^ (spread_bits_to_nibbles(b8) << 3);
+}
 // 2 mask bits -> 2 halves of +-1.0 (bit ? 0x3C00 : 0xBC00)
 __device__ __forceinline__ uint32_t pair_to_pm1_halves(uint32_t two) {
     return 0x3C003C00u | ((~two & 1u) << 15) | ((~two & 2u) << 30);

@@ -193,12 +193,7 @@ __device__ __forceinline__ void store_group(const TcParams& p, char* dbase, long
             uint32_t w[G / 8];
 #pragma unroll
             for (int j = 0; j < G; j += 8) {
-                const uint32_t b8 = (bits >> j) & 0xFFu;
-                uint32_t word = 0;
-#pragma unroll
-                for (int b = 0; b < 8; ++b) word |= ((b8 >> b) & 1u) << (4 * b);   // decision bit -> bit 0 of nibble b
-                // +1 -> 0x2, -1 -> 0xA: 0xA everywhere, clear bit 3 where the decision bit is set
-                word = 0xAAAAAAAAu ^ (word << 3);
+                uint32_t word = bits_to_e2m1x8(bits >> j);   // decision bit set -> 0x2 (+1), clear -> 0xA (-1)
                 const int live = nvalid - j;                                        // nibbles past N -> 0
                 if (live < 8) word &= live <= 0 ? 0u : (0xFFFFFFFFu >> (32 - 4 * live));
                 w[j / 8] = word;

@@ -190,16 +190,9 @@ bits_to_f4_kernel(const uint32_t* __restrict__ bits, long long R, int C, long lo
         uint32_t o[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint32_t bb = (b >> (8 * q)) & 0xFFu, lv = (live >> (8 * q)) & 0xFFu;
-            // spread 8 bits to the bit-3 position of 8 nibbles: sign bit of E2M1 (set = negative)
-            uint32_t sp = 0, lm = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                sp |= ((bb >> j) & 1u) << (4 * j);
-                lm |= ((lv >> j) & 1u) << (4 * j);
-            }
-            // live nibble: 0x2 | (bit ? 0 : 0x8); dead nibble: 0
-            o[q] = (lm * 0xAu) ^ (sp << 3);
+            // live nibble: 0x2 | (bit ? 0 : 0x8); nibble past C: 0
+            o[q] = bits_to_e2m1x8(b >> (8 * q));
+            if (valid < 32) o[q] &= spread_bits_to_nibbles(live >> (8 * q)) * 0xFu;
         }
         *reinterpret_cast<uint4*>(out + r * ld_bytes + 16 * w) = make_uint4(o[0], o[1], o[2], o[3]);
     }

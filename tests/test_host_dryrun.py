@@ -84,12 +84,12 @@ def test_weight_sweep_emits_wellformed_abi_calls(dry):
     assert sw.run_bernoulli(0.1, 6, seed=3).shape == (6,)
     assert sw.run_exactk(lambda t: 1 + t, 6, seed=3).shape == (6,)
     names = [n for n, _ in dry]
-    # 256 -> 128 is wide enough for the FP4 pipe: its flips act on packed words, expanded by bnn_bits_to_f4
-    assert sw.f4 == [False, True, False]
-    # per layer and launch group (2 groups); exact-k replicates the clean int8 / fp16 copies with a p = 0 call
-    assert names.count("bnn_flip_weights_bernoulli") == 2 * 3 + 2 * 2
+    # the +-1 x +-1 layers run on the FP4 pipe: their flips act on packed words, expanded by bnn_bits_to_f4
+    assert sw.f4 == [False, True, True]
+    # per layer and launch group (2 groups); exact-k replicates the clean fp16 copy of layer 0 with a p = 0 call
+    assert names.count("bnn_flip_weights_bernoulli") == 2 * 3 + 2 * 1
     assert names.count("bnn_flip_weights_exactk") == 2 * 3
-    assert names.count("bnn_bits_to_f4") == 2 * 1 + 2 * 1
+    assert names.count("bnn_bits_to_f4") == 2 * 2 + 2 * 2
     assert names.count("bnn_gemm") == 4 * 3
     assert all(rc in (0, -2) for _, rc in dry)
 
@@ -117,7 +117,7 @@ def test_predict_routes_wide_hidden_layers_through_fp4(dry, monkeypatch):
     del dry[:]
     nn.predict(X)
     names = [n for n, _ in dry]
-    assert names.count("bnn_bits_to_f4") == 1 and names.count("bnn_gemm") == 3
+    assert names.count("bnn_bits_to_f4") == 2 and names.count("bnn_gemm") == 3
     monkeypatch.setenv("BNN_FP4", "0")
     del dry[:]
     nn.predict(X)

@@ -186,7 +186,9 @@ def weight_sweep_section(comm, n_trials=10000, per_launch=8, cpu_trials=1, int8_
         tops = tps * ops_per_trial / 1e12
         out[name] = {"trials_per_s": tps, "seconds": ms * 1e-3, "mean_accuracy": float(np.mean(acc)),
                      "top_per_s": tops, "gpu_launches": K_.launch_count - l0,
-                     "frac_of_int8_peak": (tops / (world * int8_peak_tops)) if int8_peak_tops else None}
+                     "frac_of_int8_peak": (tops / (world * int8_peak_tops)) if int8_peak_tops else None,
+                     "int8_peak_source": "cuBLASLt int8 8192^3 on this box, per GPU; the +-1 layers run on kind::mxf4, "
+                                         "whose MMA-only rate is 2x kind::i8 (tools/probe_mxf4.cu: 8.7 vs 4.2 POP/s)"}
     out["pipes"] = ["kind::i8 (u8 x s8)" if sweep.u8 is not None else "kind::f16"] + \
                    ["kind::mxf4 (E2M1)" if f else "kind::i8" for f in sweep.f4[1:]]
     if timeline and world == 1:   # one launch group, every C-ABI call between its own pair of CUDA events
@@ -278,6 +280,18 @@ def inference_section(comm, batch=65536, reps=10, cpu_rows=2048, int8_peak_tops=
            "n_gpus": world, "samples_per_s": sps, "ms_per_batch": ms / reps, "reps": reps, "gpu_launches": launches,
            "flop_equiv_per_s": sps * ops, "binary_top_per_s": sps * pm1_ops / 1e12,
            "frac_of_int8_peak_binary_layers_only": None}
+    # the same rows as uint8 pixels (what CIFAR-10 / MNIST files hold): normalize() keeps them as bytes and layer 0
+    # becomes one exact u8 x s8 product instead of two fp16 passes (mlpcode.utils.NormalizedU8)
+    from mlpcode.utils import normalize
+    X8 = torch.randint(0, 256, (batch, UNITS5[0]), device="cuda", generator=g, dtype=torch.uint8)
+    Xn = normalize(X8, newMin=-1., newMax=1.)
+    for _ in range(2):
+        nn.predict(Xn)
+    ms8, _ = timer(lambda: [nn.predict(Xn) for _ in range(reps)])
+    out["uint8_input"] = {"samples_per_s": world * batch * reps / (ms8 * 1e-3), "ms_per_batch": ms8 / reps,
+                          "note": "same network and batch, rows given as normalize(uint8 pixels, -1, 1): layer 0 on "
+                                  "kind::i8 (u8 x s8), exact"}
+    del X8, Xn
     # host-fed: rows arrive from pinned host memory in chunks, class scores return to the host
     chunk = 16384
     Xh = torch.empty((batch, UNITS5[0]), dtype=torch.float32).pin_memory()

@@ -96,10 +96,11 @@ while [ $# -gt 0 ]; do
           -o /tmp/prof_hbm $PROFILE_CMD && raw_csv prof_hbm
       ;;
     prof-sweep)
+      # one launch group of 8 trials per sweep (plus the warm-up groups): flips, expansion, thresholds, GEMMs
       SW="python tools/bench_sweep.py --trials 8 --image-trials 8 --cpu-trials 0 --sections weights,image"
       run sweep_plain 300 $SW &&
       run prof_sweep 900 ncu --set full --clock-control none --import-source on \
-          -k regex:'flip_|thresholds' -c 24 -f -o /tmp/prof_sweep $SW && raw_csv prof_sweep
+          -k regex:'flip_|thresholds|bits_to_f4|gemm_tc|bn_apply|count_correct' -s 26 -c 40 -f -o /tmp/prof_sweep $SW && raw_csv prof_sweep
       ;;
     walk)
       # tile-walk A/B on the headline step: BNN_GEMM_GN = column tiles per super-column (16 = one super-column,
