@@ -19,6 +19,8 @@ EPI_STORE_F32, EPI_STORE_S32, EPI_STORE_S16, EPI_SGD_F32, EPI_SIGN_I8, EPI_SCATT
 MAX_RANKS = 16
 STATS_NONE, STATS_COLSUM, STATS_BN_BWD = 0, 1, 2
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
+ACT_IDENTITY, ACT_SIGMOID, ACT_TANH, ACT_RELU, ACT_LEAKY_RELU, ACT_HARD_SIGMOID, ACT_HARD_TANH = range(7)
+LOSS_CROSS_ENTROPY, LOSS_MSE, LOSS_HINGE = range(3)
 Z_F32, Z_S16, Z_S32 = 0, 1, 2
 GEMM_MAX_PASS = 4
 
@@ -75,6 +77,11 @@ PROTOTYPES = {
     "bnn_unpack_bits": [_p, _i, _i, _i64, _p, _i64, _p, _i64, _p],
     "bnn_bits_to_f4": [_p, _i64, _i, _i64, _p, _i64, _p],
     "bnn_gather_rows": [_p, _i64, _i64, _p, _i, _i64, _p, _i64, _p, _p],
+    "bnn_activation": [_p, _i64, _i, _p, _p],
+    "bnn_activation_grad": [_p, _p, _i64, _i, _p, _p],
+    "bnn_softmax_grad": [_p, _p, _i, _i, _p, _p],
+    "bnn_loss_rows": [_p, _p, _i, _i, _i, _p, _p, _p],
+    "bnn_loss_grad": [_p, _p, _i, _i, _i, _d, _p, _p],
     "bnn_absmax_f32": [_p, _i64, _p, _i, _p],
     "bnn_split_f16": [_p, _i, _i, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p, _p],
     "bnn_gemm": [C.POINTER(GemmDesc), _i, _p],

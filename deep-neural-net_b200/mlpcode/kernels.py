@@ -279,6 +279,34 @@ def bn_sign(Z, B, N, thr, sgn, act_i8=None, act_t16=None, act_bits=None, act_t8=
           ptr(act_t8), ptr(act_t8x127), _ld(act_t8) if act_t8 is not None else 0)
 
 
+def activation(x: torch.Tensor, kind: int, out: torch.Tensor) -> None:
+    assert x.is_contiguous() and out.is_contiguous() and x.dtype == out.dtype == torch.float32
+    _call("bnn_activation", ptr(x), x.numel(), kind, ptr(out))
+
+
+def activation_grad(dA: torch.Tensor, a: torch.Tensor, kind: int, out: torch.Tensor) -> None:
+    assert dA.is_contiguous() and a.is_contiguous() and out.is_contiguous() and dA.shape == a.shape
+    _call("bnn_activation_grad", ptr(dA), ptr(a), a.numel(), kind, ptr(out))
+
+
+def softmax_grad(dA: torch.Tensor, a: torch.Tensor, out: torch.Tensor) -> None:
+    R, Cc = a.shape
+    assert dA.is_contiguous() and a.is_contiguous() and out.is_contiguous()
+    _call("bnn_softmax_grad", ptr(dA), ptr(a), R, Cc, ptr(out))
+
+
+def loss_rows(ypred: torch.Tensor, y: torch.Tensor, kind: int, rows=None, loss_sum=None) -> None:
+    R, Cc = ypred.shape
+    assert ypred.is_contiguous() and y.is_contiguous() and y.dtype == torch.int8 and tuple(y.shape) == (R, Cc)
+    _call("bnn_loss_rows", ptr(ypred), ptr(y), R, Cc, kind, ptr(rows), ptr(loss_sum))
+
+
+def loss_grad(ypred: torch.Tensor, y: torch.Tensor, kind: int, count: float, out: torch.Tensor) -> None:
+    R, Cc = ypred.shape
+    assert ypred.is_contiguous() and y.is_contiguous() and y.dtype == torch.int8 and out.is_contiguous()
+    _call("bnn_loss_grad", ptr(ypred), ptr(y), R, Cc, kind, float(count), ptr(out))
+
+
 def softmax_xent(logits, B, Cc, onehot=None, probs=None, loss_rows=None, grad=None, count=None,
                  loss_sum=None) -> None:
     _call("bnn_softmax_xent", ptr(logits), B, Cc, _ld(logits), ptr(onehot), ptr(probs),

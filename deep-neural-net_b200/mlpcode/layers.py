@@ -32,6 +32,7 @@ import torch
 
 from . import _native as nat
 from . import kernels as K_
+from .activation import ACTIVATION_DERIVATIVES, ACTIVATION_FUNCTIONS
 from .activation import ActivationFuncs as af
 from .callbacks import Callback
 from .device import DeviceArray, asarray, empty, pad_to, require_cuda, to_tensor, zeros
@@ -459,8 +460,8 @@ class LinearLayer(Layer):
             w = torch.randn(self.weights_shape, dtype=torch.float32, device=dev)
             self.weights = DeviceArray(w * float(np.sqrt(1.0 / self.inputUnits)))
         self.activation = activation
-        if activation is not None and activation not in (af.sign, af.softmax, af.identity):
-            raise NotImplementedError(f"activation {activation} is outside the BNN hot path")
+        if activation is not None:
+            assert activation in ACTIVATION_FUNCTIONS
         if self.batchNorm:
             self.batchNormLayer.build()
         super().build()
@@ -734,8 +735,10 @@ class BinaryLayer(LinearLayer):
                 probs = empty((B, N))
                 K_.softmax_xent(logits, B, N, probs=probs)
                 out = SoftmaxOutput(probs, logits)
-            else:  # identity / None
+            elif self.activation in (None, af.identity):
                 out = DeviceArray(logits)
+            else:  # sigmoid / tanh / relu / leaky_relu on the batch-norm output (layers.py:230-233)
+                out = ACTIVATION_FUNCTIONS[self.activation](DeviceArray(logits))
 
         if isTrain:
             self.cache.update(input=xin, z=Z, a=out, sums=sums, mu=mu, var=var, B=B,
@@ -753,6 +756,9 @@ class BinaryLayer(LinearLayer):
         lr = float(lr)
         # STE: hard_tanh_derivative evaluated on the post-sign activations is the identity
         # (activation.py:122-131 via layers.py:252-254), and softmax+CE arrives pre-differentiated.
+        # Any other activation: delta = ACTIVATION_DERIVATIVES[act](dA, a) on the cached activations (:251-254).
+        if activDeriv and self.activation not in (None, af.sign, af.identity):
+            dA = ACTIVATION_DERIVATIVES[self.activation](dA, c["a"])
         delta = to_tensor(dA, torch.float32)
         assert tuple(delta.shape) == (B, N)
         # the layer above may already have summed this layer's batch-norm reductions in the epilogue

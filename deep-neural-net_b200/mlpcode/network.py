@@ -210,6 +210,9 @@ class Network(object):
             return
         trainX = asarray(trainX, np.float32)
         trainY = asarray(trainY)
+        if self._lossF == lf.hinge:   # one-hot {0, 1} -> {-1, +1}; the reference edits trainY in place
+            yt = trainY.t             # (network.py:301-303), here a copy carries the change
+            trainY = DeviceArray(torch.where(yt == 0, torch.full_like(yt, -1), yt))
         n = len(trainX)
         best_acc, best_epoch, best = -1.0, -1, None
         costs, train_accs, val_accs = [], [], []

@@ -293,6 +293,40 @@ int bnn_softmax_xent(const float* logits, int B, int C, int64_t ldl, const int8_
                      bnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * 8f row 4  the other output-layer activations and losses      (activation.py:8-131, loss.py:10-131)
+ * A binarized network may end in any of them (network.py:236-262, 377-387); all are element-wise or
+ * row-wise maps over [B, C] that follow the reference's operation order.
+ * ------------------------------------------------------------------------------------------- */
+enum {
+    BNN_ACT_IDENTITY = 0,     /* activation.py:8-14                                              */
+    BNN_ACT_SIGMOID = 1,      /* 1 / (1 + exp(-x));          derivative dA * (a * (1 - a))  :17-28 */
+    BNN_ACT_TANH = 2,         /* tanh(x);                    dA * (1 - a^2)                 :31-41 */
+    BNN_ACT_RELU = 3,         /* x < 0 ? 0 : x;              a <= 0 ? 0 : dA                :65-77 */
+    BNN_ACT_LEAKY_RELU = 4,   /* x < 0 ? 0.01 x : x;         a <= 0 ? 0.01 dA : dA          :80-92 */
+    BNN_ACT_HARD_SIGMOID = 5, /* clip((x + 1) / 2, 0, 1);    (no derivative in the reference) :95-99 */
+    BNN_ACT_HARD_TANH = 6     /* clip(x, -1, 1);             (a < -1 or a > 1) ? 0 * dA : dA :115-131 */
+};
+enum { BNN_LOSS_CROSS_ENTROPY = 0, BNN_LOSS_MSE = 1, BNN_LOSS_HINGE = 2 };
+
+/* out[i] = f(x[i]), i < n (out may alias x). */
+int bnn_activation(const float* x, int64_t n, int kind, float* out, bnn_stream_t stream);
+/* out[i] = dA[i] * f'(.) evaluated on the activation a[i], as ACTIVATION_DERIVATIVES does (activation.py:160-168). */
+int bnn_activation_grad(const float* dA, const float* a, int64_t n, int kind, float* out, bnn_stream_t stream);
+/* softmax_derivative (activation.py:56-68), including its second softmax of the activations:
+ * s = softmax(a[r, :]); out[r, j] = s_j * (dA[r, j] - sum_k s_k dA[r, k]).  Dense [R, C], any C. */
+int bnn_softmax_grad(const float* dA, const float* a, int R, int C, float* out, bnn_stream_t stream);
+/* rows[r] = loss of row r (loss.py:10-36 cross-entropy on arbitrary probabilities — ypred is clipped IN PLACE to
+ * [1e-15, 1] like np.clip(..., out=ypred) — :71-89 mse, :112-119 hinge with labels in {-1, +1}); y int8 [R, C];
+ * loss_sum (device double, may be NULL) = sum of the rows; rows may be NULL when only the sum is wanted. */
+int bnn_loss_rows(float* ypred, const int8_t* y, int R, int C, int kind, float* rows, double* loss_sum,
+                  bnn_stream_t stream);
+/* out = dL/dA (loss.py:39-68 cross-entropy WITHOUT the softmax fusion, clipping ypred in place; :92-107 mse;
+ * :122-131 hinge), divided by `count` (the global batch in data-parallel runs). */
+int bnn_loss_grad(float* ypred, const int8_t* y, int R, int C, int kind, double count, float* out,
+                  bnn_stream_t stream);
+
+
+/* ---------------------------------------------------------------------------------------------
  * A7/A8  backward through sign (identity STE) and batch-norm, in-place SGD on gamma/beta,
  *        running statistics                            (layers.py:101-127, :252-258;
  *                                                       hard_tanh_derivative activation.py:122-131)

@@ -177,6 +177,74 @@ def gen_epochs(A, Lo, Nw, O):
     print(f"train_epochs.npz: seed {seed}, loss {hist['loss']}, acc {hist['accuracy']}, val {list(val_acc)}")
 
 
+def gen_act_loss(A, Lo, Nw, O):
+    """tests/golden/act_loss.npz: every activation, activation derivative, loss and loss derivative of the
+    reference (activation.py:8-168, loss.py:10-156) on seeded arrays with edge values, and one training step plus a
+    prediction of a small binarized network for each output-activation / loss pairing the reference treats
+    differently (network.py:377-387: fused `ypred - y` for softmax / sigmoid + cross-entropy, activation derivative
+    otherwise).  Outputs are the reference's own; there is no oracle in between."""
+    af, lf = A.ActivationFuncs, Lo.LossFuncs
+    rng = np.random.default_rng(71)
+    x = (rng.standard_normal((37, 10)) * np.exp(rng.standard_normal((37, 10)))).astype(np.float32)
+    x[0, :8] = [0.0, -0.0, 1.0, -1.0, 1.5, -1.5, 30.0, -30.0]
+    dA = rng.standard_normal((37, 10)).astype(np.float32)
+    blob = dict(x=x, dA=dA)
+    fwd = dict(A.ACTIVATION_FUNCTIONS)
+    fwd_extra = {"hard_sigmoid": A.hard_sigmoid, "hard_tanh": A.hard_tanh}
+    for k, f in list(fwd.items()) + list(fwd_extra.items()):
+        name = k.name if hasattr(k, "name") else k
+        a = f(x.copy())
+        blob[f"act_{name}"] = np.asarray(a, np.float32)
+    for k, f in A.ACTIVATION_DERIVATIVES.items():
+        a = fwd[k](x.copy())
+        if k == af.sign:            # hard_tanh_derivative is also meaningful off the +-1 lattice
+            a = x.copy()
+        blob[f"grad_in_{k.name}"] = np.asarray(a, np.float32)
+        blob[f"grad_{k.name}"] = np.asarray(f(dA.copy(), a.copy()), np.float32)
+    R, C = 29, 10
+    p = rng.random((R, C)).astype(np.float32)
+    p /= p.sum(axis=1, keepdims=True)
+    p[0, 0], p[1, 1] = 0.0, 1e-20                       # exercised by the lower clip
+    y = np.eye(C, dtype=np.int8)[rng.integers(0, C, R)]
+    ypm = np.where(y == 0, -1, 1).astype(np.int8)
+    t = (rng.standard_normal((R, C)) * 1.5).astype(np.float32)      # tanh-like scores for hinge
+    blob.update(loss_p=p, loss_y=y, loss_ypm=ypm, loss_t=t)
+    blob["ce_rows"] = Lo.cross_entropy_loss(p.copy(), y).astype(np.float32)
+    q = p.copy()
+    blob["ce_grad_fused"] = Lo.cross_entropy_derivative(q, y, with_softmax=True).astype(np.float32)
+    q = np.clip(p, 1e-6, 1 - 1e-6).astype(np.float32)               # away from 1: the general form divides by 1 - p
+    blob["ce_general_p"] = q.copy()
+    blob["ce_grad_general"] = Lo.cross_entropy_derivative(q, y, with_softmax=False).astype(np.float32)
+    blob["mse_rows"] = Lo.mse(p.copy(), y).astype(np.float32)
+    blob["mse_grad"] = Lo.mse_derivative(p.copy(), y).astype(np.float32)
+    blob["hinge_rows"] = Lo.hinge_loss(t.copy(), ypm).astype(np.float32)
+    blob["hinge_grad"] = np.asarray(Lo.hinge_derivative(t.copy(), ypm), np.float64)
+    # one training step + a prediction per pairing, on grid inputs (layer-0 sums exact, beta = 0: every sign
+    # decision of the step is determined; tests/test_config_parity_gpu.py explains)
+    units, B = [30, 16, 12, 10], 64
+    params = O.new_params(units, rng)
+    X = (rng.integers(-16, 17, (B, units[0])) / 16.0).astype(np.float32)
+    X2 = (rng.integers(-16, 17, (B, units[0])) / 16.0).astype(np.float32)
+    Y = np.eye(10, dtype=np.int8)[rng.integers(0, 10, B)]
+    blob.update(net_units=np.array(units), net_X=X, net_X2=X2, net_Y=Y)
+    blob.update(flat_state("net_init_", params))
+    pairs = [("sigmoid", "mse"), ("sigmoid", "cross_entropy"), ("tanh", "hinge"), ("softmax", "mse"),
+             ("relu", "mse"), ("leaky_relu", "mse"), ("identity", "mse"), ("softmax", "hinge")]
+    blob["net_pairs"] = np.array(["+".join(pr) for pr in pairs])
+    for out_af, loss in pairs:
+        nn = Nw.Network(units, useGpu=False, binarized=True, useBatchNorm=True)
+        nn.compile(lr=0.01, hiddenAf=af.sign, outAf=af[out_af], lossF=lf[loss])
+        nn.load_weights([w.copy() for w in params["W"]])
+        Yt = np.where(Y == 0, -1, Y).astype(np.int8) if loss == "hinge" else Y.copy()   # network.py:301-303
+        cost = nn._Network__updateBatch((X.copy(), Yt), 0.01)
+        tag = f"net_{out_af}_{loss}_"
+        blob[tag + "cost"] = np.float64(cost)
+        blob.update(flat_state(tag, net_state(nn)))
+        blob[tag + "pred"] = np.asarray(nn.predict(X2.copy(), isTraining=False), np.float32)
+    np.savez_compressed(GOLDEN / "act_loss.npz", **blob)
+    print("act_loss.npz:", {k: float(blob[f"net_{a}_{l}_cost"]) for a, l in pairs for k in [f"{a}+{l}"]})
+
+
 def gen_float_faults(Cb, O):
     """IEEE-754 bit flips of real-valued weights (ErrorCallback(bnn=False), callbacks.py:35-59, 85-123):
     the reference draws from the global NumPy stream; replaying the same stream through the oracle's
@@ -203,11 +271,11 @@ def gen_float_faults(Cb, O):
 
 
 def main():
-    if sys.argv[1:] in (["checkpoint"], ["epochs"]):      # only this fixture (the others stay byte-identical)
+    if sys.argv[1:] in (["checkpoint"], ["epochs"], ["act_loss"]):      # only this fixture (the others stay byte-identical)
         L, A, Lo, Cb, Nw, U = import_reference()
         sys.path.insert(0, str(HERE))
         import bnn_oracle as O
-        (gen_checkpoint if sys.argv[1] == "checkpoint" else gen_epochs)(A, Lo, Nw, O)
+        {"checkpoint": gen_checkpoint, "epochs": gen_epochs, "act_loss": gen_act_loss}[sys.argv[1]](A, Lo, Nw, O)
         print(f"{sys.argv[1]} fixtures written")
         return
     _main_all()
@@ -409,6 +477,7 @@ def _main_all():
     gen_float_faults(Cb, O)
     gen_checkpoint(A, Lo, Nw, O)
     gen_epochs(A, Lo, Nw, O)
+    gen_act_loss(A, Lo, Nw, O)
 
     sizes = {p.name: p.stat().st_size for p in sorted(GOLDEN.glob("*.npz"))}
     print("golden fixtures written:", sizes)
