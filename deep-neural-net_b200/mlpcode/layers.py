@@ -391,9 +391,6 @@ class LinearLayer(Layer):
         self._weights = value
         self.version = getattr(self, "version", 0) + 1  # invalidates captured step graphs
 
-    def finish_update(self) -> None:
-        self._pending_update = None
-
     @property
     def weights_shape(self):
         return self.inputUnits, self.layerUnits
@@ -466,11 +463,239 @@ class LinearLayer(Layer):
             self.batchNormLayer.build()
         super().build()
 
-    def forward(self, X, isTrain=True):
-        raise NotImplementedError("real-valued LinearLayer is out of scope; use BinaryLayer")
+    # ------------------------------------------------------------------ operand preparation (shared)
+    def _real_input_operands(self, Xt, train: bool):
+        B, Kd = Xt.shape
+        ws = self._ws
+        amax = ws.get("x_amax", (1,), torch.float32)
+        scale = ws.get("x_scale", (1,), torch.float32)
+        hi = ws.get(f"x_hi{B}", (B, pad_to(Kd, 8)), torch.float16, zero=True)
+        lo = ws.get(f"x_lo{B}", (B, pad_to(Kd, 8)), torch.float16, zero=True)
+        hi_t = lo_t = None
+        if train:
+            hi_t = ws.get(f"xt_hi{B}", (Kd, pad_to(B, 8)), torch.float16, zero=True)
+            lo_t = ws.get(f"xt_lo{B}", (Kd, pad_to(B, 8)), torch.float16, zero=True)
+        K_.absmax_f32(Xt, amax)
+        K_.split_f16(Xt, amax, hi=hi, lo=lo, hi_t=hi_t, lo_t=lo_t, scale_out=scale)
+        return dict(hi=hi, lo=lo, hi_t=hi_t, lo_t=lo_t, scale=scale)
 
+    def finish_update(self) -> None:
+        """Apply `W -= lr * dW` of a data-parallel step once its all-reduce has landed."""
+        if self._pending_update is None:
+            return
+        work, dW, lr = self._pending_update
+        self._pending_update = None
+        if work is not None:
+            work.wait()  # stream-side wait: the update kernel queues behind the collective
+        K_.sgd_update(self.weights.t, dW, lr)
+
+    def _dw_reduce(self, lr: float, broadcast: bool) -> None:
+        dwx, li = self._dwx
+        L = dwx.layout[li]
+        K_.dw_reduce_sgd_p2p(dwx.stage_ptrs(li)[dwx.rank], dwx.w_ptrs(li), dwx.flag_ptrs(), 2 * li,
+                             2 * li + 1, dwx.rank, dwx.world, dwx.comm.step_dev, L["K"], L["N"],
+                             L["rows_per_owner"], lr, broadcast, dwx.counters[li:li + 1], signal=True)
+
+    # ------------------------------------------------------------------ forward, real-valued weights
+    def forward(self, X, isTrain=True):
+        """z = X . W with the LATENT real-valued weights (layers.py:209-238 without BinaryLayer's binarize):
+        three fp16-split tensor-core passes (hi.hi + hi.lo + lo.hi, fp32 accumulation re-rounded per chunk) at
+        SGEMM accuracy, batch-norm, activation.  Eval-mode weight hooks (layers.py:215-218) receive and return the
+        dense fp32 weight — this is where ErrorCallback(p, mode, bnn=False) injects IEEE-754 bit flips
+        (callbacks.py:85-123)."""
+        assert self.isBuilt
+        Kd, N = self.weights_shape
+        ws = self._ws
+        bn = self.batchNormLayer
+        self.cache.clear()
+        Xt = X.t if isinstance(X, DeviceArray) else to_tensor(X, torch.float32)   # +-1 activations arrive dense
+        Xt = Xt.to(torch.float32)
+        assert Xt.ndim == 2 and Xt.shape[1] == Kd, f"expected [B, {Kd}] input, got {tuple(Xt.shape)}"
+        B = Xt.shape[0]
+        xin = self._real_input_operands(Xt.contiguous(), isTrain)
+        W = self.weights
+        if not isTrain:
+            for cb in self.callbacks:
+                W = cb(W, gpu=self.gpu)
+        Wt = to_tensor(W, torch.float32).contiguous()
+        assert tuple(Wt.shape) == (Kd, N)
+        w_amax = ws.get("w_amax", (1,), torch.float32)
+        w_scale_f = ws.get("w_scale_fwd", (1,), torch.float32)
+        wt_hi = ws.get("wt_hi", (N, pad_to(Kd, 8)), torch.float16, zero=True)
+        wt_lo = ws.get("wt_lo", (N, pad_to(Kd, 8)), torch.float16, zero=True)
+        K_.absmax_f32(Wt, w_amax)      # also the bound the backward pass's split of W reads
+        K_.split_f16(Wt, w_amax, hi_t=wt_hi, lo_t=wt_lo, scale_out=w_scale_f)
+        acc = bn.stats_target() if (isTrain and K_.fused_stats_ok(N)) else None
+        stats = dict(mode=nat.STATS_COLSUM, sums=acc) if acc is not None else None
+        Z = ws.get(f"z_f32_{B}", (B, pad_to(N, 4)), torch.float32)
+        K_.gemm(M=B, N=N, K=Kd, A=(xin["hi"], xin["lo"]), B=(wt_hi, wt_lo), lda=xin["hi"].stride(0),
+                ldb=wt_hi.stride(0), D=Z, ldd=Z.stride(0), in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32,
+                passes=((0, 0), (0, 1), (1, 0)), sa=xin["scale"], sb=w_scale_f, stats=stats)
+        if isTrain:
+            sums, mu, var = bn.batch_stats(Z, B, filled=acc)
+        else:
+            sums, mu, var = None, bn.mu.t, bn.sigma.t
+        logits = empty((B, N))
+        K_.bn_apply(Z, B, N, mu, var, bn.gamma.t, bn.beta.t, bn.EPSILON, out_f32=logits)
+        if self.activation == af.softmax:
+            probs = empty((B, N))
+            K_.softmax_xent(logits, B, N, probs=probs)
+            out = SoftmaxOutput(probs, logits)
+        elif self.activation in (None, af.identity):
+            out = DeviceArray(logits)
+        else:
+            out = ACTIVATION_FUNCTIONS[self.activation](DeviceArray(logits))
+        if isTrain:
+            self.cache.update(input=xin, z=Z, a=out, sums=sums, mu=mu, var=var, B=B, real_input=True)
+        return out
+
+    # ------------------------------------------------------------------ backward
     def backwards(self, dA, lr: float, activDeriv=True):
-        raise NotImplementedError("real-valued LinearLayer is out of scope; use BinaryLayer")
+        assert "input" in self.cache
+        assert "z" in self.cache
+        Kd, N = self.weights_shape
+        ws = self._ws
+        c = self.cache
+        B, Z, xin = c["B"], c["z"], c["input"]
+        lr = float(lr)
+        # STE: hard_tanh_derivative evaluated on the post-sign activations is the identity
+        # (activation.py:122-131 via layers.py:252-254), and softmax+CE arrives pre-differentiated.
+        # Any other activation: delta = ACTIVATION_DERIVATIVES[act](dA, a) on the cached activations (:251-254).
+        if activDeriv and self.activation not in (None, af.sign, af.identity):
+            dA = ACTIVATION_DERIVATIVES[self.activation](dA, c["a"])
+        delta = to_tensor(dA, torch.float32)
+        assert tuple(delta.shape) == (B, N)
+        # the layer above may already have summed this layer's batch-norm reductions in the epilogue
+        # of the GEMM that produced dA
+        reduced = getattr(dA, "_bn_reduced_for", None) is self
+
+        Np, Bp = pad_to(N, 8), pad_to(B, 8)
+        d_hi = ws.get(f"d_hi{B}", (B, Np), torch.float16, zero=True)
+        d_lo = ws.get(f"d_lo{B}", (B, Np), torch.float16, zero=True)
+        d_scale = ws.get("d_scale", (1,), torch.float32)
+        need_dx = not self.skip_input_grad
+        # dW on the int8 tensor pipe (exact fixed-point sums, 2x the fp16 rate) when the input is a
+        # +-1 activation whose producer emitted the transposed int8 pieces; else two fp16 passes
+        use_q = ((not c["real_input"]) and getattr(xin, "t8", None) is not None
+                 and (xin.t16 is None or K_.int8_dw_ok(N, B)))  # follow what the producer emitted
+        digits = dt_hi = dt_lo = colq = None
+        if use_q:
+            Bq = pad_to(B, 16)
+            digits = tuple(ws.get(f"{nm}{B}", (N, Bq), torch.int8, zero=True) for nm in ("q1t", "q3t", "q2t"))
+        else:
+            dt_hi = ws.get(f"dt_hi{B}", (N, Bp), torch.float16, zero=True)
+            dt_lo = ws.get(f"dt_lo{B}", (N, Bp), torch.float16, zero=True)
+        colq = self.batchNormLayer.backward_kernels(
+            delta, Z, B, c["sums"], c["mu"], c["var"], lr, False, (d_hi, d_lo) if need_dx else None,
+            (dt_hi, dt_lo) if not use_q else None, d_scale, reduced=reduced, digits=digits)
+
+        # ---- dX = delta' . W^T with the latent, pre-update weights (layers.py:266)
+        dX = None
+        bstats = below = None
+        if need_dx:
+            w_amax = ws.get("w_amax", (1,), torch.float32)
+            w_scale = ws.get("w_scale", (1,), torch.float32)
+            w_hi = ws.get("w_hi", (Kd, Np), torch.float16, zero=True)
+            w_lo = ws.get("w_lo", (Kd, Np), torch.float16, zero=True)
+            # W has not changed since this step's forward, whose binarize pass left max|W| in w_amax
+            K_.split_f16(self._weights.t, w_amax, hi=w_hi, lo=w_lo, scale_out=w_scale)
+            dX = empty((B, pad_to(Kd, 4)))
+            # dX is the delta of the layer below: its batch-norm backward needs sum(delta) and
+            # sum(delta*(z-mu)) per column, which this GEMM's epilogue accumulates on the way out
+            below = getattr(self, "input_layer", None)
+            bstats = None
+            # (only when the layer below passes dX on unchanged: sign's STE or identity — any other
+            # activation multiplies dX by its derivative before its batch-norm backward)
+            if (below is not None and isinstance(below, LinearLayer) and "z" in below.cache
+                    and below.activation in (None, af.sign, af.identity)
+                    and below.cache.get("B") == B and K_.fused_stats_ok(Kd)):
+                bstats = below.batchNormLayer.bwd_reduce_target(below.cache["z"], below.cache["mu"])
+            K_.gemm(M=B, N=Kd, K=N, A=(d_hi, d_lo), B=(w_hi, w_lo), lda=Np, ldb=Np, D=dX,
+                    ldd=dX.stride(0), in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32,
+                    passes=((0, 0), (0, 1), (1, 0)), sa=d_scale, sb=w_scale, stats=bstats)
+            dX = dX[:, :Kd]
+
+        # ---- dW = X^T . delta'  (layers.py:260) and W -= lr * dW (:268)
+        if use_q:
+            # dW = 1/s_n * (X^T.q1 + 256 * ((127 X)^T.q3 + X^T.q2)): low / high int32 accumulators
+            dw = dict(in_dtype=nat.DT_I8, A=(xin.t8, xin.t8x127), B=digits, lda=xin.t8.stride(0),
+                      ldb=digits[0].stride(0), passes=((0, 0), (1, 1), (0, 2)), hi_from_pass=1,
+                      col_scale=colq[1], sa=None, sb=None)
+        elif c["real_input"]:
+            dw = dict(in_dtype=nat.DT_F16, A=(xin["hi_t"], xin["lo_t"]), B=(dt_hi, dt_lo),
+                      lda=xin["hi_t"].stride(0), ldb=Bp, passes=((0, 0), (0, 1), (1, 0)),
+                      sa=xin["scale"], sb=d_scale)
+        else:
+            dw = dict(in_dtype=nat.DT_F16, A=(xin.t16,), B=(dt_hi, dt_lo), lda=xin.t16.stride(0), ldb=Bp,
+                      passes=((0, 0), (0, 1)), sa=None, sb=d_scale)
+        Wt = self._weights.t
+        if self.capture_dw is not None:
+            cap = self.capture_dw
+            assert tuple(cap.shape) == (Kd, N) and cap.dtype == torch.float32 and cap.is_contiguous()
+            K_.gemm(M=Kd, N=N, K=B, D=cap, ldd=N, epilogue=nat.EPI_STORE_F32, **dw)
+        split = 4 if (N <= 32 and Kd >= 1024 and B % 256 == 0 and self.comm.world == 1) else 1
+        # single GPU: the dW GEMM goes to the side stream (see DwOverlap) unless it is the last kernel
+        # of the step (first layer), where there is nothing left to overlap it with
+        ov = self._dw_overlap if (self.comm.world == 1 and not self.skip_input_grad) else None
+        with (ov.branch() if ov is not None else contextlib.nullcontext()):
+            if split > 1:
+                # narrow layer (the 10-unit output): a 128 x 32 tile grid has only Kd/128 CTAs, so the
+                # contraction over the batch is cut into `split` slices run as GEMM batches (operand
+                # slices are column ranges: batch stride = slice length), summed by the update kernel
+                Ks = B // split
+                parts = ws.get("dW_parts", (split, Kd, N), torch.float32)
+                K_.gemm(M=Kd, N=N, K=Ks, D=parts, ldd=N, epilogue=nat.EPI_STORE_F32, batch=split,
+                        stride_a=Ks, stride_b=Ks, stride_d=Kd * N, **dw)
+                K_.sgd_update(Wt, parts, lr, parts=split)
+            elif self.comm.world == 1:
+                K_.gemm(M=Kd, N=N, K=B, D=Wt, ldd=N, epilogue=nat.EPI_SGD_F32, host_scale=lr, **dw)
+        if split > 1 or self.comm.world == 1:
+            pass  # done above (possibly on the side stream)
+        elif self._dwx is not None:
+            # reduce-scatter fused into the GEMM epilogue: each 128-row tile of this rank's partial dW
+            # is stored over NVLink into the staging buffer of the rank that owns those rows
+            self._home_weights()
+            dwx, li = self._dwx
+            dwx.comm.collectives += 1
+            # Like the single-GPU step, the whole weight-gradient chain — dW GEMM, the owner's sum + update (which
+            # first waits for the peers' partial rows) — runs on the side stream: nothing on this stream needs
+            # W_l before the next step, and the 40 us owner update of a 4096 x 4096 layer plus the wait for the
+            # slowest peer's GEMM no longer sit between this layer's dX and the next batch-norm exchange.
+            ovd = self._dw_overlap if not self.skip_input_grad else None
+            with (ovd.branch() if ovd is not None else contextlib.nullcontext()):
+                K_.gemm(M=Kd, N=N, K=B, D=None, ldd=N, epilogue=nat.EPI_SCATTER_F32,
+                        scatter=dict(world=dwx.world, rank=dwx.rank,
+                                     rows_per_owner=dwx.layout[li]["rows_per_owner"],
+                                     stage=dwx.stage_ptrs(li)), **dw)
+                if dwx.copy_engine_broadcast and not self.skip_input_grad:
+                    # owner update now (local rows only; the kernel also signals "pushed" to the peers);
+                    # the rows then travel to the peers on the copy engines, on their own stream, while this
+                    # stream carries on with the backward pass.  The copies are started only after the
+                    # next batch-norm exchange (dwx.start_broadcasts): queued right here, 10s of MB of
+                    # copy traffic would sit in front of that exchange's flags on the NVLink ports.
+                    self._dw_reduce(lr, broadcast=False)
+                    dwx.reduced[li].record(torch.cuda.current_stream())
+                    dwx.deferred.append(li)
+                else:
+                    # first layer (its dW GEMM ends the step and its weights open the next one, so there
+                    # is nothing left to overlap copies with) or BNN_DW_BCAST=kernel: the owner-update
+                    # kernel stores the row blocks into the peers itself
+                    self._dw_reduce(lr, broadcast=True)
+            dwx.pending.append(li)  # awaited by comm.finish_step() at the end of the training step
+        else:
+            dW = ws.get("dW", (Kd, N), torch.float32)
+            K_.gemm(M=Kd, N=N, K=B, D=dW, ldd=N, epilogue=nat.EPI_STORE_F32, **dw)
+            # batch-sharded dW -> global dW over NCCL/NVLink, started now and awaited only when the
+            # weights are next needed, so it overlaps the lower layers' backward kernels
+            self._pending_update = (self.comm.allreduce_sum_async(dW), dW, lr)
+
+        self.cache.clear()
+        if dX is None:
+            return None
+        out = DeviceArray(dX)
+        if bstats is not None:
+            out._bn_reduced_for = below
+        return out
 
 
 class BinaryLayer(LinearLayer):
@@ -503,21 +728,6 @@ class BinaryLayer(LinearLayer):
                               wt_bits=ops["bits"], absmax=ops["amax"])
         return ops
 
-    def _real_input_operands(self, Xt, train: bool):
-        B, Kd = Xt.shape
-        ws = self._ws
-        amax = ws.get("x_amax", (1,), torch.float32)
-        scale = ws.get("x_scale", (1,), torch.float32)
-        hi = ws.get(f"x_hi{B}", (B, pad_to(Kd, 8)), torch.float16, zero=True)
-        lo = ws.get(f"x_lo{B}", (B, pad_to(Kd, 8)), torch.float16, zero=True)
-        hi_t = lo_t = None
-        if train:
-            hi_t = ws.get(f"xt_hi{B}", (Kd, pad_to(B, 8)), torch.float16, zero=True)
-            lo_t = ws.get(f"xt_lo{B}", (Kd, pad_to(B, 8)), torch.float16, zero=True)
-        K_.absmax_f32(Xt, amax)
-        K_.split_f16(Xt, amax, hi=hi, lo=lo, hi_t=hi_t, lo_t=lo_t, scale_out=scale)
-        return dict(hi=hi, lo=lo, hi_t=hi_t, lo_t=lo_t, scale=scale)
-
     def _apply_foreign_callback(self, cb, wops):
         """Any callable with the reference signature `cb(weight, gpu=)` (layers.py:218): it is
         handed the binarized weight as an fp32 [K, N] device array and its result is re-packed."""
@@ -529,23 +739,6 @@ class BinaryLayer(LinearLayer):
         assert tuple(new_w.shape) == (Kd, N)
         K_.binarize_weights_t(new_w, wt_i8=wops.get("i8"), wt_f16=wops.get("f16"),
                               wt_bits=wops["bits"])
-
-    def finish_update(self) -> None:
-        """Apply `W -= lr * dW` of a data-parallel step once its all-reduce has landed."""
-        if self._pending_update is None:
-            return
-        work, dW, lr = self._pending_update
-        self._pending_update = None
-        if work is not None:
-            work.wait()  # stream-side wait: the update kernel queues behind the collective
-        K_.sgd_update(self.weights.t, dW, lr)
-
-    def _dw_reduce(self, lr: float, broadcast: bool) -> None:
-        dwx, li = self._dwx
-        L = dwx.layout[li]
-        K_.dw_reduce_sgd_p2p(dwx.stage_ptrs(li)[dwx.rank], dwx.w_ptrs(li), dwx.flag_ptrs(), 2 * li,
-                             2 * li + 1, dwx.rank, dwx.world, dwx.comm.step_dev, L["K"], L["N"],
-                             L["rows_per_owner"], lr, broadcast, dwx.counters[li:li + 1], signal=True)
 
     # ------------------------------------------------------------------ uint8-fed layer 0 (eval)
     def _u8_input_ok(self, X) -> bool:
@@ -743,149 +936,4 @@ class BinaryLayer(LinearLayer):
         if isTrain:
             self.cache.update(input=xin, z=Z, a=out, sums=sums, mu=mu, var=var, B=B,
                               real_input=real_input)
-        return out
-
-    # ------------------------------------------------------------------ backward
-    def backwards(self, dA, lr: float, activDeriv=True):
-        assert "input" in self.cache
-        assert "z" in self.cache
-        Kd, N = self.weights_shape
-        ws = self._ws
-        c = self.cache
-        B, Z, xin = c["B"], c["z"], c["input"]
-        lr = float(lr)
-        # STE: hard_tanh_derivative evaluated on the post-sign activations is the identity
-        # (activation.py:122-131 via layers.py:252-254), and softmax+CE arrives pre-differentiated.
-        # Any other activation: delta = ACTIVATION_DERIVATIVES[act](dA, a) on the cached activations (:251-254).
-        if activDeriv and self.activation not in (None, af.sign, af.identity):
-            dA = ACTIVATION_DERIVATIVES[self.activation](dA, c["a"])
-        delta = to_tensor(dA, torch.float32)
-        assert tuple(delta.shape) == (B, N)
-        # the layer above may already have summed this layer's batch-norm reductions in the epilogue
-        # of the GEMM that produced dA
-        reduced = getattr(dA, "_bn_reduced_for", None) is self
-
-        Np, Bp = pad_to(N, 8), pad_to(B, 8)
-        d_hi = ws.get(f"d_hi{B}", (B, Np), torch.float16, zero=True)
-        d_lo = ws.get(f"d_lo{B}", (B, Np), torch.float16, zero=True)
-        d_scale = ws.get("d_scale", (1,), torch.float32)
-        need_dx = not self.skip_input_grad
-        # dW on the int8 tensor pipe (exact fixed-point sums, 2x the fp16 rate) when the input is a
-        # +-1 activation whose producer emitted the transposed int8 pieces; else two fp16 passes
-        use_q = ((not c["real_input"]) and getattr(xin, "t8", None) is not None
-                 and (xin.t16 is None or K_.int8_dw_ok(N, B)))  # follow what the producer emitted
-        digits = dt_hi = dt_lo = colq = None
-        if use_q:
-            Bq = pad_to(B, 16)
-            digits = tuple(ws.get(f"{nm}{B}", (N, Bq), torch.int8, zero=True) for nm in ("q1t", "q3t", "q2t"))
-        else:
-            dt_hi = ws.get(f"dt_hi{B}", (N, Bp), torch.float16, zero=True)
-            dt_lo = ws.get(f"dt_lo{B}", (N, Bp), torch.float16, zero=True)
-        colq = self.batchNormLayer.backward_kernels(
-            delta, Z, B, c["sums"], c["mu"], c["var"], lr, False, (d_hi, d_lo) if need_dx else None,
-            (dt_hi, dt_lo) if not use_q else None, d_scale, reduced=reduced, digits=digits)
-
-        # ---- dX = delta' . W^T with the latent, pre-update weights (layers.py:266)
-        dX = None
-        bstats = below = None
-        if need_dx:
-            w_amax = ws.get("w_amax", (1,), torch.float32)
-            w_scale = ws.get("w_scale", (1,), torch.float32)
-            w_hi = ws.get("w_hi", (Kd, Np), torch.float16, zero=True)
-            w_lo = ws.get("w_lo", (Kd, Np), torch.float16, zero=True)
-            # W has not changed since this step's forward, whose binarize pass left max|W| in w_amax
-            K_.split_f16(self._weights.t, w_amax, hi=w_hi, lo=w_lo, scale_out=w_scale)
-            dX = empty((B, pad_to(Kd, 4)))
-            # dX is the delta of the layer below: its batch-norm backward needs sum(delta) and
-            # sum(delta*(z-mu)) per column, which this GEMM's epilogue accumulates on the way out
-            below = getattr(self, "input_layer", None)
-            bstats = None
-            if (below is not None and isinstance(below, BinaryLayer) and "z" in below.cache
-                    and below.cache.get("B") == B and K_.fused_stats_ok(Kd)):
-                bstats = below.batchNormLayer.bwd_reduce_target(below.cache["z"], below.cache["mu"])
-            K_.gemm(M=B, N=Kd, K=N, A=(d_hi, d_lo), B=(w_hi, w_lo), lda=Np, ldb=Np, D=dX,
-                    ldd=dX.stride(0), in_dtype=nat.DT_F16, epilogue=nat.EPI_STORE_F32,
-                    passes=((0, 0), (0, 1), (1, 0)), sa=d_scale, sb=w_scale, stats=bstats)
-            dX = dX[:, :Kd]
-
-        # ---- dW = X^T . delta'  (layers.py:260) and W -= lr * dW (:268)
-        if use_q:
-            # dW = 1/s_n * (X^T.q1 + 256 * ((127 X)^T.q3 + X^T.q2)): low / high int32 accumulators
-            dw = dict(in_dtype=nat.DT_I8, A=(xin.t8, xin.t8x127), B=digits, lda=xin.t8.stride(0),
-                      ldb=digits[0].stride(0), passes=((0, 0), (1, 1), (0, 2)), hi_from_pass=1,
-                      col_scale=colq[1], sa=None, sb=None)
-        elif c["real_input"]:
-            dw = dict(in_dtype=nat.DT_F16, A=(xin["hi_t"], xin["lo_t"]), B=(dt_hi, dt_lo),
-                      lda=xin["hi_t"].stride(0), ldb=Bp, passes=((0, 0), (0, 1), (1, 0)),
-                      sa=xin["scale"], sb=d_scale)
-        else:
-            dw = dict(in_dtype=nat.DT_F16, A=(xin.t16,), B=(dt_hi, dt_lo), lda=xin.t16.stride(0), ldb=Bp,
-                      passes=((0, 0), (0, 1)), sa=None, sb=d_scale)
-        Wt = self._weights.t
-        if self.capture_dw is not None:
-            cap = self.capture_dw
-            assert tuple(cap.shape) == (Kd, N) and cap.dtype == torch.float32 and cap.is_contiguous()
-            K_.gemm(M=Kd, N=N, K=B, D=cap, ldd=N, epilogue=nat.EPI_STORE_F32, **dw)
-        split = 4 if (N <= 32 and Kd >= 1024 and B % 256 == 0 and self.comm.world == 1) else 1
-        # single GPU: the dW GEMM goes to the side stream (see DwOverlap) unless it is the last kernel
-        # of the step (first layer), where there is nothing left to overlap it with
-        ov = self._dw_overlap if (self.comm.world == 1 and not self.skip_input_grad) else None
-        with (ov.branch() if ov is not None else contextlib.nullcontext()):
-            if split > 1:
-                # narrow layer (the 10-unit output): a 128 x 32 tile grid has only Kd/128 CTAs, so the
-                # contraction over the batch is cut into `split` slices run as GEMM batches (operand
-                # slices are column ranges: batch stride = slice length), summed by the update kernel
-                Ks = B // split
-                parts = ws.get("dW_parts", (split, Kd, N), torch.float32)
-                K_.gemm(M=Kd, N=N, K=Ks, D=parts, ldd=N, epilogue=nat.EPI_STORE_F32, batch=split,
-                        stride_a=Ks, stride_b=Ks, stride_d=Kd * N, **dw)
-                K_.sgd_update(Wt, parts, lr, parts=split)
-            elif self.comm.world == 1:
-                K_.gemm(M=Kd, N=N, K=B, D=Wt, ldd=N, epilogue=nat.EPI_SGD_F32, host_scale=lr, **dw)
-        if split > 1 or self.comm.world == 1:
-            pass  # done above (possibly on the side stream)
-        elif self._dwx is not None:
-            # reduce-scatter fused into the GEMM epilogue: each 128-row tile of this rank's partial dW
-            # is stored over NVLink into the staging buffer of the rank that owns those rows
-            self._home_weights()
-            dwx, li = self._dwx
-            dwx.comm.collectives += 1
-            # Like the single-GPU step, the whole weight-gradient chain — dW GEMM, the owner's sum + update (which
-            # first waits for the peers' partial rows) — runs on the side stream: nothing on this stream needs
-            # W_l before the next step, and the 40 us owner update of a 4096 x 4096 layer plus the wait for the
-            # slowest peer's GEMM no longer sit between this layer's dX and the next batch-norm exchange.
-            ovd = self._dw_overlap if not self.skip_input_grad else None
-            with (ovd.branch() if ovd is not None else contextlib.nullcontext()):
-                K_.gemm(M=Kd, N=N, K=B, D=None, ldd=N, epilogue=nat.EPI_SCATTER_F32,
-                        scatter=dict(world=dwx.world, rank=dwx.rank,
-                                     rows_per_owner=dwx.layout[li]["rows_per_owner"],
-                                     stage=dwx.stage_ptrs(li)), **dw)
-                if dwx.copy_engine_broadcast and not self.skip_input_grad:
-                    # owner update now (local rows only; the kernel also signals "pushed" to the peers);
-                    # the rows then travel to the peers on the copy engines, on their own stream, while this
-                    # stream carries on with the backward pass.  The copies are started only after the
-                    # next batch-norm exchange (dwx.start_broadcasts): queued right here, 10s of MB of
-                    # copy traffic would sit in front of that exchange's flags on the NVLink ports.
-                    self._dw_reduce(lr, broadcast=False)
-                    dwx.reduced[li].record(torch.cuda.current_stream())
-                    dwx.deferred.append(li)
-                else:
-                    # first layer (its dW GEMM ends the step and its weights open the next one, so there
-                    # is nothing left to overlap copies with) or BNN_DW_BCAST=kernel: the owner-update
-                    # kernel stores the row blocks into the peers itself
-                    self._dw_reduce(lr, broadcast=True)
-            dwx.pending.append(li)  # awaited by comm.finish_step() at the end of the training step
-        else:
-            dW = ws.get("dW", (Kd, N), torch.float32)
-            K_.gemm(M=Kd, N=N, K=B, D=dW, ldd=N, epilogue=nat.EPI_STORE_F32, **dw)
-            # batch-sharded dW -> global dW over NCCL/NVLink, started now and awaited only when the
-            # weights are next needed, so it overlaps the lower layers' backward kernels
-            self._pending_update = (self.comm.allreduce_sum_async(dW), dW, lr)
-
-        self.cache.clear()
-        if dX is None:
-            return None
-        out = DeviceArray(dX)
-        if bstats is not None:
-            out._bn_reduced_for = below
         return out

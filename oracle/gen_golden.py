@@ -245,6 +245,35 @@ def gen_act_loss(A, Lo, Nw, O):
     print("act_loss.npz:", {k: float(blob[f"net_{a}_{l}_cost"]) for a, l in pairs for k in [f"{a}+{l}"]})
 
 
+def gen_linear(A, Lo, Nw, O):
+    """tests/golden/linear_net.npz: the reference's real-valued network (binarized=False: LinearLayer,
+    layers.py:130-271, batch-norm, no bias) trained three steps on three batches for each smooth hidden activation,
+    plus its eval-mode prediction.  No sign() anywhere, so the comparison is well-conditioned over several steps."""
+    af, lf = A.ActivationFuncs, Lo.LossFuncs
+    rng = np.random.default_rng(83)
+    units, B = [30, 24, 16, 10], 48
+    params = O.new_params(units, rng)
+    batches = [((rng.random((B, units[0]), dtype=np.float32) * 2 - 1),
+                np.eye(10, dtype=np.int8)[rng.integers(0, 10, B)]) for _ in range(3)]
+    X2 = rng.random((B, units[0]), dtype=np.float32) * 2 - 1
+    blob = dict(units=np.array(units), X_eval=X2)
+    for i, (X, Y) in enumerate(batches):
+        blob[f"X{i}"], blob[f"Y{i}"] = X, Y
+    blob.update(flat_state("init_", params))
+    hidden = ["sigmoid", "relu", "tanh", "leaky_relu"]
+    blob["hidden"] = np.array(hidden)
+    for h in hidden:
+        nn = Nw.Network(units, useGpu=False, binarized=False, useBatchNorm=True)
+        nn.compile(lr=0.05, hiddenAf=af[h], outAf=af.softmax, lossF=lf.cross_entropy)
+        nn.load_weights([w.copy() for w in params["W"]])
+        for i, (X, Y) in enumerate(batches):
+            blob[f"{h}_cost{i}"] = np.float64(nn._Network__updateBatch((X.copy(), Y.copy()), 0.05))
+            blob.update(flat_state(f"{h}_s{i}_", net_state(nn)))
+        blob[f"{h}_pred"] = np.asarray(nn.predict(X2.copy(), isTraining=False), np.float32)
+    np.savez_compressed(GOLDEN / "linear_net.npz", **blob)
+    print("linear_net.npz:", {h: [float(blob[f"{h}_cost{i}"]) for i in range(3)] for h in hidden})
+
+
 def gen_float_faults(Cb, O):
     """IEEE-754 bit flips of real-valued weights (ErrorCallback(bnn=False), callbacks.py:35-59, 85-123):
     the reference draws from the global NumPy stream; replaying the same stream through the oracle's
@@ -271,11 +300,11 @@ def gen_float_faults(Cb, O):
 
 
 def main():
-    if sys.argv[1:] in (["checkpoint"], ["epochs"], ["act_loss"]):      # only this fixture (the others stay byte-identical)
+    if sys.argv[1:] in (["checkpoint"], ["epochs"], ["act_loss"], ["linear"]):      # only this fixture (the others stay byte-identical)
         L, A, Lo, Cb, Nw, U = import_reference()
         sys.path.insert(0, str(HERE))
         import bnn_oracle as O
-        {"checkpoint": gen_checkpoint, "epochs": gen_epochs, "act_loss": gen_act_loss}[sys.argv[1]](A, Lo, Nw, O)
+        {"checkpoint": gen_checkpoint, "epochs": gen_epochs, "act_loss": gen_act_loss, "linear": gen_linear}[sys.argv[1]](A, Lo, Nw, O)
         print(f"{sys.argv[1]} fixtures written")
         return
     _main_all()
@@ -478,6 +507,7 @@ def _main_all():
     gen_checkpoint(A, Lo, Nw, O)
     gen_epochs(A, Lo, Nw, O)
     gen_act_loss(A, Lo, Nw, O)
+    gen_linear(A, Lo, Nw, O)
 
     sizes = {p.name: p.stat().st_size for p in sorted(GOLDEN.glob("*.npz"))}
     print("golden fixtures written:", sizes)
