@@ -54,6 +54,11 @@ constexpr int kAccStages = 2;
 // stores are 32 scattered 16-byte pieces: tolerable into local L2, crippling over NVLink).
 constexpr int kXposeRows = 16;    // half a warp's rows per phase
 constexpr int kXposeStride = 36;  // floats per staged row (32 + 4: conflict-free 128-bit access)
+// per-warp staging buffer: [0, 1024) the sign epilogues' thresholds, [1024, 3328) row staging of the integer
+// epilogues (the fp32 epilogues stage their rows in [0, 2304))
+constexpr int kRowStageOff = 1024;
+constexpr int kRowStageBytes = kXposeRows * kXposeStride * 4;   // 2304
+constexpr int kXposeWarpBytes = kRowStageOff + kRowStageBytes;  // 3328
 
 // kCta2: the CTA-pair form keeps only HALF of the B tile in each CTA, so a stage is 32 KB instead of 48 KB and
 // six of them fit where the single-CTA form holds four.
@@ -72,7 +77,7 @@ struct TileCfg {
                                      (kColsNeeded <= 256 ? 256 : 512)));
     static_assert(kColsNeeded <= 512, "accumulator stages + scale factors exceed TMEM");
     static constexpr int kBarBytes = (2 * kStages + 2 * kAccStages) * 8 + 16;
-    static constexpr int kXposeBytes = kEpiWarps * kXposeRows * kXposeStride * 4;  // fp32 store staging
+    static constexpr int kXposeBytes = kEpiWarps * kXposeWarpBytes;  // store staging + thresholds
     static constexpr int kSmemBytes =
         kStages * kStageBytes + kBarBytes + 16 + kXposeBytes + 1024;  // + align slack
     static constexpr int kColsPerThread = BLOCK_N / 2;                 // per epilogue thread
@@ -154,6 +159,106 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& b,
 // sign epilogues: thr_smem is the shared-memory address of this warp's staged thresholds for the thread's column
 // range (thr at +0, orientation at +kSignStageBytes/2; columns past N hold +inf / 1), cl the group's offset in it.
 constexpr uint32_t kSignStageBytes = 1024;   // 2 x 128 floats: fits the warp's transpose buffer (2304 bytes)
+// 16 sign decisions of one row: bit j = (acc_j * s_j >= thr_j) against the thresholds staged in shared memory.
+template <bool kI8, bool kF4, int G>
+__device__ __forceinline__ uint32_t sign_bits_group(const uint32_t (&v)[G], float scale, uint32_t thr_smem, int cl) {
+    constexpr bool kIntCmp = kI8 && !kF4;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < G; j += 4) {
+        const uint4 tu = ptx::lds_v4(thr_smem + (uint32_t)((cl + j) * 4));
+        const uint4 su = ptx::lds_v4(thr_smem + 512u + (uint32_t)((cl + j) * 4));
+        const uint32_t tw[4] = {tu.x, tu.y, tu.z, tu.w}, sw[4] = {su.x, su.y, su.z, su.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (kIntCmp) {
+                bits |= (uint32_t)((int)v[j + q] * (int)sw[q] >= (int)tw[q]) << (j + q);
+            } else {
+                const float a = kF4 ? __uint_as_float(v[j + q]) : __fmul_rn(__uint_as_float(v[j + q]), scale);
+                bits |= (uint32_t)(__fmul_rn(a, __uint_as_float(sw[q])) >= __uint_as_float(tw[q])) << (j + q);
+            }
+        }
+    }
+    return bits;
+}
+
+// Integer epilogues of FULL-width tiles leave through shared memory too (round 2): a lane owns one output ROW, so
+// direct stores are 32 pieces of 8-32 bytes per instruction, each in a different row — timing experiments put them
+// at 2.6 us per tile whatever the output width (profiles/r02_summary.md), a quarter of an int8 product and more of an
+// FP4 one.  Here every lane packs its row (ROWB bytes: int8 / nibble decisions or int16 sums) into registers, the
+// rows of a phase are written to the warp's buffer, and all lanes copy them out so that consecutive lanes cover
+// consecutive 16-byte (8-byte for 56-byte rows) pieces of one row: whole 64-256 byte row segments per instruction.
+template <bool kI8, bool kF4, int EPI, int CPT>
+__device__ __forceinline__ void staged_packed_rows(const TcParams& p, uint32_t xbuf, uint8_t* g_row0,
+                                                   long long pitch_bytes, int rows_valid, const uint32_t (&sum)[CPT],
+                                                   float scale, int lane) {
+    constexpr int ROWB = EPI == BNN_EPI_STORE_S16 ? 2 * CPT : (EPI == BNN_EPI_SIGN_I8 ? CPT : CPT / 2);
+    constexpr int W = ROWB / 4;                                   // packed words per row
+    constexpr int PIECE = (ROWB % 16 == 0) ? 16 : 8;
+    constexpr int PPR = ROWB / PIECE;                             // pieces per row
+    // staged row pitch: the row plus padding that spreads a phase's rows over all banks
+    constexpr int STRIDE = (PIECE == 8) ? ROWB + 16 : (((ROWB + 16) / 4) % 32 == 0 ? ROWB + 32 : ROWB + 16);
+    constexpr int RP = (32 * STRIDE <= kRowStageBytes) ? 32 : ((16 * STRIDE <= kRowStageBytes) ? 16 : 8);
+    static_assert(8 * STRIDE <= kRowStageBytes && ROWB % 8 == 0, "a phase of 8 rows must fit the staging buffer");
+    const uint32_t sbuf = xbuf + (uint32_t)kRowStageOff;
+    // ---- pack this lane's row into registers (sign epilogues; int16 rows are packed while they are staged)
+    uint32_t pk[(EPI == BNN_EPI_STORE_S16) ? 1 : W];
+    if constexpr (EPI != BNN_EPI_STORE_S16) {
+        constexpr int G = 16;
+#pragma unroll
+        for (int g = 0; g < CPT / G; ++g) {
+            uint32_t v[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) v[j] = sum[g * G + j];
+            const uint32_t bits = sign_bits_group<kI8, kF4, G>(v, scale, xbuf, g * G);
+            if constexpr (EPI == BNN_EPI_SIGN_F4) {
+                pk[2 * g] = bits_to_e2m1x8(bits);
+                pk[2 * g + 1] = bits_to_e2m1x8(bits >> 8);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pk[4 * g + q] = nibble_to_pm1_bytes(bits >> (4 * q));
+            }
+        }
+    }
+#pragma unroll
+    for (int ph = 0; ph < 32 / RP; ++ph) {
+        if (lane / RP == ph) {
+            const uint32_t w = sbuf + (uint32_t)((lane % RP) * STRIDE);
+            if constexpr (EPI == BNN_EPI_STORE_S16) {
+#pragma unroll
+                for (int j = 0; j < CPT; j += 8)
+                    ptx::sts_v4(w + (uint32_t)(2 * j), (sum[j] & 0xffffu) | (sum[j + 1] << 16),
+                                (sum[j + 2] & 0xffffu) | (sum[j + 3] << 16), (sum[j + 4] & 0xffffu) | (sum[j + 5] << 16),
+                                (sum[j + 6] & 0xffffu) | (sum[j + 7] << 16));
+            } else if constexpr (PIECE == 16) {
+#pragma unroll
+                for (int j = 0; j < W; j += 4) ptx::sts_v4(w + (uint32_t)(4 * j), pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < W; j += 2) ptx::sts_v2(w + (uint32_t)(4 * j), pk[j], pk[j + 1]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < (RP * PPR + 31) / 32; ++i) {
+            const int pc = i * 32 + lane;
+            const int r = pc / PPR, c = pc - r * PPR;
+            const int row = ph * RP + r;
+            if (pc < RP * PPR && row < rows_valid) {
+                uint8_t* d = g_row0 + (long long)row * pitch_bytes + c * PIECE;
+                if constexpr (PIECE == 16) {
+                    const uint4 u = ptx::lds_v4(sbuf + (uint32_t)(r * STRIDE + c * 16));
+                    *reinterpret_cast<uint4*>(d) = u;
+                } else {
+                    const uint2 u = ptx::lds_v2(sbuf + (uint32_t)(r * STRIDE + c * 8));
+                    *reinterpret_cast<uint2*>(d) = u;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // kIntCmp (kind::i8 sign epilogues): the staged thresholds are INTEGERS — ceil(thr) and the orientation as +-1 —
 // and the decision is acc * s >= ceil(thr) on the int32 accumulator, identical to the float form for every
 // integer acc and free of the int -> float conversions (quarter-rate pipe) that the float form needs.
@@ -168,22 +273,7 @@ __device__ __forceinline__ void store_group(const TcParams& p, char* dbase, long
         // shared memory (staged once per tile with coalesced loads): fetched per group straight from global
         // memory, 56 dependent L2 round trips per tile made this epilogue 3x longer than an FP4 main loop.
         int8_t* d = reinterpret_cast<int8_t*>(dbase) + off;
-        uint32_t bits = 0;
-#pragma unroll
-        for (int j = 0; j < G; j += 4) {
-            const uint4 tu = ptx::lds_v4(thr_smem + (uint32_t)((cl + j) * 4));
-            const uint4 su = ptx::lds_v4(thr_smem + kSignStageBytes / 2 + (uint32_t)((cl + j) * 4));
-            const uint32_t tw[4] = {tu.x, tu.y, tu.z, tu.w}, sw[4] = {su.x, su.y, su.z, su.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (kIntCmp) {
-                    bits |= (uint32_t)((int)v[j + q] * (int)sw[q] >= (int)tw[q]) << (j + q);
-                } else {
-                    const float a = kF4 ? __uint_as_float(v[j + q]) : __fmul_rn(__uint_as_float(v[j + q]), scale);
-                    bits |= (uint32_t)(__fmul_rn(a, __uint_as_float(sw[q])) >= __uint_as_float(tw[q])) << (j + q);
-                }
-            }
-        }
+        const uint32_t bits = sign_bits_group<kI8, kF4, G>(v, scale, thr_smem, cl);
         if (EPI == BNN_EPI_SIGN_F4) {
             // E2M1 nibbles, two columns per byte (low nibble = even column): +1 = 0x2, -1 = 0xA, columns past
             // N = 0x0 (+0.0: the consumer's K padding).  Whole 8-column words; the host guarantees the pitch
@@ -646,12 +736,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int row = m_blk * kBlockM + q * 32 + lane;
             const int colbase = n_blk * BLOCK_N + h * CPT;
             const int row_w0 = m_blk * kBlockM + q * 32;  // first row of this warp
-            const uint32_t xbuf = ptx::smem_u32(xpose) + (uint32_t)((warp - 4) * kXposeRows * kXposeStride * 4);
+            const uint32_t xbuf = ptx::smem_u32(xpose) + (uint32_t)((warp - 4) * kXposeWarpBytes);
             if constexpr (EPI == BNN_EPI_SIGN_I8 || EPI == BNN_EPI_SIGN_F4) {
                 // stage this warp's thresholds (thr, orientation) of the tile's column range while the MMAs run:
                 // lane l fetches columns 4l .. 4l+3 (coalesced), columns past N get +inf / 1
-                static_assert(2 * CPT * 4 <= (int)kSignStageBytes && kSignStageBytes <= kXposeRows * kXposeStride * 4,
-                              "threshold staging must fit the warp's transpose buffer");
+                static_assert(2 * CPT * 4 <= (int)kSignStageBytes && (int)kSignStageBytes <= kRowStageOff,
+                              "threshold staging must fit its part of the warp's buffer");
                 const float* tb = p.thr + (long long)b * p.thr_stride;
                 __syncwarp();   // the previous tile's reads of the buffer are done
                 if (4 * lane < CPT) {
@@ -760,6 +850,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 // full-width tile: whole 128-byte row segments per store instruction
                 float* dst = reinterpret_cast<float*>(dbase) + (rowoff - (long long)lane * p.ldd) + colbase;
                 staged_rows<kI8, EPI, CPT, STATS, true>(p, xbuf, dst, row_w0, colbase, sum, scale, lane);
+            } else if ((EPI == BNN_EPI_SIGN_I8 || EPI == BNN_EPI_SIGN_F4 || EPI == BNN_EPI_STORE_S16) && G == 16 &&
+                       p.vec_ok && colbase + CPT <= p.N) {
+                // full-width tile of an integer epilogue: rows staged, whole row segments per store instruction
+                constexpr int kNum = EPI == BNN_EPI_STORE_S16 ? 4 : (EPI == BNN_EPI_SIGN_I8 ? 2 : 1);   // half bytes
+                uint8_t* g0 = reinterpret_cast<uint8_t*>(dbase) +
+                              (((long long)b * p.stride_d + (long long)row_w0 * p.ldd + colbase) * kNum) / 2;
+                if constexpr (G == 16 && (EPI == BNN_EPI_SIGN_I8 || EPI == BNN_EPI_SIGN_F4 || EPI == BNN_EPI_STORE_S16))
+                    staged_packed_rows<kI8, kF4, EPI, CPT>(p, xbuf, g0, (p.ldd * kNum) / 2, p.M - row_w0, sum, scale,
+                                                           lane);
             } else if (row < p.M) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {

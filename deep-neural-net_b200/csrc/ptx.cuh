@@ -24,6 +24,14 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
                  : "r"(addr));
     return v;
 }
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_b32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
