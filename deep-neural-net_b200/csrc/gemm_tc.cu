@@ -95,6 +95,7 @@ struct TcParams {
     int pb[BNN_GEMM_MAX_PASS];
     int m_tiles, n_tiles;
     int group_m, group_n;  // tile walk (tile_coords)
+    int mc;                // cluster-multicast form (launch_tc): CTA pairs share the B tile, see the kernel
     int debug;             // BNN_GEMM_DEBUG (timing experiments only): 1 = no TMA loads, 2 = no global stores
     int epilogue;
     int vec_ok;  // D base/pitch allow 16-byte vector access
@@ -578,11 +579,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_tiles = p.batch * p.m_tiles * p.n_tiles;
-    const uint32_t cta_rank = kCta2 ? ptx::cluster_ctarank() : 0u;
-// a CTA's (pair: a CTA pair's) walk over the output tiles; the single-CTA form keeps its original expressions
+    // Multicast form (p.mc, run-time, single-CTA MMAs): the two CTAs of a cluster work on vertically adjacent
+    // 128 x BLOCK_N tiles, which read the SAME B tile.  Each CTA fetches its own A tile and HALF of the B tile, and
+    // the half is delivered to both CTAs by TMA multicast — 32 KB instead of 48 KB leave the L2 per CTA and K step
+    // (profiles/r02_summary.md: the int8 / FP4 products are bound by operand delivery).  A stage may be refilled only
+    // when BOTH CTAs have consumed it (the peer writes into it), so the empty barriers count two arrivals and every
+    // MMA issuer commits onto both CTAs' barriers.  p.m_tiles counts PAIRS of row tiles in this form.
+    const bool mc = !kCta2 && p.mc != 0;
+    const uint32_t cta_rank = (kCta2 || mc) ? ptx::cluster_ctarank() : 0u;
+    const bool paired = kCta2 || mc;
+// a CTA's (pair: a CTA pair's) walk over the output tiles
 #define BNN_TILE_LOOP                                                                       \
-    for (int tile = kCta2 ? (blockIdx.x >> 1) : blockIdx.x; tile < total_tiles;             \
-         tile += kCta2 ? (gridDim.x >> 1) : gridDim.x)
+    for (int tile = paired ? (blockIdx.x >> 1) : blockIdx.x; tile < total_tiles;            \
+         tile += paired ? (gridDim.x >> 1) : gridDim.x)
     const int k_iters = p.n_pass * p.kblocks;
     // digit-split products have exactly two "chunks": the low and the high accumulator
     const int split_iters = p.hi_from_pass * p.kblocks;
@@ -599,7 +608,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S; ++s) {
             ptx::mbar_init(&full_bar[s], kCta2 ? 2 : 1);  // pair: the leader's arrive.expect_tx + the peer
-            ptx::mbar_init(&empty_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], mc ? 2 : 1);    // multicast: both CTAs' MMAs have read the stage
         }
         for (int a = 0; a < kAccStages; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
@@ -612,6 +621,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     ptx::tc_fence_before_sync();
     __syncthreads();
     ptx::cluster_sync_if<kCta2>();  // pair: the peer's barriers are initialised before anyone signals them
+    if (mc) ptx::cluster_sync();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
     if constexpr (kF4) {
@@ -640,7 +650,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             BNN_TILE_LOOP {
                 int b, m_blk, n_blk;
                 tile_coords(p, tile, b, m_blk, n_blk);
-                if constexpr (kCta2) m_blk = 2 * m_blk + (int)cta_rank;
+                if (paired) m_blk = 2 * m_blk + (int)cta_rank;
                 const int ba = p.a_batched ? b : 0;
                 const int bb = p.b_batched ? b : 0;
                 for (int pass = 0; pass < p.n_pass; ++pass) {
@@ -662,6 +672,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             ptx::mbar_arrive_expect_tx(&full_bar[s],
                                                        kCta2 ? 2u * Cfg::kStageBytes : Cfg::kStageBytes);
                         ptx::tma_load_3d_t<kCta2>(sa, ma, &full_bar[s], kb * kKElems, m_blk * kBlockM, ba);
+                        if (mc)   // this CTA's half of the B tile, to the same place in both CTAs
+                            ptx::tma_load_3d_mc(sb + (int)cta_rank * (BLOCK_N / 2) * kKBytes, mb, &full_bar[s],
+                                                kb * kKElems, n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2), bb,
+                                                (uint16_t)3);
+                        else
                         ptx::tma_load_3d_t<kCta2>(sb, mb, &full_bar[s], kb * kKElems,
                                                   kCta2 ? n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2)
                                                         : n_blk * BLOCK_N, bb);
@@ -708,6 +723,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                 ptx::mma_f16_t<kCta2>(d_tmem, da + adv, db + adv, idesc, accum);
                         }
                         first = false;
+                        if (mc) ptx::mma_commit_mc(&empty_bar[s], (uint16_t)3);   // in both CTAs
+                        else
                         ptx::mma_commit_t<kCta2>(&empty_bar[s]);  // frees the smem stage once the MMAs retire
                         if (++s == S) { s = 0; ph ^= 1u; }        // (pair: in both CTAs)
                     }
@@ -732,7 +749,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             uint32_t sum[CPT];  // running sum of the chunks (fp32 bit patterns, or int32)
             int b, m_blk, n_blk;
             tile_coords(p, tile, b, m_blk, n_blk);
-            if constexpr (kCta2) m_blk = 2 * m_blk + (int)cta_rank;
+            if (paired) m_blk = 2 * m_blk + (int)cta_rank;
             const int row = m_blk * kBlockM + q * 32 + lane;
             const int colbase = n_blk * BLOCK_N + h * CPT;
             const int row_w0 = m_blk * kBlockM + q * 32;  // first row of this warp
@@ -883,6 +900,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     ptx::tc_fence_before_sync();
     __syncthreads();
     ptx::cluster_sync_if<kCta2>();  // pair: neither CTA leaves while the other may still reach into it
+    if (mc) ptx::cluster_sync();
     if (warp == 2) {
         ptx::tc_fence_after_sync();
         ptx::tmem_dealloc_t<kCta2, Cfg::kTmemCols>(tmem_base);
@@ -966,6 +984,13 @@ void pick_tile_walk(const bnn_gemm_desc& g, int es, int block_n, int m_tiles, in
     if (group_m < 1) group_m = 1;
 }
 
+// BNN_GEMM_MC (read on every call): the cluster-multicast form of launch_tc — two CTAs on vertically adjacent
+// tiles share the B tile through TMA multicast.  1 = on for every eligible product, 0 = off; default: see launch_tc.
+int multicast_mode() {
+    const char* e = getenv("BNN_GEMM_MC");
+    return e ? atoi(e) : -1;
+}
+
 // BNN_GEMM_CTA2=1 (read on every call, like BNN_GEMM_CHUNK: the tests flip both inside one process) routes
 // 256-wide products with more than one row tile to the CTA-pair form.  Round 2, on a B200: the opt-in tests pass
 // (tests/test_gemm_pair_gpu.py) and the training step runs 1.7x SLOWER with it (profiles/r02_summary.md), so it
@@ -1016,6 +1041,7 @@ int launch_tc_pair(const bnn_gemm_desc& g, cudaStream_t stream) {
     p.m_tiles = cdiv(cdiv(g.M, kBlockM), 2);  // pairs of row tiles
     p.n_tiles = cdiv(g.N, BLOCK_N);
     pick_tile_walk(g, kI8 ? 1 : 2, BLOCK_N, p.m_tiles, p.n_tiles, p.group_m, p.group_n);
+    p.mc = 0;
     p.debug = gemm_debug_flags();
     p.epilogue = g.epilogue;
     const int esz = (g.epilogue == BNN_EPI_STORE_S16) ? 2 : (g.epilogue == BNN_EPI_SIGN_I8 ? 1 : 4);
@@ -1111,6 +1137,10 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
         BNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
+    // cluster-multicast form: wide tiles, more than one row tile, not the NVLink scatter epilogue (its row-tile
+    // rotation assumes single tiles).  Opt-in (BNN_GEMM_MC=1) until it has earned the default.
+    const int mc_env = multicast_mode();
+    const bool mc = BLOCK_N >= 128 && EPI != BNN_EPI_SCATTER_F32 && g.M > kBlockM && mc_env == 1;
     CUtensorMap mA[3], mB[3];
     const int nA = (g.A[1] != nullptr) ? 2 : 1;
     const void* Bp[3] = {g.B[0], g.B[1] ? g.B[1] : g.B[0], g.B2 ? g.B2 : g.B[0]};
@@ -1121,7 +1151,7 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
                                   g.stride_a / pack, kBlockM);
         if (rc) return rc;
         rc = make_operand_map(&mB[i], b, kI8, g.N, g.K / pack, g.ldb / pack, g.stride_b ? g.batch : 1,
-                              g.stride_b / pack, BLOCK_N);
+                              g.stride_b / pack, mc ? BLOCK_N / 2 : BLOCK_N);   // multicast: half tiles
         if (rc) return rc;
     }
     TcParams p;
@@ -1137,9 +1167,11 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
         p.pa[i] = g.pa[i];
         p.pb[i] = g.pb[i];
     }
-    p.m_tiles = cdiv(g.M, kBlockM);
+    p.m_tiles = mc ? cdiv(cdiv(g.M, kBlockM), 2) : cdiv(g.M, kBlockM);   // multicast: pairs of row tiles
     p.n_tiles = cdiv(g.N, BLOCK_N);
+    p.mc = mc ? 1 : 0;
     pick_tile_walk(g, kI8 ? 1 : 2, BLOCK_N / pack, p.m_tiles, p.n_tiles, p.group_m, p.group_n);
+    if (mc && p.group_m > 4) p.group_m = 4;   // 4 pairs = the 8 row tiles of the single-CTA walk
     p.debug = gemm_debug_flags();
     p.epilogue = g.epilogue;
     const int esz = (g.epilogue == BNN_EPI_STORE_S16) ? 2 : (g.epilogue == BNN_EPI_SIGN_I8 ? 1 : 4);
@@ -1211,6 +1243,36 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
                       "and batch == 1 (N=%d)", BLOCK_N, g.N);
             return BNN_ERR_UNSUPPORTED;
         }
+    }
+    if (mc) {
+        // clusters of two CTAs; the tile walk is static, so the grid is what the device holds at once (§3.5)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)sm_count() & ~1u, 1, 1);
+        cfg.blockDim = dim3(kThreads, 1, 1);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        static std::atomic<int> max_clusters_dev[64];
+        int max_clusters = (dev >= 0 && dev < 64) ? max_clusters_dev[dev].load() : 0;
+        if (max_clusters <= 0) {
+            BNN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
+            if (max_clusters <= 0) {
+                set_error("bnn_gemm: the device cannot hold a single cluster of this kernel");
+                return BNN_ERR_UNSUPPORTED;
+            }
+            if (dev >= 0 && dev < 64) max_clusters_dev[dev] = max_clusters;
+        }
+        const long long pairs = (long long)p.batch * p.m_tiles * p.n_tiles;
+        cfg.gridDim = dim3(2u * (unsigned)(pairs < max_clusters ? pairs : max_clusters), 1, 1);
+        BNN_CUDA(cudaLaunchKernelEx(&cfg, kernel, mA[0], mA[1], mB[0], mB[1], mB[2], p));
+        BNN_LAUNCH_CHECK("gemm_tc_kernel<multicast>");
+        return BNN_OK;
     }
     kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA[0], mA[1], mB[0], mB[1], mB[2], p);
     BNN_LAUNCH_CHECK("gemm_tc_kernel");

@@ -10,6 +10,7 @@
 #   tests         `pytest -m gpu` in one process, as the driver runs it
 #   parity        the BASELINE-config parity tests (tests/test_config_parity_gpu.py)
 #   pair          CTA-pair GEMM bring-up: opt-in tests, then the bench with the pair form on / off
+#   mc            cluster-multicast GEMM bring-up: opt-in tests, then benches with the form on / off
 #   probe         tools/probe_mxf4.cu: +-1 products on the FP4 tensor pipe (exactness + MMA rate)
 #   bench         bench.py at N=1 (BENCH_ARGS overrides "--steps 20 --warmup 5")
 #   bench-long    bench.py --steps 300 (sustained clocks)
@@ -70,6 +71,21 @@ while [ $# -gt 0 ]; do
         BNN_GEMM_CTA2=1 run pair_bench_on  240 python bench.py $BENCH_ARGS
       }
       unset BNN_TEST_CTA2
+      ;;
+    mc)
+      export BNN_TEST_MC=1
+      PM="$PT -x tests/test_gemm_multicast_gpu.py"
+      run mc_i8_small  60 $PM -k "int8 and 256-256-128" &&
+      run mc_i8_all   120 $PM -k "int8" &&
+      run mc_f16      120 $PM -k "fp16" &&
+      run mc_fp4      120 $PM -k "fp4" &&
+      run mc_step     120 $PM -k "training_step" && {
+        BNN_GEMM_MC=0 run mc_bench_off 240 python bench.py $BENCH_ARGS --no-extras --no-cpu
+        BNN_GEMM_MC=1 run mc_bench_on  240 python bench.py $BENCH_ARGS --no-extras --no-cpu
+        BNN_GEMM_MC=0 FORMS_SINGLE_ONLY=1 FORMS_CASES=f4_sign_f4,i8_store_s16,i8_sign_i8,f16_1pass_f32,f16_3pass_f32,k784_i8_sign_f4 run mc_forms_off 200 python tools/bench_gemm_forms.py
+        BNN_GEMM_MC=1 FORMS_SINGLE_ONLY=1 FORMS_CASES=f4_sign_f4,i8_store_s16,i8_sign_i8,f16_1pass_f32,f16_3pass_f32,k784_i8_sign_f4 run mc_forms_on 200 python tools/bench_gemm_forms.py
+      }
+      unset BNN_TEST_MC
       ;;
     probe)
       run probe_build 120 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a tools/probe_mxf4.cu -o /tmp/probe_mxf4 &&
