@@ -355,10 +355,10 @@ def run_gpu(args):
         cpu = world == 1 and not args.no_cpu
         if rank == 0:
             extras["config1"] = BS.config1_section(steps=50, cpu_steps=20 if cpu else 0)
+        extras["inference"] = BS.inference_section(comm, cpu_rows=2048 if cpu else 0, int8_peak_tops=int8_peak)
         extras["weight_sweep"] = BS.weight_sweep_section(comm, n_trials=args.sweep_trials, cpu_trials=1 if cpu else 0,
                                                          int8_peak_tops=int8_peak)
         extras["image_sweep"] = BS.image_sweep_section(comm, n_trials=args.image_trials, cpu_trials=1 if cpu else 0)
-        extras["inference"] = BS.inference_section(comm, cpu_rows=2048 if cpu else 0, int8_peak_tops=int8_peak)
     if rank != 0:
         return 0
 
