@@ -45,9 +45,16 @@ class PeerExchange:
     def begin(self, site: int, n_doubles: int):
         """Returns (this rank's slot of call site `site` as an fp64 tensor, call descriptor)."""
         assert n_doubles <= self.slot_doubles and 0 <= site < self.n_sites
-        # a call site is used once per step; code that drives a layer outside Network.train_step
-        # (several forwards in a row) advances the step itself, identically on every rank
+        # A call site is used once per step, and between two uses of one site every rank passes another site's
+        # barrier — that is what makes refilling the slot safe (p2p.cu).  Code that drives a layer outside
+        # Network.train_step may use the SAME site twice in a row (a stand-alone BatchNormLayer called repeatedly):
+        # then nothing orders this rank's refill after the peers' reads of the previous contents, so the step is
+        # advanced behind a full barrier (host-side, identically on every rank; never taken inside a captured step).
         if self.last_step[site] == self.comm.step:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("PeerExchange: call site used twice within one captured step")
+            torch.cuda.current_stream().synchronize()
+            self.comm.barrier()
             self.comm.begin_step()
         self.last_step[site] = self.comm.step
         off = self.flag_bytes + site * self.slot_doubles * 8
