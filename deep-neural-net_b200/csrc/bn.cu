@@ -469,7 +469,7 @@ bn_sign_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const fl
                const float* __restrict__ sgn, int8_t* __restrict__ act_i8, long long ld_i8,
                __half* __restrict__ act_t16, long long ld_t16, uint32_t* __restrict__ act_bits,
                long long ld_bits, int8_t* __restrict__ act_t8, int8_t* __restrict__ act_t8x127,
-               long long ld_t8) {
+               long long ld_t8, uint8_t* __restrict__ act_f4, long long ld_f4_bytes) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cb = lane & 3, rb = lane >> 2;
     const int c0 = blockIdx.x * SG_COLS + (warp & 3) * 32 + cb * 8;
@@ -531,6 +531,17 @@ bn_sign_kernel(const void* __restrict__ Z, int B, int N, long long ldz, const fl
             w |= __shfl_xor_sync(0xffffffffu, w, 1);
             w |= __shfl_xor_sync(0xffffffffu, w, 2);
             if (cb == 0 && i < rvalid && c0 < N) act_bits[(long long)(r0 + i) * ld_bits + (c0 >> 5)] = w;
+        }
+    }
+    if (act_f4 && valid > 0) {
+        // E2M1 nibbles (the A operand of a BNN_DT_F4 product): 8 columns = one 32-bit word per row, 4 adjacent lanes
+        // fill 16 contiguous bytes; nibbles past N stay zero (the consumer's K padding)
+        const uint32_t keep = valid == 8 ? 0xFFFFFFFFu : ((1u << (4 * valid)) - 1u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i >= rvalid) break;
+            *reinterpret_cast<uint32_t*>(act_f4 + (long long)(r0 + i) * ld_f4_bytes + (c0 >> 1)) =
+                bits_to_e2m1x8(sb[i]) & keep;
         }
     }
     if (act_t16 || act_t8) {
@@ -1174,20 +1185,23 @@ extern "C" int bnn_bn_sign_thresholds(const float* mu, const float* var, const f
 extern "C" int bnn_bn_sign(const void* Z, int z_dtype, int B, int N, int64_t ldz, const float* thr,
                            const float* sgn, int8_t* act_i8, int64_t ld_i8, void* act_t16,
                            int64_t ld_t16, uint32_t* act_bits, int64_t ld_bits, int8_t* act_t8,
-                           int8_t* act_t8x127, int64_t ld_t8, bnn_stream_t stream) {
+                           int8_t* act_t8x127, int64_t ld_t8, void* act_f4, int64_t ld_f4,
+                           bnn_stream_t stream) {
     BNN_CHECK_ARG((act_t8 == nullptr) == (act_t8x127 == nullptr) && (!act_t8 || ld_t8 >= B),
                   "bnn_bn_sign: act_t8 / act_t8x127 come as a pair with ld_t8 >= B");
     BNN_CHECK_ARG(Z && thr && sgn && B > 0 && N > 0 && ldz >= N, "bnn_bn_sign: bad input");
     BNN_CHECK_ARG(!act_i8 || ld_i8 >= N, "bnn_bn_sign: ld_i8 < N");
     BNN_CHECK_ARG(!act_t16 || ld_t16 >= B, "bnn_bn_sign: ld_t16 < B");
     BNN_CHECK_ARG(!act_bits || ld_bits >= (N + 31) / 32, "bnn_bn_sign: ld_bits too small");
+    BNN_CHECK_ARG(!act_f4 || (aligned16(act_f4) && ld_f4 % 32 == 0 && ld_f4 >= ((N + 31) / 32) * 32),
+                  "bnn_bn_sign: act_f4 must be 16-byte aligned with a pitch of whole 32-element words");
     dim3 grid(cdiv(N, SG_COLS), cdiv(B, SG_ROWS));
     BNN_CHECK_ARG(grid.y <= 65535, "bnn_bn_sign: B too large");
     cudaStream_t s = (cudaStream_t)stream;
     return dispatch_z(z_dtype, [&](auto zt) {
         bn_sign_kernel<decltype(zt)::value><<<grid, 256, 0, s>>>(
             Z, B, N, ldz, thr, sgn, act_i8, ld_i8, static_cast<__half*>(act_t16), ld_t16, act_bits,
-            ld_bits, act_t8, act_t8x127, ld_t8);
+            ld_bits, act_t8, act_t8x127, ld_t8, static_cast<uint8_t*>(act_f4), ld_f4 / 2);
         BNN_LAUNCH_CHECK("bn_sign_kernel");
         return (int)BNN_OK;
     });

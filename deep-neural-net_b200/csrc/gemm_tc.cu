@@ -383,23 +383,23 @@ __device__ __forceinline__ void store_group(const TcParams& p, char* dbase, long
 //     accumulators with one atomicAdd per column and warp.
 // The value v is what the epilogue stores: acc * scale for fp32 outputs, the raw int32 sum for
 // integer outputs.
-template <bool kI8, int EPI, int CPT, int STATS, bool kStore>
-__device__ __forceinline__ void staged_rows(const TcParams& p, uint32_t xbuf, float* dst_row0,
-                                            int row_w0, int col_w0, const uint32_t (&sum)[CPT],
-                                            float scale, int lane) {
-    constexpr int GC = CPT < 32 ? CPT : 32;   // columns per group
+// (one group of GC <= 32 columns starting at column g0 of the warp's CPT; g0 is a constant once the caller's loop
+// is unrolled, so sum[g0 + j] stays in registers)
+template <bool kI8, int EPI, int CPT, int STATS, bool kStore, int GC>
+__device__ __forceinline__ void staged_group(const TcParams& p, uint32_t xbuf, float* dst_row0,
+                                             int row_w0, int col_w0, const uint32_t (&sum)[CPT],
+                                             float scale, int lane, const int g0) {
     constexpr int LPR = GC / 4;               // lanes per row segment
     constexpr int RPI = 32 / LPR;             // rows per store instruction
     constexpr bool sgd = EPI == BNN_EPI_SGD_F32;
     constexpr bool kIntVal = EPI == BNN_EPI_STORE_S16 || EPI == BNN_EPI_STORE_S32;  // v is an integer
     const int rows_valid = p.M - row_w0;
-#pragma unroll
-    for (int g = 0; g < CPT / GC; ++g) {
+    {
         // per-group column accumulators of lane c (STATS only)
         int si = 0;
         unsigned long long qi = 0ull;
         float f1 = 0.f, f2 = 0.f, md = 0.f, mx = 0.f;
-        const int col = col_w0 + g * GC + lane;  // this lane's column in the stats phase
+        const int col = col_w0 + g0 + lane;  // this lane's column in the stats phase
         float mu = 0.f;
         if (STATS == BNN_STATS_BN_BWD && lane < GC && col < p.N) mu = __ldg(p.st_mu + col);
 #pragma unroll
@@ -442,16 +442,16 @@ __device__ __forceinline__ void staged_rows(const TcParams& p, uint32_t xbuf, fl
                 for (int j = 0; j < GC; j += 4) {
                     uint4 u;
                     if (kIntVal) {
-                        u = make_uint4(sum[g * GC + j], sum[g * GC + j + 1], sum[g * GC + j + 2],
-                                       sum[g * GC + j + 3]);
+                        u = make_uint4(sum[g0 + j], sum[g0 + j + 1], sum[g0 + j + 2],
+                                       sum[g0 + j + 3]);
                     } else {
                         // digit-split int8 products already hold float bits (low + 256 * high)
                         const bool fbits = !kI8 || p.hi_from_pass != 0;
                         float4 cs = make_float4(1.f, 1.f, 1.f, 1.f);
                         if (p.col_scale)  // per-column power of two (exact), then the scalar factor
-                            cs = __ldg(reinterpret_cast<const float4*>(p.col_scale + col_w0 + g * GC + j));
-                        const uint32_t r0 = sum[g * GC + j + 0], r1 = sum[g * GC + j + 1],
-                                       r2 = sum[g * GC + j + 2], r3 = sum[g * GC + j + 3];
+                            cs = __ldg(reinterpret_cast<const float4*>(p.col_scale + col_w0 + g0 + j));
+                        const uint32_t r0 = sum[g0 + j + 0], r1 = sum[g0 + j + 1],
+                                       r2 = sum[g0 + j + 2], r3 = sum[g0 + j + 3];
                         u.x = __float_as_uint(__fmul_rn(__fmul_rn(fbits ? __uint_as_float(r0) : (float)(int)r0, cs.x), scale));
                         u.y = __float_as_uint(__fmul_rn(__fmul_rn(fbits ? __uint_as_float(r1) : (float)(int)r1, cs.y), scale));
                         u.z = __float_as_uint(__fmul_rn(__fmul_rn(fbits ? __uint_as_float(r2) : (float)(int)r2, cs.z), scale));
@@ -471,7 +471,7 @@ __device__ __forceinline__ void staged_rows(const TcParams& p, uint32_t xbuf, fl
                     float4 f = make_float4(__uint_as_float(fu.x), __uint_as_float(fu.y),
                                            __uint_as_float(fu.z), __uint_as_float(fu.w));
                     if (row < rows_valid) {
-                        float* d = dst_row0 + (long long)row * p.ldd + g * GC + c;
+                        float* d = dst_row0 + (long long)row * p.ldd + g0 + c;
                         if (sgd) {  // weights -= lr * dw (layers.py:268): two roundings, like NumPy
                             const float4 wv = *reinterpret_cast<const float4*>(d);
                             f.x = __fsub_rn(wv.x, f.x);
@@ -548,6 +548,20 @@ __device__ __forceinline__ void staged_rows(const TcParams& p, uint32_t xbuf, fl
     }
 }
 
+template <bool kI8, int EPI, int CPT, int STATS, bool kStore>
+__device__ __forceinline__ void staged_rows(const TcParams& p, uint32_t xbuf, float* dst_row0,
+                                            int row_w0, int col_w0, const uint32_t (&sum)[CPT],
+                                            float scale, int lane) {
+    constexpr int GC = CPT < 32 ? CPT : 32;   // columns per group
+    constexpr int kTail = CPT % GC;           // 224-wide tiles: 112 columns per warp = 3 x 32 + 16
+#pragma unroll
+    for (int g = 0; g < CPT / GC; ++g)
+        staged_group<kI8, EPI, CPT, STATS, kStore, GC>(p, xbuf, dst_row0, row_w0, col_w0, sum, scale, lane, g * GC);
+    if constexpr (kTail != 0)
+        staged_group<kI8, EPI, CPT, STATS, kStore, kTail>(p, xbuf, dst_row0, row_w0, col_w0, sum, scale, lane,
+                                                          (CPT / GC) * GC);
+}
+
 // kCta2: the CTA-pair form (cta_group::2, opt-in with BNN_GEMM_CTA2=1, see launch_tc_pair).  Two CTAs of a
 // cluster share one 256 x BLOCK_N tile: each loads its own 128 rows of A and HALF of the B tile, the leader
 // issues UMMAs of M = 256 that read both halves, each CTA's TMEM receives its own 128 rows and is drained
@@ -563,7 +577,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     using Cfg = TileCfg<BLOCK_N, kCta2, kF4>;
     constexpr int S = Cfg::kStages;
     constexpr int kKElems = kI8 ? kKBytes : kKBytes / 2;   // of the tensor map's element type (bytes for i8 / f4)
-    static_assert(!kF4 || (kI8 && !kCta2 && STATS == BNN_STATS_NONE), "FP4 form: integer epilogues, single CTA");
+    static_assert(!kF4 || (kI8 && !kCta2 && STATS != BNN_STATS_BN_BWD), "FP4 form: integer epilogues, single CTA");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -1237,8 +1251,9 @@ int launch_tc(const bnn_gemm_desc& g, cudaStream_t stream) {
     p.st_zdtype = g.stats_z_dtype;
     p.st_mu = g.stats_mu;
     if (STATS != BNN_STATS_NONE) {
-        // every tile must take the staged full-width path
-        if (!(p.vec_ok && g.N % BLOCK_N == 0 && g.batch == 1)) {
+        // every tile must take the staged full-width path.  (The FP4 form only has integer outputs: their column
+        // sums are a separate staged pass with per-column guards, so ragged widths are fine there.)
+        if (!((kF4 || (p.vec_ok && g.N % BLOCK_N == 0)) && g.batch == 1)) {
             set_error("bnn_gemm: fused column statistics need N %% %d == 0, a 16-byte aligned output "
                       "and batch == 1 (N=%d)", BLOCK_N, g.N);
             return BNN_ERR_UNSUPPORTED;
@@ -1317,9 +1332,18 @@ int pick_epilogue(const bnn_gemm_desc& g, bool i8, cudaStream_t stream) {
     }
 }
 
-// E2M1 operands (BNN_DT_F4): integer epilogues only, tiles of 32 / 128 / 224 columns.
+// E2M1 operands (BNN_DT_F4): integer epilogues only, tiles of 32 / 128 / 224 columns.  The training forward asks
+// for the fused column sums (BNN_STATS_COLSUM, int16 / int32 stores) on any width.
 template <int BLOCK_N>
 int pick_epilogue_f4(const bnn_gemm_desc& g, cudaStream_t stream) {
+    if (g.stats == BNN_STATS_COLSUM) {
+        if (g.epilogue == BNN_EPI_STORE_S16)
+            return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S16, BNN_STATS_COLSUM, true>(g, stream);
+        if (g.epilogue == BNN_EPI_STORE_S32)
+            return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S32, BNN_STATS_COLSUM, true>(g, stream);
+        set_error("bnn_gemm: BNN_STATS_COLSUM on E2M1 operands goes with the int16 / int32 stores");
+        return BNN_ERR_UNSUPPORTED;
+    }
     switch (g.epilogue) {
         case BNN_EPI_STORE_S16: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S16, BNN_STATS_NONE, true>(g, stream);
         case BNN_EPI_STORE_S32: return launch_tc<true, BLOCK_N, BNN_EPI_STORE_S32, BNN_STATS_NONE, true>(g, stream);
@@ -1336,8 +1360,9 @@ int pick_epilogue_f4(const bnn_gemm_desc& g, cudaStream_t stream) {
 int gemm_tc_dispatch(const bnn_gemm_desc& g, cudaStream_t stream) {
     if (g.in_dtype == BNN_DT_F4) {
         BNN_CHECK_ARG(g.A[0] && g.B[0] && aligned16(g.A[0]) && aligned16(g.B[0]), "bnn_gemm: F4 operands not 16-byte aligned");
-        BNN_CHECK_ARG(g.n_pass == 1 && g.stats == BNN_STATS_NONE && g.hi_from_pass == 0 && !g.col_scale && !g.a_unsigned,
-                      "bnn_gemm: BNN_DT_F4 is a single-pass +-1 product without fused statistics");
+        BNN_CHECK_ARG(g.n_pass == 1 && g.stats != BNN_STATS_BN_BWD && g.hi_from_pass == 0 && !g.col_scale &&
+                          !g.a_unsigned,
+                      "bnn_gemm: BNN_DT_F4 is a single-pass +-1 product (fused statistics: column sums only)");
         BNN_CHECK_ARG(g.K % 32 == 0 && g.lda % 32 == 0 && g.ldb % 32 == 0 && g.stride_a % 32 == 0 &&
                           g.stride_b % 32 == 0 && g.lda >= g.K && g.ldb >= g.K,
                       "bnn_gemm: F4 operands need K, pitches and batch strides in multiples of 32 elements (16 bytes)");

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(256)
 binarize_t_kernel(const float* __restrict__ W, int K, int N, int8_t* __restrict__ wt_i8,
                   long long ld_i8, __half* __restrict__ wt_f16, long long ld_f16,
                   uint32_t* __restrict__ wt_bits, long long ld_bits,
+                  uint8_t* __restrict__ wt_f4, long long ld_f4_bytes,
                   uint32_t* __restrict__ absmax_bits) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k0 = blockIdx.y * BT_K + (warp & 3) * 32;
@@ -94,6 +95,15 @@ binarize_t_kernel(const float* __restrict__ W, int K, int N, int8_t* __restrict_
         const long long n = n0 + j;
         const uint32_t bits = m[j];
         if (wt_bits) wt_bits[n * ld_bits + (k0 >> 5)] = bits;
+        if (wt_f4) {   // 32 E2M1 nibbles = one 16-byte word; nibbles past K stay zero (the consumer's K padding)
+            const uint32_t keep = kvalid == 32 ? 0xFFFFFFFFu : ((1u << kvalid) - 1u);
+            uint4 o;
+            o.x = bits_to_e2m1x8(bits) & (spread_bits_to_nibbles(keep) * 0xFu);
+            o.y = bits_to_e2m1x8(bits >> 8) & (spread_bits_to_nibbles(keep >> 8) * 0xFu);
+            o.z = bits_to_e2m1x8(bits >> 16) & (spread_bits_to_nibbles(keep >> 16) * 0xFu);
+            o.w = bits_to_e2m1x8(bits >> 24) & (spread_bits_to_nibbles(keep >> 24) * 0xFu);
+            *reinterpret_cast<uint4*>(wt_f4 + n * ld_f4_bytes + (k0 >> 1)) = o;
+        }
         if (wt_i8) {
             int8_t* d = wt_i8 + n * ld_i8 + k0;
             if (i8vec) {
@@ -352,17 +362,21 @@ extern "C" int bnn_pack_i8_rows(const int8_t* x, int R, int C, int64_t ldx, uint
 
 extern "C" int bnn_binarize_weights_t(const float* W, int K, int N, int8_t* wt_i8, int64_t ld_i8,
                                       void* wt_f16, int64_t ld_f16, uint32_t* wt_bits,
-                                      int64_t ld_bits, uint32_t* absmax_bits, bnn_stream_t stream) {
+                                      int64_t ld_bits, void* wt_f4, int64_t ld_f4, uint32_t* absmax_bits,
+                                      bnn_stream_t stream) {
     BNN_CHECK_ARG(W && K > 0 && N > 0, "bnn_binarize_weights_t: bad input");
     BNN_CHECK_ARG(!wt_i8 || ld_i8 >= K, "bnn_binarize_weights_t: ld_i8 < K");
     BNN_CHECK_ARG(!wt_f16 || ld_f16 >= K, "bnn_binarize_weights_t: ld_f16 < K");
     BNN_CHECK_ARG(!wt_bits || ld_bits >= (K + 31) / 32, "bnn_binarize_weights_t: ld_bits too small");
+    BNN_CHECK_ARG(!wt_f4 || (aligned16(wt_f4) && ld_f4 % 32 == 0 && ld_f4 >= ((K + 31) / 32) * 32),
+                  "bnn_binarize_weights_t: wt_f4 must be 16-byte aligned with a pitch of whole 32-element words");
     dim3 grid(cdiv(N, BT_N), cdiv(K, BT_K));
     BNN_CHECK_ARG(grid.y <= 65535, "bnn_binarize_weights_t: K too large");
     if (absmax_bits)
         BNN_CUDA(cudaMemsetAsync(absmax_bits, 0, sizeof(uint32_t), (cudaStream_t)stream));
     binarize_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        W, K, N, wt_i8, ld_i8, static_cast<__half*>(wt_f16), ld_f16, wt_bits, ld_bits, absmax_bits);
+        W, K, N, wt_i8, ld_i8, static_cast<__half*>(wt_f16), ld_f16, wt_bits, ld_bits,
+        static_cast<uint8_t*>(wt_f4), ld_f4 / 2, absmax_bits);
     BNN_LAUNCH_CHECK("binarize_t_kernel");
     return BNN_OK;
 }

@@ -73,7 +73,7 @@ PROTOTYPES = {
     "bnn_device_query": [C.POINTER(C.c_int)] * 3,
     "bnn_pack_sign_rows": [_p, _i, _i, _i64, _p, _i64, _p],
     "bnn_pack_i8_rows": [_p, _i, _i, _i64, _p, _i64, _p],
-    "bnn_binarize_weights_t": [_p, _i, _i, _p, _i64, _p, _i64, _p, _i64, _p, _p],
+    "bnn_binarize_weights_t": [_p, _i, _i, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p],
     "bnn_unpack_bits": [_p, _i, _i, _i64, _p, _i64, _p, _i64, _p],
     "bnn_bits_to_f4": [_p, _i64, _i, _i64, _p, _i64, _p],
     "bnn_gather_rows": [_p, _i64, _i64, _p, _i, _i64, _p, _i64, _p, _p],
@@ -92,7 +92,7 @@ PROTOTYPES = {
     "bnn_bn_apply": [_p, _i, _i, _i, _i64, _p, _p, _p, _p, _f, _p, _i64, _p, _i64, _p, _i64, _p,
                      _i64, _p],
     "bnn_bn_sign_thresholds": [_p, _p, _p, _p, _f, _i, _p, _p, _p],
-    "bnn_bn_sign": [_p, _i, _i, _i, _i64, _p, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p],
+    "bnn_bn_sign": [_p, _i, _i, _i, _i64, _p, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p],
     "bnn_softmax_xent": [_p, _i, _i, _i64, _p, _p, _p, _p, _d, _p, _p],
     "bnn_bn_bwd_reduce": [_p, _i64, _p, _i, _i64, _i, _i, _p, _p, _p, _i, _p],
     "bnn_bn_bwd_finalize": [_p, _p, _i, _d, _p, _p, _f, _p, _p, _p, _p, _f, _d, _p, _p, _p, _p, _p,

@@ -53,13 +53,14 @@ def pack_i8_rows(x: torch.Tensor, C_: int, bits: torch.Tensor) -> None:
     _call("bnn_pack_i8_rows", ptr(x), x.shape[0], C_, _ld(x), ptr(bits), _ld(bits))
 
 
-def binarize_weights_t(W: torch.Tensor, wt_i8=None, wt_f16=None, wt_bits=None, absmax=None) -> None:
+def binarize_weights_t(W: torch.Tensor, wt_i8=None, wt_f16=None, wt_bits=None, absmax=None, wt_f4=None) -> None:
     K, N = W.shape
     assert W.is_contiguous()
     _call("bnn_binarize_weights_t", ptr(W), K, N,
           ptr(wt_i8), _ld(wt_i8) if wt_i8 is not None else 0,
           ptr(wt_f16), _ld(wt_f16) if wt_f16 is not None else 0,
-          ptr(wt_bits), _ld(wt_bits) if wt_bits is not None else 0, ptr(absmax))
+          ptr(wt_bits), _ld(wt_bits) if wt_bits is not None else 0,
+          ptr(wt_f4), 2 * _ld(wt_f4) if wt_f4 is not None else 0, ptr(absmax))
 
 
 def unpack_bits(bits: torch.Tensor, C_: int, out_i8=None, out_f16=None) -> None:
@@ -92,6 +93,12 @@ def f4_ok(Kd: int, N: int) -> bool:
     operand that makes that product HBM-bound.  BNN_FP4=0: int8."""
     return (Kd % 32 == 0 and N >= 1 and gemm_impl() == nat.GEMM_TCGEN05
             and os.environ.get("BNN_FP4", "1") != "0")
+
+
+def f4_train_ok(Kd: int, N: int) -> bool:
+    """The TRAINING forward of a +-1 x +-1 layer on the FP4 pipe (shapes as f4_ok; the batch-norm column sums are
+    fused into that kind's epilogue on any width).  BNN_FP4_TRAIN=0: int8."""
+    return f4_ok(Kd, N) and os.environ.get("BNN_FP4_TRAIN", "1") != "0"
 
 
 def absmax_f32(x: torch.Tensor, out_bits: torch.Tensor, zero_first=True) -> None:
@@ -178,15 +185,16 @@ def zero(t: torch.Tensor) -> None:
     _call("bnn_zero_async", ptr(t), t.numel() * t.element_size())
 
 
-def fused_stats_ok(N: int, impl=None) -> bool:
+def fused_stats_ok(N: int, impl=None, f4: bool = False) -> bool:
     """Shapes on which the tcgen05 epilogue can carry the column reductions: every tile full-width
-    (tile = 256 columns for N > 128, 128 for N > 32, else 32)."""
+    (tile = 256 columns for N > 128, 128 for N > 32, else 32).  The FP4 kind has integer outputs only, whose
+    sums are guarded per column: any N."""
     if (gemm_impl() if impl is None else impl) != nat.GEMM_TCGEN05:
         return False
     if os.environ.get("BNN_FUSE_STATS", "1") == "0":
         return False
     tile = 256 if N > 128 else (128 if N > 32 else 32)
-    return N % tile == 0
+    return f4 or N % tile == 0
 
 
 def gemm_popc(a_bits, b_bits, M, N, K, D, out_s16=True) -> None:
@@ -271,12 +279,13 @@ def bn_sign_thresholds(mu, var, gamma, beta, eps, N, thr, sgn) -> None:
 
 
 def bn_sign(Z, B, N, thr, sgn, act_i8=None, act_t16=None, act_bits=None, act_t8=None,
-            act_t8x127=None) -> None:
+            act_t8x127=None, act_f4=None) -> None:
     _call("bnn_bn_sign", ptr(Z), z_dtype_of(Z), B, N, _ld(Z), ptr(thr), ptr(sgn),
           ptr(act_i8), _ld(act_i8) if act_i8 is not None else 0,
           ptr(act_t16), _ld(act_t16) if act_t16 is not None else 0,
           ptr(act_bits), _ld(act_bits) if act_bits is not None else 0,
-          ptr(act_t8), ptr(act_t8x127), _ld(act_t8) if act_t8 is not None else 0)
+          ptr(act_t8), ptr(act_t8x127), _ld(act_t8) if act_t8 is not None else 0,
+          ptr(act_f4), 2 * _ld(act_f4) if act_f4 is not None else 0)
 
 
 def activation(x: torch.Tensor, kind: int, out: torch.Tensor) -> None:

@@ -724,19 +724,21 @@ class BinaryLayer(LinearLayer):
         return DeviceArray(i8[:, :Cn].to(torch.float32).reshape(xt.shape))
 
     # ------------------------------------------------------------------ operand preparation
-    def _weight_operands(self, real_input: bool):
+    def _weight_operands(self, real_input: bool, f4: bool = False):
         Kd, N = self.weights_shape
         ws = self._ws
         ops = {}
         ops["bits"] = ws.get("wt_bits", (N, pad_to(Kd, 32) // 32), torch.int32, zero=True)
         if real_input:
             ops["f16"] = ws.get("wt_f16", (N, pad_to(Kd, 8)), torch.float16, zero=True)
+        elif f4:   # the input arrives as E2M1 nibbles: so do the weights
+            ops["f4"] = ws.get("wt_f4", (N, pad_to(Kd, 32) // 2), torch.uint8, zero=True)
         else:
             ops["i8"] = ws.get("wt_i8", (N, pad_to(Kd, 16)), torch.int8, zero=True)
         # the same pass over W yields max|W|, the bound of the backward pass's fp16 split of W
         ops["amax"] = ws.get("w_amax", (1,), torch.float32)
         K_.binarize_weights_t(self.weights.t, wt_i8=ops.get("i8"), wt_f16=ops.get("f16"),
-                              wt_bits=ops["bits"], absmax=ops["amax"])
+                              wt_bits=ops["bits"], absmax=ops["amax"], wt_f4=ops.get("f4"))
         return ops
 
     def _apply_foreign_callback(self, cb, wops):
@@ -821,13 +823,12 @@ class BinaryLayer(LinearLayer):
         else:
             assert X.n == Kd
             B = X.rows
-        f4_in = (not real_input) and X.f4 is not None and X.i8 is None   # producer emitted nibbles (eval mode)
-        assert not (f4_in and isTrain)
+        f4_in = (not real_input) and X.f4 is not None and X.i8 is None   # the producer emitted nibbles
 
         # operand preparation of a real-valued input does not depend on W: queue it before the weight
         # read, which in data-parallel runs first waits for the peers' updated rows to land
         xin = self._real_input_operands(Xt, isTrain) if real_input else X
-        wops = self._weight_operands(real_input)
+        wops = self._weight_operands(real_input, f4=f4_in)
         # fault-injection hooks act on the already-binarized weight, eval mode only (layers.py:215-218)
         if not isTrain:
             for cb in self.callbacks:
@@ -835,9 +836,8 @@ class BinaryLayer(LinearLayer):
                     cb.apply_to_layer(self, wops)
                 else:
                     self._apply_foreign_callback(cb, wops)
-        if f4_in:   # after the hooks: the packed words are what they mutate (callbacks.py:79-83)
-            wops["f4"] = ws.get("wt_f4", (N, pad_to(Kd, 32) // 2), torch.uint8, zero=True)
-            K_.bits_to_f4(wops["bits"], Kd, wops["f4"])
+            if f4_in and self.callbacks:   # the packed words are what the hooks mutate (callbacks.py:79-83)
+                K_.bits_to_f4(wops["bits"], Kd, wops["f4"])
 
         sign_out = self.activation == af.sign
         popc = binary_gemm_variant() == "popc"
@@ -848,7 +848,12 @@ class BinaryLayer(LinearLayer):
         sgn = ws.get("sgn", (N,), torch.float32)
         act_i8 = act_f4 = None
         emit_f4 = fuse_sign and self._consumer_takes_f4()
-        if emit_f4:
+        consumer = getattr(self, "output_layer", None)
+        # training: a wide consumer multiplies on the FP4 pipe too — this layer then hands over packed sign
+        # bits (4 MB instead of 33 MB of int8 for 8192 x 4096) which bnn_bits_to_f4 expands to nibbles
+        train_f4 = (sign_out and isTrain and not popc and isinstance(consumer, BinaryLayer)
+                    and K_.f4_train_ok(N, consumer.layerUnits))
+        if emit_f4 or train_f4:
             act_f4 = ws.get(f"a_f4_{B}", (B, pad_to(N, 32) // 2), torch.uint8, zero=True)
         elif sign_out:
             act_i8 = ws.get(f"a_i8_{B}", (B, pad_to(N, 16)), torch.int8, zero=True)
@@ -858,7 +863,7 @@ class BinaryLayer(LinearLayer):
         # training: the GEMM epilogue also accumulates the batch-norm column sums (sum z, sum z^2), so
         # Z is not re-read for them (shapes the epilogue cannot cover use the bnn_colstats pass)
         acc = None
-        if isTrain and not (popc and not real_input) and K_.fused_stats_ok(N):
+        if isTrain and not (popc and not real_input) and K_.fused_stats_ok(N, f4=f4_in):
             acc = bn.stats_target()
         stats = dict(mode=nat.STATS_COLSUM, sums=acc) if acc is not None else None
 
@@ -890,10 +895,10 @@ class BinaryLayer(LinearLayer):
             elif fuse_sign:
                 K_.gemm(M=B, N=N, D=act_i8, ldd=act_i8.stride(0), epilogue=nat.EPI_SIGN_I8, epi_thr=thr,
                         epi_sgn=sgn, **pm1)
-            elif f4_in:
+            elif f4_in:   # also the training forward of wide layers: column sums fused on 128-wide tiles
                 Z = ws.get(f"z_int_{B}", (B, pad_to(N, 8)), torch.int16 if s16 else torch.int32)
                 K_.gemm(M=B, N=N, D=Z, ldd=Z.stride(0), epilogue=nat.EPI_STORE_S16 if s16 else nat.EPI_STORE_S32,
-                        **pm1)
+                        stats=stats, **pm1)
             else:
                 Z = ws.get(f"z_int_{B}", (B, pad_to(N, 8)), torch.int16 if s16 else torch.int32)
                 if popc:
@@ -915,7 +920,6 @@ class BinaryLayer(LinearLayer):
         # ---- BN + activation
         if sign_out:
             act_t16 = act_t8 = act_t8x127 = None
-            consumer = getattr(self, "output_layer", None)
             if isTrain and consumer is not None and K_.int8_dw_ok(consumer.layerUnits, B):
                 # the layer above forms its dW on the int8 tensor pipe: transposed +-1 / +-127 bytes
                 act_t8 = ws.get(f"a_t8_{B}", (N, pad_to(B, 16)), torch.int8, zero=True)
@@ -928,7 +932,7 @@ class BinaryLayer(LinearLayer):
                 # to evaluating gamma*((z-mu)/sqrt(var+eps))+beta and taking the sign
                 K_.bn_sign_thresholds(mu, var, bn.gamma.t, bn.beta.t, bn.EPSILON, N, thr, sgn)
                 K_.bn_sign(Z, B, N, thr, sgn, act_i8=act_i8, act_t16=act_t16, act_bits=act_bits,
-                           act_t8=act_t8, act_t8x127=act_t8x127)
+                           act_t8=act_t8, act_t8x127=act_t8x127, act_f4=act_f4 if train_f4 else None)
             elif act_bits is not None:
                 K_.pack_i8_rows(act_i8, N, act_bits)
             out = SignActivation(act_i8, N, t16=act_t16, bits=act_bits, t8=act_t8, t8x127=act_t8x127, f4=act_f4)

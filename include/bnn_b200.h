@@ -68,11 +68,13 @@ int bnn_pack_i8_rows(const int8_t* x, int R, int C, int64_t ldx, uint32_t* bits,
  *   wt_f16 [N, ld_f16]  fp16  +-1                 (tcgen05 kind::f16 operand, real-input layer 0)
  *   wt_bits[N, ld_bits] uint32, bit j of word w = (W[32w+j, n] >= 0), pad bits 0 (XOR+popc operand,
  *                       and the "packed weights" the fault kernels mutate)
+ *   wt_f4  [N, ld_f4 / 2 bytes] E2M1 nibbles +-1.0 (tcgen05 kind::mxf4 operand, BNN_DT_F4; layout of
+ *                       bnn_bits_to_f4: ld_f4 counts elements, a multiple of 32, nibbles past K are zero)
  *   absmax_bits         device uint32 <- bits(max|W|): the bound the backward fp16 split of W needs,
  *                       obtained from the same read of W (see bnn_absmax_f32) */
 int bnn_binarize_weights_t(const float* W, int K, int N, int8_t* wt_i8, int64_t ld_i8,
                            void* wt_f16, int64_t ld_f16, uint32_t* wt_bits, int64_t ld_bits,
-                           uint32_t* absmax_bits, bnn_stream_t stream);
+                           void* wt_f4, int64_t ld_f4, uint32_t* absmax_bits, bnn_stream_t stream);
 
 /* Expand packed sign bits [R, ldw] back to int8 +-1 [R, C] (pitch ldo) and/or fp16 +-1. */
 int bnn_unpack_bits(const uint32_t* bits, int R, int C, int64_t ldw, int8_t* out_i8, int64_t ld_i8,
@@ -128,7 +130,8 @@ enum {
                      products of the evaluation paths on tcgen05 kind::mxf4.block_scale with unit scale factors —
                      exact (fp32 accumulators hold integers, K < 2^24), twice the kind::i8 rate, half the operand
                      bytes.  K, lda, ldb, stride_a, stride_b count ELEMENTS and are multiples of 32; one pass,
-                     integer epilogues (STORE_S32 / STORE_S16 / SIGN_I8 / SIGN_F4), no fused statistics. */
+                     integer epilogues (STORE_S32 / STORE_S16 / SIGN_I8 / SIGN_F4); of the fused statistics only
+                     BNN_STATS_COLSUM with the integer stores (any N: the sums are guarded per column). */
 };
 enum {
     BNN_EPI_STORE_F32 = 0, /* D fp32  = acc * host_scale / (sa*sb)                       */
@@ -274,11 +277,12 @@ int bnn_bn_sign_thresholds(const float* mu, const float* var, const float* gamma
 
 /* The sign-only form of bnn_bn_apply on those thresholds (same outputs, no out_f32), plus optionally
  * the transposed int8 copies act_t8 [N, ld_t8] = +-1 and act_t8x127 = +-127: the A pieces of the
- * digit-split int8 dW product (bnn_gemm hi_from_pass). */
+ * digit-split int8 dW product (bnn_gemm hi_from_pass), and act_f4 [B, ld_f4 / 2 bytes] = E2M1 nibbles (the A
+ * operand of a BNN_DT_F4 product; layout of bnn_bits_to_f4, the buffer's padding nibbles are left untouched). */
 int bnn_bn_sign(const void* Z, int z_dtype, int B, int N, int64_t ldz, const float* thr,
                 const float* sgn, int8_t* act_i8, int64_t ld_i8, void* act_t16, int64_t ld_t16,
                 uint32_t* act_bits, int64_t ld_bits, int8_t* act_t8, int8_t* act_t8x127, int64_t ld_t8,
-                bnn_stream_t stream);
+                void* act_f4, int64_t ld_f4, bnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * A6/A10  output activation, loss and its gradient   (softmax activation.py:44-53;

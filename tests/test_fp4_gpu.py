@@ -76,6 +76,42 @@ def test_bits_to_f4(T, oracle, R, C):
     assert guards_intact(buf, R, ld // 2)
 
 
+@pytest.mark.parametrize("K_,N", [(32, 8), (784, 100), (1000, 33), (4096, 512), (40, 5)])
+def test_binarize_weights_emits_nibbles(T, K_, N):
+    """bnn_binarize_weights_t(wt_f4): the nibbles bnn_bits_to_f4 makes of the packed words, straight from W."""
+    from mlpcode import kernels as K
+    rng = np.random.default_rng(K_ + N)
+    W = rng.standard_normal((K_, N)).astype(np.float32)
+    W[rng.random((K_, N)) < 0.05] = 0.0                      # sign(0) = +1 (layers.py:278-279)
+    ld = (K_ + 31) // 32 * 32
+    buf, out = guarded(T, N, ld // 2, fill=0)                # the layer's buffer: zero-initialised, padding stays zero
+    bits = T.zeros((N, ld // 32), dtype=T.int32, device="cuda")
+    K.binarize_weights_t(dev(W), wt_bits=bits, wt_f4=out)
+    want = to_f4(np.where(W.T >= 0, 1, -1).astype(np.int8), ld)
+    assert np.array_equal(out.cpu().numpy(), want)
+    ref = T.zeros((N, ld // 2), dtype=T.uint8, device="cuda")
+    K.bits_to_f4(bits, K_, ref)
+    assert T.equal(ref, out) and not bool(buf[:256 + ld // 2].any()) and not bool(buf[256 + (N + 1) * (ld // 2):].any())
+
+
+@pytest.mark.parametrize("B,N", [(8, 8), (130, 100), (257, 513), (1024, 4096), (5, 33)])
+def test_bn_sign_emits_nibbles(T, B, N):
+    """bnn_bn_sign(act_f4): the nibble form of the int8 activations it writes in the same launch."""
+    from mlpcode import kernels as K
+    rng = np.random.default_rng(B + N)
+    Z = dev(rng.integers(-300, 301, (B, (N + 7) // 8 * 8)).astype(np.int16))
+    thr = dev((rng.standard_normal(N) * 100).astype(np.float32))
+    sgn = dev(np.where(rng.random(N) < 0.3, -1.0, 1.0).astype(np.float32))
+    ld8, ld4 = (N + 15) // 16 * 16, (N + 31) // 32 * 32
+    a8 = T.zeros((B, ld8), dtype=T.int8, device="cuda")
+    buf, a4 = guarded(T, B, ld4 // 2, fill=0)
+    K.bn_sign(Z, B, N, thr, sgn, act_i8=a8, act_f4=a4)
+    want = T.where(Z[:, :N].float() * sgn >= thr, 1, -1).to(T.int8)
+    assert T.equal(a8[:, :N], want)
+    assert np.array_equal(a4.cpu().numpy(), to_f4(want.cpu().numpy(), ld4))
+    assert not bool(buf[:256 + ld4 // 2].any()) and not bool(buf[256 + (B + 1) * (ld4 // 2):].any())
+
+
 F4_SHAPES = [(128, 224, 256), (130, 40, 64), (256, 10, 512), (300, 300, 800), (64, 16, 32), (1, 1, 32),
              (257, 513, 4096), (1000, 4096, 4096), (128, 128, 160), (129, 225, 8192)]
 
@@ -160,6 +196,29 @@ def test_gemm_f4_batched(T, shared):
         assert np.array_equal(from_f4(out[t].cpu().numpy(), N), want), t
 
 
+@pytest.mark.parametrize("M,N,K_", [(128, 128, 64), (300, 512, 800), (1000, 384, 256), (77, 32, 64), (200, 10, 128),
+                                    (257, 513, 64), (300, 300, 800), (130, 224, 96), (8192, 4096, 512)])
+def test_gemm_f4_fused_colstats(T, M, N, K_):
+    """BNN_STATS_COLSUM on the FP4 kind (training forward of +-1 layers; all three tile widths, ragged M and N):
+    (sum z, sum z^2) per column are exact integers and must equal the int64 sums of the stored result
+    (layers.py:81-82); nothing is written outside the result."""
+    from mlpcode import _native as nat, kernels as K
+    rng = np.random.default_rng(M + N + K_)
+    a, b = pm1(rng, (M, K_)), pm1(rng, (N, K_))
+    ref = (dev(a).float() @ dev(b).float().T).to(T.int64)
+    A4, B4 = dev(to_f4(a)), dev(to_f4(b))
+    for epi, dt, mult in ((nat.EPI_STORE_S16, T.int16, 8), (nat.EPI_STORE_S32, T.int32, 4)):
+        ldd = (N + mult - 1) // mult * mult
+        D = T.full((M + 2, ldd), 12345, dtype=dt, device="cuda")
+        sums = T.zeros((2, N), dtype=T.float64, device="cuda")
+        K.gemm(M=M, N=N, K=K_, A=(A4,), B=(B4,), lda=2 * A4.stride(0), ldb=2 * B4.stride(0), D=D[1:M + 1], ldd=ldd,
+               in_dtype=nat.DT_F4, epilogue=epi, stats=dict(mode=nat.STATS_COLSUM, sums=sums))
+        assert T.equal(D[1:M + 1, :N].to(T.int64), ref)
+        assert bool((D[1:M + 1, N:] == 12345).all()) and bool((D[0] == 12345).all()) and bool((D[M + 1] == 12345).all())
+        assert T.equal(sums[0].to(T.int64), ref.sum(0))
+        assert T.equal(sums[1].to(T.int64), (ref * ref).sum(0))
+
+
 def test_gemm_f4_rejects_bad_shapes(T):
     from mlpcode import _native as nat, kernels as K
     A = T.zeros((128, 64), dtype=T.uint8, device="cuda")
@@ -227,3 +286,32 @@ def test_sweeps_identical_with_and_without_fp4(T, monkeypatch):
                      wf.run_bernoulli(0.05, 6, 3), im.run(0.05, 10, 9))
     for a, b in zip(res["0"], res["1"]):
         assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def test_training_identical_with_and_without_fp4(T, monkeypatch):
+    """Training steps with the wide hidden layers' forward on the FP4 pipe (kernels.f4_train_ok) leave exactly the
+    weights, batch-norm parameters and loss the int8 pipe leaves: z is the same integer on both, everything after
+    it is shared."""
+    units = [784, 512, 384, 256, 10]
+    rng = np.random.default_rng(21)
+    X = (rng.integers(-16, 17, (4, 256, 784)) / 16).astype(np.float32)
+    y = np.eye(10, dtype=np.float32)[rng.integers(0, 10, (4, 256))]
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("BNN_FP4_TRAIN", flag)
+        nn, _ = _net(units, seed=8)
+        losses = [float(nn.train_step(X[i], y[i])) for i in range(4)]
+        nn.predict(X[0], isTraining=True)   # one more training-mode forward (both settings) to look at the operands
+        acts = [l.cache["a"] for l in nn._layers[:-1]]
+        if flag == "1":   # the path under test is the one that ran
+            assert acts[0].f4 is not None and acts[0].i8 is None and acts[1].f4 is not None
+            assert acts[2].f4 is not None          # the 10-wide output layer reads nibbles too
+        else:
+            assert all(a.f4 is None and a.i8 is not None for a in acts)
+        res[flag] = (losses, [l.weights.get().copy() for l in nn._layers],
+                     [l.batchNormLayer.gamma.get().copy() for l in nn._layers],
+                     [l.batchNormLayer.mu.get().copy() for l in nn._layers])
+    assert res["0"][0] == res["1"][0]
+    for grp in (1, 2, 3):
+        for a, b in zip(res["0"][grp], res["1"][grp]):
+            assert np.array_equal(a, b)

@@ -110,18 +110,43 @@ def test_weight_sweep_without_fp4_keeps_int8_copies(dry, monkeypatch):
 
 
 def test_predict_routes_wide_hidden_layers_through_fp4(dry, monkeypatch):
-    """Eval-mode forward: a layer whose consumer takes nibbles ends in BNN_EPI_SIGN_F4, the consumer expands its
-    packed weights with bnn_bits_to_f4; every call passes the library's argument validation."""
+    """Eval-mode forward: a layer whose consumer takes nibbles ends in BNN_EPI_SIGN_F4, the consumer's weights come
+    out of bnn_binarize_weights_t as nibbles — or, with a fault hook registered, out of bnn_bits_to_f4 after the
+    hook has acted on the packed words; every call passes the library's argument validation."""
+    from mlpcode.callbacks import ErrorCallback
     nn = _net([784, 256, 128, 10])
     X = np.random.default_rng(3).random((40, 784), dtype=np.float32) * 2 - 1
     del dry[:]
     nn.predict(X)
     names = [n for n, _ in dry]
-    assert names.count("bnn_bits_to_f4") == 2 and names.count("bnn_gemm") == 3
+    assert "bnn_bits_to_f4" not in names and names.count("bnn_gemm") == 3
+    nn._layers[1].callbacks = [ErrorCallback(0.1, bnn=True)]
+    del dry[:]
+    nn.predict(X)
+    assert [n for n, _ in dry].count("bnn_bits_to_f4") == 1
+    nn._layers[1].callbacks = []
     monkeypatch.setenv("BNN_FP4", "0")
     del dry[:]
     nn.predict(X)
     assert "bnn_bits_to_f4" not in [n for n, _ in dry]
+
+
+def test_training_step_routes_the_forward_through_fp4(dry, monkeypatch):
+    """Training forward: +-1 layers read nibbles written by the producer's bnn_bn_sign (no conversion kernels) and
+    fuse their column sums into the FP4 product (no bnn_colstats for them); BNN_FP4_TRAIN=0 is the int8 form."""
+    nn = _net([784, 256, 128, 10])
+    X = np.random.default_rng(3).random((64, 784), dtype=np.float32) * 2 - 1
+    y = np.eye(10, dtype=np.float32)[np.arange(64) % 10]
+    monkeypatch.setenv("BNN_GRAPH", "0")
+    monkeypatch.setenv("BNN_OVERLAP_DW", "0")      # no side stream on the CPU-only host
+    del dry[:]
+    nn.train_step(X, y, 0.01)
+    names = [n for n, _ in dry]
+    assert "bnn_bits_to_f4" not in names and "bnn_colstats" not in names
+    monkeypatch.setenv("BNN_FP4_TRAIN", "0")
+    del dry[:]
+    nn.train_step(X, y, 0.01)
+    assert [n for n, _ in dry].count("bnn_colstats") == 1      # the 10-wide int8 output layer
 
 
 def test_unchanged_script_flow_stays_on_bytes(dry):

@@ -55,7 +55,7 @@ def test_pair_kernels_use_the_two_cta_forms(kernels):
 
 def test_fp4_kernels_use_the_block_scaled_mma(kernels):
     f4 = {k: v for k, v in kernels.items() if "ELb0ELb1EEEv" in k}
-    assert len(f4) == 12                                   # 3 tile widths x 4 integer epilogues
+    assert len(f4) == 18            # 3 tile widths x (4 integer epilogues + 2 stores with column sums)
     for name, ops in f4.items():
         assert any(o.startswith("UTCOMMA") for o in ops), (name, ops)             # tcgen05.mma kind::mxf4.block_scale
         assert "UTMALDG.3D" in ops, name
