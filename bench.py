@@ -407,13 +407,20 @@ def run_gpu(args):
                     "2-3 fp16 passes per product (executed_*), so frac <= 1/2..1/3 by construction",
         }
     binary = None
-    if i8["n"]:
-        tops = i8["flops"] / (i8["ms"] * 1e-3) / 1e12
-        binary = {"kernel": "gemm_tc_kernel<i8> (+-1 x +-1 forward, layers 1..3)", "achieved": tops,
-                  "unit": "TOP/s", "peak": int8_peak, "peak_source": "cuBLASLt int8 8192^3 on this box",
+    f4 = groups.get("f4", {"ms": 0.0, "n": 0, "flops": 0.0, "exec": 0.0})
+    bg, bkind = (f4, "f4") if f4["n"] else (i8, "i8")
+    if bg["n"]:
+        tops = bg["flops"] / (bg["ms"] * 1e-3) / 1e12
+        binary = {"kernel": ("gemm_tc_kernel<mxf4> (+-1 x +-1 forward of layers 1..3 on E2M1 operands, unit scale "
+                             "factors, fused column sums)" if bkind == "f4" else
+                             "gemm_tc_kernel<i8> (+-1 x +-1 forward, layers 1..3)"),
+                  "achieved": tops, "unit": "TOP/s", "peak": int8_peak,
+                  "peak_source": "cuBLASLt int8 8192^3 on this box" +
+                                 (" (no library FP4 GEMM takes +-1 operands with integer outputs; the kind's MMA-only "
+                                  "rate is 2x kind::i8, tools/probe_mxf4.cu)" if bkind == "f4" else ""),
                   "frac": (tops / int8_peak) if int8_peak else None,
-                  "avg_launch_ms": i8["ms"] / i8["n"], "launches": i8["n"],
-                  "share_of_step": i8["ms"] / ms_total}
+                  "avg_launch_ms": bg["ms"] / bg["n"], "launches": bg["n"],
+                  "share_of_step": bg["ms"] / ms_total}
 
     dw_int8 = None
     if i8dw["n"]:
@@ -435,7 +442,8 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "i8 fwd + i8x3 fixed-point dW / f16x2-split f32-acc dX", "data": "synthetic",
+        "dtype": ("f4 (E2M1 +-1, exact)" if f4["n"] else "i8") +
+                 " fwd + i8x3 fixed-point dW / f16x2-split f32-acc dX", "data": "synthetic",
         "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(Xh.nbytes + Yh.nbytes), "d2h_bytes_per_step": 8,
