@@ -313,6 +313,18 @@ def run_gpu(args):
     K.gemm_events = []
     ms_eager = timed(lambda: nn.train_step_async(Xd, Yd, LR), args.steps, "eager")
     events, K.gemm_events = K.gemm_events, None
+    # per call site (GEMM i of the step, averaged over the steps) on every rank: shows WHICH products stretch in
+    # data-parallel runs and whether one GPU is slower than the others
+    fence()
+    per_step = len(events) // args.steps if args.steps else 0
+    site_ms = [0.0] * per_step
+    for i, (s_, e_, *_rest) in enumerate(events[: per_step * args.steps]):
+        site_ms[i % per_step] += s_.elapsed_time(e_) / args.steps
+    site_kinds = [ev[2] for ev in events[:per_step]]
+    site_ranks = [site_ms]
+    if comm:
+        site_ranks = [None] * world
+        torch.distributed.all_gather_object(site_ranks, site_ms)
 
     # ---- end-to-end through the public API with HOST buffers: every step copies its inputs in from
     # pinned memory and its loss out.  Two public calls are measured: the per-batch `train_step`
@@ -454,6 +466,12 @@ def run_gpu(args):
                                       "api": "Network.train_step(X_host, y_host) -> float"}},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "binary_gemm": binary,
         "dw_int8_gemm": dw_int8,
+        "gemm_sites": {"kinds": site_kinds, "ms_rank0": [round(x, 4) for x in site_ms],
+                       "ms_max_over_ranks": [round(max(r[i] for r in site_ranks), 4) for i in range(per_step)],
+                       "sum_ms_per_rank": [round(sum(r), 4) for r in site_ranks],
+                       "note": "eager pass, CUDA-event pair around every GEMM launch on the main stream, in step order "
+                               "(f16: layer-0 forward, 10-wide dW, dX x3, layer-0 dW; f4 / i8: +-1 forward; i8dw: dW); "
+                               "side-stream GEMMs overlap the main stream's, so the sum exceeds the step"},
         "cpu_baseline": cpu_baseline,
         "step_launch": "one CUDA graph replay per step" if use_graph else "eager kernel launches",
         "ms_per_step_eager": ms_eager / args.steps,

@@ -57,8 +57,6 @@ def main():
         for _ in range(3):
             nn.train_step_async(Xd, Yd, bench.LR)
         torch.cuda.synchronize()
-    if rank != 0:
-        return
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     ks = sorted(((e.time_range.start, e.time_range.end - e.time_range.start, e.name,
                   getattr(e, "stream", None)) for e in evs), key=lambda k: k[0])
@@ -66,9 +64,14 @@ def main():
     starts = [i for i, k in enumerate(ks) if "absmax" in k[2]]
     ks = ks[starts[-1] - 1:] if starts else ks
     t0 = ks[0][0]
-    out = [{"name": k[2][:90], "start_us": k[0] - t0, "dur_us": k[1]} for k in ks]
+    # every rank writes its own time line; abs_us is CUPTI's host-clock time stamp, comparable across the ranks of
+    # one node (to within a few microseconds), so waits can be attributed to the rank that was late
+    out = [{"name": k[2][:90], "start_us": k[0] - t0, "dur_us": k[1], "abs_us": k[0]} for k in ks]
     Path(REPO / "gpurun_out").mkdir(exist_ok=True)
-    (REPO / "gpurun_out" / f"dp_timeline_n{world}.json").write_text(json.dumps(out, indent=0))
+    suffix = "" if rank == 0 else f"_r{rank}"
+    (REPO / "gpurun_out" / f"dp_timeline_n{world}{suffix}.json").write_text(json.dumps(out, indent=0))
+    if rank != 0:
+        return
     comm_k = [k for k in ks if "nccl" in k[2].lower()]
     comp_k = [k for k in ks if "nccl" not in k[2].lower()]
     span = max(k[0] + k[1] for k in ks) - t0
