@@ -108,7 +108,7 @@ while [ $# -gt 0 ]; do
     prof-hbm)
       run profile_plain 300 $PROFILE_CMD &&
       run prof_hbm 900 ncu --set full --clock-control none --import-source on \
-          -k regex:'bn_|colstats|split_f16|binarize|absmax|softmax|sgd|gather' -s 132 -c 33 -f \
+          -k regex:'bn_|colstats|split_f16|binarize|absmax|softmax|sgd|gather' -s 128 -c 32 -f \
           -o /tmp/prof_hbm $PROFILE_CMD && raw_csv prof_hbm
       ;;
     prof-sweep)
