@@ -334,6 +334,11 @@ def run_gpu(args):
     for _ in range(2):
         nn.train_step(Xp, Yp, LR)
     ms_serial = timed(lambda: nn.train_step(Xp, Yp, LR), args.steps)
+    # the step's host->device copy alone, every rank copying at once (what the host side can deliver)
+    h2d_tmp = torch.empty_like(Xd)
+    h2d_tmp.copy_(Xp, non_blocking=True)
+    ms_h2d = timed(lambda: h2d_tmp.copy_(Xp, non_blocking=True), 10) / 10
+    del h2d_tmp
     nn.train_stream([(Xp, Yp)] * 3, LR)
     e2e_losses = []
     ms_e2e = timed(lambda: e2e_losses.extend(nn.train_stream([(Xp, Yp)] * args.steps, LR)), 1)
@@ -459,6 +464,7 @@ def run_gpu(args):
         "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(Xh.nbytes + Yh.nbytes), "d2h_bytes_per_step": 8,
+                "h2d_alone_ms": ms_h2d, "h2d_alone_gb_per_s_per_gpu": Xh.nbytes / (ms_h2d * 1e-3) / 1e9,
                 "api": "Network.train_stream(batches) - pinned host batches in, losses out, copies "
                        "overlapped with compute",
                 "serial_train_step": {"value": world * BATCH * args.steps / (ms_serial * 1e-3),
