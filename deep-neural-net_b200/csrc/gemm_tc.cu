@@ -568,7 +568,8 @@ __device__ __forceinline__ void staged_rows(const TcParams& p, uint32_t xbuf, fl
 // by that CTA's epilogue warps exactly as in the single-CTA form.  The B tile then crosses L2 -> shared
 // memory once per pair instead of once per CTA.  p.m_tiles counts PAIRS of row tiles in this form.
 // kF4 (with kI8 = true: the epilogues see exact integers): E2M1 operands on kind::mxf4.block_scale with unit scale
-// factors — the +-1 x +-1 products of the evaluation paths at twice the kind::i8 rate and half the operand bytes.
+// factors — every +-1 x +-1 product (training forward with fused column sums, sweeps, inference) at twice the
+// kind::i8 MMA rate and half the operand bytes.
 template <bool kI8, int BLOCK_N, int EPI, int STATS, bool kCta2 = false, bool kF4 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,

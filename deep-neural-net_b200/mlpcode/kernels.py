@@ -88,7 +88,7 @@ def bits_to_f4(bits: torch.Tensor, C_: int, out_f4: torch.Tensor) -> None:
 
 
 def f4_ok(Kd: int, N: int) -> bool:
-    """A +-1 x +-1 evaluation product [*, Kd] x [N, Kd] goes to the FP4 tensor pipe: tcgen05 path and K in whole
+    """A +-1 x +-1 product [*, Kd] x [N, Kd] goes to the FP4 tensor pipe: tcgen05 path and K in whole
     16-byte words.  N is free: a 10-wide output layer reads its input as nibbles too — half the bytes of the one
     operand that makes that product HBM-bound.  BNN_FP4=0: int8."""
     return (Kd % 32 == 0 and N >= 1 and gemm_impl() == nat.GEMM_TCGEN05

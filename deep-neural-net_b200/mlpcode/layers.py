@@ -52,7 +52,7 @@ class SignActivation(DeviceArray):
     def __init__(self, i8, n, t16=None, bits=None, t8=None, t8x127=None, f4=None):
         self.i8, self.n, self.t16, self.bits = i8, n, t16, bits
         self.t8, self.t8x127 = t8, t8x127   # transposed int8 +-1 / +-127 (int8 dW operand pieces)
-        self.f4 = f4                        # E2M1 nibbles [B, pad32(n) / 2] (FP4 forward operand, eval mode)
+        self.f4 = f4                        # E2M1 nibbles [B, pad32(n) / 2] (the consumer's FP4 forward operand)
         self.rows = (i8 if i8 is not None else f4).shape[0]
         self._dense = None
 
